@@ -1,0 +1,320 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (container-only).
+
+Every array written here is an output of the reference's own code
+(rocket_environment_pre_wrap, pso_wrapped_env, rl_wrapped_env_pytorch, LandingBurn
+loop) imported through tools/ref_harness.py; inputs (states, actions, weights,
+noise tapes) are stored alongside so the oracle and the CUDA path can be fed the
+identical data on a box where /root/reference does not exist.
+
+    python tools/make_golden.py            # rewrites tests/golden/
+"""
+import io
+import contextlib
+import math
+import os
+import random
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from tools.ref_harness import load_reference, NoiseTapeWind  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+P, G = "landing_burn_pure_throttle", "landing_burn"
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def info_row(info):
+    ai = info["action_info"]
+    return [info["mach_number"], info["dynamic_pressure"], info["CL"], info["CD"],
+            info["air_density"], info["atmospheric_pressure"], info["speed_of_sound"],
+            info["x_cog"], info["inertia"], float(info["mass_flow"]), float(ai["throttle"]),
+            info["alpha_effective"], info["g_load_1_sec_window"]]
+
+
+INFO_COLS = ["mach", "q", "CL", "CD", "rho", "p_atm", "a", "x_cog", "inertia", "mass_flow",
+             "throttle", "alpha_eff", "g1"]
+
+
+def tape_replay():
+    import pandas as pd
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    g = pd.read_csv("data/reference_trajectory/landing_burn_controls_pure_throttle/"
+                    "state_action_landing_burn_pure_throttle_control.csv")
+    env = rocket_environment_pre_wrap(type="pso", flight_phase=P, enable_wind=False)
+    env.reset()
+    u = g["u0"].values
+    S, R, D, T, TID, INFO = [], [], [], [], [], []
+    for k in range(len(u)):
+        s, r, d, t, info = quiet(env.step, np.array([[u[k]]]))
+        S.append([float(v) for v in s]); R.append(float(r)); D.append(d); T.append(t)
+        TID.append(env.truncation_id); INFO.append(info_row(info))
+        if d or t:
+            break
+    csv_cols = ["x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "theta[rad]", "theta_dot[rad/s]",
+                "gamma[rad]", "alpha[rad]", "mass[kg]", "masspropellant[kg]", "time[s]"]
+    np.savez_compressed(os.path.join(OUT, "p_tape_replay.npz"), u0=u, states=np.array(S),
+                        rewards=np.array(R), done=np.array(D), truncated=np.array(T),
+                        trunc_id=np.array(TID), info=np.array(INFO), info_cols=INFO_COLS,
+                        csv_states=g[csv_cols].values)
+    print("tape_replay", len(S), "steps; final reward", R[-1], "done", D[-1])
+
+
+def _collect_states(phase, rng, n_roll, act_dim):
+    """States visited by short random-policy rollouts (reference env, pso rtd)."""
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    env = rocket_environment_pre_wrap(type="pso", flight_phase=phase, enable_wind=False)
+    out = []
+    for r in range(n_roll):
+        env.reset()
+        bias = rng.uniform(-1, 1, act_dim)
+        prev = env.state
+        win = []
+        for k in range(3000):
+            a = np.clip(bias + 0.5 * rng.uniform(-1, 1, act_dim), -1, 1)
+            s, rew, d, t, info = quiet(env.step, a.astype(np.float64))
+            prevs = (0.0, 0.0, 0.0)
+            if phase == G:
+                prevs = (env.gimbal_angle_deg_prev, env.delta_command_left_rad_prev,
+                         env.delta_command_right_rad_prev)
+            out.append(([float(v) for v in s], [float(v) for v in prev], list(env.g_loads_window),
+                        [float(v) for v in prevs]))
+            prev = s
+            if d or t:
+                break
+    return out
+
+
+def single_step(phase, tag, n=192, seed=0):
+    """(state, prev_state, g-window, actuator prevs, action) -> one reference step."""
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    rng = np.random.default_rng(seed)
+    act_dim = 1 if phase == P else 4
+    pool = _collect_states(phase, rng, 6 if phase == P else 24, act_dim)
+    env = rocket_environment_pre_wrap(type="pso", flight_phase=phase, enable_wind=False)
+    rows = dict(state=[], prev=[], win=[], nwin=[], aprev=[], act32=[], act64=[],
+                o64=[], o32=[])
+    for i in range(n):
+        s, sp, win, aprev = pool[rng.integers(len(pool))]
+        s = np.array(s); sp = np.array(sp)
+        if i % 3 == 1:      # perturb: low-altitude / slow cases to exercise done / y<0 branches
+            s = s.copy()
+            s[1] = rng.uniform(-2.0, 40.0)
+            s[3] = -rng.uniform(0.5, 30.0)
+            s[2] = rng.uniform(-3.0, 3.0)
+            s[6] = math.atan2(s[3], s[2]) % (2 * math.pi)
+            s[7] = s[4] - s[6]
+        elif i % 3 == 2:    # generic perturbation
+            s = s * (1 + 0.02 * rng.standard_normal(11))
+            s[6] = math.atan2(s[3], s[2]) % (2 * math.pi)
+            s[7] = s[4] - s[6]
+        a64 = rng.uniform(-1, 1, act_dim)
+        a32 = a64.astype(np.float32)
+        win = list(win)
+        outs = {}
+        for key, a in (("o64", a32.astype(np.float64)), ("o32", a32)):
+            env.reset()
+            env.state = [np.float64(v) for v in s]
+            env.previous_state = [np.float64(v) for v in sp]
+            env.g_loads_window = list(win)
+            if phase == G:
+                env.gimbal_angle_deg_prev = aprev[0]
+                env.delta_command_left_rad_prev = aprev[1]
+                env.delta_command_right_rad_prev = aprev[2]
+            ns, r, d, t, info = quiet(env.step, a)
+            ap = [0.0, 0.0, 0.0]
+            if phase == G:
+                ap = [float(env.gimbal_angle_deg_prev), float(env.delta_command_left_rad_prev),
+                      float(env.delta_command_right_rad_prev)]
+            outs[key] = [float(v) for v in ns] + [float(r), float(d), float(t),
+                                                  float(env.truncation_id)] + ap + info_row(info)
+        rows["state"].append(s); rows["prev"].append(sp)
+        w = np.zeros(10); w[:len(win)] = win
+        rows["win"].append(w); rows["nwin"].append(len(win)); rows["aprev"].append(aprev)
+        rows["act32"].append(a32); rows["act64"].append(a32.astype(np.float64))
+        rows["o64"].append(outs["o64"]); rows["o32"].append(outs["o32"])
+    cols = ["x", "y", "vx", "vy", "theta", "theta_dot", "gamma", "alpha", "mass", "m_prop", "time",
+            "reward", "done", "truncated", "trunc_id", "gimbal_prev", "dl_prev", "dr_prev"] + INFO_COLS
+    np.savez_compressed(os.path.join(OUT, f"single_step_{tag}.npz"),
+                        **{k: np.array(v) for k, v in rows.items()}, out_cols=cols)
+    o = np.array(rows["o64"])
+    print("single_step", tag, n, "done", int(o[:, 12].sum()), "trunc ids",
+          np.unique(o[:, 14], return_counts=True))
+
+
+def pso_fitness(phase, tag, n=12, seed=0):
+    from src.envs.pso.env_wrapped_ea import pso_wrapped_env
+    model = pso_wrapped_env(flight_phase=phase, enable_wind=False)
+    random.seed(seed)
+    # exactly ParticleSubswarmOptimisation.initialize_swarms' draw order
+    pos = [np.array([random.uniform(b[0], b[1]) for b in model.bounds]) for _ in range(n)]
+    fit, steps, tid, term = [], [], [], []
+    for p_ in pos:
+        f = quiet(model.objective_function, p_)
+        fit.append(float(f)); tid.append(model.env.truncation_id())
+        term.append([float(v) for v in model.env.env.state])
+        steps.append(round((float(model.env.env.state[-1]) - float(model.env.env.state_initial[-1]))
+                           / (0.1 if phase == P else 0.4)))
+        model.reset()
+    np.savez_compressed(os.path.join(OUT, f"pso_fitness_{tag}.npz"), positions=np.array(pos),
+                        fitness=np.array(fit), steps=np.array(steps), trunc_id=np.array(tid),
+                        terminal_state=np.array(term), seed=seed)
+    print("pso_fitness", tag, "fitness", np.round(fit, 3), "steps", steps, "tid", tid)
+
+
+def pso_best_actor():
+    """The reference's own saved best P actor: weights -> fitness / trajectory."""
+    import pandas as pd
+    from src.envs.pso.env_wrapped_ea import pso_wrapped_env
+    d = "data/pso_saves/landing_burn_pure_throttle/PSO_different_starting_point/"
+    res = pd.read_csv(d + "particle_subswarm_optimisation_results.csv")
+    w = res.iloc[0].values[1:-1].astype(float)      # col 0 = 'Algorithm', last = 'Best Fitness'
+    stored = float(res.iloc[0].values[-1])
+    model = pso_wrapped_env(flight_phase=P, enable_wind=False)
+    # record the per-step trajectory by driving the loop ourselves with the reference objects
+    model.individual_update_model(w)
+    obs = model.env.reset()
+    S, A, R = [], [], []
+    tot = 0
+    while True:
+        a = model.actor.forward(obs)
+        obs, r, dn, tr, info = quiet(model.env.step, a)
+        S.append([float(v) for v in model.env.env.state]); A.append(float(a.detach().numpy()[0]))
+        R.append(float(r)); tot -= r
+        if dn or tr:
+            break
+    ref_states = pd.read_csv(d + "trajectory_data/states.csv").values
+    ref_actions = pd.read_csv(d + "trajectory_data/actions.csv").values
+    np.savez_compressed(os.path.join(OUT, "pso_best_actor_P.npz"), weights=w, stored_fitness=stored,
+                        fitness=float(tot), steps=len(S), states=np.array(S), actions=np.array(A),
+                        rewards=np.array(R), trunc_id=model.env.truncation_id(),
+                        stored_states=ref_states, stored_actions=ref_actions)
+    print("best actor: stored", stored, "re-run", float(tot), "steps", len(S))
+
+
+def rl_sequence(phase, tag, n_steps, seed=1):
+    from src.envs.rl.env_wrapped_rl_pytorch import rl_wrapped_env_pytorch
+    rng = np.random.default_rng(seed)
+    env = rl_wrapped_env_pytorch(flight_phase=phase, enable_wind=False, trajectory_length=1,
+                                 discount_factor=0.99)
+    act_dim = env.action_dim
+    obs0 = env.reset()
+    O, R, D, T, A, S = [np.array(obs0, float)], [], [], [], [], []
+    bias = 0.6 if phase == P else 0.0
+    for k in range(n_steps):
+        a = np.clip(bias + 0.4 * rng.uniform(-1, 1, act_dim), -1, 1).astype(np.float32)
+        o, r, d, t, info = quiet(env.step, a)
+        O.append(np.array(o, float)); R.append(r); D.append(d); T.append(t); A.append(a)
+        S.append([float(v) for v in env.env.state])
+        if d or t:
+            break
+    np.savez_compressed(os.path.join(OUT, f"rl_sequence_{tag}.npz"), actions=np.array(A),
+                        obs=np.array(O), rewards=np.array(R), done=np.array(D),
+                        truncated=np.array(T), states=np.array(S),
+                        trunc_id=env.truncation_id())
+    print("rl_sequence", tag, len(R), "steps, last reward", R[-1], "trunc", T[-1], env.truncation_id())
+
+
+def wind_sequence(n_steps=260, seed=3):
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    rng = np.random.default_rng(seed)
+    tape = rng.standard_normal(8 * n_steps + 16)
+    sig_u, sig_v = 1.7, 1.4
+    nt = NoiseTapeWind(tape, sig_u, sig_v)
+    nt.install()
+    try:
+        env = rocket_environment_pre_wrap(type="pso", flight_phase=P, enable_wind=True,
+                                          stochastic_wind=True, horiontal_wind_percentile=50)
+        nt.pos = 0
+        env.reset()
+        nt.pos = 0
+        S, UG = [], []
+        # strong braking so the episode gets below 15 km where the gust filter switches on
+        for k in range(n_steps):
+            a = np.array([0.9 + 0.1 * math.sin(0.05 * k)], dtype=np.float32)
+            s, r, d, t, info = quiet(env.step, a)
+            S.append([float(v) for v in s]); UG.append([float(info["ug"]), float(info["vg"])])
+            if d or t:
+                break
+        Adu, Bdu = env.wind_generator.von_karman_generator_class.u_filter.Ad, \
+            env.wind_generator.von_karman_generator_class.u_filter.Bd
+        Adv, Bdv = env.wind_generator.von_karman_generator_class.v_filter.Ad, \
+            env.wind_generator.von_karman_generator_class.v_filter.Bd
+    finally:
+        nt.uninstall()
+    np.savez_compressed(os.path.join(OUT, "wind_sequence_P.npz"), tape=tape, sigma_u=sig_u,
+                        sigma_v=sig_v, states=np.array(S), ug_vg=np.array(UG),
+                        actions=np.array([0.9 + 0.1 * math.sin(0.05 * k) for k in range(len(S))],
+                                         dtype=np.float32),
+                        Adu=Adu, Bdu=Bdu, Adv=Adv, Bdv=Bdv, tape_used=nt.pos, percentile=50)
+    print("wind_sequence", len(S), "steps; min y", min(s[1] for s in S), "tape used", nt.pos,
+          "last ug", UG[-1])
+
+
+def classical():
+    from src.classical_controls.landing_burn_pure_throttle import LandingBurn
+    lb = quiet(LandingBurn, test_case="control")
+    n = 0
+    while lb.mass_propellant > 0 and lb.y > 1 and lb.dynamic_pressure < lb.max_q and n < 50000 \
+            and lb.vy < 0 and lb.alpha_effective < math.degrees(5):
+        quiet(lb.closed_loop_step)
+        n += 1
+    st = np.array([lb.x_vals, lb.y_vals, lb.vx_vals, lb.vy_vals, lb.theta_vals, lb.theta_dot_vals,
+                   lb.gamma_vals, lb.alpha_vals, lb.mass_vals, lb.m_prop_vals, lb.time_vals]).T
+    np.savez_compressed(os.path.join(OUT, "classical_rollout_P.npz"), steps=n, states=st.astype(float),
+                        u0=np.array(lb.u0_vals, float))
+    print("classical", n, "steps; final", st[-1])
+
+
+def aero_probe(seed=5, n=400):
+    """C_D / C_L through the reference's own compiled closures at random (Mach, alpha_eff)."""
+    import src.envs.rockets_physics as rp
+    rng = np.random.default_rng(seed)
+    mach = rng.uniform(0.0, 6.0, n)
+    mach[::7] = rng.uniform(0.0, 10.0, len(mach[::7]))
+    alpha = rng.uniform(-4e-3, 4e-3, n)
+    alpha[::5] = rng.uniform(-0.3, 0.3, len(alpha[::5]))
+    CL_func = lambda M, a: rp.rocket_CL(M, math.degrees(a))
+    CD_func = lambda M, a: rp.rocket_CD(M, math.degrees(a))
+    cl = np.array([CL_func(m, a) for m, a in zip(mach, alpha)])
+    cd = np.array([CD_func(m, a) for m, a in zip(mach, alpha)])
+    from src.envs.utils.acs_model import Ca_func, Cn_func
+    ca = np.array([float(Ca_func(m)) for m in mach])
+    cn = np.array([float(Cn_func(m, a)) for m, a in zip(mach, alpha)])
+    from src.envs.utils.atmosphere_dynamics import endo_atmospheric_model
+    alt = rng.uniform(-100, 90000, n)
+    atm = np.array([endo_atmospheric_model(h) for h in alt])
+    np.savez_compressed(os.path.join(OUT, "aero_probe.npz"), mach=mach, alpha=alpha, cl=cl, cd=cd,
+                        ca=ca, cn=cn, alt=alt, atm=atm)
+    print("aero_probe", n)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    load_reference()
+    which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero"]
+    if "aero" in which:
+        aero_probe()
+    if "tape" in which:
+        tape_replay()
+    if "ss" in which:
+        single_step(P, "P")
+        single_step(G, "G")
+    if "pso" in which:
+        pso_fitness(P, "P", n=10)
+        pso_fitness(G, "G", n=16)
+    if "best" in which:
+        pso_best_actor()
+    if "rl" in which:
+        rl_sequence(P, "P", 220)
+        rl_sequence(G, "G", 12)
+    if "wind" in which:
+        wind_sequence()
+    if "classical" in which:
+        classical()
