@@ -1,0 +1,208 @@
+/*
+ * pd_b200.h - C ABI of the B200-native batched powered-descent hot path.
+ *
+ * The reference (JvanZyl1/PSSO-SAC-for-powered-descent) is pure Python and has no FFI;
+ * its seam for this path is duck-typed Python.  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference
+ * root).  The Python host layer (psso_sac_for_powered_descent_b200/envs.py, pso.py)
+ * binds these with ctypes and presents the reference's own class / method names.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pd_last_error() gives text;
+ *   - pointers marked "dev" are caller-owned CUDA device memory (e.g. torch tensors);
+ *     pointers marked "host" are read during the call only;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work
+ *     is asynchronous on that stream;
+ *   - one PdEnv per GPU / per batch, not thread-safe per handle;
+ *   - there is no CPU fallback: without a CUDA device pd_create fails.
+ *
+ * State layout: 11 doubles per env, [x, y, vx, vy, theta, theta_dot, gamma, alpha, mass,
+ * mass_propellant, time] (src/envs/rockets_physics.py:475,646).  Inside the handle the
+ * batch is stored SoA (field-major) in fp64 for both precisions; the AoS views of
+ * pd_get_state/pd_set_state exist for parity tests and checkpointing.
+ */
+#ifndef PD_B200_H
+#define PD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_STATE_DIM 11
+#define PD_MAX_LEVELS 5
+#define PD_RBF_NEIGHBOURS 50
+#define PD_RBF_COEF_STRIDE 58
+#define PD_DBG_DIM 16
+
+enum { PD_PHASE_PURE_THROTTLE = 0, PD_PHASE_GIMBALLED = 1 };   /* flight_phase strings   */
+enum { PD_RTD_PSO = 0, PD_RTD_RL = 1 };                        /* type = 'pso' | 'rl'     */
+enum { PD_FP64 = 0, PD_FP32 = 1 };                             /* compute precision build */
+enum { PD_ACT_F64 = 0, PD_ACT_F32 = 1 };                       /* dtype of the action     */
+enum { PD_POLICY_MLP = 0, PD_POLICY_TAPE = 1, PD_POLICY_CLASSICAL = 2 };
+
+/* Local thin-plate-spline table (host pointers, copied by pd_create);
+ * built by psso_sac_for_powered_descent_b200/rbf_sets.py.  Replaces the per-call
+ * scipy RBFInterpolator(neighbors=50) of src/envs/utils/aerodynamic_coefficients.py:57-66. */
+typedef struct {
+    int32_t n_levels;
+    int32_t n_points;
+    int32_t n_sets;
+    int32_t hash_size;                    /* power of two */
+    double levels[PD_MAX_LEVELS];         /* AoA coordinate of each level */
+    int32_t level_off[PD_MAX_LEVELS + 1];
+    const double *mach_sorted;            /* host [n_points] */
+    const double *coeffs;                 /* host [n_sets * PD_RBF_COEF_STRIDE] */
+    const uint64_t *hash_keys;            /* host [hash_size] */
+    const int32_t *hash_vals;             /* host [hash_size] */
+    uint64_t initial_hint;                /* packed neighbour set at the initial state */
+} PdRbfTable;
+
+/* Constants the reference loads in compile_physics (src/envs/rockets_physics.py:707-957),
+ * module import side effects (rockets_physics.py:12-14, acs_model.py:10-11),
+ * load_landing_burn_initial_state (src/envs/load_initial_states.py:56-62) and
+ * landing_burn_input_normalisation (src/envs/utils/input_normalisation.py:73-89). */
+typedef struct {
+    double thrust_per_engine, nozzle_exit_pressure, nozzle_exit_area, v_exhaust;
+    int32_t n_engines_gimballed;
+    int32_t _pad0;
+    double grid_fin_area, d_base_grid_fin, rocket_radius, frontal_area;
+    double propellant_mass_stage1;        /* kg */
+    double c_gust_x, c_gust_y;
+    /* stage_inertia closure cells: I_dry, h_f, h_lower, h_ox, m_dry, m_f, m_ox, x_dry */
+    double inertia[8];
+    double engine_height, cop;
+    double initial_state[PD_STATE_DIM];
+    double norm_vals[7];
+    double v_opt_a, v_opt_b;              /* classical controller velocity profile */
+    /* grid-fin tables sorted ascending in Mach (scipy interp1d sorts them) */
+    int32_t n_gf_ca, n_gf_cn;
+    const double *gf_ca_mach, *gf_ca_val; /* host */
+    const double *gf_cn_mach, *gf_cn_val; /* host */
+    /* wind: altitude profile (km, m/s; sorted) and the unit-sigma discretised gust filters */
+    int32_t n_wind, _pad1;
+    const double *wind_alt_km, *wind_speed;   /* host */
+    double vk_Adu[4], vk_Bdu[2], vk_Adv[4], vk_Bdv[2];
+    PdRbfTable cd, cl;
+} PdParams;
+
+/* rocket_environment_pre_wrap.__init__ kwargs (src/envs/base_environment.py:12-20) + batch */
+typedef struct {
+    int32_t phase;            /* PD_PHASE_* */
+    int32_t rtd;              /* PD_RTD_*   */
+    int32_t precision;        /* PD_FP64 | PD_FP32 */
+    int32_t enable_wind;
+    int32_t stochastic_wind;
+    int32_t auto_reset;       /* reset an env in the step that ends its episode */
+    int32_t n_envs;
+    int32_t device;
+    uint64_t seed;            /* Philox key for gust noise / sigma draws */
+    double rl_reward_scale;   /* (1-g)/(1-g^L) of rtd_rl.py:266 (phase G, rl only) */
+} PdConfig;
+
+typedef struct PdEnv PdEnv;
+
+const char *pd_last_error(void);
+int pd_version(void);
+
+/* rocket_environment_pre_wrap(...)  (base_environment.py:12-78) for a batch of n_envs */
+int pd_create(const PdConfig *cfg, const PdParams *params, PdEnv **out);
+int pd_destroy(PdEnv *env);
+
+/* .reset()  (base_environment.py:80-97).  mask: dev uint8[n_envs] or NULL = all. */
+int pd_reset(PdEnv *env, const uint8_t *mask, void *stream);
+
+/* .step(actions)  (base_environment.py:99-154) for every env of the batch.
+ *   actions   dev [n_envs * A], double or float per action_dtype (A = 1 | 4).  A float32
+ *             action reproduces NumPy's NEP-50 float32 contamination of throttle, thrust and
+ *             mass flow in the fp64 build (SURVEY.md 8a "dtype rule").
+ *   obs       dev [n_envs * O] pso: pso_wrapper.augment_state (env_wrapped_ea.py:97-123);
+ *             rl: rl_wrapped_env_pytorch._process_state/augment_state
+ *             (env_wrapped_rl_pytorch.py:42-47,167-202).  Element type = double (PD_FP64) or
+ *             float (PD_FP32).  Observation of the post-step, pre-reset state.
+ *   reward    dev [n_envs] same element type as obs
+ *   done, truncated  dev uint8[n_envs];  trunc_id dev int32[n_envs] (env.truncation_id)
+ *   next_obs  dev or NULL: observation after the auto-reset (== obs where no reset happened)
+ *   dbg       dev double[n_envs * PD_DBG_DIM] or NULL: last sub-step's info values
+ *             (mach, q, CL, CD, rho, p_atm, a, x_cog, inertia, mass_flow, throttle,
+ *              alpha_eff, g_load_1_sec_window, ug, vg, rbf_status) */
+int pd_step(PdEnv *env, const void *actions, int action_dtype, void *obs, void *reward,
+            uint8_t *done, uint8_t *truncated, int32_t *trunc_id, void *next_obs, double *dbg,
+            void *stream);
+
+/* AoS state access (dev double[n_envs*11]); g_window dev double[n_envs*10] + n_window dev
+ * int32[n_envs]; act_prev dev double[n_envs*3] = gimbal_angle_deg_prev,
+ * delta_command_left_rad_prev, delta_command_right_rad_prev.  NULL = leave untouched /
+ * do not return. */
+int pd_get_state(PdEnv *env, double *state, double *g_window, int32_t *n_window,
+                 double *act_prev, void *stream);
+int pd_set_state(PdEnv *env, const double *state, const double *g_window,
+                 const int32_t *n_window, const double *act_prev, void *stream);
+
+/* Parity hook for the stochastic wind: replace Philox by an explicit N(0,1) tape
+ * (dev double[n_envs * tape_len], consumed u-then-v per sub-step below 15 km exactly like
+ * src/envs/wind/vonkarman.py:33-36) and explicit (sigma_u, sigma_v) per env
+ * (dev double[n_envs*2]).  tape = NULL returns to Philox. */
+int pd_set_wind_tape(PdEnv *env, const double *tape, int tape_len, const double *sigma_uv);
+
+/* pso_wrapped_env.objective_function for a whole swarm
+ * (src/envs/pso/env_wrapped_ea.py:200-222; replaces parallel_evaluate,
+ * src/particle_swarm_optimisation/particle_swarm_optimisation.py:334-350).
+ * One persistent kernel: reset -> [obs -> per-particle MLP -> 4 sub-steps -> rtd]* .
+ *   weights   dev float[n_particles * n_params], named_parameters() order
+ *             (weight row-major then bias per layer, env_wrapped_ea.py:46-59)
+ *   n_seeds   episodes per particle (wind seeds); episode e = particle * n_seeds + seed
+ *   max_steps step cap (the reference has none; capped episodes report trunc_id = -1)
+ *   fitness   dev double[n_particles*n_seeds] = -sum(reward)
+ *   steps, trunc_id  dev int32[...] or NULL;  terminal_state dev double[... * 11] or NULL
+ *   traj / actions_out / rewards: optional per-step trace, step-major
+ *   (dev double[max_steps*E*11], float[max_steps*E*A], double[max_steps*E]) - what
+ *   collect_trajectory_data (particle_swarm_optimisation.py:759-785) records. */
+int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_params, int n_seeds,
+                   int max_steps, double *fitness, int32_t *steps, int32_t *trunc_id,
+                   double *terminal_state, double *traj, float *actions_out, double *rewards,
+                   void *stream);
+
+/* Whole-episode rollouts with a scripted policy, one launch:
+ *   PD_POLICY_TAPE       actions dev [max_steps * n_episodes * A] (step-major), dtype per
+ *                        action_dtype; env.step loop (base_environment.py:99-154)
+ *   PD_POLICY_CLASSICAL  LandingBurn(test_case='control').run_closed_loop
+ *                        (src/classical_controls/landing_burn_pure_throttle.py:261-339);
+ *                        physics only, its own stop condition, no rtd
+ * traj: dev double[max_steps * n_episodes * 11] or NULL (state after every step).
+ * rewards: dev double[max_steps * n_episodes] or NULL. */
+int pd_rollout_policy(PdEnv *env, int policy, const void *actions, int action_dtype,
+                      int n_episodes, int max_steps, double *ret, int32_t *steps,
+                      int32_t *trunc_id, double *terminal_state, double *traj, double *rewards,
+                      void *stream);
+
+/* SAC data collection with one shared actor over the env batch
+ * (sac_pytorch_powered_descent.py:160-183 loop body; Actor.sample, src/agents/sac_pytorch.py:
+ * 129-179).  n_steps env steps with auto-reset; writes transitions step-major.
+ *   w1 [H*O], b1 [H], w2 [H*H], b2 [H], wm [A*H], bm [A], ws [A*H], bs [A]  dev float
+ *   obs_out dev float[n_steps*n_envs*O], act_out dev float[n_steps*n_envs*A],
+ *   rew_out dev float[n_steps*n_envs], done_out/trunc_out dev uint8[n_steps*n_envs]
+ *   (any output may be NULL). deterministic != 0 -> tanh(mean). */
+typedef struct {
+    int32_t hidden;           /* H (multiple of 16, <= 256) */
+    int32_t deterministic;
+    float max_action;
+    float _pad;
+    const float *w1, *b1, *w2, *b2, *wm, *bm, *ws, *bs;
+} PdSharedActor;
+int pd_collect_shared_actor(PdEnv *env, const PdSharedActor *actor, int n_steps, float *obs_out,
+                            float *act_out, float *rew_out, uint8_t *done_out,
+                            uint8_t *trunc_out, void *stream);
+
+/* Sticky device status (synchronises): 0 = ok; bit 0 = an aero-table query fell outside the
+ * enumerated neighbour-set table, bit 1 = neighbour search did not converge. */
+int pd_check_status(PdEnv *env, int32_t *status);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t pd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PD_B200_H */

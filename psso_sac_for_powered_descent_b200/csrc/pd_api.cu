@@ -1,0 +1,380 @@
+// pd_api.cu - the C ABI (include/pd_b200.h): handle management, constant/table upload,
+// launch dispatch.  No torch types, no C++ exceptions across the boundary.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pd_b200.h"
+#include "pd_device.cuh"
+#include "pd_impl.h"
+
+using namespace pd;
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(const std::string &m) {
+    g_err = m;
+    return 1;
+}
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess)                                                         \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(_e));           \
+    } while (0)
+
+struct PdEnv {
+    PdConfig cfg;
+    const Impl *impl;
+    EnvSoA soa;
+    Scalars<double> sd;
+    Scalars<float> sf;
+    Tables tb;
+    std::vector<void *> allocs;
+    const double *tape = nullptr;
+    int tape_len = 0;
+    const double *sigma_uv = nullptr;
+    float *wT = nullptr;
+    size_t wT_cap = 0;
+    int *roll_status = nullptr;
+};
+
+// the __constant__ blocks are per precision TU and per process: re-upload on handle switch
+static PdEnv *g_active[2] = {nullptr, nullptr};
+
+static int activate(PdEnv *e) {
+    int p = e->cfg.precision;
+    if (g_active[p] == e) return 0;
+    CK(cudaDeviceSynchronize());
+    if (e->impl->upload(&e->sd, &e->sf, &e->tb)) return fail("constant upload failed");
+    g_active[p] = e;
+    return 0;
+}
+
+template <typename T>
+static int dev_copy(PdEnv *e, const T *host, size_t n, const T **out) {
+    T *d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(T)));
+    e->allocs.push_back(d);
+    CK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *out = d;
+    return 0;
+}
+template <typename T>
+static int dev_alloc(PdEnv *e, size_t n, T **out) {
+    T *d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(T)));
+    e->allocs.push_back(d);
+    CK(cudaMemset(d, 0, n * sizeof(T)));
+    *out = d;
+    return 0;
+}
+
+static int upload_rbf(PdEnv *e, const PdRbfTable &t, RbfDev &d, double *levels_out) {
+    if (t.n_levels < 1 || t.n_levels > PD_MAX_LEVELS) return fail("rbf table: bad level count");
+    if (t.hash_size <= 0 || (t.hash_size & (t.hash_size - 1))) return fail("rbf table: hash size");
+    d.n_levels = t.n_levels;
+    d.hash_mask = t.hash_size - 1;
+    for (int l = 0; l < 6; ++l) d.off[l] = l <= t.n_levels ? t.level_off[l] : t.level_off[t.n_levels];
+    for (int l = 0; l < 5; ++l) levels_out[l] = l < t.n_levels ? t.levels[l] : 1e30;
+    if (dev_copy(e, t.mach_sorted, (size_t)t.n_points, &d.mach)) return 1;
+    if (dev_copy(e, t.coeffs, (size_t)t.n_sets * PD_RBF_COEF_STRIDE, &d.coeffs)) return 1;
+    const unsigned long long *hk = nullptr;
+    if (dev_copy(e, (const unsigned long long *)t.hash_keys, (size_t)t.hash_size, &hk)) return 1;
+    d.hkeys = hk;
+    if (dev_copy(e, t.hash_vals, (size_t)t.hash_size, &d.hvals)) return 1;
+    return 0;
+}
+
+static int upload_segments(PdEnv *e, const double *x, const double *y, int n, const double **dx,
+                           const double **dy, const double **ds) {
+    if (n < 2) return fail("grid fin table too short");
+    std::vector<double> s(n);
+    for (int i = 0; i + 1 < n; ++i) s[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+    s[n - 1] = s[n - 2];
+    if (dev_copy(e, x, (size_t)n, dx)) return 1;
+    if (dev_copy(e, y, (size_t)n, dy)) return 1;
+    if (dev_copy(e, s.data(), (size_t)n, ds)) return 1;
+    return 0;
+}
+
+template <typename R>
+static void to_float(const Scalars<double> &a, Scalars<R> &b) {
+    const double *src = reinterpret_cast<const double *>(&a);
+    R *dst = reinterpret_cast<R *>(&b);
+    for (size_t i = 0; i < sizeof(a) / sizeof(double); ++i) dst[i] = (R)src[i];
+}
+
+static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double> &s) {
+    memset(&s, 0, sizeof(s));
+    const double d2r = PD_PI / 180.0, r2d = 180.0 / PD_PI;
+    const int n_gim = p.n_engines_gimballed;
+    s.T_e = p.thrust_per_engine;
+    s.p_e = p.nozzle_exit_pressure;
+    s.A_e = p.nozzle_exit_area;
+    s.te_over_vex = p.thrust_per_engine / p.v_exhaust;
+    if (cfg.phase == PD_PHASE_PURE_THROTTLE) {       // rockets_physics.py:909-934
+        s.n_eng = n_gim;
+        s.nominal = (0 * 0.4) / n_gim;
+        s.dt_phys = 0.025;
+    } else {                                         // rockets_physics.py:803-836
+        s.n_eng = n_gim + 2;
+        s.nominal = (3 * 0.4) / n_gim;
+        s.dt_phys = 0.1;
+    }
+    s.dt_act = 0.025;
+    s.one_minus_nominal = 1 - s.nominal;
+    s.S_gf = p.grid_fin_area;
+    s.d_gf = p.d_base_grid_fin;
+    s.R_rocket = p.rocket_radius;
+    s.S_ref = p.frontal_area;
+    s.m_prop0 = p.propellant_mass_stage1;
+    s.c_gust_x = p.c_gust_x;
+    s.I_dry = p.inertia[0]; s.h_f = p.inertia[1]; s.h_lower = p.inertia[2]; s.h_ox = p.inertia[3];
+    s.m_dry = p.inertia[4]; s.m_f = p.inertia[5]; s.m_ox = p.inertia[6]; s.x_dry = p.inertia[7];
+    s.engine_height = p.engine_height;
+    s.cop = p.cop;
+    s.max_gimbal_rad = 5 * d2r;
+    s.max_gimbal_deg = (5 * d2r) * r2d;
+    s.max_defl_rad = 20 * d2r;
+    s.norm_y = p.norm_vals[0]; s.norm_vy = p.norm_vals[1];
+    s.norm_x = p.norm_vals[5]; s.norm_vx = p.norm_vals[6];
+    s.y0 = p.initial_state[1];
+    s.mass0 = p.initial_state[8];
+    s.k_theta_pso = atanh(0.75) / (25 * d2r);
+    s.k_theta_rl = atanh(0.75) / (5 * d2r);
+    s.k_thetadot_rl = atanh(0.75) / 0.01;
+    s.rl_reward_scale = cfg.rl_reward_scale;
+    s.v_opt_a = p.v_opt_a;
+    s.v_opt_b = p.v_opt_b;
+    static const double L[8][4] = {
+        {-5.0e3, 320.65, -6.5e-3, 1.77687e5}, {0.0e3, 288.15, -6.5e-3, 1.01325e5},
+        {11.0e3, 216.65, 0.0, 2.26320e4},     {20.0e3, 216.65, 1.0e-3, 5.47487e3},
+        {32.0e3, 228.65, 2.8e-3, 8.68014e2},  {47.0e3, 270.65, 0.0, 1.10906e2},
+        {51.0e3, 270.65, -2.8e-3, 6.69384e1}, {71.0e3, 214.65, -2.0e-3, 3.95639e0}};
+    const double G0 = 9.80665, Rg = 287.05287;
+    for (int k = 0; k < 8; ++k) {
+        s.isa_Hb[k] = L[k][0]; s.isa_Tb[k] = L[k][1]; s.isa_beta[k] = L[k][2]; s.isa_pb[k] = L[k][3];
+        s.isa_boT[k] = L[k][2] / L[k][1];
+        s.isa_expo[k] = L[k][2] != 0.0 ? -G0 / (L[k][2] * Rg) : 0.0;
+        s.isa_iso[k] = -G0 / (Rg * L[k][1]);
+    }
+    for (int i = 0; i < 16; ++i) {
+        int j = i < p.n_wind ? i : (p.n_wind > 0 ? p.n_wind - 1 : 0);
+        s.wind_x[i] = p.n_wind > 0 ? p.wind_alt_km[j] : 0.0;
+        s.wind_y[i] = p.n_wind > 0 ? p.wind_speed[j] : 0.0;
+    }
+    for (int i = 0; i + 1 < p.n_wind && i < 15; ++i)
+        s.wind_slope[i] = (p.wind_speed[i + 1] - p.wind_speed[i]) / (p.wind_alt_km[i + 1] - p.wind_alt_km[i]);
+    for (int i = 0; i < 4; ++i) { s.Adu[i] = p.vk_Adu[i]; s.Adv[i] = p.vk_Adv[i]; }
+    for (int i = 0; i < 2; ++i) { s.Bdu[i] = p.vk_Bdu[i]; s.Bdv[i] = p.vk_Bdv[i]; }
+}
+
+extern "C" {
+
+const char *pd_last_error(void) { return g_err.c_str(); }
+int pd_version(void) { return 100; }
+uint64_t pd_launch_count(void) { return g_launches.load(); }
+
+int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
+    if (!cfg || !p || !out) return fail("pd_create: null argument");
+    if (cfg->n_envs <= 0) return fail("pd_create: n_envs must be positive");
+    if (cfg->phase != 0 && cfg->phase != 1) return fail("pd_create: unknown flight phase");
+    if (cfg->rtd != 0 && cfg->rtd != 1) return fail("pd_create: unknown rtd type");
+    if (p->n_wind > 16) return fail("pd_create: wind profile longer than 16 points");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("pd_create: no CUDA device (this library has no CPU fallback)");
+    CK(cudaSetDevice(cfg->device));
+    PdEnv *e = new PdEnv();
+    e->cfg = *cfg;
+    e->impl = cfg->precision == PD_FP64 ? impl_fp64() : impl_fp32();
+    fill_scalars(*cfg, *p, e->sd);
+    memset(&e->tb, 0, sizeof(e->tb));
+    int rc = upload_rbf(e, p->cd, e->tb.cd, e->sd.cd_levels) || upload_rbf(e, p->cl, e->tb.cl, e->sd.cl_levels);
+    rc = rc || upload_segments(e, p->gf_ca_mach, p->gf_ca_val, p->n_gf_ca, &e->tb.ca_x, &e->tb.ca_y, &e->tb.ca_s);
+    rc = rc || upload_segments(e, p->gf_cn_mach, p->gf_cn_val, p->n_gf_cn, &e->tb.cn_x, &e->tb.cn_y, &e->tb.cn_s);
+    if (rc) { pd_destroy(e); return 1; }
+    to_float(e->sd, e->sf);
+    e->tb.n_ca = p->n_gf_ca;
+    e->tb.n_cn = p->n_gf_cn;
+    e->tb.n_wind = p->n_wind;
+    for (int k = 0; k < 11; ++k) e->tb.init[k] = p->initial_state[k];
+    e->tb.cd_hint0 = p->cd.initial_hint;
+    e->tb.cl_hint0 = p->cl.initial_hint;
+    const size_t B = (size_t)cfg->n_envs;
+    EnvSoA &s = e->soa;
+    s.n = cfg->n_envs;
+    rc = dev_alloc(e, 11 * B, &s.st) || dev_alloc(e, 10 * B, &s.gwin) || dev_alloc(e, B, &s.gwin_n) ||
+         dev_alloc(e, 3 * B, &s.aprev) || dev_alloc(e, 6 * B, &s.wst) || dev_alloc(e, B, &s.wctr) ||
+         dev_alloc(e, B, &s.episode) || dev_alloc(e, 2 * B, &s.hint) || dev_alloc(e, 2 * B, &s.hint_id) ||
+         dev_alloc(e, B, &s.trunc_id) || dev_alloc(e, B, &s.ep_steps) || dev_alloc(e, (size_t)1, &s.status) ||
+         dev_alloc(e, (size_t)1, &e->roll_status);
+    if (rc) { pd_destroy(e); return 1; }
+    *out = e;
+    if (pd_reset(e, nullptr, nullptr)) { pd_destroy(e); *out = nullptr; return 1; }
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int pd_destroy(PdEnv *e) {
+    if (!e) return 0;
+    for (int p = 0; p < 2; ++p)
+        if (g_active[p] == e) g_active[p] = nullptr;
+    for (void *a : e->allocs) cudaFree(a);
+    if (e->wT) cudaFree(e->wT);
+    delete e;
+    return 0;
+}
+
+static WindCtx wind_ctx(const PdEnv *e) {
+    WindCtx wc;
+    wc.tape = e->tape;
+    wc.tape_len = e->tape_len;
+    wc.seed = e->cfg.seed;
+    wc.stochastic = e->cfg.stochastic_wind;
+    return wc;
+}
+
+int pd_reset(PdEnv *e, const uint8_t *mask, void *stream) {
+    if (!e) return fail("pd_reset: null handle");
+    if (activate(e)) return 1;
+    e->impl->reset(e->soa, mask, wind_ctx(e), e->sigma_uv, (cudaStream_t)stream);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pd_step(PdEnv *e, const void *actions, int action_dtype, void *obs, void *reward, uint8_t *done,
+            uint8_t *truncated, int32_t *trunc_id, void *next_obs, double *dbg, void *stream) {
+    if (!e || !actions) return fail("pd_step: null argument");
+    if (action_dtype != PD_ACT_F64 && action_dtype != PD_ACT_F32) return fail("pd_step: action dtype");
+    if (activate(e)) return 1;
+    StepIO io;
+    io.actions = actions; io.action_dtype = action_dtype; io.obs = obs; io.reward = reward;
+    io.next_obs = next_obs; io.done = done; io.truncated = truncated; io.trunc_id = trunc_id;
+    io.dbg = dbg;
+    e->impl->step(e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
+                  e->cfg.auto_reset, (cudaStream_t)stream);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pd_get_state(PdEnv *e, double *state, double *g_window, int32_t *n_window, double *act_prev,
+                 void *stream) {
+    if (!e) return fail("pd_get_state: null handle");
+    e->impl->get_state(e->soa, state, g_window, n_window, act_prev, (cudaStream_t)stream);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pd_set_state(PdEnv *e, const double *state, const double *g_window, const int32_t *n_window,
+                 const double *act_prev, void *stream) {
+    if (!e) return fail("pd_set_state: null handle");
+    e->impl->set_state(e->soa, state, g_window, n_window, act_prev, (cudaStream_t)stream);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pd_set_wind_tape(PdEnv *e, const double *tape, int tape_len, const double *sigma_uv) {
+    if (!e) return fail("pd_set_wind_tape: null handle");
+    e->tape = tape;
+    e->tape_len = tape ? tape_len : 0;
+    e->sigma_uv = sigma_uv;
+    return 0;
+}
+
+int pd_check_status(PdEnv *e, int32_t *status) {
+    if (!e || !status) return fail("pd_check_status: null argument");
+    int a = 0, b = 0;
+    CK(cudaMemcpy(&a, e->soa.status, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&b, e->roll_status, sizeof(int), cudaMemcpyDeviceToHost));
+    *status = a | b;
+    if (*status) return fail("device status: aero-table neighbourhood outside the enumerated set table "
+                             "(bit 0) or selection did not converge (bit 1)");
+    return 0;
+}
+
+static int ensure_wT(PdEnv *e, size_t n) {
+    if (e->wT_cap >= n) return 0;
+    if (e->wT) cudaFree(e->wT);
+    e->wT = nullptr;
+    e->wT_cap = 0;
+    CK(cudaMalloc(&e->wT, n * sizeof(float)));
+    e->wT_cap = n;
+    return 0;
+}
+
+int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params, int n_seeds,
+                   int max_steps, double *fitness, int32_t *steps, int32_t *trunc_id,
+                   double *terminal_state, double *traj, float *actions_out, double *rewards,
+                   void *stream) {
+    if (!e || !weights || !fitness) return fail("pd_rollout_pso: null argument");
+    const int expect = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 249 : 372;
+    if (n_params != expect) return fail("pd_rollout_pso: n_params does not match the phase's actor");
+    if (n_particles <= 0 || n_seeds <= 0 || max_steps <= 0) return fail("pd_rollout_pso: bad sizes");
+    if (e->cfg.rtd != PD_RTD_PSO) return fail("pd_rollout_pso: handle was not created with type='pso'");
+    if (activate(e)) return 1;
+    if (ensure_wT(e, (size_t)n_particles * n_params)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    e->impl->transpose(weights, e->wT, n_particles, n_params, st);
+    g_launches++;
+    RolloutIO io;
+    memset(&io, 0, sizeof(io));
+    io.n_episodes = n_particles * n_seeds;
+    io.n_seeds = n_seeds;
+    io.max_steps = max_steps;
+    io.wT = e->wT;
+    io.w_stride = (size_t)n_particles;
+    io.ret = fitness; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
+    io.traj = traj; io.act_out = actions_out; io.rewards = rewards;
+    if (e->impl->rollout(PD_POLICY_MLP, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
+                         e->sigma_uv, e->roll_status, st))
+        return fail("pd_rollout_pso: unsupported configuration");
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pd_rollout_policy(PdEnv *e, int policy, const void *actions, int action_dtype, int n_episodes,
+                      int max_steps, double *ret, int32_t *steps, int32_t *trunc_id,
+                      double *terminal_state, double *traj, double *rewards, void *stream) {
+    if (!e) return fail("pd_rollout_policy: null handle");
+    if (policy != PD_POLICY_TAPE && policy != PD_POLICY_CLASSICAL) return fail("pd_rollout_policy: policy");
+    if (policy == PD_POLICY_TAPE && !actions) return fail("pd_rollout_policy: tape policy needs actions");
+    if (n_episodes <= 0 || max_steps <= 0) return fail("pd_rollout_policy: bad sizes");
+    if (activate(e)) return 1;
+    RolloutIO io;
+    memset(&io, 0, sizeof(io));
+    io.n_episodes = n_episodes;
+    io.n_seeds = 1;
+    io.max_steps = max_steps;
+    io.actions = actions;
+    io.action_dtype = action_dtype;
+    io.ret = ret; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
+    io.traj = traj; io.rewards = rewards;
+    if (e->impl->rollout(policy, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
+                         e->sigma_uv, e->roll_status, (cudaStream_t)stream))
+        return fail("pd_rollout_policy: unsupported configuration (classical controller is "
+                    "landing_burn_pure_throttle only)");
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, float *obs_out,
+                            float *act_out, float *rew_out, uint8_t *done_out, uint8_t *trunc_out,
+                            void *stream) {
+    (void)e; (void)actor; (void)n_steps; (void)obs_out; (void)act_out; (void)rew_out;
+    (void)done_out; (void)trunc_out; (void)stream;
+    return fail("pd_collect_shared_actor: not built in this revision");
+}
+
+}  // extern "C"

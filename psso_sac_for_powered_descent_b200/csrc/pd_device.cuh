@@ -1,0 +1,924 @@
+// pd_device.cuh - device-side physics of the powered-descent hot path (sm_100a).
+//
+// One environment per thread, state in registers.  Everything here is templated on the
+// compute type R (double = parity build, float = production build); the 11-state itself
+// is always carried in double (HBM traffic is <1% of the roofline for this path, see
+// DESIGN.md), and quantities that are differences of large state values (alpha_effective,
+// gamma) are formed in double in both builds.
+//
+// Reference algorithm (file:line relative to the reference root):
+//   isa()            src/envs/utils/atmosphere_dynamics.py:5-27 (+ ambiance ISA)
+//   cog_inertia()    src/RocketSizing/functions/rocket_dimensions.py:167-196
+//   rbf_*()          src/envs/utils/aerodynamic_coefficients.py:57-66 (scipy local TPS RBF)
+//   coef_cd/cl()     aerodynamic_coefficients.py:105-132 + rockets_physics.py:711-712
+//   gridfin_*()      src/envs/utils/grid_fin_aerodynamics.py:7-46
+//   acs()            src/envs/utils/acs_model.py:13-86
+//   control_*()      src/envs/rockets_physics.py:340-400 (P), 168-269 (G)
+//   substep()        src/envs/rockets_physics.py:455-646
+//   wind             src/envs/wind/full_wind_model.py:35-43, vonkarman.py:33-36
+//   rtd_*()          src/envs/pso/rtd_pso.py:172-317, src/envs/rl/rtd_rl.py:194-336
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define PD_PI 3.141592653589793
+#define PD_TWO_PI 6.283185307179586
+
+namespace pd {
+
+// ------------------------------------------------------------------ constants
+template <typename R>
+struct Scalars {
+    R T_e, p_e, A_e, te_over_vex, n_eng, te_neng_dummy;
+    R nominal, one_minus_nominal;
+    R S_gf, d_gf, R_rocket, S_ref, m_prop0, c_gust_x;
+    R I_dry, h_f, h_lower, h_ox, m_dry, m_f, m_ox, x_dry, engine_height, cop;
+    R dt_phys, dt_act;
+    R max_gimbal_rad, max_gimbal_deg, max_defl_rad;
+    R norm_y, norm_vy, norm_x, norm_vx;
+    R y0, mass0;
+    R k_theta_pso, k_theta_rl, k_thetadot_rl;
+    R rl_reward_scale;
+    R v_opt_a, v_opt_b;
+    // ISA layers 0..7
+    R isa_Hb[8], isa_Tb[8], isa_beta[8], isa_pb[8], isa_boT[8], isa_expo[8], isa_iso[8];
+    // wind profile
+    R wind_x[16], wind_y[16], wind_slope[16];
+    R Adu[4], Bdu[2], Adv[4], Bdv[2];
+    R cd_levels[5], cl_levels[5];
+};
+
+struct RbfDev {
+    const double *mach;      // [n_points] level-major sorted
+    const double *coeffs;    // [n_sets*58]
+    const unsigned long long *hkeys;
+    const int *hvals;
+    int hash_mask;
+    int n_levels;
+    int off[6];
+};
+
+struct Tables {
+    RbfDev cd, cl;
+    const double *ca_x, *ca_y, *ca_s;   // grid fin C_a segments (x_lo, y_lo, slope)
+    const double *cn_x, *cn_y, *cn_s;
+    int n_ca, n_cn;
+    int n_wind;
+    double init[11];
+    unsigned long long cd_hint0, cl_hint0;
+};
+
+// per-TU copies (no relocatable device code): each precision TU uploads its own
+static __constant__ Scalars<double> g_sd;
+static __constant__ Scalars<float> g_sf;
+static __constant__ Tables g_tb;
+
+template <typename R> __device__ __forceinline__ const Scalars<R> &SC();
+template <> __device__ __forceinline__ const Scalars<double> &SC<double>() { return g_sd; }
+template <> __device__ __forceinline__ const Scalars<float> &SC<float>() { return g_sf; }
+
+// ------------------------------------------------------------------ small math shims
+__device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double m_exp(double x) { return exp(x); }
+__device__ __forceinline__ float m_exp(float x) { return expf(x); }
+__device__ __forceinline__ double m_pow(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ float m_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double m_log(double x) { return log(x); }
+__device__ __forceinline__ float m_log(float x) { return logf(x); }
+__device__ __forceinline__ double m_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ float m_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ void m_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __forceinline__ void m_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __forceinline__ double m_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float m_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double m_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float m_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double m_hypot(double a, double b) { return hypot(a, b); }
+__device__ __forceinline__ float m_hypot(float a, float b) { return hypotf(a, b); }
+
+// ------------------------------------------------------------------ per-env registers
+struct State {
+    double x, y, vx, vy, theta, theta_dot, gamma, alpha, mass, m_prop, time;
+};
+
+struct ActPrev {   // landing_burn only: gimbal_angle_deg_prev, delta_command_{left,right}_rad_prev
+    double gimbal_deg, dl, dr;
+};
+
+struct WindState {
+    double xu0, xu1, xv0, xv1;     // gust filter states
+    double sigma_u, sigma_v;
+    unsigned int ctr;              // draws consumed (tape position / Philox counter)
+};
+
+struct RbfHint {
+    unsigned long long cd, cl;     // packed [lo,hi) per level, 6 bits each
+    int cd_id, cl_id;
+};
+
+template <typename R>
+struct Info {                      // values of the last sub-step (reference `info` dict)
+    R mach, q, CL, CD, rho, p_atm, a, x_cog, inertia, mass_flow, throttle, alpha_eff, ug, vg;
+    int rbf_status;
+};
+
+// ------------------------------------------------------------------ ISA
+template <typename R>
+__device__ __forceinline__ void isa(R alt, R &rho, R &p, R &a) {
+    const Scalars<R> &c = SC<R>();
+    if (alt < R(0)) alt = R(0);
+    if (!(alt < R(81020))) {
+        rho = p = a = R(0);
+        return;
+    }
+    const R RE = R(6356766.0);
+    R H = RE * alt / (RE + alt);
+    int k = 1;
+#pragma unroll
+    for (int j = 2; j < 8; ++j)
+        if (H >= c.isa_Hb[j]) k = j;
+    R dH = H - c.isa_Hb[k];
+    R beta = c.isa_beta[k];
+    R T = c.isa_Tb[k] + beta * dH;
+    if (beta == R(0))
+        p = c.isa_pb[k] * m_exp(c.isa_iso[k] * dH);
+    else
+        p = c.isa_pb[k] * m_pow(R(1) + c.isa_boT[k] * dH, c.isa_expo[k]);
+    const R Rgas = R(287.05287);
+    rho = p / (Rgas * T);
+    a = m_sqrt(R(1.4 * 287.05287) * T);
+}
+
+// density only (the rtd closures need q at the new state)
+template <typename R>
+__device__ __forceinline__ R isa_rho(R alt) {
+    R rho, p, a;
+    isa<R>(alt, rho, p, a);
+    return rho;
+}
+
+// ------------------------------------------------------------------ inertia
+template <typename R>
+__device__ __forceinline__ void cog_inertia(R fill, R &x_cog, R &inertia) {
+    const Scalars<R> &c = SC<R>();
+    R h_ox_t = c.h_ox * fill;
+    R h_f_t = c.h_f * fill;
+    R m_ox_t = c.m_ox * fill;
+    R m_f_t = c.m_f * fill;
+    R a_ox = c.h_lower + h_ox_t / R(2);
+    R a_f = c.h_lower + c.h_ox + h_f_t / R(2);
+    R m_p = m_ox_t + m_f_t;
+    R x_prop = (m_ox_t * a_ox + m_f_t * a_f) / m_p;
+    R d_ox = a_ox - x_prop;
+    R d_f = a_f - x_prop;
+    const R twelfth = R(1.0 / 12);
+    R I_ox = twelfth * m_ox_t * (h_ox_t * h_ox_t) + m_ox_t * (d_ox * d_ox);
+    R I_f = twelfth * m_f_t * (h_f_t * h_f_t) + m_f_t * (d_f * d_f);
+    R I_prop = I_ox + I_f;
+    R x_wet = (c.m_dry * c.x_dry + m_p * x_prop) / (c.m_dry + m_ox_t + m_f_t);
+    R dd = c.x_dry - x_wet;
+    R dp = x_prop - x_wet;
+    R I_dry_hat = c.I_dry + c.m_dry * (dd * dd);
+    R I_prop_hat = I_prop + m_p * (dp * dp);
+    x_cog = x_wet;
+    inertia = I_dry_hat + I_prop_hat;
+}
+
+// ------------------------------------------------------------------ local TPS RBF
+__device__ __forceinline__ unsigned long long hash_u64(unsigned long long k) {
+    k ^= k >> 30;
+    k *= 0xBF58476D1CE4E5B9ULL;
+    k ^= k >> 27;
+    k *= 0x94D049BB133111EBULL;
+    k ^= k >> 31;
+    return k;
+}
+
+#define PD_RBF_OK 0
+#define PD_RBF_MISS 1
+#define PD_RBF_ITER 2
+
+// Move the thread's cached neighbour set to the exact 50-NN set of (M, a).
+// Sets are one contiguous [lo,hi) interval per level; the check compares the farthest
+// interval end against the nearest point just outside any interval (4 distances / level).
+template <int NL>
+__device__ __forceinline__ int rbf_select(const RbfDev &T, const double *levels_d, double M,
+                                          double a, unsigned long long &hint, int &sid) {
+    int lo[NL], hi[NL];
+    double dl2[NL];
+    const unsigned long long hint_in = hint;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        lo[l] = (int)((hint >> (12 * l)) & 63);
+        hi[l] = (int)((hint >> (12 * l + 6)) & 63);
+        double d = levels_d[l] - a;
+        dl2[l] = d * d;
+    }
+    int status = PD_RBF_OK;
+    int it = 0;
+    for (; it < 400; ++it) {
+        double max_in = -1.0, min_out = 1e300;
+        int in_l = 0, in_side = 0, out_l = 0, out_side = 0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const double *m = T.mach + T.off[l];
+            const int n = T.off[l + 1] - T.off[l];
+            if (lo[l] == hi[l]) {     // empty level: park at the insertion point of M
+                int p = lo[l];
+                while (p > 0 && __ldg(m + p - 1) > M) --p;
+                while (p < n && __ldg(m + p) < M) ++p;
+                lo[l] = hi[l] = p;
+            } else {
+                double d0 = __ldg(m + lo[l]) - M;
+                d0 = d0 * d0 + dl2[l];
+                double d1 = __ldg(m + hi[l] - 1) - M;
+                d1 = d1 * d1 + dl2[l];
+                if (d0 > max_in) { max_in = d0; in_l = l; in_side = 0; }
+                if (d1 > max_in) { max_in = d1; in_l = l; in_side = 1; }
+            }
+            if (lo[l] > 0) {
+                double d = __ldg(m + lo[l] - 1) - M;
+                d = d * d + dl2[l];
+                if (d < min_out) { min_out = d; out_l = l; out_side = 0; }
+            }
+            if (hi[l] < n) {
+                double d = __ldg(m + hi[l]) - M;
+                d = d * d + dl2[l];
+                if (d < min_out) { min_out = d; out_l = l; out_side = 1; }
+            }
+        }
+        if (max_in <= min_out) break;
+        // swap: drop the farthest member, take the nearest outsider.  A one-point interval
+        // that trades its point with a neighbour on the same level must give up the end
+        // opposite to the one it grows at (otherwise the two updates cancel).
+        if (in_l == out_l) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+                if (l == in_l && hi[l] - lo[l] == 1) in_side = 1 - out_side;
+        }
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (l == in_l) { if (in_side == 0) ++lo[l]; else --hi[l]; }
+        }
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (l == out_l) { if (out_side == 0) --lo[l]; else ++hi[l]; }
+        }
+    }
+    if (it >= 400) status = PD_RBF_ITER;
+    unsigned long long h = 0, key = 1ULL << 63;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        h |= ((unsigned long long)lo[l] << (12 * l)) | ((unsigned long long)hi[l] << (12 * l + 6));
+        if (lo[l] != hi[l])
+            key |= ((unsigned long long)lo[l] << (12 * l)) | ((unsigned long long)hi[l] << (12 * l + 6));
+    }
+    hint = h;
+    if (h != hint_in || sid < 0) {
+        unsigned int slot = (unsigned int)hash_u64(key) & T.hash_mask;
+        int found = -1;
+        for (int probe = 0; probe < 64; ++probe) {
+            unsigned long long k = __ldg(T.hkeys + slot);
+            if (k == key) { found = __ldg(T.hvals + slot); break; }
+            if (k == 0ULL) break;
+            slot = (slot + 1) & T.hash_mask;
+        }
+        if (found < 0) status |= PD_RBF_MISS; else sid = found;
+    }
+    return status;
+}
+
+__device__ __forceinline__ double tps_phi(double r2) {
+    // r^2 log r = 0.5 r^2 log r^2 ; phi(0) = 0
+    return r2 > 0.0 ? 0.5 * r2 * log(r2) : 0.0;
+}
+__device__ __forceinline__ float tps_phi(float r2) {
+    return r2 > 0.0f ? 0.5f * r2 * __logf(r2) : 0.0f;
+}
+
+// Evaluate the interpolant of set `sid` at (M, a).  RT = accumulation type.
+template <typename RT, int NL>
+__device__ __forceinline__ RT rbf_eval(const RbfDev &T, const double *levels_d, double M, double a,
+                                       unsigned long long hint, int sid) {
+    const double *c = T.coeffs + (size_t)(sid < 0 ? 0 : sid) * 58;
+    RT acc = RT(0);
+    int k = 0;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int lo = (int)((hint >> (12 * l)) & 63);
+        const int hi = (int)((hint >> (12 * l + 6)) & 63);
+        const double *m = T.mach + T.off[l];
+        const double da = a - levels_d[l];
+        const RT da2 = (RT)(da * da);
+        for (int i = lo; i < hi; ++i) {
+            RT dm = (RT)(M - __ldg(m + i));
+            RT r2 = dm * dm + da2;
+            acc += (RT)__ldg(c + k) * tps_phi(r2);
+            ++k;
+        }
+    }
+    RT xh = (RT)((M - __ldg(c + 53)) / __ldg(c + 55));
+    RT yh = (RT)((a - __ldg(c + 54)) / __ldg(c + 56));
+    return acc + (RT)__ldg(c + 50) + (RT)__ldg(c + 51) * xh + (RT)__ldg(c + 52) * yh;
+}
+
+// C_D: CD_func passes degrees into a clamp written for radians
+// (rockets_physics.py:712, aerodynamic_coefficients.py:108-114)
+template <typename R, typename RT>
+__device__ __forceinline__ R coef_cd(R mach, R alpha_eff, RbfHint &h, int &status) {
+    double aoa = (double)alpha_eff * (180.0 / PD_PI);
+    const double lim = 10.0 * (PD_PI / 180.0);
+    if (aoa > lim) aoa = lim;
+    else if (aoa < -lim) aoa = -lim;
+    status |= rbf_select<5>(g_tb.cd, g_sd.cd_levels, (double)mach, aoa, h.cd, h.cd_id);
+    return (R)rbf_eval<RT, 5>(g_tb.cd, g_sd.cd_levels, (double)mach, aoa, h.cd, h.cd_id);
+}
+
+// C_L: degrees applied twice (rockets_physics.py:711, aerodynamic_coefficients.py:120-131)
+template <typename R, typename RT>
+__device__ __forceinline__ R coef_cl(R mach, R alpha_eff, RbfHint &h, int &status) {
+    double aoa = ((double)alpha_eff * (180.0 / PD_PI)) * (180.0 / PD_PI);
+    double q;
+    double sign = 1.0;
+    if (aoa > 10.0) q = 10.0;
+    else if (aoa < -10.0) q = -10.0;            // not negated upstream
+    else if (fabs(aoa) < 1e-6) return R(0);
+    else if (aoa < 0.0) { q = fabs(aoa); sign = -1.0; }
+    else q = aoa;
+    status |= rbf_select<5>(g_tb.cl, g_sd.cl_levels, (double)mach, q, h.cl, h.cl_id);
+    RT v = rbf_eval<RT, 5>(g_tb.cl, g_sd.cl_levels, (double)mach, q, h.cl, h.cl_id);
+    return (R)(sign < 0 ? -v : v);
+}
+
+// ------------------------------------------------------------------ grid fins
+// scipy interp1d(kind='linear'): idx = clip(searchsorted(x, v, 'left'), 1, n-1); lo = idx-1;
+// y = slope[lo]*(v - x[lo]) + y[lo]
+__device__ __forceinline__ int seg_index(const double *x, int n, double v) {
+    int a = 0, b = n;            // number of elements < v
+    while (a < b) {
+        int mid = (a + b) >> 1;
+        if (__ldg(x + mid) < v) a = mid + 1; else b = mid;
+    }
+    int idx = a < 1 ? 1 : (a > n - 1 ? n - 1 : a);
+    return idx - 1;
+}
+
+template <typename R>
+__device__ __forceinline__ R gridfin_ca(R mach) {
+    const double M = (double)mach;
+    if (M < __ldg(g_tb.ca_x)) return (R)__ldg(g_tb.ca_y);
+    int lo = seg_index(g_tb.ca_x, g_tb.n_ca, M);
+    return (R)(__ldg(g_tb.ca_s + lo) * (M - __ldg(g_tb.ca_x + lo)) + __ldg(g_tb.ca_y + lo));
+}
+
+// returns C_n_alpha(M); caller multiplies by degrees(alpha_local)
+template <typename R>
+__device__ __forceinline__ R gridfin_cn_alpha(R mach) {
+    const double M = (double)mach;
+    const int n = g_tb.n_cn;
+    if (M < __ldg(g_tb.cn_x)) return (R)__ldg(g_tb.cn_y);
+    double xmax = __ldg(g_tb.cn_x + n - 1);
+    if (M <= xmax) {
+        int lo = seg_index(g_tb.cn_x, n, M);
+        return (R)(__ldg(g_tb.cn_s + lo) * (M - __ldg(g_tb.cn_x + lo)) + __ldg(g_tb.cn_y + lo));
+    }
+    return (R)(__ldg(g_tb.cn_y + n - 1) + __ldg(g_tb.cn_s + n - 2) * (M - xmax));
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox4x32(unsigned int c0, unsigned int c1, unsigned int c2,
+                                           unsigned int c3, unsigned int k0, unsigned int k1,
+                                           unsigned int out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned int n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double u01(unsigned int a, unsigned int b) {
+    // 53-bit uniform in (0,1)
+    unsigned long long v = (((unsigned long long)a << 32) | b) >> 11;
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+struct WindCtx {
+    const double *tape;     // N(0,1) tape or nullptr -> Philox
+    int tape_len;
+    unsigned long long seed;
+    int stochastic;
+};
+
+// ------------------------------------------------------------------ wind
+template <typename R>
+__device__ __forceinline__ void wind_sample(double y, WindState &w, const WindCtx &wc,
+                                            unsigned int env_id, R &ug, R &vg) {
+    const Scalars<double> &c = g_sd;
+    const int n = g_tb.n_wind;
+    double akm = y / 1000.0;
+    double fixed;
+    if (akm < c.wind_x[0]) fixed = c.wind_y[0];
+    else if (akm > c.wind_x[n - 1]) fixed = c.wind_y[n - 1];
+    else {
+        int a = 0;
+        for (int j = 0; j < n; ++j) a += (c.wind_x[j] < akm) ? 1 : 0;
+        int idx = a < 1 ? 1 : (a > n - 1 ? n - 1 : a);
+        int lo = idx - 1;
+        fixed = c.wind_slope[lo] * (akm - c.wind_x[lo]) + c.wind_y[lo];
+    }
+    double gu = 0.0, gv = 0.0;
+    if (y < 15000.0 && wc.stochastic) {
+        double n0, n1;
+        if (wc.tape) {
+            size_t base = (size_t)env_id * wc.tape_len;
+            unsigned int p0 = w.ctr, p1 = w.ctr + 1;
+            n0 = p0 < (unsigned)wc.tape_len ? wc.tape[base + p0] : 0.0;
+            n1 = p1 < (unsigned)wc.tape_len ? wc.tape[base + p1] : 0.0;
+        } else {
+            unsigned int r[4];
+            philox4x32(env_id, w.ctr, 0x57494E44u, 0u, (unsigned int)wc.seed,
+                       (unsigned int)(wc.seed >> 32), r);
+            double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+            double rad = sqrt(-2.0 * log(u1));
+            double s, co;
+            sincospi(2.0 * u2, &s, &co);
+            n0 = rad * co;
+            n1 = rad * s;
+        }
+        w.ctr += 2;
+        double bu0 = c.Bdu[0] * w.sigma_u, bu1 = c.Bdu[1] * w.sigma_u;
+        double nu0 = (c.Adu[0] * w.xu0 + c.Adu[1] * w.xu1) + bu0 * n0;
+        double nu1 = (c.Adu[2] * w.xu0 + c.Adu[3] * w.xu1) + bu1 * n0;
+        w.xu0 = nu0; w.xu1 = nu1;
+        double bv0 = c.Bdv[0] * w.sigma_v, bv1 = c.Bdv[1] * w.sigma_v;
+        double nv0 = (c.Adv[0] * w.xv0 + c.Adv[1] * w.xv1) + bv0 * n1;
+        double nv1 = (c.Adv[2] * w.xv0 + c.Adv[3] * w.xv1) + bv1 * n1;
+        w.xv0 = nv0; w.xv1 = nv1;
+        gu = nu1;      // C = [0, 1]
+        gv = nv1;
+    }
+    ug = (R)(fixed + gu);
+    vg = (R)gv;
+}
+
+// sigma_u ~ U(0.5, 2.25), sigma_v ~ U(1.25, 2.0) per reset (vonkarman.py:62-63)
+__device__ __forceinline__ void wind_reset(WindState &w, const WindCtx &wc, unsigned int env_id,
+                                           unsigned int episode, const double *sigma_uv) {
+    w.xu0 = w.xu1 = w.xv0 = w.xv1 = 0.0;
+    w.ctr = 0;
+    if (sigma_uv) {
+        w.sigma_u = sigma_uv[2 * (size_t)env_id];
+        w.sigma_v = sigma_uv[2 * (size_t)env_id + 1];
+    } else {
+        unsigned int r[4];
+        philox4x32(env_id, episode, 0x5349474Du, 1u, (unsigned int)wc.seed,
+                   (unsigned int)(wc.seed >> 32), r);
+        w.sigma_u = 0.5 + (2.25 - 0.5) * u01(r[0], r[1]);
+        w.sigma_v = 1.25 + (2.0 - 1.25) * u01(r[2], r[3]);
+    }
+}
+
+// ------------------------------------------------------------------ actions
+// The action as the reference sees it: either float64 (pure fp64 step) or float32
+// (NumPy NEP-50: throttle / thrust / mass-flow become float32; SURVEY 8a dtype rule).
+template <int A>
+struct Action {
+    double u[A];
+    bool f32;
+};
+
+template <typename R>
+struct Control {
+    R par, perp, mz, mass_flow_dt;   // mass_flow * dt_phys, rounded as the reference rounds it
+    R mass_flow, throttle;
+    double gimbal_deg, dl_cmd, dr_cmd;
+};
+
+// ACS (grid fins), acs_model.py:13-86.  d_cmd_* = delta_command_*_rad =
+// radians(deflection_command_deg * 60), formed by the caller (its dtype depends on the action).
+template <typename R>
+__device__ __forceinline__ void acs(R alpha_eff, R q, R mach, R x_cog, double d_cmd_l, double d_cmd_r,
+                                    double prev_l, double prev_r, R &f_perp, R &f_par, R &m_z) {
+    const Scalars<R> &c = SC<R>();
+    const double dt = g_sd.dt_act;
+    R d_l = (R)(prev_l + dt * ((-prev_l + d_cmd_l) / 0.5));
+    R d_r = (R)(prev_r + dt * ((-prev_r + d_cmd_r) / 0.5));
+    R a_l = alpha_eff - d_l;
+    R a_r = alpha_eff - d_r;
+    R qS = q * c.S_gf;
+    R Ca = gridfin_ca<R>(mach);
+    R cna = gridfin_cn_alpha<R>(mach);
+    const R r2d = R(180.0 / PD_PI);
+    R Cn_L = cna * (a_l * r2d);
+    R Cn_R = cna * (a_r * r2d);
+    R sl, cl, sr, cr;
+    m_sincos(d_l, &sl, &cl);
+    m_sincos(d_r, &sr, &cr);
+    f_perp = qS * (Cn_R * cr - Cn_L * cl - Ca * (sl - sr));
+    f_par = qS * (Ca * (R(2) + cl + cr) - Cn_L * sl + Cn_R * sr);
+    m_z = -(c.d_gf - x_cog) * f_perp + c.R_rocket * qS * (Ca * (sr - sl) - Cn_L * cl + Cn_R * cr);
+}
+
+// float32-contaminated thrust chain shared by P and G (fp64 build, float32 action):
+//   throttle f32, thrust = f32(t_full*n_eng) * throttle, n_tot = thrust / f32(t_full),
+//   mass_flow = f32(T_e/v_ex) * n_tot, mass_flow*dt in f32.
+__device__ __forceinline__ float f32_throttle(float u) {
+    float nn = __fdiv_rn(__fadd_rn(u, 1.0f), 2.0f);
+    return __fadd_rn(__fmul_rn(nn, g_sf.one_minus_nominal), g_sf.nominal);
+}
+
+// landing_burn_pure_throttle: rockets_physics.py:340-400
+template <typename R>
+__device__ __forceinline__ void control_P(const Action<1> &act, R p_atm, R alpha_eff, R q, R x_cog,
+                                          R mach, Control<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    // ACS with zero deflection and zero memory: perpendicular force and moment cancel
+    // exactly, axial force = 4 q S C_a(M) (acs_model.py:49-59 with delta = 0)
+    R qS = q * c.S_gf;
+    R Ca = gridfin_ca<R>(mach);
+    R f_par = qS * (Ca * R(4));
+    R t_full = c.T_e + (c.p_e - p_atm) * c.A_e;
+    if (sizeof(R) == 8 && act.f32) {
+        float thr = f32_throttle((float)act.u[0]);
+        float thrust = __fmul_rn((float)((double)t_full * (double)c.n_eng), thr);
+        float n_tot = __fdiv_rn(thrust, (float)t_full);
+        float mf = __fmul_rn(g_sf.te_over_vex, n_tot);
+        o.par = (R)thrust + f_par;
+        o.mass_flow = (R)mf;
+        o.mass_flow_dt = (R)__fmul_rn(mf, g_sf.dt_phys);
+        o.throttle = (R)thr;
+    } else {
+        R u0 = (R)act.u[0];
+        R throttle = (u0 + R(1)) / R(2) * c.one_minus_nominal + c.nominal;
+        R thrust = t_full * c.n_eng * throttle;
+        R n_tot = thrust / t_full;
+        R mf = c.te_over_vex * n_tot;
+        o.par = thrust + f_par;
+        o.mass_flow = mf;
+        o.mass_flow_dt = mf * c.dt_phys;
+        o.throttle = throttle;
+    }
+    o.perp = R(0);
+    o.mz = R(0);
+}
+
+// landing_burn (gimballed + grid fins): rockets_physics.py:168-269
+template <typename R>
+__device__ __forceinline__ void control_G(const Action<4> &act, const ActPrev &prev, R p_atm,
+                                          R d_thrust_cg, R alpha_eff, R q, R x_cog, R mach,
+                                          Control<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    const bool f32 = (sizeof(R) == 8) && act.f32;
+    R t_full = c.T_e + (c.p_e - p_atm) * c.A_e;
+    // gimbal: first-order low-pass (tau 1.0, dt_act) on degrees, clipped
+    double gimbal_cmd_deg;
+    if (f32) gimbal_cmd_deg = (double)__fmul_rn((float)act.u[0], g_sf.max_gimbal_rad) * (180.0 / PD_PI);
+    else gimbal_cmd_deg = (act.u[0] * g_sd.max_gimbal_rad) * (180.0 / PD_PI);
+    double x = prev.gimbal_deg;
+    double gdeg = x + g_sd.dt_act * ((-x + gimbal_cmd_deg) / 1.0);
+    const double gmax = g_sd.max_gimbal_deg;
+    gdeg = gdeg < -gmax ? -gmax : (gdeg > gmax ? gmax : gdeg);
+    double grad = gdeg * (PD_PI / 180.0);
+    R sg, cg;
+    m_sincos((R)grad, &sg, &cg);
+    R t_par, t_perp, m_z;
+    if (f32) {
+        float thr = f32_throttle((float)act.u[1]);
+        float thrust = __fmul_rn((float)((double)t_full * (double)c.n_eng), thr);
+        float fpar = __fmul_rn(thrust, (float)cg);
+        float fperp = __fmul_rn(-thrust, (float)sg);
+        m_z = (R)((double)__fmul_rn(-thrust, (float)sg) * (double)d_thrust_cg);
+        float total = __fsqrt_rn(__fadd_rn(__fmul_rn(fpar, fpar), __fmul_rn(fperp, fperp)));
+        float n_tot = __fdiv_rn(total, (float)t_full);
+        float mf = __fmul_rn(g_sf.te_over_vex, n_tot);
+        t_par = (R)fpar;
+        t_perp = (R)fperp;
+        o.mass_flow = (R)mf;
+        o.mass_flow_dt = (R)__fmul_rn(mf, g_sf.dt_phys);
+        o.throttle = (R)thr;
+    } else {
+        R u1 = (R)act.u[1];
+        R throttle = (u1 + R(1)) / R(2) * c.one_minus_nominal + c.nominal;
+        R thrust = t_full * c.n_eng * throttle;
+        t_par = thrust * cg;
+        t_perp = -thrust * sg;
+        m_z = -thrust * sg * d_thrust_cg;
+        R total = m_sqrt(t_par * t_par + t_perp * t_perp);
+        R n_tot = total / t_full;
+        R mf = c.te_over_vex * n_tot;
+        o.mass_flow = mf;
+        o.mass_flow_dt = mf * c.dt_phys;
+        o.throttle = throttle;
+    }
+    o.gimbal_deg = grad * (180.0 / PD_PI);
+    // fin commands: u * radians(20) is called "deg" upstream and multiplied by 60 in ACS
+    if (f32) {
+        float cl60 = __fmul_rn(__fmul_rn((float)act.u[2], g_sf.max_defl_rad), 60.0f);
+        float cr60 = __fmul_rn(__fmul_rn((float)act.u[3], g_sf.max_defl_rad), 60.0f);
+        o.dl_cmd = (double)cl60 * (PD_PI / 180.0);
+        o.dr_cmd = (double)cr60 * (PD_PI / 180.0);
+    } else {
+        o.dl_cmd = ((act.u[2] * g_sd.max_defl_rad) * 60.0) * (PD_PI / 180.0);
+        o.dr_cmd = ((act.u[3] * g_sd.max_defl_rad) * 60.0) * (PD_PI / 180.0);
+    }
+    R f_perp, f_par, a_mz;
+    acs<R>(alpha_eff, q, mach, x_cog, o.dl_cmd, o.dr_cmd, prev.dl, prev.dr, f_perp, f_par, a_mz);
+    o.par = t_par + f_par;
+    o.perp = t_perp + f_perp;
+    o.mz = m_z + a_mz;
+}
+
+// ------------------------------------------------------------------ one Euler sub-step
+// RT = accumulation type of the RBF dot products.
+template <typename R, typename RT, int PHASE, bool WIND>
+__device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
+                                        const ActPrev &prev, WindState &w, const WindCtx &wc,
+                                        unsigned int env_id, RbfHint &h, Info<R> &info,
+                                        Control<R> &ctl) {
+    const Scalars<R> &c = SC<R>();
+    R y = (R)s.y, vx = (R)s.vx, vy = (R)s.vy;
+    R rho, p_atm, a_snd;
+    isa<R>(y, rho, p_atm, a_snd);
+    R speed = m_sqrt(vx * vx + vy * vy);
+    R mach = a_snd != R(0) ? m_min(speed / a_snd, R(10)) : R(0);
+    R q = R(0.5) * rho * (speed * speed);
+    R fuel = (c.m_prop0 - (R)s.m_prop) / c.m_prop0;
+    if (fuel == R(0)) fuel = R(1e-6);
+    R x_cog, inertia;
+    cog_inertia<R>(R(1) - fuel, x_cog, inertia);
+    R d_thrust_cg = x_cog + c.engine_height;
+    R alpha_eff = s.vy < 0.0 ? (R)(s.gamma - s.theta - PD_PI) : (R)s.alpha;
+    R d_cp_cg = x_cog - c.cop;
+    R ug = R(0), vg = R(0);
+    R f_wind_x = R(0);
+    if (WIND) {
+        wind_sample<R>(s.y, w, wc, env_id, ug, vg);
+        f_wind_x = R(0.5) * rho * (ug * ug) * c.S_ref * c.c_gust_x;
+    }
+    R C_L = R(0), C_D = R(0);
+    int status = 0;
+    if (a_snd != R(0)) {
+        C_L = coef_cl<R, RT>(mach, alpha_eff, h, status);
+        C_D = coef_cd<R, RT>(mach, alpha_eff, h, status);
+    }
+    R qdyn = R(0.5) * rho * (speed * speed);
+    R drag = qdyn * C_D * c.S_ref;
+    R lift = qdyn * C_L * c.S_ref;
+    R sa, ca;
+    m_sincos(alpha_eff, &sa, &ca);
+    R a_par, a_perp;
+    if (s.vy >= 0.0) {
+        a_par = lift * sa - drag * ca;
+        a_perp = -lift * ca - drag * sa;
+    } else {
+        a_par = drag * ca - lift * sa;
+        a_perp = -drag * sa - lift * ca;
+    }
+    R st, ct;
+    m_sincos((R)s.theta, &st, &ct);
+    R aero_x = a_par * ct + a_perp * st;
+    R aero_y = a_par * st - a_perp * ct;
+    R aero_mz = a_perp * d_cp_cg;
+    if constexpr (PHASE == 0)
+        control_P<R>(act, p_atm, alpha_eff, q, x_cog, mach, ctl);
+    else
+        control_G<R>(act, prev, p_atm, d_thrust_cg, alpha_eff, q, x_cog, mach, ctl);
+    R c_par = ctl.par, c_perp = ctl.perp, c_mz = ctl.mz;
+    // NaN guards are an if/elif chain upstream: only the first NaN is cleared
+    if (c_par != c_par) c_par = R(0);
+    else if (c_perp != c_perp) c_perp = R(0);
+    else if (c_mz != c_mz) c_mz = R(0);
+    R c_x = c_par * ct + c_perp * st;
+    R c_y = c_par * st - c_perp * ct;
+    const R RE = R(6371000.0);
+    R gr = RE / (RE + y);
+    R g = R(9.80665) * (gr * gr);
+    R fx = aero_x + c_x + f_wind_x;
+    R fy = aero_y + c_y;
+    R mass = (R)s.mass;
+    R vx_dot = fx / mass;
+    R vy_dot = fy / mass - g;
+    const double dt = g_sd.dt_phys;
+    s.vx += (double)(vx_dot * c.dt_phys);
+    s.vy += (double)(vy_dot * c.dt_phys);
+    s.x += s.vx * dt;
+    s.y += s.vy * dt;
+    R mz = c_mz + aero_mz;
+    R tdd = mz / inertia;
+    s.theta_dot += (double)(tdd * c.dt_phys);
+    s.theta += s.theta_dot * dt;
+    double gam = atan2(s.vy, s.vx);
+    if (s.theta > PD_TWO_PI) s.theta -= PD_TWO_PI;
+    if (gam < 0.0) gam = PD_TWO_PI + gam;
+    s.gamma = gam;
+    s.alpha = s.theta - gam;
+    s.m_prop -= (double)ctl.mass_flow_dt;
+    s.mass -= (double)ctl.mass_flow_dt;
+    s.time += dt;
+    info.mach = mach; info.q = q; info.CL = C_L; info.CD = C_D; info.rho = rho;
+    info.p_atm = p_atm; info.a = a_snd; info.x_cog = x_cog; info.inertia = inertia;
+    info.mass_flow = ctl.mass_flow; info.throttle = ctl.throttle; info.alpha_eff = alpha_eff;
+    info.ug = ug; info.vg = vg;
+    info.rbf_status |= status;
+}
+
+// ------------------------------------------------------------------ g-load window
+template <typename R>
+struct GWindow {
+    R w[10];
+    int n;
+};
+
+template <typename R>
+__device__ __forceinline__ R gwindow_push(GWindow<R> &g, R g_load) {
+    if (g.n < 10) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+            if (i == g.n) g.w[i] = g_load;
+        g.n += 1;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g.w[i] = g.w[i + 1];
+        g.w[9] = g_load;
+    }
+    R sum = R(0);
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        if (i < g.n) sum += g.w[i];
+    return sum / R(10);       // divided by the window length even while it is filling
+}
+
+// ------------------------------------------------------------------ reward / truncation / done
+template <typename R>
+struct Rtd {
+    R reward;
+    int done, truncated, trunc_id;
+};
+
+template <typename R>
+__device__ __forceinline__ R overshoot(double x, double y) {
+    if (x < 0.0 && y < 0.0) return m_sqrt((R)x * (R)x + (R)y * (R)y);
+    if (x < 0.0) return (R)(-x);
+    if (y < 0.0) return (R)(-y);
+    return R(0);
+}
+
+template <typename R, int PHASE, int RTD>
+__device__ __forceinline__ void rtd_eval(const State &s, R g1, R u0, Rtd<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    R vx = (R)s.vx, vy = (R)s.vy;
+    R speed = m_sqrt(vx * vx + vy * vy);
+    R rho = isa_rho<R>((R)s.y);
+    R q = R(0.5) * rho * (speed * speed);
+    R a_eff = s.vy < 0.0 ? (R)fabs(s.gamma - s.theta - PD_PI) : (R)fabs(s.theta - s.gamma);
+    const double theta_lim = PD_PI + 2.0 * (PD_PI / 180.0);
+    int tr = 0, id = 0, dn = 0;
+    R reward = R(0);
+    if (RTD == 0 && PHASE == 0) {
+        if (s.y < 0.0) { tr = 1; id = 1; }
+        else if (s.m_prop <= 0.0) { tr = 1; id = 2; }
+        else if (s.theta > theta_lim) { tr = 1; id = 3; }
+        else if (q > R(65000)) { tr = 1; id = 4; }
+        else if (s.vy > 0.0) { tr = 1; id = 6; }
+        else if (g1 > R(6.0)) { tr = 1; id = 7; }
+        dn = (s.y > 0.0 && s.y < 1.0 && speed < R(5.5)) ? 1 : 0;
+        if (tr && s.y > 0.0) reward = -(R)fabs(s.y);
+        else if (tr && s.y < 0.0) reward = R(200) - speed;
+        else if (dn) reward = (R)s.m_prop;
+    } else if (RTD == 0) {
+        R over = overshoot<R>(s.x, s.y);
+        R dist = m_sqrt((R)s.x * (R)s.x + (R)s.y * (R)s.y);
+        if (over > R(0.5)) { tr = 1; id = 1; }
+        else if (s.m_prop <= 0.0) { tr = 1; id = 2; }
+        else if (a_eff > R(10.0 * (PD_PI / 180.0))) { tr = 1; id = 3; }
+        else if (q > R(65000)) { tr = 1; id = 4; }
+        else if (s.vy > 0.0) { tr = 1; id = 6; }
+        else if (g1 > R(6.0)) { tr = 1; id = 7; }
+        else if (s.y > 1000.0 && s.vx > 0.0) { tr = 1; id = 8; }
+        dn = (dist > R(0) && dist < R(1) && speed < R(2.5)) ? 1 : 0;
+        if (tr && over < R(0.5)) reward = -dist;
+        else if (tr) reward = R(200) - speed;
+        else if (dn) reward = (R)s.m_prop;
+    } else {
+        // rl closures are shared by both landing phases (rtd_rl.py:194-240)
+        if (s.y < -10.0) { tr = 1; id = 1; }
+        else if (s.m_prop <= 0.0) { tr = 1; id = 2; }
+        else if (s.theta > theta_lim) { tr = 1; id = 3; }
+        else if (q > R(65000)) { tr = 1; id = 4; }
+        else if (g1 > R(6.0)) { tr = 1; id = 5; }
+        else if (s.vy > 0.0) { tr = 1; id = 6; }
+        else if (s.vx > 0.01) { tr = 1; id = 7; }
+        dn = (s.y > 0.0 && s.y < 1.0 && speed < R(5.0)) ? 1 : 0;
+        if (PHASE == 0) {
+            // dense pure-throttle reward, rtd_rl.py:286-336 (speed via hypot upstream)
+            R sp = m_hypot(vx, vy);
+            R qq = R(0.5) * rho * (sp * sp);
+            R r = R(0);
+            if (qq > R(60000)) {
+                R e = (qq - R(60000)) / R(5000);
+                r -= m_min(e * e, R(1));
+            }
+            if (g1 > R(5.5)) {
+                R e = (g1 - R(5.5)) / R(0.5);
+                r -= m_min(e * e, R(1));
+            }
+            R prog = (R)((g_sd.y0 - s.y) / g_sd.y0);
+            R wp = (qq <= R(60000) && g1 <= R(5.5)) ? R(0.5) : R(0.5 * 0.1);
+            r += wp * prog;
+            if (s.y < 100.0) r += R(5.5) * (R(1) - m_abs(vy) / R(50));
+            if (dn && !tr) r += R(400) * (R)s.m_prop / c.mass0;
+            else if (tr && s.y > 0.0) r -= R(50) * ((R)fabs(s.y) / c.y0);
+            else if (tr && s.y < 0.0) r -= R(50) * (m_abs(vy) / R(10));
+            if (!dn || !(tr && s.y < 0.0)) r = r < R(-10) ? R(-10) : (r > R(10) ? R(10) : r);
+            reward = r;
+        } else {
+            // gimballed landing burn, rtd_rl.py:243-269
+            R ae = (R)fabs(s.gamma - s.theta - PD_PI);
+            R tau = (u0 + R(1)) / R(2);
+            const R lmax = R(0.29941239026616734);    // math.log(1 + math.radians(20))
+            R r = (R(1.5) - m_log(R(1) + ae) / lmax - tau * R(0.5)) * (R)(1.0 - s.y / g_sd.y0) * R(2) / R(3);
+            if (s.y < 100.0) r += R(1) - m_tanh((speed - R(15)) / R(15));
+            if (tr && s.y < 5.0) r += R(1) - m_tanh((speed - R(5)) / R(5));
+            if (dn) r += R(5);
+            reward = r * c.rl_reward_scale;
+        }
+    }
+    o.reward = reward; o.done = dn; o.truncated = tr; o.trunc_id = id;
+}
+
+// ------------------------------------------------------------------ observations
+// pso: env_wrapped_ea.py:97-123 ; rl: env_wrapped_rl_pytorch.py:42-47,167-202 (state is
+// rounded to float32 first)
+template <typename R, int PHASE, int RTD>
+__device__ __forceinline__ void observe(const State &s, R *o) {
+    const Scalars<R> &c = SC<R>();
+    if (RTD == 0) {
+        if (PHASE == 0) {
+            o[0] = (R)s.y / c.norm_y;
+            o[1] = (R)s.vy / c.norm_vy;
+        } else {
+            o[0] = (R)s.x / c.norm_x;
+            o[1] = (R)s.y / c.norm_y;
+            o[2] = (R)s.vx / c.norm_vx;
+            o[3] = (R)s.vy / c.norm_vy;
+            o[4] = m_tanh(c.k_theta_pso * (R)(s.theta - PD_PI / 2));
+        }
+    } else {
+        float yf = (float)s.y, vyf = (float)s.vy;
+        // np.float32 scalar / np.float64 norm -> float64 arithmetic on fp32-rounded inputs
+        if (PHASE == 0) {
+            o[0] = (R)((1.0 - (double)yf / g_sd.norm_y) * 2 - 1);
+            o[1] = (R)((1.0 - (double)vyf / g_sd.norm_vy) * 2 - 1);
+        } else {
+            float th = (float)s.theta, thd = (float)s.theta_dot, gm = (float)s.gamma;
+            o[0] = (R)((double)yf / g_sd.norm_y);
+            o[1] = (R)((double)vyf / g_sd.norm_vy);
+            o[2] = (R)tanh(g_sd.k_theta_rl * ((double)th - PD_PI / 2));
+            o[3] = (R)tanh(g_sd.k_thetadot_rl * (double)thd);
+            o[4] = (R)tanh(g_sd.k_theta_rl * ((double)gm - 1.5 * PD_PI));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ one env.step()
+// 4 sub-steps with the same action (and, for G, the same actuator memory), g-load window,
+// truncation -> done -> reward on the new state.  base_environment.py:99-154.
+template <typename R, typename RT, int PHASE, int RTD, bool WIND>
+__device__ __forceinline__ void env_step(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
+                                         ActPrev &prev, WindState &w, const WindCtx &wc,
+                                         unsigned int env_id, RbfHint &h, GWindow<R> &gw,
+                                         Info<R> &info, Rtd<R> &out, R &g1_out) {
+    R vxp = (R)s.vx, vyp = (R)s.vy;
+    R v_p = m_sqrt(vxp * vxp + vyp * vyp);
+    Control<R> ctl;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k)
+        substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, env_id, h, info, ctl);
+    if (PHASE == 1) {
+        prev.gimbal_deg = ctl.gimbal_deg;
+        prev.dl = ctl.dl_cmd;
+        prev.dr = ctl.dr_cmd;
+    }
+    R vx = (R)s.vx, vy = (R)s.vy;
+    R v = m_sqrt(vx * vx + vy * vy);
+    R g_load = m_abs(v - v_p) / R(0.1) * R(1) / R(9.81);
+    R g1 = gwindow_push<R>(gw, g_load);
+    g1_out = g1;
+    R u0 = (R)act.u[0];
+    if (sizeof(R) == 8 && act.f32) u0 = (R)(float)act.u[0];
+    rtd_eval<R, PHASE, RTD>(s, g1, u0, out);
+}
+
+__device__ __forceinline__ void state_reset(State &s) {
+    const double *i = g_tb.init;
+    s.x = i[0]; s.y = i[1]; s.vx = i[2]; s.vy = i[3]; s.theta = i[4]; s.theta_dot = i[5];
+    s.gamma = i[6]; s.alpha = i[7]; s.mass = i[8]; s.m_prop = i[9]; s.time = i[10];
+}
+
+}  // namespace pd

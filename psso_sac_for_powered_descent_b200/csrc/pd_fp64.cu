@@ -1,0 +1,8 @@
+// Parity build: every arithmetic step in double.
+#include "pd_kernels.cuh"
+namespace pd {
+static const Impl k_impl = {
+    impl_upload, impl_reset<double, double>, Launch<double, double>::step,
+    Launch<double, double>::rollout, impl_get_state, impl_set_state, impl_transpose};
+const Impl *impl_fp64() { return &k_impl; }
+}  // namespace pd

@@ -1,0 +1,67 @@
+// pd_impl.h - plain structs shared by the precision TUs (pd_fp64.cu / pd_fp32.cu) and the
+// C-ABI front end (pd_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pd {
+
+template <typename R> struct Scalars;
+struct Tables;
+struct WindCtx;
+
+// Per-env persistent data, field-major (SoA) so that a warp touches 32 consecutive words.
+struct EnvSoA {
+    int n;
+    double *st;            // [11][n] state
+    double *gwin;          // [10][n] g-load FIFO (oldest first)
+    int *gwin_n;           // [n]
+    double *aprev;         // [3][n]  gimbal_deg_prev, delta_left_prev, delta_right_prev
+    double *wst;           // [6][n]  gust filter states + sigma_u, sigma_v
+    unsigned int *wctr;    // [n]     noise draws consumed this episode
+    unsigned int *episode; // [n]     episode counter (Philox stream id for sigma draws)
+    unsigned long long *hint;  // [2][n] cached C_D / C_L neighbour sets
+    int *hint_id;          // [2][n]
+    int *trunc_id;         // [n]
+    int *ep_steps;         // [n]
+    int *status;           // [1] sticky error bits (PD_RBF_MISS ...)
+};
+
+struct StepIO {
+    const void *actions;
+    int action_dtype;
+    void *obs, *reward, *next_obs;
+    uint8_t *done, *truncated;
+    int32_t *trunc_id;
+    double *dbg;
+};
+
+struct RolloutIO {
+    int n_episodes, n_seeds, max_steps;
+    const float *wT;       // [n_params][w_stride]
+    size_t w_stride;
+    const void *actions;   // tape [max_steps][n_episodes][A]
+    int action_dtype;
+    double *ret;
+    int32_t *steps, *trunc_id;
+    double *terminal, *traj, *rewards;
+    float *act_out;        // [max_steps][n_episodes][A] actions applied (MLP policy)
+};
+
+struct Impl {
+    int (*upload)(const Scalars<double> *, const Scalars<float> *, const Tables *);
+    void (*reset)(const EnvSoA &, const uint8_t *, const WindCtx &, const double *, cudaStream_t);
+    void (*step)(int phase, int rtd, int wind, const EnvSoA &, const StepIO &, const WindCtx &,
+                 const double *, int auto_reset, cudaStream_t);
+    int (*rollout)(int policy, int phase, int rtd, int wind, const RolloutIO &, const WindCtx &,
+                   const double *, int *status, cudaStream_t);
+    void (*get_state)(const EnvSoA &, double *, double *, int *, double *, cudaStream_t);
+    void (*set_state)(const EnvSoA &, const double *, const double *, const int *, const double *,
+                      cudaStream_t);
+    void (*transpose)(const float *, float *, int, int, cudaStream_t);
+};
+
+const Impl *impl_fp64();
+const Impl *impl_fp32();
+
+}  // namespace pd

@@ -1,0 +1,463 @@
+// pd_kernels.cuh - kernels of the powered-descent hot path, templated on the compute type.
+// Included by pd_fp64.cu (R = double) and pd_fp32.cu (R = float); each TU owns its copy of
+// the __constant__ parameter blocks and exports an Impl table to pd_api.cu.
+#pragma once
+#include "pd_device.cuh"
+#include "pd_impl.h"
+
+namespace pd {
+
+// ------------------------------------------------------------------ SoA views
+__device__ __forceinline__ void load_state(const EnvSoA &e, int i, State &s) {
+    const size_t B = e.n;
+    const double *p = e.st + i;
+    s.x = p[0]; s.y = p[B]; s.vx = p[2 * B]; s.vy = p[3 * B]; s.theta = p[4 * B];
+    s.theta_dot = p[5 * B]; s.gamma = p[6 * B]; s.alpha = p[7 * B]; s.mass = p[8 * B];
+    s.m_prop = p[9 * B]; s.time = p[10 * B];
+}
+__device__ __forceinline__ void store_state(const EnvSoA &e, int i, const State &s) {
+    const size_t B = e.n;
+    double *p = e.st + i;
+    p[0] = s.x; p[B] = s.y; p[2 * B] = s.vx; p[3 * B] = s.vy; p[4 * B] = s.theta;
+    p[5 * B] = s.theta_dot; p[6 * B] = s.gamma; p[7 * B] = s.alpha; p[8 * B] = s.mass;
+    p[9 * B] = s.m_prop; p[10 * B] = s.time;
+}
+template <typename R>
+__device__ __forceinline__ void load_window(const EnvSoA &e, int i, GWindow<R> &g) {
+    g.n = e.gwin_n[i];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) g.w[k] = (R)e.gwin[(size_t)k * e.n + i];
+}
+template <typename R>
+__device__ __forceinline__ void store_window(const EnvSoA &e, int i, const GWindow<R> &g) {
+    e.gwin_n[i] = g.n;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) e.gwin[(size_t)k * e.n + i] = (double)g.w[k];
+}
+__device__ __forceinline__ void load_wind(const EnvSoA &e, int i, WindState &w) {
+    const size_t B = e.n;
+    w.xu0 = e.wst[i]; w.xu1 = e.wst[B + i]; w.xv0 = e.wst[2 * B + i]; w.xv1 = e.wst[3 * B + i];
+    w.sigma_u = e.wst[4 * B + i]; w.sigma_v = e.wst[5 * B + i];
+    w.ctr = e.wctr[i];
+}
+__device__ __forceinline__ void store_wind(const EnvSoA &e, int i, const WindState &w) {
+    const size_t B = e.n;
+    e.wst[i] = w.xu0; e.wst[B + i] = w.xu1; e.wst[2 * B + i] = w.xv0; e.wst[3 * B + i] = w.xv1;
+    e.wst[4 * B + i] = w.sigma_u; e.wst[5 * B + i] = w.sigma_v;
+    e.wctr[i] = w.ctr;
+}
+__device__ __forceinline__ void load_hint(const EnvSoA &e, int i, RbfHint &h) {
+    h.cd = e.hint[i]; h.cl = e.hint[(size_t)e.n + i];
+    h.cd_id = e.hint_id[i]; h.cl_id = e.hint_id[(size_t)e.n + i];
+}
+__device__ __forceinline__ void store_hint(const EnvSoA &e, int i, const RbfHint &h) {
+    e.hint[i] = h.cd; e.hint[(size_t)e.n + i] = h.cl;
+    e.hint_id[i] = h.cd_id; e.hint_id[(size_t)e.n + i] = h.cl_id;
+}
+__device__ __forceinline__ void hint_reset(RbfHint &h) {
+    h.cd = g_tb.cd_hint0; h.cl = g_tb.cl_hint0; h.cd_id = -1; h.cl_id = -1;
+}
+
+// rl_wrapped_env_pytorch.augment_action for landing_burn (env_wrapped_rl_pytorch.py:144-157)
+__device__ __forceinline__ double log_compress(double u, double cfac) {
+    return copysign(log(1.0 + cfac * fabs(u)) / log(1.0 + cfac), u);
+}
+
+template <int A>
+__device__ __forceinline__ void read_action(const void *actions, int dtype, size_t idx, Action<A> &a) {
+    a.f32 = (dtype == 1);
+#pragma unroll
+    for (int k = 0; k < A; ++k)
+        a.u[k] = dtype == 1 ? (double)((const float *)actions)[idx * A + k]
+                            : ((const double *)actions)[idx * A + k];
+}
+
+template <int PHASE, int RTD>
+__device__ __forceinline__ void shape_action(Action<(PHASE == 0 ? 1 : 4)> &a) {
+    if constexpr (PHASE == 1 && RTD == 1) {
+        // np.array([...python floats...]) -> float64 action
+        a.u[0] = log_compress(a.u[0], 10.0);
+        a.u[2] = log_compress(a.u[2], 5.0);
+        a.u[3] = log_compress(a.u[3], 5.0);
+        a.f32 = false;
+    }
+}
+
+// ------------------------------------------------------------------ reset kernel
+template <typename R>
+__global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const double *sigma_uv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n) return;
+    if (mask && !mask[i]) return;
+    State s;
+    state_reset(s);
+    store_state(e, i, s);
+    e.gwin_n[i] = 0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) e.gwin[(size_t)k * e.n + i] = 0.0;
+    e.aprev[i] = 0.0; e.aprev[(size_t)e.n + i] = 0.0; e.aprev[2 * (size_t)e.n + i] = 0.0;
+    unsigned int ep = e.episode[i] + 1;
+    e.episode[i] = ep;
+    WindState w;
+    wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
+    store_wind(e, i, w);
+    RbfHint h;
+    hint_reset(h);
+    store_hint(e, i, h);
+    e.trunc_id[i] = 0;
+    e.ep_steps[i] = 0;
+}
+
+// ------------------------------------------------------------------ fused step kernel
+// physics (4 sub-steps) + g-window + truncation/done/reward + observation + auto-reset.
+template <typename R, typename RT, int PHASE, int RTD, bool WIND>
+__global__ void __launch_bounds__(128)
+step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
+    constexpr int A = PHASE == 0 ? 1 : 4;
+    constexpr int O = PHASE == 0 ? 2 : 5;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n) return;
+    State s;
+    load_state(e, i, s);
+    GWindow<R> gw;
+    load_window<R>(e, i, gw);
+    ActPrev prev = {0.0, 0.0, 0.0};
+    if (PHASE == 1) {
+        prev.gimbal_deg = e.aprev[i]; prev.dl = e.aprev[(size_t)e.n + i];
+        prev.dr = e.aprev[2 * (size_t)e.n + i];
+    }
+    WindState w = {};
+    if (WIND) load_wind(e, i, w);
+    RbfHint h;
+    load_hint(e, i, h);
+    Action<A> act;
+    read_action<A>(io.actions, io.action_dtype, (size_t)i, act);
+    shape_action<PHASE, RTD>(act);
+    Info<R> info;
+    info.rbf_status = 0;
+    Rtd<R> out;
+    R g1;
+    env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)i, h, gw, info, out, g1);
+    if (info.rbf_status) atomicOr(e.status, info.rbf_status);
+    R obs[O];
+    observe<R, PHASE, RTD>(s, obs);
+    if (io.obs) {
+#pragma unroll
+        for (int k = 0; k < O; ++k) ((R *)io.obs)[(size_t)i * O + k] = obs[k];
+    }
+    if (io.reward) ((R *)io.reward)[i] = out.reward;
+    if (io.done) io.done[i] = (uint8_t)out.done;
+    if (io.truncated) io.truncated[i] = (uint8_t)out.truncated;
+    if (io.trunc_id) io.trunc_id[i] = out.trunc_id;
+    if (io.dbg) {
+        double *d = io.dbg + (size_t)i * 16;
+        d[0] = info.mach; d[1] = info.q; d[2] = info.CL; d[3] = info.CD; d[4] = info.rho;
+        d[5] = info.p_atm; d[6] = info.a; d[7] = info.x_cog; d[8] = info.inertia;
+        d[9] = info.mass_flow; d[10] = info.throttle; d[11] = info.alpha_eff; d[12] = g1;
+        d[13] = info.ug; d[14] = info.vg; d[15] = (double)info.rbf_status;
+    }
+    e.trunc_id[i] = out.trunc_id;
+    int ep_steps = e.ep_steps[i] + 1;
+    if (auto_reset && (out.done || out.truncated)) {
+        state_reset(s);
+        gw.n = 0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
+        prev.gimbal_deg = prev.dl = prev.dr = 0.0;
+        unsigned int ep = e.episode[i] + 1;
+        e.episode[i] = ep;
+        if (WIND) wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
+        hint_reset(h);
+        ep_steps = 0;
+        observe<R, PHASE, RTD>(s, obs);
+    }
+    if (io.next_obs) {
+#pragma unroll
+        for (int k = 0; k < O; ++k) ((R *)io.next_obs)[(size_t)i * O + k] = obs[k];
+    }
+    e.ep_steps[i] = ep_steps;
+    store_state(e, i, s);
+    store_window<R>(e, i, gw);
+    if (PHASE == 1) {
+        e.aprev[i] = prev.gimbal_deg; e.aprev[(size_t)e.n + i] = prev.dl;
+        e.aprev[2 * (size_t)e.n + i] = prev.dr;
+    }
+    if (WIND) store_wind(e, i, w);
+    store_hint(e, i, h);
+}
+
+// ------------------------------------------------------------------ per-particle actor MLP
+// simple_actor (env_wrapped_ea.py:18-44): Linear(in,8)+ReLU, NH x [Linear(8,8)+ReLU],
+// Linear(8,out)+Tanh in float32.  Parameters in named_parameters() order, transposed on the
+// device to [param][particle] so that a warp's 32 lanes read 32 consecutive floats: a
+// warp-level batch of 32 independent GEMVs, one particle per lane.
+template <int IN, int OUT, int NH>
+__device__ __forceinline__ void actor_mlp(const float *__restrict__ wT, size_t stride, size_t col,
+                                          const float *obs, float *act) {
+    constexpr int H = 8;
+    float h[H], g[H];
+    const float *p = wT + col;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < IN; ++k) acc = fmaf(__ldg(p + (size_t)(j * IN + k) * stride), obs[k], acc);
+        h[j] = acc;
+    }
+    p += (size_t)(H * IN) * stride;
+#pragma unroll
+    for (int j = 0; j < H; ++j) { h[j] = fmaxf(h[j] + __ldg(p + (size_t)j * stride), 0.f); }
+    p += (size_t)H * stride;
+#pragma unroll 1
+    for (int l = 0; l < NH; ++l) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < H; ++k) acc = fmaf(__ldg(p + (size_t)(j * H + k) * stride), h[k], acc);
+            g[j] = acc;
+        }
+        p += (size_t)(H * H) * stride;
+#pragma unroll
+        for (int j = 0; j < H; ++j) h[j] = fmaxf(g[j] + __ldg(p + (size_t)j * stride), 0.f);
+        p += (size_t)H * stride;
+    }
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < H; ++k) acc = fmaf(__ldg(p + (size_t)(j * H + k) * stride), h[k], acc);
+        act[j] = acc;
+    }
+    p += (size_t)(OUT * H) * stride;
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) act[j] = tanhf(act[j] + __ldg(p + (size_t)j * stride));
+}
+
+// weights [n_particles][n_params] -> wT [n_params][n_particles]
+static __global__ void transpose_weights_kernel(const float *__restrict__ w, float *__restrict__ wT,
+                                         int n_particles, int n_params) {
+    __shared__ float tile[32][33];
+    int p0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int p = p0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (p < n_particles && k < n_params) ? w[(size_t)p * n_params + k] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, p = p0 + threadIdx.x;
+        if (k < n_params && p < n_particles) wT[(size_t)k * n_particles + p] = tile[threadIdx.x][r];
+    }
+}
+
+// ------------------------------------------------------------------ persistent rollout kernel
+// One episode per thread from reset to done/truncated: objective_function
+// (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for POLICY_TAPE,
+// LandingBurn.run_closed_loop for POLICY_CLASSICAL.
+template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY>
+__global__ void __launch_bounds__(128)
+rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
+    constexpr int A = PHASE == 0 ? 1 : 4;
+    constexpr int O = PHASE == 0 ? 2 : 5;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= io.n_episodes) return;
+    State s;
+    state_reset(s);
+    GWindow<R> gw;
+    gw.n = 0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
+    ActPrev prev = {0.0, 0.0, 0.0};
+    WindState w = {};
+    if (WIND) wind_reset(w, wc, (unsigned)e, 1u, sigma_uv);
+    RbfHint h;
+    hint_reset(h);
+    Info<R> info;
+    info.rbf_status = 0;
+    info.q = R(0);
+    double total = 0.0;
+    int steps = 0, tid = -1;
+    const size_t col = (size_t)(e / io.n_seeds);
+    for (int t = 0; t < io.max_steps; ++t) {
+        Action<A> act;
+        if constexpr (POLICY == 0) {
+            R obs[O];
+            observe<R, PHASE, 0>(s, obs);
+            float of[O], af[A];
+#pragma unroll
+            for (int k = 0; k < O; ++k) of[k] = (float)obs[k];
+            actor_mlp<O, A, (PHASE == 0 ? 3 : 4)>(io.wT, io.w_stride, col, of, af);
+            act.f32 = true;
+#pragma unroll
+            for (int k = 0; k < A; ++k) act.u[k] = (double)af[k];
+            if (io.act_out) {
+#pragma unroll
+                for (int k = 0; k < A; ++k) io.act_out[((size_t)t * io.n_episodes + e) * A + k] = af[k];
+            }
+        } else if constexpr (POLICY == 1) {
+            read_action<A>(io.actions, io.action_dtype, (size_t)t * io.n_episodes + e, act);
+            shape_action<PHASE, RTD>(act);
+        } else {
+            // classical P controller on v_ref(y) (landing_burn_pure_throttle.py:261-339)
+            double alpha_eff = s.gamma - s.theta - PD_PI;
+            if (!(s.m_prop > 0.0 && s.y > 1.0 && (double)info.q < 65e3 && s.vy < 0.0 &&
+                  alpha_eff < 5.0 * (180.0 / PD_PI)))
+                break;
+            double speed = sqrt(s.vx * s.vx + s.vy * s.vy);
+            double v_ref = g_sd.v_opt_a * (s.y * s.y) + g_sd.v_opt_b * s.y;
+            double nn = -0.10 * (v_ref - speed) + 0.0;
+            nn = nn < 0.0 ? 0.0 : (nn > 1.0 ? 1.0 : nn);
+            act.u[0] = 2.0 * (nn - 0.5);
+            act.f32 = false;
+        }
+        Rtd<R> out;
+        out.reward = R(0); out.done = 0; out.truncated = 0; out.trunc_id = 0;
+        if constexpr (POLICY == 2) {
+            Control<R> ctl;
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k)
+                substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, (unsigned)e, h, info, ctl);
+        } else {
+            R g1;
+            env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)e, h, gw, info, out, g1);
+        }
+        steps = t + 1;
+        total -= (double)out.reward;
+        if (io.traj) {
+            double *p = io.traj + ((size_t)t * io.n_episodes + e) * 11;
+            p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
+            p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
+        }
+        if (io.rewards) io.rewards[(size_t)t * io.n_episodes + e] = (double)out.reward;
+        if (out.done || out.truncated) { tid = out.trunc_id; break; }
+    }
+    if (info.rbf_status) atomicOr(status, info.rbf_status);
+    if (io.ret) io.ret[e] = total;
+    if (io.steps) io.steps[e] = steps;
+    if (io.trunc_id) io.trunc_id[e] = tid;
+    if (io.terminal) {
+        double *p = io.terminal + (size_t)e * 11;
+        p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
+        p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
+    }
+}
+
+// ------------------------------------------------------------------ AoS <-> SoA
+static __global__ void get_state_kernel(EnvSoA e, double *state, double *gwin, int *nwin, double *aprev) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n) return;
+    if (state)
+        for (int k = 0; k < 11; ++k) state[(size_t)i * 11 + k] = e.st[(size_t)k * e.n + i];
+    if (gwin)
+        for (int k = 0; k < 10; ++k) gwin[(size_t)i * 10 + k] = e.gwin[(size_t)k * e.n + i];
+    if (nwin) nwin[i] = e.gwin_n[i];
+    if (aprev)
+        for (int k = 0; k < 3; ++k) aprev[(size_t)i * 3 + k] = e.aprev[(size_t)k * e.n + i];
+}
+static __global__ void set_state_kernel(EnvSoA e, const double *state, const double *gwin, const int *nwin,
+                                 const double *aprev) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n) return;
+    if (state)
+        for (int k = 0; k < 11; ++k) e.st[(size_t)k * e.n + i] = state[(size_t)i * 11 + k];
+    if (gwin)
+        for (int k = 0; k < 10; ++k) e.gwin[(size_t)k * e.n + i] = gwin[(size_t)i * 10 + k];
+    if (nwin) e.gwin_n[i] = nwin[i];
+    if (aprev)
+        for (int k = 0; k < 3; ++k) e.aprev[(size_t)k * e.n + i] = aprev[(size_t)i * 3 + k];
+}
+
+// ------------------------------------------------------------------ launch tables
+template <typename R, typename RT>
+struct Launch {
+    template <int PHASE, int RTD, bool WIND>
+    static void step_t(const EnvSoA &e, const StepIO &io, const WindCtx &wc, const double *sig,
+                       int auto_reset, cudaStream_t st) {
+        int threads = 128, blocks = (e.n + threads - 1) / threads;
+        step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, 0, st>>>(e, io, wc, sig, auto_reset);
+    }
+    static void step(int phase, int rtd, int wind, const EnvSoA &e, const StepIO &io,
+                     const WindCtx &wc, const double *sig, int auto_reset, cudaStream_t st) {
+        int key = phase * 4 + rtd * 2 + (wind ? 1 : 0);
+        switch (key) {
+            case 0: step_t<0, 0, false>(e, io, wc, sig, auto_reset, st); break;
+            case 1: step_t<0, 0, true>(e, io, wc, sig, auto_reset, st); break;
+            case 2: step_t<0, 1, false>(e, io, wc, sig, auto_reset, st); break;
+            case 3: step_t<0, 1, true>(e, io, wc, sig, auto_reset, st); break;
+            case 4: step_t<1, 0, false>(e, io, wc, sig, auto_reset, st); break;
+            case 5: step_t<1, 0, true>(e, io, wc, sig, auto_reset, st); break;
+            case 6: step_t<1, 1, false>(e, io, wc, sig, auto_reset, st); break;
+            default: step_t<1, 1, true>(e, io, wc, sig, auto_reset, st); break;
+        }
+    }
+    template <int PHASE, int RTD, bool WIND, int POLICY>
+    static void roll_t(const RolloutIO &io, const WindCtx &wc, const double *sig, int *status,
+                       cudaStream_t st) {
+        int threads = 128, blocks = (io.n_episodes + threads - 1) / threads;
+        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY><<<blocks, threads, 0, st>>>(io, wc, sig, status);
+    }
+    static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
+                       const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {
+        if (policy == 0) {          // per-particle MLP: pso rtd only
+            int key = phase * 2 + (wind ? 1 : 0);
+            switch (key) {
+                case 0: roll_t<0, 0, false, 0>(io, wc, sig, status, st); break;
+                case 1: roll_t<0, 0, true, 0>(io, wc, sig, status, st); break;
+                case 2: roll_t<1, 0, false, 0>(io, wc, sig, status, st); break;
+                default: roll_t<1, 0, true, 0>(io, wc, sig, status, st); break;
+            }
+            return 0;
+        }
+        if (policy == 1) {
+            int key = phase * 4 + rtd * 2 + (wind ? 1 : 0);
+            switch (key) {
+                case 0: roll_t<0, 0, false, 1>(io, wc, sig, status, st); break;
+                case 1: roll_t<0, 0, true, 1>(io, wc, sig, status, st); break;
+                case 2: roll_t<0, 1, false, 1>(io, wc, sig, status, st); break;
+                case 3: roll_t<0, 1, true, 1>(io, wc, sig, status, st); break;
+                case 4: roll_t<1, 0, false, 1>(io, wc, sig, status, st); break;
+                case 5: roll_t<1, 0, true, 1>(io, wc, sig, status, st); break;
+                case 6: roll_t<1, 1, false, 1>(io, wc, sig, status, st); break;
+                default: roll_t<1, 1, true, 1>(io, wc, sig, status, st); break;
+            }
+            return 0;
+        }
+        if (policy == 2) {
+            if (phase != 0) return 1;
+            if (wind) roll_t<0, 0, true, 2>(io, wc, sig, status, st);
+            else roll_t<0, 0, false, 2>(io, wc, sig, status, st);
+            return 0;
+        }
+        return 1;
+    }
+};
+
+template <typename R, typename RT>
+static void impl_reset(const EnvSoA &e, const uint8_t *mask, const WindCtx &wc, const double *sig,
+                       cudaStream_t st) {
+    int threads = 128, blocks = (e.n + threads - 1) / threads;
+    reset_kernel<R><<<blocks, threads, 0, st>>>(e, mask, wc, sig);
+}
+
+static void impl_get_state(const EnvSoA &e, double *state, double *gwin, int *nwin, double *aprev,
+                           cudaStream_t st) {
+    int threads = 128, blocks = (e.n + threads - 1) / threads;
+    get_state_kernel<<<blocks, threads, 0, st>>>(e, state, gwin, nwin, aprev);
+}
+static void impl_set_state(const EnvSoA &e, const double *state, const double *gwin, const int *nwin,
+                           const double *aprev, cudaStream_t st) {
+    int threads = 128, blocks = (e.n + threads - 1) / threads;
+    set_state_kernel<<<blocks, threads, 0, st>>>(e, state, gwin, nwin, aprev);
+}
+static void impl_transpose(const float *w, float *wT, int n_particles, int n_params, cudaStream_t st) {
+    dim3 grid((n_particles + 31) / 32, (n_params + 31) / 32), block(32, 8);
+    transpose_weights_kernel<<<grid, block, 0, st>>>(w, wT, n_particles, n_params);
+}
+static int impl_upload(const Scalars<double> *sd, const Scalars<float> *sf, const Tables *tb) {
+    if (cudaMemcpyToSymbol(g_sd, sd, sizeof(*sd)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(g_sf, sf, sizeof(*sf)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(g_tb, tb, sizeof(*tb)) != cudaSuccess) return 1;
+    return 0;
+}
+
+}  // namespace pd

@@ -1,0 +1,412 @@
+"""Host-side mirror of the reference's env interfaces on top of the CUDA library.
+
+Batched API
+    BatchedRocketEnv          n_envs copies of rocket_environment_pre_wrap
+                              (src/envs/base_environment.py:12-154) living on one GPU.
+
+Drop-in, scalar-compatible mirrors (same constructor kwargs - including the misspelt
+`horiontal_wind_percentile` - same method names, return shapes and error behaviour):
+    rocket_environment_pre_wrap   src/envs/base_environment.py
+    pso_wrapped_env               src/envs/pso/env_wrapped_ea.py:137-230
+    rl_wrapped_env_pytorch        src/envs/rl/env_wrapped_rl_pytorch.py:68-205
+
+All arithmetic of reset/step/objective_function happens in the kernels behind
+include/pd_b200.h; torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .params import RocketParams
+
+WORKING_PHASES = ("landing_burn_pure_throttle", "landing_burn")
+ALL_PHASES = ["subsonic", "supersonic", "flip_over_boostbackburn", "ballistic_arc_descent",
+              "landing_burn", "landing_burn_ACS", "landing_burn_pure_throttle",
+              "landing_burn_pure_throttle_Pcontrol"]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class BatchedRocketEnv:
+    """A batch of landing-burn environments resident on one GPU.
+
+    type / flight_phase / enable_wind / stochastic_wind / horiontal_wind_percentile /
+    trajectory_length / discount_factor have the reference's meaning
+    (base_environment.py:12-20).  precision = 'fp64' (parity build) | 'fp32' (production).
+    """
+
+    def __init__(self, n_envs, type="pso", flight_phase="landing_burn_pure_throttle",
+                 enable_wind=False, stochastic_wind=False, horiontal_wind_percentile=50,
+                 trajectory_length=1, discount_factor=0.99, precision="fp32", auto_reset=False,
+                 device=None, seed=0, params: RocketParams | None = None):
+        assert flight_phase in ALL_PHASES
+        if flight_phase not in WORKING_PHASES:
+            raise NotImplementedError(
+                f"flight phase {flight_phase!r} is outside the B200 hot path "
+                "(landing_burn_pure_throttle, landing_burn); see DESIGN.md")
+        assert type in ("rl", "pso", "supervisory")
+        if type == "supervisory":
+            raise NotImplementedError("supervisory rtd closures are outside the hot path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedRocketEnv needs a CUDA device (no CPU fallback)")
+        if enable_wind:
+            assert 50 <= horiontal_wind_percentile <= 99, \
+                "Given percentile must be between 50 and 99"
+        self.lib = N.load_library()
+        self.params = params or RocketParams.default()
+        self.flight_phase, self.type = flight_phase, type
+        self.phase_id = N.PHASES[flight_phase]
+        self.n_envs = int(n_envs)
+        self.precision = precision
+        self.dtype = torch.float64 if precision == "fp64" else torch.float32
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else device.index or 0)
+        self.obs_dim, self.act_dim = N.OBS_DIM[self.phase_id], N.ACT_DIM[self.phase_id]
+        self.n_actor_params = N.N_PARAMS[self.phase_id]
+        self.dt = 0.1
+        self.enable_wind = bool(enable_wind)
+        cfg = N.PdConfig()
+        cfg.phase, cfg.rtd, cfg.precision = self.phase_id, N.RTD[type], N.PRECISION[precision]
+        cfg.enable_wind, cfg.stochastic_wind = int(bool(enable_wind)), int(bool(stochastic_wind))
+        cfg.auto_reset, cfg.n_envs, cfg.device = int(bool(auto_reset)), self.n_envs, self.device.index
+        cfg.seed = int(seed)
+        g, L = discount_factor, trajectory_length
+        cfg.rl_reward_scale = (1 - g) / (1 - g ** L) if (g is not None and L) else 1.0
+        self._cparams, self._keep = N.make_params(self.params, horiontal_wind_percentile)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.pd_create(C.byref(cfg), C.byref(self._cparams), C.byref(self._h)))
+        B, dev = self.n_envs, self.device
+        self.obs = torch.empty(B, self.obs_dim, dtype=self.dtype, device=dev)
+        self.next_obs = torch.empty(B, self.obs_dim, dtype=self.dtype, device=dev)
+        self.reward = torch.empty(B, dtype=self.dtype, device=dev)
+        self.done = torch.empty(B, dtype=torch.uint8, device=dev)
+        self.truncated = torch.empty(B, dtype=torch.uint8, device=dev)
+        self.trunc_id = torch.empty(B, dtype=torch.int32, device=dev)
+        self._tape = self._sigma = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.pd_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    close = __del__
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, mask: torch.Tensor | None = None):
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        N.check(self.lib.pd_reset(self._h, _ptr(mask), _stream()))
+        return self.get_state()
+
+    def step(self, actions: torch.Tensor, dbg: torch.Tensor | None = None):
+        """actions: cuda tensor [n_envs, A] float64 or float32 (its dtype selects the
+        reference's pure-fp64 or float32-contaminated arithmetic).  Returns the handle's
+        (obs, reward, done, truncated, trunc_id) tensors, overwritten in place every step."""
+        if actions.dtype not in (torch.float64, torch.float32):
+            raise TypeError("actions must be float64 or float32")
+        a = actions.reshape(self.n_envs, self.act_dim).contiguous()
+        if a.device != self.device:
+            raise ValueError("actions must live on the env's device")
+        N.check(self.lib.pd_step(self._h, _ptr(a), 1 if a.dtype == torch.float32 else 0,
+                                 _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
+                                 _ptr(self.truncated), _ptr(self.trunc_id), _ptr(self.next_obs),
+                                 _ptr(dbg), _stream()))
+        return self.obs, self.reward, self.done, self.truncated, self.trunc_id
+
+    # ------------------------------------------------------------------ state access
+    def get_state(self, full=False):
+        B = self.n_envs
+        st = torch.empty(B, 11, dtype=torch.float64, device=self.device)
+        if not full:
+            N.check(self.lib.pd_get_state(self._h, _ptr(st), None, None, None, _stream()))
+            return st
+        gw = torch.empty(B, 10, dtype=torch.float64, device=self.device)
+        nw = torch.empty(B, dtype=torch.int32, device=self.device)
+        ap = torch.empty(B, 3, dtype=torch.float64, device=self.device)
+        N.check(self.lib.pd_get_state(self._h, _ptr(st), _ptr(gw), _ptr(nw), _ptr(ap), _stream()))
+        return st, gw, nw, ap
+
+    def set_state(self, state, g_window=None, n_window=None, act_prev=None):
+        def prep(x, dt, shape):
+            if x is None:
+                return None
+            return torch.as_tensor(x, dtype=dt).to(self.device).reshape(shape).contiguous()
+        B = self.n_envs
+        st = prep(state, torch.float64, (B, 11))
+        gw = prep(g_window, torch.float64, (B, 10))
+        nw = prep(n_window, torch.int32, (B,))
+        ap = prep(act_prev, torch.float64, (B, 3))
+        N.check(self.lib.pd_set_state(self._h, _ptr(st), _ptr(gw), _ptr(nw), _ptr(ap), _stream()))
+        torch.cuda.current_stream().synchronize()
+
+    def set_wind_tape(self, tape, sigma_uv):
+        """Parity hook: N(0,1) tape [n_envs, T] and (sigma_u, sigma_v) [n_envs, 2]."""
+        if tape is None:
+            self._tape = self._sigma = None
+            N.check(self.lib.pd_set_wind_tape(self._h, None, 0, None))
+            return
+        self._tape = torch.as_tensor(tape, dtype=torch.float64).to(self.device).reshape(self.n_envs, -1).contiguous()
+        self._sigma = torch.as_tensor(sigma_uv, dtype=torch.float64).to(self.device).reshape(-1, 2).contiguous()
+        N.check(self.lib.pd_set_wind_tape(self._h, _ptr(self._tape), self._tape.shape[1], _ptr(self._sigma)))
+
+    def check_status(self):
+        st = C.c_int32(0)
+        N.check(self.lib.pd_check_status(self._h, C.byref(st)))
+
+    # ------------------------------------------------------------------ rollouts
+    def rollout_pso(self, weights: torch.Tensor, n_seeds=1, max_steps=4096, terminal=False,
+                    trace=False):
+        """weights: cuda float32 [n_particles, n_params].  Returns fitness (float64
+        [n_particles*n_seeds]), steps, trunc_id (, terminal_state).  trace=True returns a dict
+        with the per-step states / actions / rewards as well."""
+        w = weights.to(device=self.device, dtype=torch.float32).contiguous()
+        n, p = w.shape
+        E = n * n_seeds
+        fit = torch.empty(E, dtype=torch.float64, device=self.device)
+        steps = torch.empty(E, dtype=torch.int32, device=self.device)
+        tid = torch.empty(E, dtype=torch.int32, device=self.device)
+        term = torch.empty(E, 11, dtype=torch.float64, device=self.device) if terminal else None
+        traj = acts = rews = None
+        if trace:
+            term = torch.empty(E, 11, dtype=torch.float64, device=self.device)
+            traj = torch.zeros(max_steps, E, 11, dtype=torch.float64, device=self.device)
+            acts = torch.zeros(max_steps, E, self.act_dim, dtype=torch.float32, device=self.device)
+            rews = torch.zeros(max_steps, E, dtype=torch.float64, device=self.device)
+        N.check(self.lib.pd_rollout_pso(self._h, _ptr(w), n, p, n_seeds, max_steps, _ptr(fit),
+                                        _ptr(steps), _ptr(tid), _ptr(term), _ptr(traj), _ptr(acts),
+                                        _ptr(rews), _stream()))
+        if trace:
+            return dict(fitness=fit, steps=steps, trunc_id=tid, terminal=term, traj=traj,
+                        actions=acts, rewards=rews)
+        return (fit, steps, tid, term) if terminal else (fit, steps, tid)
+
+    def rollout_tape(self, actions: torch.Tensor, record=False):
+        """actions [T, n_episodes, A] (float64 or float32): an env.reset() + env.step loop per
+        episode, stopping at done/truncated."""
+        T, E = actions.shape[0], actions.shape[1]
+        a = actions.to(self.device).contiguous()
+        ret = torch.empty(E, dtype=torch.float64, device=self.device)
+        steps = torch.empty(E, dtype=torch.int32, device=self.device)
+        tid = torch.empty(E, dtype=torch.int32, device=self.device)
+        term = torch.empty(E, 11, dtype=torch.float64, device=self.device)
+        traj = torch.zeros(T, E, 11, dtype=torch.float64, device=self.device) if record else None
+        rew = torch.zeros(T, E, dtype=torch.float64, device=self.device) if record else None
+        N.check(self.lib.pd_rollout_policy(self._h, 1, _ptr(a), 1 if a.dtype == torch.float32 else 0,
+                                           E, T, _ptr(ret), _ptr(steps), _ptr(tid), _ptr(term),
+                                           _ptr(traj), _ptr(rew), _stream()))
+        return dict(ret=ret, steps=steps, trunc_id=tid, terminal=term, traj=traj, rewards=rew)
+
+    def rollout_classical(self, n_episodes=1, max_steps=50000, record=False):
+        """LandingBurn(test_case='control').run_closed_loop()
+        (src/classical_controls/landing_burn_pure_throttle.py:332-339)."""
+        E, T = n_episodes, max_steps
+        steps = torch.empty(E, dtype=torch.int32, device=self.device)
+        term = torch.empty(E, 11, dtype=torch.float64, device=self.device)
+        traj = torch.zeros(T, E, 11, dtype=torch.float64, device=self.device) if record else None
+        N.check(self.lib.pd_rollout_policy(self._h, 2, None, 0, E, T, None, _ptr(steps), None,
+                                           _ptr(term), _ptr(traj), None, _stream()))
+        return dict(steps=steps, terminal=term, traj=traj)
+
+
+# =======================================================================================
+# scalar-compatible drop-ins
+# =======================================================================================
+def _action_tensor(actions, act_dim, device):
+    """Accept what the reference's decomposers accept (tuple, list, 1-D / 2-D ndarray, torch
+    tensor; rockets_physics.py:199-219, 360-370) and keep its dtype semantics: float32
+    ndarrays stay float32, everything else is float64."""
+    if isinstance(actions, torch.Tensor):
+        a = actions.detach()
+        a = a.to(torch.float32 if a.dtype == torch.float32 else torch.float64)
+        return a.reshape(1, act_dim).to(device)
+    if isinstance(actions, np.ndarray):
+        dt = torch.float32 if actions.dtype == np.float32 else torch.float64
+        return torch.as_tensor(np.ascontiguousarray(actions).reshape(1, act_dim), dtype=dt).to(device)
+    if isinstance(actions, (tuple, list)):
+        return torch.tensor([float(v) for v in actions], dtype=torch.float64).reshape(1, act_dim).to(device)
+    return torch.tensor([[float(actions)]], dtype=torch.float64).to(device)
+
+
+class rocket_environment_pre_wrap:
+    """One reference env (base_environment.py:12-154) backed by a 1-env GPU batch."""
+
+    def __init__(self, type="rl", flight_phase="subsonic", enable_wind=True, stochastic_wind=True,
+                 horiontal_wind_percentile=50, trajectory_length=100, discount_factor=0.99,
+                 precision="fp64", seed=0):
+        assert flight_phase in ALL_PHASES
+        assert type in ["rl", "pso", "supervisory"]
+        self.flight_phase, self.type, self.dt = flight_phase, type, 0.1
+        self.enable_wind = enable_wind
+        self._b = BatchedRocketEnv(1, type, flight_phase, enable_wind, stochastic_wind,
+                                   horiontal_wind_percentile, trajectory_length, discount_factor,
+                                   precision=precision, seed=seed)
+        self.state_initial = list(self._b.params.initial_state)
+        self.wind_generator = self._b if enable_wind else None
+        self._dbg = torch.zeros(1, 16, dtype=torch.float64, device=self._b.device)
+        self.truncation_id = 0
+        self.reset()
+
+    def reset(self):
+        self.state = self._b.reset()[0].tolist()
+        self.previous_state = self.state
+        self.truncation_id = 0
+        return self.state
+
+    def step(self, actions):
+        a = _action_tensor(actions, self._b.act_dim, self._b.device)
+        obs, rew, done, trunc, tid = self._b.step(a, dbg=self._dbg)
+        self.previous_state = self.state
+        self.state = self._b.get_state()[0].tolist()
+        d = self._dbg[0].tolist()
+        self.truncation_id = int(tid[0])
+        info = dict(mach_number=d[0], dynamic_pressure=d[1], CL=d[2], CD=d[3], air_density=d[4],
+                    atmospheric_pressure=d[5], speed_of_sound=d[6], x_cog=d[7], inertia=d[8],
+                    mass_flow=d[9], action_info=dict(throttle=d[10]), alpha_effective=d[11],
+                    g_load_1_sec_window=d[12], ug=d[13], vg=d[14], state=self.state, actions=actions)
+        self._obs = obs[0]
+        return self.state, float(rew[0]), bool(done[0]), bool(trunc[0]), info
+
+
+class simple_actor_spec:
+    """Shape bookkeeping of env_wrapped_ea.simple_actor (env_wrapped_ea.py:18-75): parameter
+    names/order of nn.Sequential(Linear, ReLU, n x Sequential(Linear, ReLU), Linear, Tanh)."""
+
+    def __init__(self, input_dim, output_dim, number_of_hidden_layers, hidden_dim):
+        self.shapes = [("0", (hidden_dim, input_dim))]
+        for l in range(number_of_hidden_layers):
+            self.shapes.append((f"{2 + l}.0", (hidden_dim, hidden_dim)))
+        self.shapes.append((f"{2 + number_of_hidden_layers}", (output_dim, hidden_dim)))
+        self.number_of_network_parameters = sum(o * i + o for _, (o, i) in self.shapes)
+
+    def return_setup_vals(self):
+        names, bounds = {}, []
+        for name, (o, i) in self.shapes:
+            for kind, n in (("weight", o * i), ("bias", o)):
+                for j in range(n):
+                    names[f'{name.replace(".", "_")}_{kind}_{j}'] = 0.0
+                    bounds.append((-1.5, 1.5))
+        return names, bounds
+
+
+class pso_wrapped_env:
+    """PSO model (env_wrapped_ea.py:137-230): .objective_function(individual) -> float,
+    .bounds, .mock_dictionary_of_opt_params, .individual_update_model, .reset,
+    .env.truncation_id().  The whole episode (actor MLP in the loop) is one kernel launch;
+    `evaluate(positions)` is the batched form used by parallel_evaluate."""
+
+    def __init__(self, flight_phase="subsonic", enable_wind=False, stochastic_wind=False,
+                 horiontal_wind_percentile=50, precision="fp64", max_steps=8192, seed=0):
+        assert flight_phase in ["subsonic", "supersonic", "flip_over_boostbackburn",
+                                "ballistic_arc_descent", "landing_burn_pure_throttle", "landing_burn"]
+        self.flight_phase, self.enable_wind = flight_phase, enable_wind
+        self._b = BatchedRocketEnv(1, "pso", flight_phase, enable_wind, stochastic_wind,
+                                   horiontal_wind_percentile, precision=precision, seed=seed)
+        if flight_phase == "landing_burn_pure_throttle":
+            self.actor = simple_actor_spec(2, 1, 3, 8)
+        else:
+            self.actor = simple_actor_spec(5, 4, 4, 8)
+        self.mock_dictionary_of_opt_params, self.bounds = self.actor.return_setup_vals()
+        self.max_steps = max_steps
+        self.experience_buffer = []
+        self.episode_idx = 0
+        self._individual = None
+        self._last_tid = 0
+        self.env = self          # model.env.truncation_id() as in the reference
+
+    def truncation_id(self):
+        return self._last_tid
+
+    def individual_update_model(self, individual):
+        self._individual = np.asarray(individual, dtype=np.float64)
+
+    def reset(self):
+        self.experience_buffer = []
+
+    def evaluate(self, positions, n_seeds=1, terminal=False):
+        w = np.asarray(positions, dtype=np.float64).reshape(-1, self.actor.number_of_network_parameters)
+        wt = torch.as_tensor(w.astype(np.float32)).to(self._b.device)
+        out = self._b.rollout_pso(wt, n_seeds=n_seeds, max_steps=self.max_steps, terminal=terminal)
+        self._b.check_status()
+        return out
+
+    def objective_function(self, individual):
+        self.individual_update_model(individual)
+        fit, steps, tid = self.evaluate(self._individual[None, :])
+        self._last_tid = int(tid[0])
+        self.last_steps = int(steps[0])
+        self.episode_idx += 1
+        return float(fit[0])
+
+
+class rl_wrapped_env_pytorch:
+    """rl_wrapped_env_pytorch (env_wrapped_rl_pytorch.py:68-205) for the landing phases:
+    float32-rounded observation, G action log-compression, state_dim/action_dim."""
+
+    def __init__(self, flight_phase="subsonic", enable_wind=False, stochastic_wind=True,
+                 horiontal_wind_percentile=50, trajectory_length=None, discount_factor=None,
+                 precision="fp64", seed=0):
+        assert flight_phase in ALL_PHASES
+        self.flight_phase = flight_phase
+        self.env = rocket_environment_pre_wrap("rl", flight_phase, enable_wind, stochastic_wind,
+                                               horiontal_wind_percentile, trajectory_length,
+                                               discount_factor, precision=precision, seed=seed)
+        self.enable_wind = enable_wind
+        self.state_dim, self.action_dim = self.env._b.obs_dim, self.env._b.act_dim
+
+    def truncation_id(self):
+        return self.env.truncation_id
+
+    def reset(self):
+        self.env.reset()
+        # observation of the reset state: one kernel-side observe() via a zero-length trick is
+        # not exposed, so evaluate augment_state's closed form on the fp32-rounded state
+        return self._obs_from_state(self.env.state)
+
+    def _obs_from_state(self, state):
+        s = np.asarray(state, dtype=np.float32)
+        nv = np.array(self.env._b.params.norm_vals)     # np.float64 scalars, as upstream
+        if self.flight_phase == "landing_burn_pure_throttle":
+            return np.array([(1 - s[1] / nv[0]) * 2 - 1, (1 - s[3] / nv[1]) * 2 - 1])
+        k = float(np.arctanh(0.75) / math.radians(5))
+        kd = float(np.arctanh(0.75) / 0.01)
+        return np.array([s[1] / nv[0], s[3] / nv[1], math.tanh(k * (s[4] - math.pi / 2)),
+                         math.tanh(kd * s[5]), math.tanh(k * (s[6] - 3 / 2 * math.pi))])
+
+    def step(self, action):
+        if isinstance(action, np.ndarray):
+            a = action
+        else:
+            try:
+                a = action.cpu().numpy()
+            except Exception:
+                a = np.array(action)
+        if a.ndim == 2:
+            a = a[0]
+        state, reward, done, truncated, info = self.env.step(a)
+        obs = self.env._obs.to(torch.float64).cpu().numpy()
+        return obs, float(reward), bool(done), bool(truncated), info
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def render(self):
+        pass
+
+    def close(self):
+        pass

@@ -103,7 +103,15 @@ def single_step(phase, tag, n=192, seed=0):
     for i in range(n):
         s, sp, win, aprev = pool[rng.integers(len(pool))]
         s = np.array(s); sp = np.array(sp)
-        if i % 3 == 1:      # perturb: low-altitude / slow cases to exercise done / y<0 branches
+        if i % 6 == 1:      # touchdown window: exercises done (0<y<1, slow) and y<0
+            s = s.copy()
+            s[1] = rng.uniform(0.05, 2.5)
+            s[3] = -rng.uniform(0.5, 7.0)
+            s[2] = rng.uniform(-1.0, 1.0)
+            s[0] = rng.uniform(-1.0, 1.0) if phase == G else s[0]
+            s[6] = math.atan2(s[3], s[2]) % (2 * math.pi)
+            s[7] = s[4] - s[6]
+        elif i % 3 == 1:    # perturb: low-altitude / slow cases to exercise done / y<0 branches
             s = s.copy()
             s[1] = rng.uniform(-2.0, 40.0)
             s[3] = -rng.uniform(0.5, 30.0)
@@ -121,7 +129,8 @@ def single_step(phase, tag, n=192, seed=0):
         for key, a in (("o64", a32.astype(np.float64)), ("o32", a32)):
             env.reset()
             env.state = [np.float64(v) for v in s]
-            env.previous_state = [np.float64(v) for v in sp]
+            # invariant of the reference: previous_state is the state the step starts from
+            env.previous_state = env.state
             env.g_loads_window = list(win)
             if phase == G:
                 env.gimbal_angle_deg_prev = aprev[0]
@@ -149,23 +158,56 @@ def single_step(phase, tag, n=192, seed=0):
 
 
 def pso_fitness(phase, tag, n=12, seed=0):
+    """objective_function of randomly initialised particles + a conditioning probe: the same
+    episode replayed through the reference env with every action nudged by one float32 ulp.
+    Episodes whose length changes under that nudge are ill-conditioned in the reference itself
+    (phase G tumbles within ~20 steps) and are only sanity-checked by the parity tests."""
     from src.envs.pso.env_wrapped_ea import pso_wrapped_env
+    from src.envs.base_environment import rocket_environment_pre_wrap
     model = pso_wrapped_env(flight_phase=phase, enable_wind=False)
     random.seed(seed)
     # exactly ParticleSubswarmOptimisation.initialize_swarms' draw order
     pos = [np.array([random.uniform(b[0], b[1]) for b in model.bounds]) for _ in range(n)]
-    fit, steps, tid, term = [], [], [], []
+    env = rocket_environment_pre_wrap(type="pso", flight_phase=phase, enable_wind=False)
+    adim = 1 if phase == P else 4
+    fit, steps, tid, term, cond, acts_all = [], [], [], [], [], []
     for p_ in pos:
         f = quiet(model.objective_function, p_)
         fit.append(float(f)); tid.append(model.env.truncation_id())
         term.append([float(v) for v in model.env.env.state])
-        steps.append(round((float(model.env.env.state[-1]) - float(model.env.env.state_initial[-1]))
-                           / (0.1 if phase == P else 0.4)))
         model.reset()
+        # re-drive the same episode to record the float32 actions
+        model.individual_update_model(p_)
+        obs = model.env.reset()
+        acts = []
+        while True:
+            a = model.actor.forward(obs)
+            acts.append(a.detach().numpy().copy())
+            obs, r, dn, tr, info = quiet(model.env.step, a)
+            if dn or tr:
+                break
+        steps.append(len(acts))
+        ok = True
+        for direction in (2.0, -2.0):
+            env.reset()
+            tot, k = 0.0, 0
+            for a in acts:
+                a2 = np.nextafter(a.astype(np.float32), np.float32(direction)).astype(np.float32)
+                s_, r, dn, tr, info = quiet(env.step, a2)
+                tot -= r; k += 1
+                if dn or tr:
+                    break
+            if k != len(acts) or not (dn or tr) or abs(tot - f) > 1e-6 * abs(f):
+                ok = False
+        cond.append(ok)
+        pad = np.zeros((512, adim), np.float32)
+        pad[:min(len(acts), 512)] = np.array(acts)[:512]
+        acts_all.append(pad)
     np.savez_compressed(os.path.join(OUT, f"pso_fitness_{tag}.npz"), positions=np.array(pos),
                         fitness=np.array(fit), steps=np.array(steps), trunc_id=np.array(tid),
-                        terminal_state=np.array(term), seed=seed)
-    print("pso_fitness", tag, "fitness", np.round(fit, 3), "steps", steps, "tid", tid)
+                        terminal_state=np.array(term), seed=seed, well_conditioned=np.array(cond),
+                        actions=np.array(acts_all))
+    print("pso_fitness", tag, "fitness", np.round(fit, 3), "steps", steps, "tid", tid, "well-conditioned", cond)
 
 
 def pso_best_actor():
