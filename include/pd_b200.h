@@ -33,7 +33,7 @@ extern "C" {
 #define PD_STATE_DIM 11
 #define PD_MAX_LEVELS 5
 #define PD_RBF_NEIGHBOURS 50
-#define PD_RBF_COEF_STRIDE 58
+#define PD_RBF_ROW_BYTES 512
 #define PD_DBG_DIM 16
 
 enum { PD_PHASE_PURE_THROTTLE = 0, PD_PHASE_GIMBALLED = 1 };   /* flight_phase strings   */
@@ -41,6 +41,18 @@ enum { PD_RTD_PSO = 0, PD_RTD_RL = 1 };                        /* type = 'pso' |
 enum { PD_FP64 = 0, PD_FP32 = 1 };                             /* compute precision build */
 enum { PD_ACT_F64 = 0, PD_ACT_F32 = 1 };                       /* dtype of the action     */
 enum { PD_POLICY_MLP = 0, PD_POLICY_TAPE = 1, PD_POLICY_CLASSICAL = 2 };
+
+/* Uniform (Mach, AoA) lookup grid over one query region of a local RBF table.
+ * cells[ia*nm+im] >= 0 : set id valid for the whole grid cell;
+ * cells < 0            : -(k+1) indexes (imp_hint, imp_id): candidate set to walk from. */
+typedef struct {
+    double m0, dm, a0, da;
+    int32_t nm, na;
+    int32_t n_impure, _pad;
+    const int32_t *cells;                 /* host [nm*na] */
+    const uint64_t *imp_hint;             /* host [n_impure] */
+    const int32_t *imp_id;                /* host [n_impure] */
+} PdRbfGrid;
 
 /* Local thin-plate-spline table (host pointers, copied by pd_create);
  * built by psso_sac_for_powered_descent_b200/rbf_sets.py.  Replaces the per-call
@@ -52,11 +64,13 @@ typedef struct {
     int32_t hash_size;                    /* power of two */
     double levels[PD_MAX_LEVELS];         /* AoA coordinate of each level */
     int32_t level_off[PD_MAX_LEVELS + 1];
-    const double *mach_sorted;            /* host [n_points] */
-    const double *coeffs;                 /* host [n_sets * PD_RBF_COEF_STRIDE] */
+    int32_t n_grids;
+    const double *mach_sorted;            /* host [n_points] level-major, Mach ascending */
+    const double *points;                 /* host [n_points*2] (Mach, AoA) per slot */
+    const uint8_t *rows;                  /* host [n_sets*512]: 57 doubles + 50 index bytes */
     const uint64_t *hash_keys;            /* host [hash_size] */
     const int32_t *hash_vals;             /* host [hash_size] */
-    uint64_t initial_hint;                /* packed neighbour set at the initial state */
+    PdRbfGrid grids[2];
 } PdRbfTable;
 
 /* Constants the reference loads in compile_physics (src/envs/rockets_physics.py:707-957),

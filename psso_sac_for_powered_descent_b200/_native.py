@@ -23,11 +23,18 @@ ACT_DIM = {0: 1, 1: 4}
 N_PARAMS = {0: 249, 1: 372}
 
 
+class PdRbfGrid(C.Structure):
+    _fields_ = [("m0", C.c_double), ("dm", C.c_double), ("a0", C.c_double), ("da", C.c_double),
+                ("nm", C.c_int32), ("na", C.c_int32), ("n_impure", C.c_int32), ("_pad", C.c_int32),
+                ("cells", C.c_void_p), ("imp_hint", C.c_void_p), ("imp_id", C.c_void_p)]
+
+
 class PdRbfTable(C.Structure):
     _fields_ = [("n_levels", C.c_int32), ("n_points", C.c_int32), ("n_sets", C.c_int32),
                 ("hash_size", C.c_int32), ("levels", C.c_double * 5), ("level_off", C.c_int32 * 6),
-                ("mach_sorted", C.c_void_p), ("coeffs", C.c_void_p), ("hash_keys", C.c_void_p),
-                ("hash_vals", C.c_void_p), ("initial_hint", C.c_uint64)]
+                ("n_grids", C.c_int32), ("mach_sorted", C.c_void_p), ("points", C.c_void_p),
+                ("rows", C.c_void_p), ("hash_keys", C.c_void_p), ("hash_vals", C.c_void_p),
+                ("grids", PdRbfGrid * 2)]
 
 
 class PdParams(C.Structure):
@@ -180,21 +187,15 @@ _table_cache = {}
 def aero_tables(p: RocketParams):
     key = id(p)
     if key not in _table_cache:
-        cd = rbf_sets.build_table(p.cd_mach, p.cd_aoa, p.cd_val, rbf_sets.CD_BOXES, cache_dir=CACHE_DIR)
-        cl = rbf_sets.build_table(p.cl_mach, p.cl_aoa, p.cl_val, rbf_sets.CL_BOXES, cache_dir=CACHE_DIR)
+        cd = rbf_sets.build_table(p.cd_mach, p.cd_aoa, p.cd_val, rbf_sets.CD_BOXES,
+                                  cache_dir=CACHE_DIR, grids=rbf_sets.CD_GRIDS)
+        cl = rbf_sets.build_table(p.cl_mach, p.cl_aoa, p.cl_val, rbf_sets.CL_BOXES,
+                                  cache_dir=CACHE_DIR, grids=rbf_sets.CL_GRIDS)
         _table_cache[key] = (cd, cl)
     return _table_cache[key]
 
 
-def _pack_hint(lo, hi):
-    h = 0
-    for l in range(len(lo)):
-        h |= (int(lo[l]) & 63) << (12 * l)
-        h |= (int(hi[l]) & 63) << (12 * l + 6)
-    return h
-
-
-def _rbf_struct(tbl, m0, aoa0, keep):
+def _rbf_struct(tbl, keep):
     t = PdRbfTable()
     L = len(tbl.levels)
     t.n_levels, t.n_points, t.n_sets, t.hash_size = L, len(tbl.mach_sorted), tbl.n_sets, len(tbl.hash_keys)
@@ -203,13 +204,22 @@ def _rbf_struct(tbl, m0, aoa0, keep):
     for l in range(6):
         t.level_off[l] = int(tbl.level_off[min(l, L)])
     arrs = [np.ascontiguousarray(tbl.mach_sorted, np.float64),
-            np.ascontiguousarray(tbl.coeffs, np.float64).reshape(-1),
+            np.ascontiguousarray(tbl.points, np.float64).reshape(-1),
+            np.ascontiguousarray(tbl.rows, np.uint8).reshape(-1),
             np.ascontiguousarray(tbl.hash_keys, np.uint64),
             np.ascontiguousarray(tbl.hash_vals, np.int32)]
     keep.extend(arrs)
-    t.mach_sorted, t.coeffs, t.hash_keys, t.hash_vals = [a.ctypes.data for a in arrs]
-    lo, hi = tbl.find_set(m0, aoa0)
-    t.initial_hint = _pack_hint(lo, hi)
+    t.mach_sorted, t.points, t.rows, t.hash_keys, t.hash_vals = [a.ctypes.data for a in arrs]
+    t.n_grids = len(tbl.grids)
+    for i, g in enumerate(tbl.grids):
+        cg = t.grids[i]
+        cg.m0, cg.dm, cg.a0, cg.da, cg.nm, cg.na = g.m0, g.dm, g.a0, g.da, g.nm, g.na
+        cells = np.ascontiguousarray(g.cells, np.int32)
+        ih = np.ascontiguousarray(g.imp_hint, np.uint64)
+        ii = np.ascontiguousarray(g.imp_id, np.int32)
+        keep.extend([cells, ih, ii])
+        cg.n_impure = len(ii)
+        cg.cells, cg.imp_hint, cg.imp_id = cells.ctypes.data, ih.ctypes.data, ii.ctypes.data
     return t
 
 
@@ -255,13 +265,6 @@ def make_params(p: RocketParams, percentile=50):
     for i in range(2):
         c.vk_Bdu[i], c.vk_Bdv[i] = Bdu[i], Bdv[i]
     cd, cl = aero_tables(p)
-    s = p.initial_state
-    speed = math.hypot(s[2], s[3])
-    m0 = min(speed / _speed_of_sound(s[1]), 10.0)
-    a_eff = s[6] - s[4] - math.pi if s[3] < 0 else s[7]
-    cd_aoa = max(-math.radians(10), min(math.radians(10), math.degrees(a_eff)))
-    cl_aoa = math.degrees(math.degrees(a_eff))
-    cl_aoa = 10.0 if cl_aoa > 10 else (-10.0 if cl_aoa < -10 else abs(cl_aoa))
-    c.cd = _rbf_struct(cd, m0, cd_aoa, keep)
-    c.cl = _rbf_struct(cl, m0, cl_aoa, keep)
+    c.cd = _rbf_struct(cd, keep)
+    c.cl = _rbf_struct(cl, keep)
     return c, keep

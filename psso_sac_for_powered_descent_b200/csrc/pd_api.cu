@@ -74,19 +74,41 @@ static int dev_alloc(PdEnv *e, size_t n, T **out) {
     return 0;
 }
 
-static int upload_rbf(PdEnv *e, const PdRbfTable &t, RbfDev &d, double *levels_out) {
+static int upload_rbf(PdEnv *e, const PdRbfTable &t, RbfDev &d, double *levels_out, int max_points) {
     if (t.n_levels < 1 || t.n_levels > PD_MAX_LEVELS) return fail("rbf table: bad level count");
     if (t.hash_size <= 0 || (t.hash_size & (t.hash_size - 1))) return fail("rbf table: hash size");
+    if (t.n_points > max_points) return fail("rbf table: too many data points for the shared staging");
+    if (t.n_grids < 1 || t.n_grids > 2) return fail("rbf table: needs 1 or 2 lookup grids");
     d.n_levels = t.n_levels;
+    d.n_points = t.n_points;
     d.hash_mask = t.hash_size - 1;
     for (int l = 0; l < 6; ++l) d.off[l] = l <= t.n_levels ? t.level_off[l] : t.level_off[t.n_levels];
     for (int l = 0; l < 5; ++l) levels_out[l] = l < t.n_levels ? t.levels[l] : 1e30;
     if (dev_copy(e, t.mach_sorted, (size_t)t.n_points, &d.mach)) return 1;
-    if (dev_copy(e, t.coeffs, (size_t)t.n_sets * PD_RBF_COEF_STRIDE, &d.coeffs)) return 1;
+    const double *pts = nullptr;
+    if (dev_copy(e, t.points, (size_t)t.n_points * 2, &pts)) return 1;
+    d.points = reinterpret_cast<const double2 *>(pts);
+    const uint8_t *rows = nullptr;
+    if (dev_copy(e, t.rows, (size_t)t.n_sets * PD_RBF_ROW_BYTES, &rows)) return 1;
+    d.rows = reinterpret_cast<const double *>(rows);
     const unsigned long long *hk = nullptr;
     if (dev_copy(e, (const unsigned long long *)t.hash_keys, (size_t)t.hash_size, &hk)) return 1;
     d.hkeys = hk;
     if (dev_copy(e, t.hash_vals, (size_t)t.hash_size, &d.hvals)) return 1;
+    for (int g = 0; g < 2; ++g) {
+        const PdRbfGrid &s = t.grids[g < t.n_grids ? g : 0];
+        RbfGrid &o = d.grid[g];
+        o.m0 = s.m0; o.inv_dm = 1.0 / s.dm; o.a0 = s.a0; o.inv_da = 1.0 / s.da;
+        o.nm = s.nm; o.na = s.na;
+        if (dev_copy(e, s.cells, (size_t)s.nm * s.na, &o.cells)) return 1;
+        const unsigned long long *ih = nullptr;
+        static const uint64_t zero64 = 0;
+        static const int32_t zero32 = 0;
+        if (dev_copy(e, (const unsigned long long *)(s.n_impure ? s.imp_hint : &zero64),
+                     (size_t)(s.n_impure ? s.n_impure : 1), &ih)) return 1;
+        o.imp_hint = ih;
+        if (dev_copy(e, s.n_impure ? s.imp_id : &zero32, (size_t)(s.n_impure ? s.n_impure : 1), &o.imp_id)) return 1;
+    }
     return 0;
 }
 
@@ -195,23 +217,33 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     e->impl = cfg->precision == PD_FP64 ? impl_fp64() : impl_fp32();
     fill_scalars(*cfg, *p, e->sd);
     memset(&e->tb, 0, sizeof(e->tb));
-    int rc = upload_rbf(e, p->cd, e->tb.cd, e->sd.cd_levels) || upload_rbf(e, p->cl, e->tb.cl, e->sd.cl_levels);
+    int rc = upload_rbf(e, p->cd, e->tb.cd, e->sd.cd_levels, 192) || upload_rbf(e, p->cl, e->tb.cl, e->sd.cl_levels, 144);
     rc = rc || upload_segments(e, p->gf_ca_mach, p->gf_ca_val, p->n_gf_ca, &e->tb.ca_x, &e->tb.ca_y, &e->tb.ca_s);
     rc = rc || upload_segments(e, p->gf_cn_mach, p->gf_cn_val, p->n_gf_cn, &e->tb.cn_x, &e->tb.cn_y, &e->tb.cn_s);
     if (rc) { pd_destroy(e); return 1; }
+    {   // fast_log table: u_j = double(1/c_j), c_j = 1 + (j + 0.5)/128; second word -log(u_j)
+        std::vector<double> tab(256);
+        for (int j = 0; j < 128; ++j) {
+            long double cj = 1.0L + ((long double)j + 0.5L) / 128.0L;
+            double u = (double)(1.0L / cj);
+            tab[2 * j] = u;
+            tab[2 * j + 1] = (double)(-logl((long double)u));
+        }
+        const double *d = nullptr;
+        if (dev_copy(e, tab.data(), tab.size(), &d)) { pd_destroy(e); return 1; }
+        e->tb.logtab = reinterpret_cast<const double2 *>(d);
+    }
     to_float(e->sd, e->sf);
     e->tb.n_ca = p->n_gf_ca;
     e->tb.n_cn = p->n_gf_cn;
     e->tb.n_wind = p->n_wind;
     for (int k = 0; k < 11; ++k) e->tb.init[k] = p->initial_state[k];
-    e->tb.cd_hint0 = p->cd.initial_hint;
-    e->tb.cl_hint0 = p->cl.initial_hint;
     const size_t B = (size_t)cfg->n_envs;
     EnvSoA &s = e->soa;
     s.n = cfg->n_envs;
     rc = dev_alloc(e, 11 * B, &s.st) || dev_alloc(e, 10 * B, &s.gwin) || dev_alloc(e, B, &s.gwin_n) ||
          dev_alloc(e, 3 * B, &s.aprev) || dev_alloc(e, 6 * B, &s.wst) || dev_alloc(e, B, &s.wctr) ||
-         dev_alloc(e, B, &s.episode) || dev_alloc(e, 2 * B, &s.hint) || dev_alloc(e, 2 * B, &s.hint_id) ||
+         dev_alloc(e, B, &s.episode) ||
          dev_alloc(e, B, &s.trunc_id) || dev_alloc(e, B, &s.ep_steps) || dev_alloc(e, (size_t)1, &s.status) ||
          dev_alloc(e, (size_t)1, &e->roll_status);
     if (rc) { pd_destroy(e); return 1; }

@@ -49,24 +49,45 @@ struct Scalars {
     R cd_levels[5], cl_levels[5];
 };
 
+// Uniform (Mach, AoA) lookup grid over one query box.  cells >= 0: the grid cell lies
+// wholly inside one order-50 Voronoi cell, value = set id (no search).  cells < 0:
+// -(k+1) -> (imp_hint[k], imp_id[k]) = the set at the cell centre; walk from there.
+struct RbfGrid {
+    double m0, inv_dm, a0, inv_da;
+    int nm, na;
+    const int *cells;
+    const unsigned long long *imp_hint;
+    const int *imp_id;
+};
+
 struct RbfDev {
-    const double *mach;      // [n_points] level-major sorted
-    const double *coeffs;    // [n_sets*58]
+    const double *mach;      // [n_points] level-major, Mach ascending (used by the walk)
+    const double2 *points;   // [n_points] (Mach, AoA) of every slot; staged to shared memory
+    const double *rows;      // [n_sets][64]: 50 coeffs, 3 poly, shift(2), scale(2), 50 index bytes
     const unsigned long long *hkeys;
     const int *hvals;
     int hash_mask;
     int n_levels;
+    int n_points;
     int off[6];
+    RbfGrid grid[2];
 };
 
 struct Tables {
     RbfDev cd, cl;
+    const double2 *logtab;              // [128] (1/c_j rounded, -log of that), see fast_log
     const double *ca_x, *ca_y, *ca_s;   // grid fin C_a segments (x_lo, y_lo, slope)
     const double *cn_x, *cn_y, *cn_s;
     int n_ca, n_cn;
     int n_wind;
     double init[11];
-    unsigned long long cd_hint0, cl_hint0;
+};
+
+// block-shared staging of the small hot tables (7.4 KB)
+struct SharedTables {
+    double2 logtab[128];
+    double2 cd_pts[192];
+    double2 cl_pts[144];
 };
 
 // per-TU copies (no relocatable device code): each precision TU uploads its own
@@ -111,11 +132,6 @@ struct WindState {
     double xu0, xu1, xv0, xv1;     // gust filter states
     double sigma_u, sigma_v;
     unsigned int ctr;              // draws consumed (tape position / Philox counter)
-};
-
-struct RbfHint {
-    unsigned long long cd, cl;     // packed [lo,hi) per level, 6 bits each
-    int cd_id, cl_id;
 };
 
 template <typename R>
@@ -200,12 +216,12 @@ __device__ __forceinline__ unsigned long long hash_u64(unsigned long long k) {
 #define PD_RBF_MISS 1
 #define PD_RBF_ITER 2
 
-// Move the thread's cached neighbour set to the exact 50-NN set of (M, a).
-// Sets are one contiguous [lo,hi) interval per level; the check compares the farthest
-// interval end against the nearest point just outside any interval (4 distances / level).
+// Slow path (impure grid cells only): walk from the candidate set `hint` to the exact 50-NN set
+// of (M, a).  Sets are one contiguous [lo,hi) interval per level; the check compares the
+// farthest interval end against the nearest point just outside any interval.
 template <int NL>
-__device__ __forceinline__ int rbf_select(const RbfDev &T, const double *levels_d, double M,
-                                          double a, unsigned long long &hint, int &sid) {
+__device__ __noinline__ int rbf_walk(const RbfDev &T, const double *levels_d, double M, double a,
+                                     unsigned long long hint, int &sid) {
     int lo[NL], hi[NL];
     double dl2[NL];
     const unsigned long long hint_in = hint;
@@ -275,8 +291,7 @@ __device__ __forceinline__ int rbf_select(const RbfDev &T, const double *levels_
         if (lo[l] != hi[l])
             key |= ((unsigned long long)lo[l] << (12 * l)) | ((unsigned long long)hi[l] << (12 * l + 6));
     }
-    hint = h;
-    if (h != hint_in || sid < 0) {
+    if (h != hint_in) {
         unsigned int slot = (unsigned int)hash_u64(key) & T.hash_mask;
         int found = -1;
         for (int probe = 0; probe < 64; ++probe) {
@@ -290,66 +305,112 @@ __device__ __forceinline__ int rbf_select(const RbfDev &T, const double *levels_
     return status;
 }
 
-__device__ __forceinline__ double tps_phi(double r2) {
-    // r^2 log r = 0.5 r^2 log r^2 ; phi(0) = 0
-    return r2 > 0.0 ? 0.5 * r2 * log(r2) : 0.0;
-}
-__device__ __forceinline__ float tps_phi(float r2) {
-    return r2 > 0.0f ? 0.5f * r2 * __logf(r2) : 0.0f;
+// Stateless set lookup: grid cell -> set id; only cells cut by a Voronoi edge take the walk.
+template <int NL>
+__device__ __forceinline__ int rbf_locate(const RbfDev &T, const RbfGrid &G, const double *levels_d,
+                                          double M, double a, int &status) {
+    int im = (int)((M - G.m0) * G.inv_dm);
+    int ia = (int)((a - G.a0) * G.inv_da);
+    im = max(0, min(im, G.nm - 1));
+    ia = max(0, min(ia, G.na - 1));
+    int cell = __ldg(G.cells + ia * G.nm + im);
+    if (cell >= 0) return cell;
+    const int k = -cell - 1;
+    int sid = __ldg(G.imp_id + k);
+    status |= rbf_walk<NL>(T, levels_d, M, a, __ldg(G.imp_hint + k), sid);
+    return sid;
 }
 
-// Evaluate the interpolant of set `sid` at (M, a).  RT = accumulation type.
-template <typename RT, int NL>
-__device__ __forceinline__ RT rbf_eval(const RbfDev &T, const double *levels_d, double M, double a,
-                                       unsigned long long hint, int sid) {
-    const double *c = T.coeffs + (size_t)(sid < 0 ? 0 : sid) * 58;
-    RT acc = RT(0);
-    int k = 0;
+// Natural log of a positive normal double, ~1 ulp, ~20 instructions (CUDA's log() costs ~130
+// here and was 83% of the step kernel, profiles/r1_step_kernel_baseline.txt).
+//   x = 2^e * m, m in [1,2); j = top 7 mantissa bits; tab[j] = (u_j, -log(u_j)) with
+//   u_j = double(1 / (1 + (j + 0.5)/128)); r = m*u_j - 1 (exact in one fma, |r| < 2^-8);
+//   log x = e ln2 - log u_j + log1p(r), log1p by a degree-7 Taylor polynomial (|r|^8/8 < 2e-21).
+__device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab) {
+    const long long ix = __double_as_longlong(x);
+    const int e = (int)(ix >> 52) - 1023;
+    const int j = (int)(ix >> 45) & 127;
+    const double m = __longlong_as_double((ix & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
+    const double2 t = tab[j];
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma(p, r, 1.0 / 5.0);
+    p = fma(p, r, -1.0 / 4.0);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p * r, r, r);
+    return fma((double)e, 0.6931471805599453, t.y + p);
+}
+
+// one thin-plate-spline term: c * r^2 log r = c * (0.5 r^2) log r^2 ; phi(0) = 0
+__device__ __forceinline__ double tps_term(double c, double M, double a, double2 pt,
+                                           const double2 *__restrict__ logtab) {
+    const double dm = M - pt.x, da = a - pt.y;
+    const double r2 = fma(dm, dm, da * da);
+    const double phi = (0.5 * r2) * fast_log(r2, logtab);
+    return r2 > 0.0 ? c * phi : 0.0;
+}
+
+// Value of the interpolant of set `sid` at (M, a): a flat, uniform 50-term loop (no
+// per-lane trip counts), coefficients streamed from the set's 512-byte row, data points
+// gathered from the block-shared copy by the row's byte indices.
+__device__ __forceinline__ double rbf_eval(const double *__restrict__ rows, int sid,
+                                           const double2 *__restrict__ pts, double M, double a,
+                                           const double2 *__restrict__ logtab) {
+    const double2 *c2 = reinterpret_cast<const double2 *>(rows + (size_t)sid * 64);
+    const unsigned long long *ib = reinterpret_cast<const unsigned long long *>(rows + (size_t)sid * 64 + 57);
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 1
+    for (int w = 0; w < 6; ++w) {
+        const unsigned long long word = __ldg(ib + w);
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        const int lo = (int)((hint >> (12 * l)) & 63);
-        const int hi = (int)((hint >> (12 * l + 6)) & 63);
-        const double *m = T.mach + T.off[l];
-        const double da = a - levels_d[l];
-        const RT da2 = (RT)(da * da);
-        for (int i = lo; i < hi; ++i) {
-            RT dm = (RT)(M - __ldg(m + i));
-            RT r2 = dm * dm + da2;
-            acc += (RT)__ldg(c + k) * tps_phi(r2);
-            ++k;
+        for (int b = 0; b < 4; ++b) {
+            const double2 cc = __ldg(c2 + 4 * w + b);
+            const int i0 = (int)(word >> (16 * b)) & 255, i1 = (int)(word >> (16 * b + 8)) & 255;
+            acc0 += tps_term(cc.x, M, a, pts[i0], logtab);
+            acc1 += tps_term(cc.y, M, a, pts[i1], logtab);
         }
     }
-    RT xh = (RT)((M - __ldg(c + 53)) / __ldg(c + 55));
-    RT yh = (RT)((a - __ldg(c + 54)) / __ldg(c + 56));
-    return acc + (RT)__ldg(c + 50) + (RT)__ldg(c + 51) * xh + (RT)__ldg(c + 52) * yh;
+    {
+        const unsigned long long word = __ldg(ib + 6);
+        const double2 cc = __ldg(c2 + 24);
+        acc0 += tps_term(cc.x, M, a, pts[(int)word & 255], logtab);
+        acc1 += tps_term(cc.y, M, a, pts[(int)(word >> 8) & 255], logtab);
+    }
+    const double2 p0 = __ldg(c2 + 25);     // c50, c51
+    const double2 p1 = __ldg(c2 + 26);     // c52, shift_m
+    const double2 p2 = __ldg(c2 + 27);     // shift_a, scale_m
+    const double sa = __ldg(rows + (size_t)sid * 64 + 56);
+    const double xh = (M - p1.y) / p2.y;
+    const double yh = (a - p2.x) / sa;
+    return (acc0 + acc1) + p0.x + p0.y * xh + p1.x * yh;
 }
 
 // C_D: CD_func passes degrees into a clamp written for radians
 // (rockets_physics.py:712, aerodynamic_coefficients.py:108-114)
-template <typename R, typename RT>
-__device__ __forceinline__ R coef_cd(R mach, R alpha_eff, RbfHint &h, int &status) {
+template <typename R>
+__device__ __forceinline__ R coef_cd(R mach, R alpha_eff, int &status, const SharedTables *sh) {
     double aoa = (double)alpha_eff * (180.0 / PD_PI);
     const double lim = 10.0 * (PD_PI / 180.0);
     if (aoa > lim) aoa = lim;
     else if (aoa < -lim) aoa = -lim;
-    status |= rbf_select<5>(g_tb.cd, g_sd.cd_levels, (double)mach, aoa, h.cd, h.cd_id);
-    return (R)rbf_eval<RT, 5>(g_tb.cd, g_sd.cd_levels, (double)mach, aoa, h.cd, h.cd_id);
+    const int sid = rbf_locate<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, (double)mach, aoa, status);
+    return (R)rbf_eval(g_tb.cd.rows, sid, sh->cd_pts, (double)mach, aoa, sh->logtab);
 }
 
 // C_L: degrees applied twice (rockets_physics.py:711, aerodynamic_coefficients.py:120-131)
-template <typename R, typename RT>
-__device__ __forceinline__ R coef_cl(R mach, R alpha_eff, RbfHint &h, int &status) {
-    double aoa = ((double)alpha_eff * (180.0 / PD_PI)) * (180.0 / PD_PI);
-    double q;
-    double sign = 1.0;
-    if (aoa > 10.0) q = 10.0;
-    else if (aoa < -10.0) q = -10.0;            // not negated upstream
-    else if (fabs(aoa) < 1e-6) return R(0);
-    else if (aoa < 0.0) { q = fabs(aoa); sign = -1.0; }
-    else q = aoa;
-    status |= rbf_select<5>(g_tb.cl, g_sd.cl_levels, (double)mach, q, h.cl, h.cl_id);
-    RT v = rbf_eval<RT, 5>(g_tb.cl, g_sd.cl_levels, (double)mach, q, h.cl, h.cl_id);
-    return (R)(sign < 0 ? -v : v);
+template <typename R>
+__device__ __forceinline__ R coef_cl(R mach, R alpha_eff, int &status, const SharedTables *sh) {
+    const double aoa = ((double)alpha_eff * (180.0 / PD_PI)) * (180.0 / PD_PI);
+    if (fabs(aoa) < 1e-6) return R(0);
+    const bool neg_line = aoa < -10.0;           // cl_interp(mach, -10): not negated upstream
+    const double q = neg_line ? -10.0 : fmin(fabs(aoa), 10.0);
+    const bool flip = !neg_line && aoa < 0.0;
+    int sid;
+    if (neg_line) sid = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[1], g_sd.cl_levels, (double)mach, q, status);
+    else sid = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[0], g_sd.cl_levels, (double)mach, q, status);
+    const double v = rbf_eval(g_tb.cl.rows, sid, sh->cl_pts, (double)mach, q, sh->logtab);
+    return (R)(flip ? -v : v);
 }
 
 // ------------------------------------------------------------------ grid fins
@@ -639,8 +700,8 @@ __device__ __forceinline__ void control_G(const Action<4> &act, const ActPrev &p
 template <typename R, typename RT, int PHASE, bool WIND>
 __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
                                         const ActPrev &prev, WindState &w, const WindCtx &wc,
-                                        unsigned int env_id, RbfHint &h, Info<R> &info,
-                                        Control<R> &ctl) {
+                                        unsigned int env_id, Info<R> &info, Control<R> &ctl,
+                                        const SharedTables *sh) {
     const Scalars<R> &c = SC<R>();
     R y = (R)s.y, vx = (R)s.vx, vy = (R)s.vy;
     R rho, p_atm, a_snd;
@@ -664,8 +725,8 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     R C_L = R(0), C_D = R(0);
     int status = 0;
     if (a_snd != R(0)) {
-        C_L = coef_cl<R, RT>(mach, alpha_eff, h, status);
-        C_D = coef_cd<R, RT>(mach, alpha_eff, h, status);
+        C_L = coef_cl<R>(mach, alpha_eff, status, sh);
+        C_D = coef_cd<R>(mach, alpha_eff, status, sh);
     }
     R qdyn = R(0.5) * rho * (speed * speed);
     R drag = qdyn * C_D * c.S_ref;
@@ -892,14 +953,14 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
 template <typename R, typename RT, int PHASE, int RTD, bool WIND>
 __device__ __forceinline__ void env_step(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
                                          ActPrev &prev, WindState &w, const WindCtx &wc,
-                                         unsigned int env_id, RbfHint &h, GWindow<R> &gw,
-                                         Info<R> &info, Rtd<R> &out, R &g1_out) {
+                                         unsigned int env_id, GWindow<R> &gw, Info<R> &info,
+                                         Rtd<R> &out, R &g1_out, const SharedTables *sh) {
     R vxp = (R)s.vx, vyp = (R)s.vy;
     R v_p = m_sqrt(vxp * vxp + vyp * vyp);
     Control<R> ctl;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k)
-        substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, env_id, h, info, ctl);
+        substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, env_id, info, ctl, sh);
     if (PHASE == 1) {
         prev.gimbal_deg = ctl.gimbal_deg;
         prev.dl = ctl.dl_cmd;

@@ -20,8 +20,6 @@ struct EnvSoA {
     double *wst;           // [6][n]  gust filter states + sigma_u, sigma_v
     unsigned int *wctr;    // [n]     noise draws consumed this episode
     unsigned int *episode; // [n]     episode counter (Philox stream id for sigma draws)
-    unsigned long long *hint;  // [2][n] cached C_D / C_L neighbour sets
-    int *hint_id;          // [2][n]
     int *trunc_id;         // [n]
     int *ep_steps;         // [n]
     int *status;           // [1] sticky error bits (PD_RBF_MISS ...)

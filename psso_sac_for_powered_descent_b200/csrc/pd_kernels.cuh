@@ -46,18 +46,6 @@ __device__ __forceinline__ void store_wind(const EnvSoA &e, int i, const WindSta
     e.wst[4 * B + i] = w.sigma_u; e.wst[5 * B + i] = w.sigma_v;
     e.wctr[i] = w.ctr;
 }
-__device__ __forceinline__ void load_hint(const EnvSoA &e, int i, RbfHint &h) {
-    h.cd = e.hint[i]; h.cl = e.hint[(size_t)e.n + i];
-    h.cd_id = e.hint_id[i]; h.cl_id = e.hint_id[(size_t)e.n + i];
-}
-__device__ __forceinline__ void store_hint(const EnvSoA &e, int i, const RbfHint &h) {
-    e.hint[i] = h.cd; e.hint[(size_t)e.n + i] = h.cl;
-    e.hint_id[i] = h.cd_id; e.hint_id[(size_t)e.n + i] = h.cl_id;
-}
-__device__ __forceinline__ void hint_reset(RbfHint &h) {
-    h.cd = g_tb.cd_hint0; h.cl = g_tb.cl_hint0; h.cd_id = -1; h.cl_id = -1;
-}
-
 // rl_wrapped_env_pytorch.augment_action for landing_burn (env_wrapped_rl_pytorch.py:144-157)
 __device__ __forceinline__ double log_compress(double u, double cfac) {
     return copysign(log(1.0 + cfac * fabs(u)) / log(1.0 + cfac), u);
@@ -83,6 +71,14 @@ __device__ __forceinline__ void shape_action(Action<(PHASE == 0 ? 1 : 4)> &a) {
     }
 }
 
+// small hot tables -> shared memory; every thread of the block must call this
+__device__ __forceinline__ void stage_tables(SharedTables *sh) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) sh->logtab[i] = g_tb.logtab[i];
+    for (int i = threadIdx.x; i < g_tb.cd.n_points; i += blockDim.x) sh->cd_pts[i] = g_tb.cd.points[i];
+    for (int i = threadIdx.x; i < g_tb.cl.n_points; i += blockDim.x) sh->cl_pts[i] = g_tb.cl.points[i];
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ reset kernel
 template <typename R>
 __global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const double *sigma_uv) {
@@ -101,9 +97,6 @@ __global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const do
     WindState w;
     wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
     store_wind(e, i, w);
-    RbfHint h;
-    hint_reset(h);
-    store_hint(e, i, h);
     e.trunc_id[i] = 0;
     e.ep_steps[i] = 0;
 }
@@ -115,6 +108,8 @@ __global__ void __launch_bounds__(128)
 step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
+    __shared__ SharedTables sh;
+    stage_tables(&sh);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n) return;
     State s;
@@ -128,8 +123,6 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     }
     WindState w = {};
     if (WIND) load_wind(e, i, w);
-    RbfHint h;
-    load_hint(e, i, h);
     Action<A> act;
     read_action<A>(io.actions, io.action_dtype, (size_t)i, act);
     shape_action<PHASE, RTD>(act);
@@ -137,7 +130,7 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     info.rbf_status = 0;
     Rtd<R> out;
     R g1;
-    env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)i, h, gw, info, out, g1);
+    env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
     if (info.rbf_status) atomicOr(e.status, info.rbf_status);
     R obs[O];
     observe<R, PHASE, RTD>(s, obs);
@@ -167,7 +160,6 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
         unsigned int ep = e.episode[i] + 1;
         e.episode[i] = ep;
         if (WIND) wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
-        hint_reset(h);
         ep_steps = 0;
         observe<R, PHASE, RTD>(s, obs);
     }
@@ -183,7 +175,6 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
         e.aprev[2 * (size_t)e.n + i] = prev.dr;
     }
     if (WIND) store_wind(e, i, w);
-    store_hint(e, i, h);
 }
 
 // ------------------------------------------------------------------ per-particle actor MLP
@@ -259,6 +250,8 @@ __global__ void __launch_bounds__(128)
 rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
+    __shared__ SharedTables sh;
+    stage_tables(&sh);
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= io.n_episodes) return;
     State s;
@@ -270,8 +263,6 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     ActPrev prev = {0.0, 0.0, 0.0};
     WindState w = {};
     if (WIND) wind_reset(w, wc, (unsigned)e, 1u, sigma_uv);
-    RbfHint h;
-    hint_reset(h);
     Info<R> info;
     info.rbf_status = 0;
     info.q = R(0);
@@ -316,10 +307,10 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
             Control<R> ctl;
 #pragma unroll 1
             for (int k = 0; k < 4; ++k)
-                substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, (unsigned)e, h, info, ctl);
+                substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, (unsigned)e, info, ctl, &sh);
         } else {
             R g1;
-            env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)e, h, gw, info, out, g1);
+            env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)e, gw, info, out, g1, &sh);
         }
         steps = t + 1;
         total -= (double)out.reward;

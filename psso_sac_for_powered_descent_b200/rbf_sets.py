@@ -70,6 +70,9 @@ class LocalRbfTable:
     hash_keys: np.ndarray     # [H] uint64 (0 = empty)
     hash_vals: np.ndarray     # [H] int32
     box: tuple                # (mach_lo, mach_hi, aoa_lo, aoa_hi) the enumeration covered
+    rows: np.ndarray = None   # [S, ROW_BYTES] uint8: device row = 57 doubles + 50 point indices
+    points: np.ndarray = None  # [n, 2] (Mach, AoA) of every sorted slot
+    grids: list = None        # QueryGrid per device lookup region
 
     @property
     def n_sets(self):
@@ -276,21 +279,116 @@ def enumerate_sets(mach_lv, levels, box, seeds):
     return [k for k, ok in seen.items() if ok]
 
 
-def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24)) -> LocalRbfTable:
-    """`boxes`: list of (mach_lo, mach_hi, aoa_lo, aoa_hi) query regions to cover."""
+ROW_BYTES = 512        # 57 doubles (coeffs, poly, shift, scale) + 50 point-index bytes, padded
+
+
+@dataclass
+class QueryGrid:
+    """Uniform (Mach, AoA) grid over one query box.  cells[ia*nm+im] >= 0: the whole grid cell
+    lies inside one order-50 Voronoi cell (all four corners and the centre give the same set;
+    the Voronoi cells are convex) and the value is that set's id - no search needed on the
+    device.  cells < 0: -(k+1) indexes (imp_hint[k], imp_id[k]), the set at the cell centre,
+    from which the device walks to the exact set."""
+    m0: float
+    dm: float
+    nm: int
+    a0: float
+    da: float
+    na: int
+    cells: np.ndarray
+    imp_hint: np.ndarray
+    imp_id: np.ndarray
+
+    @property
+    def pure_fraction(self):
+        return float(np.mean(self.cells >= 0))
+
+
+def _sets_of_queries(tbl, M, A):
+    """Vectorised brute-force 50-NN for many queries -> (lo[n,L], hi[n,L]) with empty levels
+    parked at the insertion point of M."""
+    L = len(tbl.levels)
+    n = len(M)
+    lo = np.zeros((n, L), np.int64)
+    hi = np.zeros((n, L), np.int64)
+    lvl_of = np.repeat(np.arange(L), np.diff(tbl.level_off))
+    a_pts = tbl.levels[lvl_of]
+    for s in range(0, n, 8192):
+        m, a = M[s:s + 8192, None], A[s:s + 8192, None]
+        d2 = (tbl.mach_sorted[None, :] - m) ** 2 + (a_pts[None, :] - a) ** 2
+        sel = np.argpartition(d2, K_NEIGHBOURS - 1, axis=1)[:, :K_NEIGHBOURS]
+        mask = np.zeros(d2.shape, bool)
+        np.put_along_axis(mask, sel, True, axis=1)
+        for l in range(L):
+            o0, o1 = tbl.level_off[l], tbl.level_off[l + 1]
+            ml = mask[:, o0:o1]
+            cnt = ml.sum(1)
+            first = np.argmax(ml, axis=1)
+            ins = np.searchsorted(tbl.mach_sorted[o0:o1], M[s:s + 8192])
+            lo[s:s + 8192, l] = np.where(cnt > 0, first, ins)
+            hi[s:s + 8192, l] = np.where(cnt > 0, first + cnt, ins)
+    return lo, hi
+
+
+def pack_hint(lo, hi):
+    h = 0
+    for l in range(len(lo)):
+        h |= (int(lo[l]) & 63) << (12 * l)
+        h |= (int(hi[l]) & 63) << (12 * l + 6)
+    return h
+
+
+def build_grid(tbl, box, nm, na) -> QueryGrid:
+    m0, m1, a0, a1 = box
+    dm = (m1 - m0) / nm
+    da = (a1 - a0) / na if na > 1 else max(a1 - a0, 1e-9)
+    key_of = {}
+    for sid in range(tbl.n_sets):
+        key_of[pack_key(tbl.set_lo[sid], tbl.set_hi[sid])] = sid
+
+    def ids(M, A):
+        lo, hi = _sets_of_queries(tbl, M, A)
+        out = np.empty(len(M), np.int64)
+        for i in range(len(M)):
+            out[i] = key_of.get(pack_key(lo[i], hi[i]), -1)
+        return out, lo, hi
+    # corners (na+1) x (nm+1)
+    cm = m0 + dm * np.arange(nm + 1)
+    ca = a0 + da * np.arange(na + 1) if na > 1 else np.array([a0, a1])
+    CM, CA = np.meshgrid(cm, ca)
+    cid, _, _ = ids(CM.ravel(), CA.ravel())
+    cid = cid.reshape(len(ca), nm + 1)
+    mm = m0 + dm * (np.arange(nm) + 0.5)
+    aa = a0 + da * (np.arange(na) + 0.5) if na > 1 else np.array([0.5 * (a0 + a1)])
+    MM, AA = np.meshgrid(mm, aa)
+    zid, zlo, zhi = ids(MM.ravel(), AA.ravel())
+    assert (cid >= 0).all() and (zid >= 0).all(), "query grid meets a set missing from the table"
+    zid2 = zid.reshape(len(aa), nm)
+    pure = (cid[:-1, :-1] == zid2) & (cid[:-1, 1:] == zid2) & (cid[1:, :-1] == zid2) & (cid[1:, 1:] == zid2)
+    cells = np.where(pure, zid2, 0).astype(np.int32).ravel()
+    imp = np.nonzero(~pure.ravel())[0]
+    cells[imp] = -(np.arange(len(imp), dtype=np.int32) + 1)
+    imp_hint = np.array([pack_hint(zlo[i], zhi[i]) for i in imp], np.uint64)
+    imp_id = zid[imp].astype(np.int32)
+    return QueryGrid(float(m0), float(dm), int(nm), float(a0), float(da), int(len(aa)), cells,
+                     imp_hint, imp_id)
+
+
+def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None) -> LocalRbfTable:
+    """`boxes`: list of (mach_lo, mach_hi, aoa_lo, aoa_hi) query regions whose neighbour sets
+    are enumerated.  `grids`: list of (box, nm, na) device lookup grids."""
+    import pickle
     mach = np.asarray(mach, float)
     aoa = np.asarray(aoa, float)
     val = np.asarray(val, float)
     box = np.asarray(boxes, float).reshape(-1)
-    tag = hashlib.sha256(mach.tobytes() + aoa.tobytes() + val.tobytes()
-                         + box.tobytes() + b"v4").hexdigest()[:16]
+    tag = hashlib.sha256(mach.tobytes() + aoa.tobytes() + val.tobytes() + box.tobytes()
+                         + repr(grids).encode() + b"v7").hexdigest()[:16]
     if cache_dir:
-        path = os.path.join(cache_dir, f"rbf_{tag}.npz")
+        path = os.path.join(cache_dir, f"rbf_{tag}.pkl")
         if os.path.exists(path):
-            z = np.load(path)
-            return LocalRbfTable(z["levels"], z["level_off"], z["mach_sorted"], z["orig_index"],
-                                 z["set_lo"], z["set_hi"], z["coeffs"], z["hash_keys"],
-                                 z["hash_vals"], tuple(z["box"]))
+            with open(path, "rb") as f:
+                return pickle.load(f)
     levels = np.unique(aoa)
     assert len(levels) <= MAX_LEVELS
     mach_lv, orig_lv = [], []
@@ -303,6 +401,7 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24)) -> LocalRb
     level_off = np.concatenate([[0], np.cumsum([len(m) for m in mach_lv])]).astype(np.int32)
     mach_sorted = np.concatenate(mach_lv)
     orig_index = np.concatenate(orig_lv).astype(np.int32)
+    assert len(mach_sorted) < 256
     tbl = LocalRbfTable(levels, level_off, mach_sorted, orig_index, None, None, None, None, None,
                         tuple(box))
     # seeds: a coarse brute-force grid per box, then the exhaustive cell walk
@@ -321,20 +420,24 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24)) -> LocalRb
     set_hi = np.array([s[1] for s in sets], np.uint8).reshape(S, len(levels))
     # scipy coefficients per set, permuted into level-major / Mach-ascending order
     points = np.column_stack((mach, aoa))
-    index_sets, perms = [], []
+    index_sets, perms, mine_all = [], [], []
     for lo, hi in sets:
         mine = np.concatenate([orig_lv[l][lo[l]:hi[l]] for l in range(len(levels))])
         assert len(mine) == K_NEIGHBOURS
         asc = np.sort(mine)
         index_sets.append(asc)
         perms.append(np.searchsorted(asc, mine))     # position of my k-th point in scipy's order
+        mine_all.append(np.concatenate([level_off[l] + np.arange(lo[l], hi[l]) for l in range(len(levels))]))
     solved = _solve_sets(points, val, index_sets)
     coeffs = np.zeros((S, COEF_STRIDE))
+    rows = np.zeros((S, ROW_BYTES), np.uint8)
     for s, ((shift, scale, c), perm) in enumerate(zip(solved, perms)):
         coeffs[s, :50] = c[:50][perm]
         coeffs[s, 50:53] = c[50:53]
         coeffs[s, 53:55] = shift
         coeffs[s, 55:57] = scale
+        rows[s, :57 * 8] = coeffs[s, :57].view(np.uint8)
+        rows[s, 57 * 8:57 * 8 + 50] = mine_all[s].astype(np.uint8)
     H = 1
     while H < 4 * S:
         H *= 2
@@ -348,11 +451,14 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24)) -> LocalRb
         hk[h] = key
         hv[h] = s
     tbl.set_lo, tbl.set_hi, tbl.coeffs, tbl.hash_keys, tbl.hash_vals = set_lo, set_hi, coeffs, hk, hv
+    tbl.rows = rows
+    lvl_of = np.repeat(np.arange(len(levels)), np.diff(level_off))
+    tbl.points = np.ascontiguousarray(np.column_stack((mach_sorted, levels[lvl_of])))
+    tbl.grids = [build_grid(tbl, bx, nm, na) for (bx, nm, na) in (grids or [])]
     if cache_dir:
         os.makedirs(cache_dir, exist_ok=True)
-        np.savez_compressed(path, levels=levels, level_off=level_off, mach_sorted=mach_sorted,
-                            orig_index=orig_index, set_lo=set_lo, set_hi=set_hi, coeffs=coeffs,
-                            hash_keys=hk, hash_vals=hv, box=np.asarray(box, float))
+        with open(path, "wb") as f:
+            pickle.dump(tbl, f)
     return tbl
 
 
@@ -362,3 +468,8 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24)) -> LocalRb
 # un-negated (Mach, -10) branch (aerodynamic_coefficients.py:120-131).
 CD_BOXES = [(-0.02, 10.02, -0.2, 0.2)]
 CL_BOXES = [(-0.02, 10.02, -0.01, 10.01), (-0.02, 10.02, -10.01, -9.99)]
+_LIM = 0.17453292519943295 * (1 + 1e-9)
+# device lookup grids: (box, n_mach, n_aoa).  Mach is clamped to [0, 10] upstream; beyond the
+# last data point (Mach 5.51) the neighbour set no longer changes.
+CD_GRIDS = [((0.0, 10.0, -_LIM, _LIM), 2048, 8)]
+CL_GRIDS = [((0.0, 10.0, 0.0, 10.0), 1024, 256), ((0.0, 10.0, -10.0 - 1e-9, -10.0 + 1e-9), 2048, 1)]
