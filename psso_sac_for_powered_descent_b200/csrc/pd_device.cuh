@@ -326,11 +326,15 @@ __device__ __forceinline__ int rbf_locate(const RbfDev &T, const RbfGrid &G, con
 //   x = 2^e * m, m in [1,2); j = top 7 mantissa bits; tab[j] = (u_j, -log(u_j)) with
 //   u_j = double(1 / (1 + (j + 0.5)/128)); r = m*u_j - 1 (exact in one fma, |r| < 2^-8);
 //   log x = e ln2 - log u_j + log1p(r), log1p by a degree-7 Taylor polynomial (|r|^8/8 < 2e-21).
+// Integer work stays on the high 32-bit word; e is converted with the 2^52 magic-number trick
+// (one DADD) instead of an I2F on the XU pipe.
 __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab) {
-    const long long ix = __double_as_longlong(x);
-    const int e = (int)(ix >> 52) - 1023;
-    const int j = (int)(ix >> 45) & 127;
-    const double m = __longlong_as_double((ix & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
+    const int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    const int j = (hi >> 13) & 127;
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    // (double)((hi >> 20) - 1023): biased exponent in the low word of 2^52, minus (2^52 + 1023)
+    const double ed = __hiloint2double(0x43300000, (hi >> 20) & 0x7FF) - 4503599627371519.0;
     const double2 t = tab[j];
     const double r = fma(m, t.x, -1.0);
     double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
@@ -339,78 +343,105 @@ __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__
     p = fma(p, r, 1.0 / 3.0);
     p = fma(p, r, -0.5);
     p = fma(p * r, r, r);
-    return fma((double)e, 0.6931471805599453, t.y + p);
+    return fma(ed, 0.6931471805599453, t.y + p);
 }
 
-// one thin-plate-spline term: c * r^2 log r = c * (0.5 r^2) log r^2 ; phi(0) = 0
-__device__ __forceinline__ double tps_term(double c, double M, double a, double2 pt,
-                                           const double2 *__restrict__ logtab) {
+// one thin-plate-spline term accumulated into acc: c2 * r^2 * log r^2 with c2 = c/2 folded on
+// the host (exact).  r^2 is clamped to 1e-300 so that phi(0) = 0 needs no branch/select
+// (1e-300 * log 1e-300 = -7e-298 vanishes against any accumulator).
+__device__ __forceinline__ double tps_acc(double acc, double c2, double M, double a, double2 pt,
+                                          const double2 *__restrict__ logtab) {
     const double dm = M - pt.x, da = a - pt.y;
-    const double r2 = fma(dm, dm, da * da);
-    const double phi = (0.5 * r2) * fast_log(r2, logtab);
-    return r2 > 0.0 ? c * phi : 0.0;
+    const double r2 = fmax(fma(dm, dm, da * da), 1e-300);
+    return fma(c2 * r2, fast_log(r2, logtab), acc);
 }
 
-// Value of the interpolant of set `sid` at (M, a): a flat, uniform 50-term loop (no
-// per-lane trip counts), coefficients streamed from the set's 512-byte row, data points
-// gathered from the block-shared copy by the row's byte indices.
-__device__ __forceinline__ double rbf_eval(const double *__restrict__ rows, int sid,
-                                           const double2 *__restrict__ pts, double M, double a,
-                                           const double2 *__restrict__ logtab) {
-    const double2 *c2 = reinterpret_cast<const double2 *>(rows + (size_t)sid * 64);
-    const unsigned long long *ib = reinterpret_cast<const unsigned long long *>(rows + (size_t)sid * 64 + 57);
-    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 1
-    for (int w = 0; w < 6; ++w) {
-        const unsigned long long word = __ldg(ib + w);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const double2 cc = __ldg(c2 + 4 * w + b);
-            const int i0 = (int)(word >> (16 * b)) & 255, i1 = (int)(word >> (16 * b + 8)) & 255;
-            acc0 += tps_term(cc.x, M, a, pts[i0], logtab);
-            acc1 += tps_term(cc.y, M, a, pts[i1], logtab);
-        }
-    }
-    {
-        const unsigned long long word = __ldg(ib + 6);
-        const double2 cc = __ldg(c2 + 24);
-        acc0 += tps_term(cc.x, M, a, pts[(int)word & 255], logtab);
-        acc1 += tps_term(cc.y, M, a, pts[(int)(word >> 8) & 255], logtab);
-    }
-    const double2 p0 = __ldg(c2 + 25);     // c50, c51
-    const double2 p1 = __ldg(c2 + 26);     // c52, shift_m
-    const double2 p2 = __ldg(c2 + 27);     // shift_a, scale_m
-    const double sa = __ldg(rows + (size_t)sid * 64 + 56);
+// Row of one neighbour set: 64 doubles = 50 coefficients (already halved), 3 polynomial
+// coefficients, shift(2), scale(2), then 50 point-index bytes.
+struct RbfRow {
+    const double2 *c2;
+    const unsigned int *ib;
+    const double *base;
+};
+__device__ __forceinline__ RbfRow rbf_row(const double *__restrict__ rows, int sid) {
+    RbfRow r;
+    r.base = rows + (size_t)sid * 64;
+    r.c2 = reinterpret_cast<const double2 *>(r.base);
+    r.ib = reinterpret_cast<const unsigned int *>(r.base + 57);
+    return r;
+}
+__device__ __forceinline__ double rbf_poly(const RbfRow &r, double acc, double M, double a) {
+    const double2 p0 = __ldg(r.c2 + 25);     // c50, c51
+    const double2 p1 = __ldg(r.c2 + 26);     // c52, shift_m
+    const double2 p2 = __ldg(r.c2 + 27);     // shift_a, scale_m
+    const double sa = __ldg(r.base + 56);
     const double xh = (M - p1.y) / p2.y;
     const double yh = (a - p2.x) / sa;
-    return (acc0 + acc1) + p0.x + p0.y * xh + p1.x * yh;
+    return acc + p0.x + p0.y * xh + p1.x * yh;
 }
 
-// C_D: CD_func passes degrees into a clamp written for radians
-// (rockets_physics.py:712, aerodynamic_coefficients.py:108-114)
+// Values of two interpolants (C_L at (M, aL) from set sidL, C_D at (M, aD) from set sidD) in one
+// flat, uniform 50-trip loop: no per-lane trip counts, 8 + 8 independent chains per trip to hide
+// the fp64 / shared-memory latency at the 3-4 warps per scheduler this workload gives.
+__device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int sidL,
+                                          const double2 *__restrict__ ptsL, double aL,
+                                          const double *__restrict__ rowsD, int sidD,
+                                          const double2 *__restrict__ ptsD, double aD, double M,
+                                          const double2 *__restrict__ logtab, double &vL, double &vD) {
+    const RbfRow rl = rbf_row(rowsL, sidL), rd = rbf_row(rowsD, sidD);
+    double l0 = 0.0, l1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 1
+    for (int w = 0; w < 12; ++w) {
+        const unsigned int wl = __ldg(rl.ib + w), wd = __ldg(rd.ib + w);
+        const double2 cl0 = __ldg(rl.c2 + 2 * w), cl1 = __ldg(rl.c2 + 2 * w + 1);
+        const double2 cd0 = __ldg(rd.c2 + 2 * w), cd1 = __ldg(rd.c2 + 2 * w + 1);
+        l0 = tps_acc(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
+        d0 = tps_acc(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
+        l1 = tps_acc(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
+        d1 = tps_acc(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
+        l0 = tps_acc(l0, cl1.x, M, aL, ptsL[(wl >> 16) & 255], logtab);
+        d0 = tps_acc(d0, cd1.x, M, aD, ptsD[(wd >> 16) & 255], logtab);
+        l1 = tps_acc(l1, cl1.y, M, aL, ptsL[wl >> 24], logtab);
+        d1 = tps_acc(d1, cd1.y, M, aD, ptsD[wd >> 24], logtab);
+    }
+    {
+        const unsigned int wl = __ldg(rl.ib + 12), wd = __ldg(rd.ib + 12);
+        const double2 cl0 = __ldg(rl.c2 + 24), cd0 = __ldg(rd.c2 + 24);
+        l0 = tps_acc(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
+        d0 = tps_acc(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
+        l1 = tps_acc(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
+        d1 = tps_acc(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
+    }
+    vL = rbf_poly(rl, l0 + l1, M, aL);
+    vD = rbf_poly(rd, d0 + d1, M, aD);
+}
+
+// C_L and C_D of one sub-step.
+//  C_D: CD_func passes degrees into a clamp written for radians
+//       (rockets_physics.py:712, aerodynamic_coefficients.py:108-114)
+//  C_L: degrees applied twice (rockets_physics.py:711, aerodynamic_coefficients.py:120-131);
+//       the aoa < -10 branch evaluates (Mach, -10) and is not negated upstream.
 template <typename R>
-__device__ __forceinline__ R coef_cd(R mach, R alpha_eff, int &status, const SharedTables *sh) {
-    double aoa = (double)alpha_eff * (180.0 / PD_PI);
+__device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R &C_D, int &status,
+                                                  const SharedTables *sh) {
+    const double M = (double)mach;
+    const double deg = (double)alpha_eff * (180.0 / PD_PI);
     const double lim = 10.0 * (PD_PI / 180.0);
-    if (aoa > lim) aoa = lim;
-    else if (aoa < -lim) aoa = -lim;
-    const int sid = rbf_locate<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, (double)mach, aoa, status);
-    return (R)rbf_eval(g_tb.cd.rows, sid, sh->cd_pts, (double)mach, aoa, sh->logtab);
-}
-
-// C_L: degrees applied twice (rockets_physics.py:711, aerodynamic_coefficients.py:120-131)
-template <typename R>
-__device__ __forceinline__ R coef_cl(R mach, R alpha_eff, int &status, const SharedTables *sh) {
-    const double aoa = ((double)alpha_eff * (180.0 / PD_PI)) * (180.0 / PD_PI);
-    if (fabs(aoa) < 1e-6) return R(0);
-    const bool neg_line = aoa < -10.0;           // cl_interp(mach, -10): not negated upstream
-    const double q = neg_line ? -10.0 : fmin(fabs(aoa), 10.0);
+    const double aD = fmin(fmax(deg, -lim), lim);
+    const double aoa = deg * (180.0 / PD_PI);
+    const bool zero = fabs(aoa) < 1e-6;
+    const bool neg_line = aoa < -10.0;
+    const double aL = neg_line ? -10.0 : fmin(fmax(fabs(aoa), 1e-6), 10.0);
     const bool flip = !neg_line && aoa < 0.0;
-    int sid;
-    if (neg_line) sid = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[1], g_sd.cl_levels, (double)mach, q, status);
-    else sid = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[0], g_sd.cl_levels, (double)mach, q, status);
-    const double v = rbf_eval(g_tb.cl.rows, sid, sh->cl_pts, (double)mach, q, sh->logtab);
-    return (R)(flip ? -v : v);
+    const int sidD = rbf_locate<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, M, aD, status);
+    int sidL;
+    if (neg_line) sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[1], g_sd.cl_levels, M, aL, status);
+    else sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[0], g_sd.cl_levels, M, aL, status);
+    double vL, vD;
+    rbf_eval2(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts, aD, M, sh->logtab,
+              vL, vD);
+    C_L = zero ? R(0) : (R)(flip ? -vL : vL);
+    C_D = (R)vD;
 }
 
 // ------------------------------------------------------------------ grid fins
@@ -725,8 +756,7 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     R C_L = R(0), C_D = R(0);
     int status = 0;
     if (a_snd != R(0)) {
-        C_L = coef_cl<R>(mach, alpha_eff, status, sh);
-        C_D = coef_cd<R>(mach, alpha_eff, status, sh);
+        aero_coefficients<R>(mach, alpha_eff, C_L, C_D, status, sh);
     }
     R qdyn = R(0.5) * rho * (speed * speed);
     R drag = qdyn * C_D * c.S_ref;

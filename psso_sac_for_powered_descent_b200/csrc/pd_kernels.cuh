@@ -104,7 +104,7 @@ __global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const do
 // ------------------------------------------------------------------ fused step kernel
 // physics (4 sub-steps) + g-window + truncation/done/reward + observation + auto-reset.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
@@ -246,7 +246,7 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
 // (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for POLICY_TAPE,
 // LandingBurn.run_closed_loop for POLICY_CLASSICAL.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
@@ -364,7 +364,7 @@ struct Launch {
     template <int PHASE, int RTD, bool WIND>
     static void step_t(const EnvSoA &e, const StepIO &io, const WindCtx &wc, const double *sig,
                        int auto_reset, cudaStream_t st) {
-        int threads = 128, blocks = (e.n + threads - 1) / threads;
+        int threads = 64, blocks = (e.n + threads - 1) / threads;   // 65 536 envs -> 6.9 blocks / SM
         step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, 0, st>>>(e, io, wc, sig, auto_reset);
     }
     static void step(int phase, int rtd, int wind, const EnvSoA &e, const StepIO &io,
@@ -384,7 +384,9 @@ struct Launch {
     template <int PHASE, int RTD, bool WIND, int POLICY>
     static void roll_t(const RolloutIO &io, const WindCtx &wc, const double *sig, int *status,
                        cudaStream_t st) {
-        int threads = 128, blocks = (io.n_episodes + threads - 1) / threads;
+        // small swarms: one warp per block so that 4 096 episodes still reach 128 SMs
+        int threads = io.n_episodes >= 148 * 64 * 4 ? 64 : 32;
+        int blocks = (io.n_episodes + threads - 1) / threads;
         rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY><<<blocks, threads, 0, st>>>(io, wc, sig, status);
     }
     static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,

@@ -383,7 +383,7 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None
     val = np.asarray(val, float)
     box = np.asarray(boxes, float).reshape(-1)
     tag = hashlib.sha256(mach.tobytes() + aoa.tobytes() + val.tobytes() + box.tobytes()
-                         + repr(grids).encode() + b"v7").hexdigest()[:16]
+                         + repr(grids).encode() + b"v8").hexdigest()[:16]
     if cache_dir:
         path = os.path.join(cache_dir, f"rbf_{tag}.pkl")
         if os.path.exists(path):
@@ -436,7 +436,9 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None
         coeffs[s, 50:53] = c[50:53]
         coeffs[s, 53:55] = shift
         coeffs[s, 55:57] = scale
-        rows[s, :57 * 8] = coeffs[s, :57].view(np.uint8)
+        dev = coeffs[s, :57].copy()
+        dev[:50] *= 0.5            # r^2 log r = (c/2) r^2 log r^2 ; exact scaling
+        rows[s, :57 * 8] = dev.view(np.uint8)
         rows[s, 57 * 8:57 * 8 + 50] = mine_all[s].astype(np.uint8)
     H = 1
     while H < 4 * S:
