@@ -204,6 +204,7 @@ typedef struct {
     float max_action;
     float _pad;
     const float *w1, *b1, *w2, *b2, *wm, *bm, *ws, *bs;
+    uint64_t seed;            /* Philox key of the action noise */
 } PdSharedActor;
 int pd_collect_shared_actor(PdEnv *env, const PdSharedActor *actor, int n_steps, float *obs_out,
                             float *act_out, float *rew_out, uint8_t *done_out,

