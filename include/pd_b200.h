@@ -192,23 +192,36 @@ int pd_rollout_policy(PdEnv *env, int policy, const void *actions, int action_dt
                       void *stream);
 
 /* SAC data collection with one shared actor over the env batch
- * (sac_pytorch_powered_descent.py:160-183 loop body; Actor.sample, src/agents/sac_pytorch.py:
- * 129-179).  n_steps env steps with auto-reset; writes transitions step-major.
+ * (sac_pytorch_powered_descent.py:160-183 loop body; Actor.forward/sample,
+ * src/agents/sac_pytorch.py:129-179: state -> [Linear+ReLU] x 2 -> (mean, clamp(log_std,-20,2)),
+ * action = tanh(mean + std * eps) * max_action).  Runs n_steps x [actor inference -> fused env
+ * step with auto-reset] on the handle's batch (type 'rl', PD_FP32 build) and writes the
+ * transitions step-major.  hidden == 256 and fp32_path == 0: the 256x256 layer runs on the
+ * tcgen05 tensor cores in bf16 with fp32 accumulation; otherwise an fp32 CUDA-core kernel.
  *   w1 [H*O], b1 [H], w2 [H*H], b2 [H], wm [A*H], bm [A], ws [A*H], bs [A]  dev float
- *   obs_out dev float[n_steps*n_envs*O], act_out dev float[n_steps*n_envs*A],
- *   rew_out dev float[n_steps*n_envs], done_out/trunc_out dev uint8[n_steps*n_envs]
- *   (any output may be NULL). deterministic != 0 -> tanh(mean). */
+ *   (torch nn.Linear layouts: weight[out][in])
+ *   obs_out      dev float[n_steps*n_envs*O]  observation the action was computed from
+ *   act_out      dev float[n_steps*n_envs*A]  (required: the step kernel reads its action here)
+ *   rew_out      dev float[n_steps*n_envs]
+ *   done_out, trunc_out  dev uint8[n_steps*n_envs]
+ *   next_obs_out dev float[n_steps*n_envs*O]  observation of the post-step, pre-reset state
+ *   (obs_out, rew_out, done_out, trunc_out, next_obs_out may be NULL). */
 typedef struct {
-    int32_t hidden;           /* H (multiple of 16, <= 256) */
-    int32_t deterministic;
+    int32_t hidden;           /* H */
+    int32_t deterministic;    /* != 0 -> tanh(mean) */
     float max_action;
-    float _pad;
+    int32_t fp32_path;        /* != 0 -> force the fp32 CUDA-core actor */
     const float *w1, *b1, *w2, *b2, *wm, *bm, *ws, *bs;
     uint64_t seed;            /* Philox key of the action noise */
 } PdSharedActor;
 int pd_collect_shared_actor(PdEnv *env, const PdSharedActor *actor, int n_steps, float *obs_out,
                             float *act_out, float *rew_out, uint8_t *done_out,
-                            uint8_t *trunc_out, void *stream);
+                            uint8_t *trunc_out, float *next_obs_out, void *stream);
+
+/* Actor inference alone on a caller-supplied observation batch (dev float[n*O] -> dev
+ * float[n*A]; mean_out optional): the numerics hook for the tensor-core path. */
+int pd_actor_forward(PdEnv *env, const PdSharedActor *actor, const float *obs, int n, float *act,
+                     float *mean_out, void *stream);
 
 /* Sticky device status (synchronises): 0 = ok; bit 0 = an aero-table query fell outside the
  * enumerated neighbour-set table, bit 1 = neighbour search did not converge. */

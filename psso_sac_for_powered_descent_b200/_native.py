@@ -67,14 +67,14 @@ class PdConfig(C.Structure):
 
 class PdSharedActor(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("deterministic", C.c_int32), ("max_action", C.c_float),
-                ("_pad", C.c_float), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p),
+                ("fp32_path", C.c_int32), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p),
                 ("b2", C.c_void_p), ("wm", C.c_void_p), ("bm", C.c_void_p), ("ws", C.c_void_p),
                 ("bs", C.c_void_p), ("seed", C.c_uint64)]
 
 
 EXPORTS = ["pd_last_error", "pd_version", "pd_create", "pd_destroy", "pd_reset", "pd_step",
            "pd_get_state", "pd_set_state", "pd_set_wind_tape", "pd_rollout_pso", "pd_rollout_policy",
-           "pd_collect_shared_actor", "pd_check_status", "pd_launch_count"]
+           "pd_collect_shared_actor", "pd_actor_forward", "pd_check_status", "pd_launch_count"]
 
 _lib = None
 
@@ -102,7 +102,8 @@ def load_library():
     lib.pd_set_wind_tape.argtypes = [vp, vp, i32, vp]
     lib.pd_rollout_pso.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pd_rollout_policy.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
-    lib.pd_collect_shared_actor.argtypes = [vp, C.POINTER(PdSharedActor), i32, vp, vp, vp, vp, vp, vp]
+    lib.pd_collect_shared_actor.argtypes = [vp, C.POINTER(PdSharedActor), i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.pd_actor_forward.argtypes = [vp, C.POINTER(PdSharedActor), vp, i32, vp, vp, vp]
     lib.pd_check_status.argtypes = [vp, C.POINTER(C.c_int32)]
     for name in EXPORTS:
         fn = getattr(lib, name)

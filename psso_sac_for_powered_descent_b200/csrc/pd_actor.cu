@@ -1,0 +1,355 @@
+// pd_actor.cu - shared-weight SAC actor over a large env batch (BASELINE config 4).
+//
+// Reference: Actor.forward / Actor.sample, src/agents/sac_pytorch.py:129-179
+//     h1 = relu(W1 obs + b1); h2 = relu(W2 h1 + b2); mean = Wm h2 + bm;
+//     log_std = clamp(Ws h2 + bs, -20, 2); action = tanh(mean + exp(log_std) * eps) * max_action
+// with the script default hidden = 256, two hidden layers (sac_pytorch_powered_descent.py:55-56).
+//
+// Only the 256x256 layer is a real GEMM (2*65536 flop/env of 133 120).  It runs on the
+// 5th-generation tensor cores:
+//   * a persistent CTA per SM owns a 128-env row tile at a time (UMMA M = 128, N = 256);
+//   * W2 is converted once to bf16 and stored in global memory as the exact shared-memory
+//     image (K-major, 128-byte swizzle, four 64-wide K blocks); each CTA pulls the 128 KB image
+//     with 1-D TMA bulk copies (cp.async.bulk, completes on an mbarrier) once per launch;
+//   * layer 1 (K = 2 or 5: plain FMAs) is computed by the 128 threads straight into the
+//     swizzled A tile in shared memory as bf16;
+//   * one elected thread issues 16 tcgen05.mma (K = 16 each) accumulating fp32 into 256 TMEM
+//     columns, commits to an mbarrier;
+//   * the epilogue reads each env's row back with tcgen05.ld (one TMEM lane per thread), applies
+//     bias + ReLU, the two 256->A heads (GEMV, fp32 FMAs), Philox noise, tanh - h2 never
+//     leaves TMEM/registers.
+// An fp32 CUDA-core variant (actor_fp32_kernel) serves other hidden sizes and is the numerics
+// reference for the tensor-core path in the GPU tests.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pd_actor.h"
+
+namespace pd {
+
+__device__ __forceinline__ void philox4x32_a(unsigned int c0, unsigned int c1, unsigned int c2,
+                                             unsigned int c3, unsigned int k0, unsigned int k1,
+                                             unsigned int out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned int n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// N(0,1) x 4 for (env, step)
+__device__ __forceinline__ void normal4(unsigned long long seed, unsigned int env, unsigned int step,
+                                        float z[4]) {
+    unsigned int r[4];
+    philox4x32_a(env, step, 0x41435452u, 0u, (unsigned int)seed, (unsigned int)(seed >> 32), r);
+    float u0 = ((r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float u2 = ((r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((r[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+    float s, c;
+    sincospif(2.0f * u1, &s, &c);
+    z[0] = ra * c; z[1] = ra * s;
+    sincospif(2.0f * u3, &s, &c);
+    z[2] = rb * c; z[3] = rb * s;
+}
+
+template <int A>
+__device__ __forceinline__ void head_and_sample(const ActorArgs &p, const float *mean, const float *lstd,
+                                                unsigned int env, float *act_out, float *mean_out) {
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!p.deterministic) normal4(p.seed, env, p.step, z);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        float ls = fminf(fmaxf(lstd[a], -20.0f), 2.0f);
+        float pre = p.deterministic ? mean[a] : fmaf(expf(ls), z[a], mean[a]);
+        act_out[(size_t)env * A + a] = tanhf(pre) * p.max_action;
+        if (mean_out) mean_out[(size_t)env * A + a] = mean[a];
+    }
+}
+
+// ------------------------------------------------------------------ fp32 CUDA-core variant
+template <int O, int A>
+__global__ void __launch_bounds__(128) actor_fp32_kernel(ActorArgs p, const float *__restrict__ obs,
+                                                         float *__restrict__ act, float *mean_out, int B) {
+    extern __shared__ float sh[];      // h1[H] per thread would be too big: recompute per tile of k
+    const int H = p.hidden;
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= B) return;
+    float o[O];
+#pragma unroll
+    for (int k = 0; k < O; ++k) o[k] = obs[(size_t)env * O + k];
+    float mean[A], lstd[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) { mean[a] = __ldg(p.bm + a); lstd[a] = __ldg(p.bs + a); }
+    // h2[n] = relu(b2[n] + sum_k W2[n][k] h1[k]); h1 recomputed on the fly (K <= 5 FMAs each)
+    for (int n = 0; n < H; ++n) {
+        float acc = __ldg(p.b2 + n);
+        for (int k = 0; k < H; ++k) {
+            float h = __ldg(p.b1 + k);
+#pragma unroll
+            for (int j = 0; j < O; ++j) h = fmaf(__ldg(p.w1 + k * O + j), o[j], h);
+            acc = fmaf(__ldg(p.w2 + (size_t)n * H + k), fmaxf(h, 0.f), acc);
+        }
+        float h2 = fmaxf(acc, 0.f);
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            mean[a] = fmaf(__ldg(p.wm + a * H + n), h2, mean[a]);
+            lstd[a] = fmaf(__ldg(p.ws + a * H + n), h2, lstd[a]);
+        }
+    }
+    head_and_sample<A>(p, mean, lstd, (unsigned)env, act, mean_out);
+}
+
+// ------------------------------------------------------------------ W2 -> bf16 smem image
+// image[kb][n][swizzled 128 B row]: K block kb (64 k's), row n of W2 (N = 256 rows, K-major),
+// 16-byte chunk c stored at chunk position c ^ (n & 7)  (UMMA SWIZZLE_128B canonical layout).
+__global__ void actor_prep_w2_kernel(const float *__restrict__ w2, __nv_bfloat16 *__restrict__ img) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 elements) each
+    if (idx >= 4 * 256 * 8) return;
+    int c = idx & 7, n = (idx >> 3) & 255, kb = idx >> 11;
+    const float *src = w2 + (size_t)n * 256 + kb * 64 + c * 8;
+    __nv_bfloat16 *dst = img + (size_t)kb * 256 * 64 + (size_t)n * 64 + ((c ^ (n & 7)) * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+}
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 in [0,14), LBO in [16,30) (unused for swizzled K-major), SBO >> 4 in
+// [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout type 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 256
+__device__ __forceinline__ uint32_t umma_idesc_bf16_m128_n256() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ tensor-core actor kernel
+constexpr int ACT_H = 256;
+constexpr int TILE_M = 128;
+constexpr uint32_t A_BYTES = TILE_M * ACT_H * 2;        // 64 KB: 4 K-blocks x 16 KB
+constexpr uint32_t B_BYTES = ACT_H * ACT_H * 2;         // 128 KB: 4 K-blocks x 32 KB
+
+template <int O, int A>
+__global__ void __launch_bounds__(128, 1)
+actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ act, float *mean_out,
+                int B, int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                  // [4][128][64] bf16, swizzled
+    uint8_t *sB = smem + A_BYTES;                        // [4][256][64] bf16, swizzled (W2 image)
+    float *s_w1 = (float *)(smem + A_BYTES + B_BYTES);   // [256][O]
+    float *s_b1 = s_w1 + ACT_H * O;
+    float *s_b2 = s_b1 + ACT_H;
+    float *s_wm = s_b2 + ACT_H;                          // [A][256]
+    float *s_ws = s_wm + A * ACT_H;
+    uint64_t *bars = (uint64_t *)(s_ws + A * ACT_H);     // [0] W2 landed, [1] MMA done
+    uint32_t *s_tmem = (uint32_t *)(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar_w2 = smem_u32(bars), bar_mma = smem_u32(bars + 1);
+
+    if (tid == 0) {
+        mbar_init(bar_w2, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {      // one warp allocates 256 TMEM columns (fp32 accumulator 128 x 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(s_tmem)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < ACT_H * O; i += 128) s_w1[i] = p.w1[i];
+    for (int i = tid; i < ACT_H; i += 128) { s_b1[i] = p.b1[i]; s_b2[i] = p.b2[i]; }
+    for (int i = tid; i < A * ACT_H; i += 128) { s_wm[i] = p.wm[i]; s_ws[i] = p.ws[i]; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+
+    if (tid == 0) {       // W2 image: 8 TMA bulk copies of 16 KB, one mbarrier
+        mbar_expect_tx(bar_w2, B_BYTES);
+        const uint8_t *src = (const uint8_t *)p.w2_img;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tma_bulk_g2s(smem_u32(sB) + i * 16384, src + (size_t)i * 16384, 16384, bar_w2);
+    }
+    const uint32_t idesc = umma_idesc_bf16_m128_n256();
+    uint32_t mma_phase = 0;
+    bool w2_ready = false;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int env = tile * TILE_M + tid;
+        float o[O];
+#pragma unroll
+        for (int k = 0; k < O; ++k) o[k] = env < B ? obs[(size_t)env * O + k] : 0.f;
+        // layer 1 -> bf16 -> swizzled A tile (row = tid)
+        const uint32_t row_off = (uint32_t)(tid >> 3) * 1024 + (uint32_t)(tid & 7) * 128;
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t packed[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float h[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = kb * 64 + c * 8 + j * 2 + e;
+                        float acc = s_b1[k];
+#pragma unroll
+                        for (int q = 0; q < O; ++q) acc = fmaf(s_w1[k * O + q], o[q], acc);
+                        h[e] = fmaxf(acc, 0.f);
+                    }
+                    __nv_bfloat162 b2v = __floats2bfloat162_rn(h[0], h[1]);
+                    packed[j] = *reinterpret_cast<uint32_t *>(&b2v);
+                }
+                uint8_t *dst = sA + kb * 16384 + row_off + ((c ^ (tid & 7)) * 16);
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+        }
+        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            if (!w2_ready) mbar_wait(bar_w2, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {      // UMMA_K = 16 bf16 = 32 bytes inside the 128 B atom
+                    uint64_t ad = umma_desc_sw128(smem_u32(sA) + kb * 16384 + k * 32);
+                    uint64_t bd = umma_desc_sw128(smem_u32(sB) + kb * 32768 + k * 32);
+                    umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_mma);
+        }
+        w2_ready = true;
+        mbar_wait(bar_mma, mma_phase);
+        mma_phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: thread tid owns TMEM lane tid (warp w may touch lanes 32w..32w+31)
+        float mean[A], lstd[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) { mean[a] = p.bm[a]; lstd[a] = p.bs[a]; }
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int cb = 0; cb < 8; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + cb * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = cb * 32 + j;
+                const float h2 = fmaxf(__uint_as_float(v[j]) + s_b2[n], 0.f);
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    mean[a] = fmaf(s_wm[a * ACT_H + n], h2, mean[a]);
+                    lstd[a] = fmaf(s_ws[a * ACT_H + n], h2, lstd[a]);
+                }
+            }
+        }
+        if (env < B) head_and_sample<A>(p, mean, lstd, (unsigned)env, act, mean_out);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();      // all TMEM reads done before the next tile's MMAs overwrite it
+    }
+    if (!w2_ready && tid == 0) mbar_wait(bar_w2, 0);      // never leave with a TMA in flight
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+size_t actor_tc_smem_bytes(int O, int A) {
+    return 1024 + A_BYTES + B_BYTES + sizeof(float) * (ACT_H * O + 3 * ACT_H + 2 * A * ACT_H) + 64;
+}
+
+int actor_prep_w2(const float *w2, void *img, cudaStream_t st) {
+    actor_prep_w2_kernel<<<(4 * 256 * 8 + 255) / 256, 256, 0, st>>>(w2, (__nv_bfloat16 *)img);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+template <int O, int A>
+static int launch_t(const ActorArgs &p, const float *obs, float *act, float *mean_out, int B, int use_tc,
+                    int n_sm, cudaStream_t st) {
+    if (use_tc) {
+        size_t smem = actor_tc_smem_bytes(O, A);
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(actor_tc_kernel<O, A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem) != cudaSuccess) return 1;
+            attr_set = true;
+        }
+        int n_tiles = (B + TILE_M - 1) / TILE_M;
+        int grid = n_tiles < n_sm ? n_tiles : n_sm;
+        actor_tc_kernel<O, A><<<grid, 128, smem, st>>>(p, obs, act, mean_out, B, n_tiles);
+    } else {
+        actor_fp32_kernel<O, A><<<(B + 127) / 128, 128, 0, st>>>(p, obs, act, mean_out, B);
+    }
+    return cudaGetLastError() != cudaSuccess;
+}
+
+int actor_launch(int O, int A, const ActorArgs &p, const float *obs, float *act, float *mean_out, int B,
+                 int use_tc, int n_sm, cudaStream_t st) {
+    if (O == 2 && A == 1) return launch_t<2, 1>(p, obs, act, mean_out, B, use_tc, n_sm, st);
+    if (O == 5 && A == 4) return launch_t<5, 4>(p, obs, act, mean_out, B, use_tc, n_sm, st);
+    return 1;
+}
+
+}  // namespace pd

@@ -10,6 +10,7 @@
 #include "../../include/pd_b200.h"
 #include "pd_device.cuh"
 #include "pd_impl.h"
+#include "pd_actor.h"
 
 using namespace pd;
 
@@ -41,6 +42,13 @@ struct PdEnv {
     float *wT = nullptr;
     size_t wT_cap = 0;
     int *roll_status = nullptr;
+    // shared-actor collection
+    void *w2_img = nullptr;          // bf16 smem image of W2
+    const float *w2_src = nullptr;   // which W2 the image was built from
+    float *obs_carry = nullptr;      // [n_envs*O] observation the next action is computed from
+    bool obs_valid = false;
+    unsigned int collect_step = 0;
+    int n_sm = 148;
 };
 
 // the __constant__ blocks are per precision TU and per process: re-upload on handle switch
@@ -276,6 +284,7 @@ int pd_reset(PdEnv *e, const uint8_t *mask, void *stream) {
     if (!e) return fail("pd_reset: null handle");
     if (activate(e)) return 1;
     e->impl->reset(e->soa, mask, wind_ctx(e), e->sigma_uv, (cudaStream_t)stream);
+    e->obs_valid = false;
     g_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -310,6 +319,7 @@ int pd_set_state(PdEnv *e, const double *state, const double *g_window, const in
                  const double *act_prev, void *stream) {
     if (!e) return fail("pd_set_state: null handle");
     e->impl->set_state(e->soa, state, g_window, n_window, act_prev, (cudaStream_t)stream);
+    e->obs_valid = false;
     g_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -401,12 +411,94 @@ int pd_rollout_policy(PdEnv *e, int policy, const void *actions, int action_dtyp
     return 0;
 }
 
+static int actor_args(PdEnv *e, const PdSharedActor *a, ActorArgs &p, int &use_tc, cudaStream_t st) {
+    if (!a->w1 || !a->b1 || !a->w2 || !a->b2 || !a->wm || !a->bm || !a->ws || !a->bs)
+        return fail("shared actor: null weight pointer");
+    if (a->hidden <= 0) return fail("shared actor: hidden must be positive");
+    p.w1 = a->w1; p.b1 = a->b1; p.w2 = a->w2; p.b2 = a->b2; p.wm = a->wm; p.bm = a->bm;
+    p.ws = a->ws; p.bs = a->bs;
+    p.hidden = a->hidden; p.deterministic = a->deterministic; p.max_action = a->max_action;
+    p.seed = a->seed; p.step = e->collect_step;
+    use_tc = (a->hidden == 256 && !a->fp32_path) ? 1 : 0;
+    p.w2_img = nullptr;
+    if (use_tc) {
+        if (!e->w2_img) {
+            CK(cudaMalloc(&e->w2_img, 256 * 256 * 2));
+            e->allocs.push_back(e->w2_img);
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+            e->n_sm = prop.multiProcessorCount;
+        }
+        // weights change between collection phases (the learner updates them): rebuild the image
+        if (actor_prep_w2(a->w2, e->w2_img, st)) return fail("shared actor: W2 image kernel failed");
+        g_launches++;
+        e->w2_src = a->w2;
+        p.w2_img = e->w2_img;
+    }
+    return 0;
+}
+
+int pd_actor_forward(PdEnv *e, const PdSharedActor *actor, const float *obs, int n, float *act,
+                     float *mean_out, void *stream) {
+    if (!e || !actor || !obs || !act || n <= 0) return fail("pd_actor_forward: bad argument");
+    const int O = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 2 : 5, A = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 1 : 4;
+    ActorArgs p;
+    int use_tc = 0;
+    if (actor_args(e, actor, p, use_tc, (cudaStream_t)stream)) return 1;
+    if (actor_launch(O, A, p, obs, act, mean_out, n, use_tc, e->n_sm, (cudaStream_t)stream))
+        return fail(std::string("pd_actor_forward: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    g_launches++;
+    return 0;
+}
+
 int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, float *obs_out,
                             float *act_out, float *rew_out, uint8_t *done_out, uint8_t *trunc_out,
-                            void *stream) {
-    (void)e; (void)actor; (void)n_steps; (void)obs_out; (void)act_out; (void)rew_out;
-    (void)done_out; (void)trunc_out; (void)stream;
-    return fail("pd_collect_shared_actor: not built in this revision");
+                            float *next_obs_out, void *stream) {
+    if (!e || !actor || !act_out || n_steps <= 0) return fail("pd_collect_shared_actor: bad argument");
+    if (e->cfg.precision != PD_FP32) return fail("pd_collect_shared_actor: needs the PD_FP32 build (float obs)");
+    if (!e->cfg.auto_reset) return fail("pd_collect_shared_actor: handle must be created with auto_reset");
+    if (activate(e)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int O = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 2 : 5, A = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 1 : 4;
+    const size_t B = (size_t)e->cfg.n_envs;
+    if (!e->obs_carry) {
+        CK(cudaMalloc(&e->obs_carry, B * O * sizeof(float)));
+        e->allocs.push_back(e->obs_carry);
+    }
+    if (!e->obs_valid) {
+        e->impl->observe(e->cfg.phase, e->cfg.rtd, e->soa, e->obs_carry, st);
+        g_launches++;
+        e->obs_valid = true;
+    }
+    ActorArgs p;
+    int use_tc = 0;
+    if (actor_args(e, actor, p, use_tc, st)) return 1;
+    for (int t = 0; t < n_steps; ++t) {
+        float *obs_t = obs_out ? obs_out + (size_t)t * B * O : e->obs_carry;
+        if (obs_out && t == 0)
+            CK(cudaMemcpyAsync(obs_t, e->obs_carry, B * O * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        float *act_t = act_out + (size_t)t * B * A;
+        p.step = e->collect_step++;
+        if (actor_launch(O, A, p, obs_t, act_t, nullptr, (int)B, use_tc, e->n_sm, st))
+            return fail(std::string("pd_collect_shared_actor: actor launch failed: ") +
+                        cudaGetErrorString(cudaGetLastError()));
+        g_launches++;
+        StepIO io;
+        io.actions = act_t; io.action_dtype = PD_ACT_F32;
+        io.obs = next_obs_out ? next_obs_out + (size_t)t * B * O : nullptr;
+        io.reward = rew_out ? rew_out + (size_t)t * B : nullptr;
+        io.done = done_out ? done_out + (size_t)t * B : nullptr;
+        io.truncated = trunc_out ? trunc_out + (size_t)t * B : nullptr;
+        io.trunc_id = nullptr;
+        io.dbg = nullptr;
+        // post-reset observation feeds the next action
+        io.next_obs = (obs_out && t + 1 < n_steps) ? (void *)(obs_out + (size_t)(t + 1) * B * O) : (void *)e->obs_carry;
+        e->impl->step(e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
+                      e->cfg.auto_reset, st);
+        g_launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
 }
 
 }  // extern "C"

@@ -57,6 +57,7 @@ struct Impl {
     void (*set_state)(const EnvSoA &, const double *, const double *, const int *, const double *,
                       cudaStream_t);
     void (*transpose)(const float *, float *, int, int, cudaStream_t);
+    void (*observe)(int phase, int rtd, const EnvSoA &, void *obs, cudaStream_t);
 };
 
 const Impl *impl_fp64();

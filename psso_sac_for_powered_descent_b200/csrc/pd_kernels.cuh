@@ -101,6 +101,20 @@ __global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const do
     e.ep_steps[i] = 0;
 }
 
+// observation of the current state (first step of a collection run)
+template <typename R, int PHASE, int RTD>
+__global__ void observe_kernel(EnvSoA e, R *obs) {
+    constexpr int O = PHASE == 0 ? 2 : 5;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n) return;
+    State s;
+    load_state(e, i, s);
+    R o[O];
+    observe<R, PHASE, RTD>(s, o);
+#pragma unroll
+    for (int k = 0; k < O; ++k) obs[(size_t)i * O + k] = o[k];
+}
+
 // ------------------------------------------------------------------ fused step kernel
 // physics (4 sub-steps) + g-window + truncation/done/reward + observation + auto-reset.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND>
@@ -424,6 +438,18 @@ struct Launch {
         return 1;
     }
 };
+
+template <typename R>
+static void impl_observe(int phase, int rtd, const EnvSoA &e, void *obs, cudaStream_t st) {
+    int threads = 128, blocks = (e.n + threads - 1) / threads;
+    int key = phase * 2 + rtd;
+    switch (key) {
+        case 0: observe_kernel<R, 0, 0><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        case 1: observe_kernel<R, 0, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        case 2: observe_kernel<R, 1, 0><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        default: observe_kernel<R, 1, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+    }
+}
 
 template <typename R, typename RT>
 static void impl_reset(const EnvSoA &e, const uint8_t *mask, const WindCtx &wc, const double *sig,

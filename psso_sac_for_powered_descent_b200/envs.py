@@ -224,6 +224,56 @@ class BatchedRocketEnv:
         return dict(steps=steps, terminal=term, traj=traj)
 
 
+    # ------------------------------------------------------------------ shared SAC actor
+    def _actor_struct(self, actor, deterministic, seed, fp32_path):
+        """actor: src/agents/sac_pytorch.Actor-like module (layers Sequential of Linear+ReLU,
+        mean, log_std, max_action) or a dict with w1,b1,w2,b2,wm,bm,ws,bs."""
+        if isinstance(actor, dict):
+            t = actor
+        else:
+            lin = [m for m in actor.layers if isinstance(m, torch.nn.Linear)]
+            if len(lin) != 2:
+                raise NotImplementedError("shared-actor kernel supports number_of_hidden_layers = 2")
+            t = dict(w1=lin[0].weight, b1=lin[0].bias, w2=lin[1].weight, b2=lin[1].bias,
+                     wm=actor.mean.weight, bm=actor.mean.bias, ws=actor.log_std.weight, bs=actor.log_std.bias)
+            t["max_action"] = float(getattr(actor, "max_action", 1.0))
+        keep = {k: v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                for k, v in t.items() if k != "max_action"}
+        a = N.PdSharedActor()
+        a.hidden, a.deterministic = keep["w1"].shape[0], int(bool(deterministic))
+        a.max_action, a.fp32_path, a.seed = float(t.get("max_action", 1.0)), int(bool(fp32_path)), int(seed)
+        for k in ("w1", "b1", "w2", "b2", "wm", "bm", "ws", "bs"):
+            setattr(a, k, keep[k].data_ptr())
+        return a, keep
+
+    def actor_forward(self, actor, obs, deterministic=True, seed=0, fp32_path=False, want_mean=False):
+        a, keep = self._actor_struct(actor, deterministic, seed, fp32_path)
+        obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
+        n = obs.shape[0]
+        act = torch.empty(n, self.act_dim, dtype=torch.float32, device=self.device)
+        mean = torch.empty(n, self.act_dim, dtype=torch.float32, device=self.device) if want_mean else None
+        N.check(self.lib.pd_actor_forward(self._h, C.byref(a), _ptr(obs), n, _ptr(act), _ptr(mean), _stream()))
+        return (act, mean) if want_mean else act
+
+    def collect(self, actor, n_steps, deterministic=False, seed=0, fp32_path=False, next_obs=True):
+        """n_steps of [shared-actor inference -> fused env step with auto-reset] on the whole
+        batch (the loop body of sac_pytorch_powered_descent.py:160-183).  Returns step-major
+        tensors obs, actions, rewards, done, truncated (, next_obs)."""
+        a, keep = self._actor_struct(actor, deterministic, seed, fp32_path)
+        B, T, dev = self.n_envs, n_steps, self.device
+        out = dict(obs=torch.empty(T, B, self.obs_dim, dtype=torch.float32, device=dev),
+                   actions=torch.empty(T, B, self.act_dim, dtype=torch.float32, device=dev),
+                   rewards=torch.empty(T, B, dtype=torch.float32, device=dev),
+                   done=torch.empty(T, B, dtype=torch.uint8, device=dev),
+                   truncated=torch.empty(T, B, dtype=torch.uint8, device=dev))
+        if next_obs:
+            out["next_obs"] = torch.empty(T, B, self.obs_dim, dtype=torch.float32, device=dev)
+        N.check(self.lib.pd_collect_shared_actor(self._h, C.byref(a), T, _ptr(out["obs"]), _ptr(out["actions"]),
+                                                 _ptr(out["rewards"]), _ptr(out["done"]), _ptr(out["truncated"]),
+                                                 _ptr(out.get("next_obs")), _stream()))
+        return out
+
+
 # =======================================================================================
 # scalar-compatible drop-ins
 # =======================================================================================

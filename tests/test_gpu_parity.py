@@ -303,3 +303,78 @@ def test_full_size_properties(envs_mod):
     assert (steps[0::3] == 101).all() and (tid[0::3] == 4).all()
     assert (steps[1::3] == 131).all() and (tid[1::3] == 4).all()
     assert (steps[2::3] == 397).all() and (tid[2::3] == 6).all()
+
+
+# --------------------------------------------------------------------------- shared SAC actor
+def _make_actor(state_dim, action_dim, hidden=256, seed=0):
+    """Same module structure and default init as src/agents/sac_pytorch.Actor (:129-160)."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+
+    class Actor(nn.Module):
+        def __init__(self):
+            super().__init__()
+            layers, d = [], state_dim
+            for _ in range(2):
+                layers += [nn.Linear(d, hidden), nn.ReLU()]
+                d = hidden
+            self.layers = nn.Sequential(*layers)
+            self.mean = nn.Linear(hidden, action_dim)
+            self.log_std = nn.Linear(hidden, action_dim)
+            self.max_action = 1.0
+
+        def forward(self, s):
+            x = self.layers(s)
+            return self.mean(x), torch.clamp(self.log_std(x), -20, 2)
+    return Actor()
+
+
+@pytest.mark.parametrize("phase,O,A", [(P, 2, 1), (G, 5, 4)])
+def test_shared_actor_tensor_core_vs_torch_fp32(envs_mod, phase, O, A):
+    env = envs_mod.BatchedRocketEnv(256, "rl", phase, precision="fp32", auto_reset=True)
+    actor = _make_actor(O, A)
+    # make the GEMM matter: scale the hidden layer so activations are O(1)
+    with torch.no_grad():
+        actor.layers[2].weight.mul_(4.0)
+    n = 1000                                       # ragged last tile (1000 = 7*128 + 104)
+    g = torch.Generator().manual_seed(1)
+    obs = (torch.rand(n, O, generator=g) * 2 - 1)
+    with torch.no_grad():
+        mean_ref, _ = actor(obs)
+        act_ref = torch.tanh(mean_ref)
+    act32, mean32 = env.actor_forward(actor, obs.cuda(), deterministic=True, fp32_path=True, want_mean=True)
+    assert torch.allclose(mean32.cpu(), mean_ref, rtol=1e-5, atol=2e-6)
+    assert torch.allclose(act32.cpu(), act_ref, rtol=1e-5, atol=2e-6)
+    act_tc, mean_tc = env.actor_forward(actor, obs.cuda(), deterministic=True, want_mean=True)
+    # bf16 operands (8-bit mantissa), fp32 accumulation over K = 256: ~2e-3 of the activation scale
+    scale = float(mean_ref.abs().max())
+    assert float((mean_tc.cpu() - mean_ref).abs().max()) < 1e-2 * max(scale, 1.0)
+    assert float((act_tc.cpu() - act_ref).abs().max()) < 1e-2
+    # and it must not be a trivially-zero output
+    assert float(mean_tc.abs().max()) > 0.05
+
+
+def test_collect_shared_actor_matches_stepwise(envs_mod):
+    """collect() == manual loop of actor_forward + step on a twin env (deterministic actor)."""
+    B, T = 512, 6
+    actor = _make_actor(2, 1)
+    e1 = envs_mod.BatchedRocketEnv(B, "rl", P, precision="fp32", auto_reset=True)
+    e2 = envs_mod.BatchedRocketEnv(B, "rl", P, precision="fp32", auto_reset=True)
+    out = e1.collect(actor, T, deterministic=True)
+    nv = np.array(e2.params.norm_vals)
+    st = e2.get_state().cpu().numpy().astype(np.float32)
+    obs = torch.as_tensor(np.stack([(1 - st[:, 1] / nv[0]) * 2 - 1, (1 - st[:, 3] / nv[1]) * 2 - 1], 1),
+                          dtype=torch.float32).cuda()
+    for t in range(T):
+        assert torch.allclose(out["obs"][t], obs, atol=1e-6)
+        a = e2.actor_forward(actor, obs, deterministic=True)
+        assert torch.equal(out["actions"][t], a)
+        o, r, d, tr, tid = e2.step(a)
+        assert torch.equal(out["rewards"][t], r) and torch.equal(out["done"][t], d)
+        assert torch.equal(out["next_obs"][t], o)
+        obs = e2.next_obs.clone()
+    e1.check_status()
+    # stochastic mode: actions differ between envs and stay in (-1, 1)
+    out2 = e1.collect(actor, 2, deterministic=False, seed=3)
+    a = out2["actions"]
+    assert float(a.abs().max()) <= 1.0 and float(a.std()) > 1e-3
