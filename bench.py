@@ -205,6 +205,7 @@ def run_cuda(args):
         l0 = lib.pd_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        _native.check(lib.pd_activate(env._h))
         e0.record(stream)
         graph.replay()
         e1.record(stream)
@@ -235,62 +236,72 @@ def run_cuda(args):
     kern_ms = durs[len(durs) // 2]
     del flush
 
-    # ---- end-to-end through the public call: pinned host actions in, results out, every step
-    host_tape = torch.empty(K + W, B, 1, dtype=torch.float32).pin_memory()
-    host_tape.copy_(tape.cpu())
-    h_obs = torch.empty(B, 2, dtype=env.dtype).pin_memory()
-    h_rew = torch.empty(B, dtype=env.dtype).pin_memory()
-    h_done = torch.empty(B, dtype=torch.uint8).pin_memory()
-    h_trunc = torch.empty(B, dtype=torch.uint8).pin_memory()
-    d_act = torch.empty(B, 1, dtype=torch.float32, device=dev)
-    Ke = min(K, 200)
-    with torch.cuda.stream(stream):
-        env.reset()
-        for w in range(min(W, 3)):
-            d_act.copy_(host_tape[w], non_blocking=True)
-            env.step(d_act)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(Ke):
-            d_act.copy_(host_tape[W + k], non_blocking=True)
-            obs, rew, done, trunc, tid = env.step(d_act)
-            h_obs.copy_(obs, non_blocking=True)
-            h_rew.copy_(rew, non_blocking=True)
-            h_done.copy_(done, non_blocking=True)
-            h_trunc.copy_(trunc, non_blocking=True)
-            stream.synchronize()          # the caller needs the result before the next action
-        barrier()
-        e2e_s = time.perf_counter() - t0
+    # ---- end-to-end through the public host-facing call: numpy actions in, numpy results out,
+    # every step (BatchedRocketEnv.step_host: H2D copy + fused step + ONE D2H copy, CUDA graph)
+    host_tape = tape.cpu().numpy()
+    Ke = min(K, 300)
+    env.reset()
+    torch.cuda.synchronize(dev)
+    for w in range(min(W, 3) + 1):
+        env.step_host(host_tape[w])
+    barrier()
+    t0 = time.perf_counter()
+    chk = 0.0
+    for k in range(Ke):
+        obs, rew, done, trunc, tid = env.step_host(host_tape[W + k])
+        chk += float(rew[0])                      # the caller reads the result before the next action
+    barrier()
+    e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * B * Ke / float(t.item())
-    esz = 8 if args.precision == "fp64" else 4
     h2d = B * 4
-    d2h = B * (2 * esz + esz + 1 + 1)
+    d2h = int(env._host["n_copy"])
 
-    # ---- PSO fitness evaluation rate (config 3: 4 096 particles, full episodes)
+    # ---- PSO fitness evaluation (config 3 / 5): the swarm is block-sharded over the ranks, each
+    # rank rolls out its particles (x wind seeds) in one persistent kernel, then one fp64
+    # all-gather of the fitness vector and one broadcast of the best position (NCCL).
     pso = None
     if not args.no_pso:
-        model = envs.pso_wrapped_env(flight_phase=P, precision=args.precision)
-        rngp = np.random.default_rng(7 + rank)
-        pos = torch.as_tensor(rngp.uniform(-1.5, 1.5, (args.particles, 249)).astype(np.float32)).to(dev)
-        model._b.rollout_pso(pos, max_steps=4096)
-        torch.cuda.synchronize(dev)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        from psso_sac_for_powered_descent_b200 import pso as pso_mod
+        phase = args.pso_phase
+        n_par = 249 if phase == P else 372
+        model = envs.pso_wrapped_env(flight_phase=phase, enable_wind=args.pso_wind,
+                                     stochastic_wind=args.pso_wind, precision=args.precision,
+                                     max_steps=4096, seed=99)
+        rngp = np.random.default_rng(7)
+        pos = rngp.uniform(-1.5, 1.5, (args.particles, n_par))        # identical on every rank
+        stats = {}
+
+        def local_eval(p):
+            fit, steps, tid = model.evaluate(p, n_seeds=args.seeds)
+            stats["steps"] = float(steps.sum())
+            stats["capped"] = int((tid < 0).sum())
+            return fit.reshape(len(p), args.seeds).mean(dim=1).cpu().numpy()
+        ev = pso_mod.ShardedEvaluator(local_eval)
+        lo, hi = pso_mod.shard_bounds(args.particles, world, rank)
+        ev(pos)                                                     # warm-up (weights upload, caches)
         barrier()
-        p0.record()
-        fit, steps, tid = model._b.rollout_pso(pos, max_steps=4096)
-        p1.record()
+        t0 = time.perf_counter()
+        fitness = ev(pos)
+        idx, best, best_pos = ev.broadcast_best(fitness, pos[lo:hi], args.particles)
         barrier()
-        pms = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
-        tot_steps = torch.tensor([float(steps.sum())], device=dev, dtype=torch.float64)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, stats["steps"], stats["capped"]], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tot_steps, op=dist.ReduceOp.SUM)
-        pso = {"particles_per_gpu": args.particles, "fitness_evals_per_s": world * args.particles / (pms.item() * 1e-3),
-               "env_steps_per_s": tot_steps.item() / (pms.item() * 1e-3), "ms": pms.item(),
-               "mean_episode_steps": tot_steps.item() / (world * args.particles)}
+            mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            dt, tot_steps, capped = float(mx[0]), float(sm[1]), int(sm[2])
+        else:
+            tot_steps, capped = stats["steps"], stats["capped"]
+        episodes = args.particles * args.seeds
+        pso = {"phase": phase, "particles": args.particles, "wind_seeds": args.seeds, "wind": bool(args.pso_wind),
+               "fitness_evals_per_s": args.particles / dt, "episodes_per_s": episodes / dt,
+               "env_steps_per_s": tot_steps / dt, "ms": dt * 1e3, "mean_episode_steps": tot_steps / episodes,
+               "episodes_hitting_step_cap": capped, "best_fitness": best, "best_index": idx,
+               "collectives": "1 all_gather(fp64 fitness) + 1 broadcast(best position) per generation",
+               "timing": "wall clock between device-synchronised barriers, max over ranks"}
 
     if rank != 0:
         if world > 1:
@@ -349,6 +360,9 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--particles", type=int, default=4096)
+    ap.add_argument("--seeds", type=int, default=1)
+    ap.add_argument("--pso-phase", default=P, choices=[P, "landing_burn"])
+    ap.add_argument("--pso-wind", action="store_true")
     ap.add_argument("--cpu-steps-per-core", type=int, default=1500)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pso", action="store_true")

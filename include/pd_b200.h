@@ -223,6 +223,12 @@ int pd_collect_shared_actor(PdEnv *env, const PdSharedActor *actor, int n_steps,
 int pd_actor_forward(PdEnv *env, const PdSharedActor *actor, const float *obs, int n, float *act,
                      float *mean_out, void *stream);
 
+/* The physics constants of a handle live in __constant__ memory shared by all handles of the
+ * same precision in the process; every entry point re-uploads them when the active handle
+ * changes.  A caller that replays launches captured in a CUDA graph must call pd_activate
+ * before the replay if another handle was used since the capture. */
+int pd_activate(PdEnv *env);
+
 /* Sticky device status (synchronises): 0 = ok; bit 0 = an aero-table query fell outside the
  * enumerated neighbour-set table, bit 1 = neighbour search did not converge. */
 int pd_check_status(PdEnv *env, int32_t *status);

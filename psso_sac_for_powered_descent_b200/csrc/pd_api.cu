@@ -333,6 +333,11 @@ int pd_set_wind_tape(PdEnv *e, const double *tape, int tape_len, const double *s
     return 0;
 }
 
+int pd_activate(PdEnv *e) {
+    if (!e) return fail("pd_activate: null handle");
+    return activate(e);
+}
+
 int pd_check_status(PdEnv *e, int32_t *status) {
     if (!e || !status) return fail("pd_check_status: null argument");
     int a = 0, b = 0;

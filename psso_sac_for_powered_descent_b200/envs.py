@@ -89,13 +89,29 @@ class BatchedRocketEnv:
         with torch.cuda.device(self.device):
             N.check(self.lib.pd_create(C.byref(cfg), C.byref(self._cparams), C.byref(self._h)))
         B, dev = self.n_envs, self.device
-        self.obs = torch.empty(B, self.obs_dim, dtype=self.dtype, device=dev)
+        # step outputs live in ONE device allocation so that a host caller needs a single
+        # device->host copy per step: [obs | reward | trunc_id | done | truncated]
+        esz = 8 if precision == "fp64" else 4
+        self._out_layout = []
+        off = 0
+        for name, nbytes in (("obs", B * self.obs_dim * esz), ("reward", B * esz),
+                             ("done", B), ("truncated", B), ("trunc_id", B * 4)):
+            self._out_layout.append((name, off, nbytes))
+            off += (nbytes + 15) // 16 * 16
+        self._out = torch.empty(off, dtype=torch.uint8, device=dev)
+
+        def view(buf, name, dt, shape):
+            _, o, nb = next(x for x in self._out_layout if x[0] == name)
+            return buf[o:o + nb].view(dt).reshape(shape)
+        self._view = view
+        self.obs = view(self._out, "obs", self.dtype, (B, self.obs_dim))
+        self.reward = view(self._out, "reward", self.dtype, (B,))
+        self.trunc_id = view(self._out, "trunc_id", torch.int32, (B,))
+        self.done = view(self._out, "done", torch.uint8, (B,))
+        self.truncated = view(self._out, "truncated", torch.uint8, (B,))
         self.next_obs = torch.empty(B, self.obs_dim, dtype=self.dtype, device=dev)
-        self.reward = torch.empty(B, dtype=self.dtype, device=dev)
-        self.done = torch.empty(B, dtype=torch.uint8, device=dev)
-        self.truncated = torch.empty(B, dtype=torch.uint8, device=dev)
-        self.trunc_id = torch.empty(B, dtype=torch.int32, device=dev)
         self._tape = self._sigma = None
+        self._host = None
 
     def __del__(self):
         try:
@@ -128,6 +144,51 @@ class BatchedRocketEnv:
                                  _ptr(self.truncated), _ptr(self.trunc_id), _ptr(self.next_obs),
                                  _ptr(dbg), _stream()))
         return self.obs, self.reward, self.done, self.truncated, self.trunc_id
+
+    def step_host(self, actions):
+        """Host-facing step: `actions` is a float32/float64 numpy array (or CPU tensor)
+        [n_envs, A]; returns numpy views (obs, reward, done, truncated, trunc_id) of a pinned
+        host buffer, valid until the next call (trunc_id is only refreshed by
+        `self.trunc_id.cpu()`).  One host->device copy, the fused step kernel and one
+        device->host copy, replayed from a CUDA graph."""
+        a = torch.as_tensor(actions)
+        if a.dtype not in (torch.float32, torch.float64):
+            a = a.to(torch.float64)
+        a = a.reshape(self.n_envs, self.act_dim)
+        if self._host is None or self._host["dtype"] != a.dtype:
+            h = dict(dtype=a.dtype)
+            h["act_pin"] = torch.empty(self.n_envs, self.act_dim, dtype=a.dtype).pin_memory()
+            h["act_dev"] = torch.empty(self.n_envs, self.act_dim, dtype=a.dtype, device=self.device)
+            # trunc_id (diagnostic) is last in the layout and stays on the device unless asked for
+            n_copy = next(o for nm, o, nb in self._out_layout if nm == "trunc_id")
+            h["n_copy"] = n_copy
+            h["out_pin"] = torch.empty(self._out.numel(), dtype=torch.uint8).pin_memory()
+            h["stream"] = torch.cuda.Stream(device=self.device)
+            v = lambda n, dt, sh: self._view(h["out_pin"], n, dt, sh).numpy()
+            B = self.n_envs
+            h["views"] = (v("obs", self.dtype, (B, self.obs_dim)), v("reward", self.dtype, (B,)),
+                          v("done", torch.uint8, (B,)), v("truncated", torch.uint8, (B,)),
+                          v("trunc_id", torch.int32, (B,)))
+            with torch.cuda.stream(h["stream"]):
+                def body():
+                    h["act_dev"].copy_(h["act_pin"], non_blocking=True)
+                    self.step(h["act_dev"])
+                    h["out_pin"][:n_copy].copy_(self._out[:n_copy], non_blocking=True)
+                h["act_pin"].zero_()
+                N.check(self.lib.pd_activate(self._h))      # not allowed inside a capture
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=h["stream"]):
+                    body()
+                h["graph"] = g
+            self._host = h
+        h = self._host
+        h["act_pin"].copy_(a)
+        N.check(self.lib.pd_activate(self._h))
+        with torch.cuda.stream(h["stream"]):
+            h["graph"].replay()
+        h["stream"].synchronize()
+        return h["views"]
 
     # ------------------------------------------------------------------ state access
     def get_state(self, full=False):
