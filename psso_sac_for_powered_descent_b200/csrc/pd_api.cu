@@ -229,10 +229,10 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     rc = rc || upload_segments(e, p->gf_ca_mach, p->gf_ca_val, p->n_gf_ca, &e->tb.ca_x, &e->tb.ca_y, &e->tb.ca_s);
     rc = rc || upload_segments(e, p->gf_cn_mach, p->gf_cn_val, p->n_gf_cn, &e->tb.cn_x, &e->tb.cn_y, &e->tb.cn_s);
     if (rc) { pd_destroy(e); return 1; }
-    {   // fast_log table: u_j = double(1/c_j), c_j = 1 + (j + 0.5)/128; second word -log(u_j)
-        std::vector<double> tab(256);
-        for (int j = 0; j < 128; ++j) {
-            long double cj = 1.0L + ((long double)j + 0.5L) / 128.0L;
+    {   // fast_log table: u_j = double(1/c_j), c_j = 1 + (j + 0.5)/256; second word -log(u_j)
+        std::vector<double> tab(512);
+        for (int j = 0; j < 256; ++j) {
+            long double cj = 1.0L + ((long double)j + 0.5L) / 256.0L;
             double u = (double)(1.0L / cj);
             tab[2 * j] = u;
             tab[2 * j + 1] = (double)(-logl((long double)u));

@@ -75,7 +75,7 @@ struct RbfDev {
 
 struct Tables {
     RbfDev cd, cl;
-    const double2 *logtab;              // [128] (1/c_j rounded, -log of that), see fast_log
+    const double2 *logtab;              // [256] (1/c_j rounded, -log of that), see fast_log
     const double *ca_x, *ca_y, *ca_s;   // grid fin C_a segments (x_lo, y_lo, slope)
     const double *cn_x, *cn_y, *cn_s;
     int n_ca, n_cn;
@@ -83,9 +83,9 @@ struct Tables {
     double init[11];
 };
 
-// block-shared staging of the small hot tables (7.4 KB)
+// block-shared staging of the small hot tables (9.4 KB)
 struct SharedTables {
-    double2 logtab[128];
+    double2 logtab[256];
     double2 cd_pts[192];
     double2 cl_pts[144];
 };
@@ -321,39 +321,47 @@ __device__ __forceinline__ int rbf_locate(const RbfDev &T, const RbfGrid &G, con
     return sid;
 }
 
-// Natural log of a positive normal double, ~1 ulp, ~20 instructions (CUDA's log() costs ~130
-// here and was 83% of the step kernel, profiles/r1_step_kernel_baseline.txt).
-//   x = 2^e * m, m in [1,2); j = top 7 mantissa bits; tab[j] = (u_j, -log(u_j)) with
-//   u_j = double(1 / (1 + (j + 0.5)/128)); r = m*u_j - 1 (exact in one fma, |r| < 2^-8);
-//   log x = e ln2 - log u_j + log1p(r), log1p by a degree-7 Taylor polynomial (|r|^8/8 < 2e-21).
+// Natural log of a positive normal double, ~1 ulp, ~18 instructions (CUDA's log() costs ~130
+// here and was 83% of the first step kernel, profiles/r1_step_kernel_baseline.txt).
+//   x = 2^e * m, m in [1,2); j = top 8 mantissa bits; tab[j] = (u_j, -log(u_j)) with
+//   u_j = double(1 / (1 + (j + 0.5)/256)); r = m*u_j - 1 (exact in one fma, |r| < 2^-9);
+//   log x = e ln2 - log u_j + log1p(r); log1p by a Taylor polynomial of degree PD_LOG_DEG
+//   (degree 5: |r|^6/6 < 1e-17, full double; the fp32 production build uses degree 4,
+//   |r|^5/5 < 6e-15, still 1e3 x below what its 1e-5 state tolerance needs after the
+//   thin-plate-spline cancellation factor of ~5e4).
 // Integer work stays on the high 32-bit word; e is converted with the 2^52 magic-number trick
-// (one DADD) instead of an I2F on the XU pipe.
+// (one DADD) instead of an I2F on the XU pipe.  x = 0 yields a finite value (-709), so
+// phi(0) = 0 * finite = 0 needs no special case.
+template <int DEG>
 __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab) {
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
-    const int j = (hi >> 13) & 127;
+    const int j = (hi >> 12) & 255;
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // (double)((hi >> 20) - 1023): biased exponent in the low word of 2^52, minus (2^52 + 1023)
     const double ed = __hiloint2double(0x43300000, (hi >> 20) & 0x7FF) - 4503599627371519.0;
     const double2 t = tab[j];
     const double r = fma(m, t.x, -1.0);
-    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
-    p = fma(p, r, 1.0 / 5.0);
-    p = fma(p, r, -1.0 / 4.0);
-    p = fma(p, r, 1.0 / 3.0);
+    double p;
+    if (DEG >= 5) {
+        p = fma(r, 1.0 / 5.0, -1.0 / 4.0);
+        p = fma(p, r, 1.0 / 3.0);
+    } else {
+        p = fma(r, -1.0 / 4.0, 1.0 / 3.0);
+    }
     p = fma(p, r, -0.5);
     p = fma(p * r, r, r);
     return fma(ed, 0.6931471805599453, t.y + p);
 }
 
 // one thin-plate-spline term accumulated into acc: c2 * r^2 * log r^2 with c2 = c/2 folded on
-// the host (exact).  r^2 is clamped to 1e-300 so that phi(0) = 0 needs no branch/select
-// (1e-300 * log 1e-300 = -7e-298 vanishes against any accumulator).
+// the host (exact).
+template <int DEG>
 __device__ __forceinline__ double tps_acc(double acc, double c2, double M, double a, double2 pt,
                                           const double2 *__restrict__ logtab) {
     const double dm = M - pt.x, da = a - pt.y;
-    const double r2 = fmax(fma(dm, dm, da * da), 1e-300);
-    return fma(c2 * r2, fast_log(r2, logtab), acc);
+    const double r2 = fma(dm, dm, da * da);
+    return fma(c2 * r2, fast_log<DEG>(r2, logtab), acc);
 }
 
 // Row of one neighbour set: 64 doubles = 50 coefficients (already halved), 3 polynomial
@@ -383,6 +391,7 @@ __device__ __forceinline__ double rbf_poly(const RbfRow &r, double acc, double M
 // Values of two interpolants (C_L at (M, aL) from set sidL, C_D at (M, aD) from set sidD) in one
 // flat, uniform 50-trip loop: no per-lane trip counts, 8 + 8 independent chains per trip to hide
 // the fp64 / shared-memory latency at the 3-4 warps per scheduler this workload gives.
+template <int DEG>
 __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int sidL,
                                           const double2 *__restrict__ ptsL, double aL,
                                           const double *__restrict__ rowsD, int sidD,
@@ -395,22 +404,22 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
         const unsigned int wl = __ldg(rl.ib + w), wd = __ldg(rd.ib + w);
         const double2 cl0 = __ldg(rl.c2 + 2 * w), cl1 = __ldg(rl.c2 + 2 * w + 1);
         const double2 cd0 = __ldg(rd.c2 + 2 * w), cd1 = __ldg(rd.c2 + 2 * w + 1);
-        l0 = tps_acc(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
-        d0 = tps_acc(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
-        l1 = tps_acc(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
-        d1 = tps_acc(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
-        l0 = tps_acc(l0, cl1.x, M, aL, ptsL[(wl >> 16) & 255], logtab);
-        d0 = tps_acc(d0, cd1.x, M, aD, ptsD[(wd >> 16) & 255], logtab);
-        l1 = tps_acc(l1, cl1.y, M, aL, ptsL[wl >> 24], logtab);
-        d1 = tps_acc(d1, cd1.y, M, aD, ptsD[wd >> 24], logtab);
+        l0 = tps_acc<DEG>(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
+        d0 = tps_acc<DEG>(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
+        l1 = tps_acc<DEG>(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
+        d1 = tps_acc<DEG>(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
+        l0 = tps_acc<DEG>(l0, cl1.x, M, aL, ptsL[(wl >> 16) & 255], logtab);
+        d0 = tps_acc<DEG>(d0, cd1.x, M, aD, ptsD[(wd >> 16) & 255], logtab);
+        l1 = tps_acc<DEG>(l1, cl1.y, M, aL, ptsL[wl >> 24], logtab);
+        d1 = tps_acc<DEG>(d1, cd1.y, M, aD, ptsD[wd >> 24], logtab);
     }
     {
         const unsigned int wl = __ldg(rl.ib + 12), wd = __ldg(rd.ib + 12);
         const double2 cl0 = __ldg(rl.c2 + 24), cd0 = __ldg(rd.c2 + 24);
-        l0 = tps_acc(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
-        d0 = tps_acc(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
-        l1 = tps_acc(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
-        d1 = tps_acc(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
+        l0 = tps_acc<DEG>(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
+        d0 = tps_acc<DEG>(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
+        l1 = tps_acc<DEG>(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
+        d1 = tps_acc<DEG>(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
     }
     vL = rbf_poly(rl, l0 + l1, M, aL);
     vD = rbf_poly(rd, d0 + d1, M, aD);
@@ -438,8 +447,8 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     if (neg_line) sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[1], g_sd.cl_levels, M, aL, status);
     else sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[0], g_sd.cl_levels, M, aL, status);
     double vL, vD;
-    rbf_eval2(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts, aD, M, sh->logtab,
-              vL, vD);
+    rbf_eval2<(sizeof(R) == 8 ? 5 : 4)>(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts,
+                                         aD, M, sh->logtab, vL, vD);
     C_L = zero ? R(0) : (R)(flip ? -vL : vL);
     C_D = (R)vD;
 }

@@ -73,7 +73,7 @@ __device__ __forceinline__ void shape_action(Action<(PHASE == 0 ? 1 : 4)> &a) {
 
 // small hot tables -> shared memory; every thread of the block must call this
 __device__ __forceinline__ void stage_tables(SharedTables *sh) {
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) sh->logtab[i] = g_tb.logtab[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->logtab[i] = g_tb.logtab[i];
     for (int i = threadIdx.x; i < g_tb.cd.n_points; i += blockDim.x) sh->cd_pts[i] = g_tb.cd.points[i];
     for (int i = threadIdx.x; i < g_tb.cl.n_points; i += blockDim.x) sh->cl_pts[i] = g_tb.cl.points[i];
     __syncthreads();
