@@ -42,6 +42,7 @@ struct PdEnv {
     float *wT = nullptr;
     size_t wT_cap = 0;
     int *roll_status = nullptr;
+    int *roll_queue = nullptr;
     // shared-actor collection
     void *w2_img = nullptr;          // bf16 smem image of W2
     const float *w2_src = nullptr;   // which W2 the image was built from
@@ -253,7 +254,7 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
          dev_alloc(e, 3 * B, &s.aprev) || dev_alloc(e, 6 * B, &s.wst) || dev_alloc(e, B, &s.wctr) ||
          dev_alloc(e, B, &s.episode) ||
          dev_alloc(e, B, &s.trunc_id) || dev_alloc(e, B, &s.ep_steps) || dev_alloc(e, (size_t)1, &s.status) ||
-         dev_alloc(e, (size_t)1, &e->roll_status);
+         dev_alloc(e, (size_t)1, &e->roll_status) || dev_alloc(e, (size_t)1, &e->roll_queue);
     if (rc) { pd_destroy(e); return 1; }
     *out = e;
     if (pd_reset(e, nullptr, nullptr)) { pd_destroy(e); *out = nullptr; return 1; }
@@ -382,6 +383,7 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
     io.w_stride = (size_t)n_particles;
     io.ret = fitness; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
     io.traj = traj; io.act_out = actions_out; io.rewards = rewards;
+    io.queue = e->roll_queue;
     if (e->impl->rollout(PD_POLICY_MLP, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
                          e->sigma_uv, e->roll_status, st))
         return fail("pd_rollout_pso: unsupported configuration");
@@ -407,6 +409,7 @@ int pd_rollout_policy(PdEnv *e, int policy, const void *actions, int action_dtyp
     io.action_dtype = action_dtype;
     io.ret = ret; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
     io.traj = traj; io.rewards = rewards;
+    io.queue = e->roll_queue;
     if (e->impl->rollout(policy, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
                          e->sigma_uv, e->roll_status, (cudaStream_t)stream))
         return fail("pd_rollout_policy: unsupported configuration (classical controller is "

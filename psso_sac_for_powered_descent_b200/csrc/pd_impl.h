@@ -44,6 +44,7 @@ struct RolloutIO {
     int32_t *steps, *trunc_id;
     double *terminal, *traj, *rewards;
     float *act_out;        // [max_steps][n_episodes][A] actions applied (MLP policy)
+    int *queue;            // work-queue head (next episode index to hand out)
 };
 
 struct Impl {

@@ -239,6 +239,8 @@ __device__ __forceinline__ void actor_mlp(const float *__restrict__ wT, size_t s
     for (int j = 0; j < OUT; ++j) act[j] = tanhf(act[j] + __ldg(p + (size_t)j * stride));
 }
 
+static __global__ void init_queue_kernel(int *q, int v) { *q = v; }
+
 // weights [n_particles][n_params] -> wT [n_params][n_particles]
 static __global__ void transpose_weights_kernel(const float *__restrict__ w, float *__restrict__ wT,
                                          int n_particles, int n_params) {
@@ -266,25 +268,37 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int O = PHASE == 0 ? 2 : 5;
     __shared__ SharedTables sh;
     stage_tables(&sh);
+    // Persistent lanes with a work queue: episode lengths are ragged (P: 101..460 steps,
+    // G: 7..27), so a lane that finishes pulls the next episode index instead of idling until
+    // the slowest lane of its warp is done.
     int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= io.n_episodes) return;
+    bool active = e < io.n_episodes;
     State s;
-    state_reset(s);
     GWindow<R> gw;
-    gw.n = 0;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
-    ActPrev prev = {0.0, 0.0, 0.0};
+    ActPrev prev;
     WindState w = {};
-    if (WIND) wind_reset(w, wc, (unsigned)e, 1u, sigma_uv);
     Info<R> info;
     info.rbf_status = 0;
-    info.q = R(0);
     double total = 0.0;
-    int steps = 0, tid = -1;
-    const size_t col = (size_t)(e / io.n_seeds);
-    for (int t = 0; t < io.max_steps; ++t) {
+    int t = 0;
+    size_t col = 0;
+    auto begin_episode = [&]() {
+        state_reset(s);
+        gw.n = 0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
+        prev.gimbal_deg = prev.dl = prev.dr = 0.0;
+        if (WIND) wind_reset(w, wc, (unsigned)e, 1u, sigma_uv);
+        info.q = R(0);
+        total = 0.0;
+        t = 0;
+        col = (size_t)(e / io.n_seeds);
+    };
+    if (active) begin_episode();
+    while (__any_sync(0xffffffffu, active)) {
+        if (!active) continue;
         Action<A> act;
+        bool stop = false;
         if constexpr (POLICY == 0) {
             R obs[O];
             observe<R, PHASE, 0>(s, obs);
@@ -305,9 +319,8 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
         } else {
             // classical P controller on v_ref(y) (landing_burn_pure_throttle.py:261-339)
             double alpha_eff = s.gamma - s.theta - PD_PI;
-            if (!(s.m_prop > 0.0 && s.y > 1.0 && (double)info.q < 65e3 && s.vy < 0.0 &&
-                  alpha_eff < 5.0 * (180.0 / PD_PI)))
-                break;
+            stop = !(s.m_prop > 0.0 && s.y > 1.0 && (double)info.q < 65e3 && s.vy < 0.0 &&
+                     alpha_eff < 5.0 * (180.0 / PD_PI));
             double speed = sqrt(s.vx * s.vx + s.vy * s.vy);
             double v_ref = g_sd.v_opt_a * (s.y * s.y) + g_sd.v_opt_b * s.y;
             double nn = -0.10 * (v_ref - speed) + 0.0;
@@ -317,34 +330,43 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
         }
         Rtd<R> out;
         out.reward = R(0); out.done = 0; out.truncated = 0; out.trunc_id = 0;
-        if constexpr (POLICY == 2) {
-            Control<R> ctl;
+        int tid = -1;
+        if (!stop) {
+            if constexpr (POLICY == 2) {
+                Control<R> ctl;
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k)
-                substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, (unsigned)e, info, ctl, &sh);
-        } else {
-            R g1;
-            env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)e, gw, info, out, g1, &sh);
+                for (int k = 0; k < 4; ++k)
+                    substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, (unsigned)e, info, ctl, &sh);
+            } else {
+                R g1;
+                env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)e, gw, info, out, g1, &sh);
+            }
+            total -= (double)out.reward;
+            if (io.traj) {
+                double *p = io.traj + ((size_t)t * io.n_episodes + e) * 11;
+                p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
+                p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
+            }
+            if (io.rewards) io.rewards[(size_t)t * io.n_episodes + e] = (double)out.reward;
+            ++t;
+            if (out.done || out.truncated) { tid = out.trunc_id; stop = true; }
+            else if (t >= io.max_steps) stop = true;
         }
-        steps = t + 1;
-        total -= (double)out.reward;
-        if (io.traj) {
-            double *p = io.traj + ((size_t)t * io.n_episodes + e) * 11;
-            p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
-            p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
+        if (stop) {
+            if (io.ret) io.ret[e] = total;
+            if (io.steps) io.steps[e] = t;
+            if (io.trunc_id) io.trunc_id[e] = tid;
+            if (io.terminal) {
+                double *p = io.terminal + (size_t)e * 11;
+                p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
+                p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
+            }
+            e = atomicAdd(io.queue, 1);
+            active = e < io.n_episodes;
+            if (active) begin_episode();
         }
-        if (io.rewards) io.rewards[(size_t)t * io.n_episodes + e] = (double)out.reward;
-        if (out.done || out.truncated) { tid = out.trunc_id; break; }
     }
     if (info.rbf_status) atomicOr(status, info.rbf_status);
-    if (io.ret) io.ret[e] = total;
-    if (io.steps) io.steps[e] = steps;
-    if (io.trunc_id) io.trunc_id[e] = tid;
-    if (io.terminal) {
-        double *p = io.terminal + (size_t)e * 11;
-        p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
-        p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
-    }
 }
 
 // ------------------------------------------------------------------ AoS <-> SoA
@@ -398,9 +420,14 @@ struct Launch {
     template <int PHASE, int RTD, bool WIND, int POLICY>
     static void roll_t(const RolloutIO &io, const WindCtx &wc, const double *sig, int *status,
                        cudaStream_t st) {
-        // small swarms: one warp per block so that 4 096 episodes still reach 128 SMs
+        // small swarms: one warp per block so that 4 096 episodes still reach 128 SMs; large
+        // ones: a persistent grid (8 blocks of 64 per SM at 128 registers) fed by the work queue
         int threads = io.n_episodes >= 148 * 64 * 4 ? 64 : 32;
         int blocks = (io.n_episodes + threads - 1) / threads;
+        const int cap = 148 * 8;
+        if (blocks > cap) blocks = cap;
+        cudaMemsetAsync(io.queue, 0, sizeof(int), st);
+        init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads);
         rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY><<<blocks, threads, 0, st>>>(io, wc, sig, status);
     }
     static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
