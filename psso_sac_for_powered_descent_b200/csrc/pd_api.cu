@@ -201,6 +201,8 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
     }
     for (int i = 0; i + 1 < p.n_wind && i < 15; ++i)
         s.wind_slope[i] = (p.wind_speed[i + 1] - p.wind_speed[i]) / (p.wind_alt_km[i + 1] - p.wind_alt_km[i]);
+    s.log_c[0] = 1.0 / 5.0; s.log_c[1] = -1.0 / 4.0; s.log_c[2] = 1.0 / 3.0; s.log_c[3] = -0.5;
+    s.log_c[4] = 0.6931471805599453; s.log_c[5] = 4503599627371519.0; s.log_c[6] = -1.0;
     for (int i = 0; i < 4; ++i) { s.Adu[i] = p.vk_Adu[i]; s.Adv[i] = p.vk_Adv[i]; }
     for (int i = 0; i < 2; ++i) { s.Bdu[i] = p.vk_Bdu[i]; s.Bdv[i] = p.vk_Bdv[i]; }
 }

@@ -47,6 +47,9 @@ struct Scalars {
     R wind_x[16], wind_y[16], wind_slope[16];
     R Adu[4], Bdu[2], Adv[4], Bdv[2];
     R cd_levels[5], cl_levels[5];
+    // fast_log constants, read as constant-bank operands (64-bit immediates would cost a pair
+    // of UMOVs per use): 1/5, -1/4, 1/3, -1/2, ln 2, 2^52 + 1023, -1
+    R log_c[8];
 };
 
 // Uniform (Mach, AoA) lookup grid over one query box.  cells >= 0: the grid cell lies
@@ -334,24 +337,25 @@ __device__ __forceinline__ int rbf_locate(const RbfDev &T, const RbfGrid &G, con
 // phi(0) = 0 * finite = 0 needs no special case.
 template <int DEG>
 __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab) {
+    const double *K = g_sd.log_c;
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
-    const int j = (hi >> 12) & 255;
+    const double2 t = tab[(hi >> 12) & 255];
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
-    // (double)((hi >> 20) - 1023): biased exponent in the low word of 2^52, minus (2^52 + 1023)
-    const double ed = __hiloint2double(0x43300000, (hi >> 20) & 0x7FF) - 4503599627371519.0;
-    const double2 t = tab[j];
-    const double r = fma(m, t.x, -1.0);
+    // (double)((hi >> 20) - 1023): biased exponent in the low word of 2^52, minus (2^52 + 1023);
+    // x > 0 here, so the sign bit needs no masking
+    const double ed = __hiloint2double(0x43300000, hi >> 20) - K[5];
+    const double r = fma(m, t.x, K[6]);
     double p;
     if (DEG >= 5) {
-        p = fma(r, 1.0 / 5.0, -1.0 / 4.0);
-        p = fma(p, r, 1.0 / 3.0);
+        p = fma(r, K[0], K[1]);
+        p = fma(p, r, K[2]);
     } else {
-        p = fma(r, -1.0 / 4.0, 1.0 / 3.0);
+        p = fma(r, K[1], K[2]);
     }
-    p = fma(p, r, -0.5);
+    p = fma(p, r, K[3]);
     p = fma(p * r, r, r);
-    return fma(ed, 0.6931471805599453, t.y + p);
+    return fma(ed, K[4], t.y + p);
 }
 
 // one thin-plate-spline term accumulated into acc: c2 * r^2 * log r^2 with c2 = c/2 folded on
@@ -425,12 +429,44 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
     vD = rbf_poly(rd, d0 + d1, M, aD);
 }
 
+// Cooperative variant: the COOP lanes of a group all hold the same env; lane `sub` takes the
+// terms k = sub, sub + COOP, ... of both sums and a butterfly all-reduce (identical result in
+// every lane) replaces 50 sequential terms by 50/COOP + log2(COOP) shuffle rounds.  Used by the
+// rollout kernel when there are fewer episodes than lanes on the GPU (latency, not throughput).
+template <int DEG, int COOP>
+__device__ __forceinline__ void rbf_eval2_coop(const double *__restrict__ rowsL, int sidL,
+                                               const double2 *__restrict__ ptsL, double aL,
+                                               const double *__restrict__ rowsD, int sidD,
+                                               const double2 *__restrict__ ptsD, double aD, double M,
+                                               const double2 *__restrict__ logtab, double &vL, double &vD) {
+    const RbfRow rl = rbf_row(rowsL, sidL), rd = rbf_row(rowsD, sidD);
+    const int sub = threadIdx.x & (COOP - 1);
+    const unsigned char *ibl = reinterpret_cast<const unsigned char *>(rl.ib);
+    const unsigned char *ibd = reinterpret_cast<const unsigned char *>(rd.ib);
+    double l = 0.0, d = 0.0;
+#pragma unroll
+    for (int k = sub; k < 50; k += COOP) {
+        l = tps_acc<DEG>(l, __ldg(rl.base + k), M, aL, ptsL[__ldg(ibl + k)], logtab);
+        d = tps_acc<DEG>(d, __ldg(rd.base + k), M, aD, ptsD[__ldg(ibd + k)], logtab);
+    }
+    // only the lanes of this group are guaranteed to be here (other groups of the warp may be
+    // between episodes), so the shuffles name exactly the group
+    const unsigned gmask = (COOP == 32 ? 0xffffffffu : ((1u << COOP) - 1u)) << ((threadIdx.x & 31) & ~(COOP - 1));
+#pragma unroll
+    for (int off = 1; off < COOP; off <<= 1) {
+        l += __shfl_xor_sync(gmask, l, off);
+        d += __shfl_xor_sync(gmask, d, off);
+    }
+    vL = rbf_poly(rl, l, M, aL);
+    vD = rbf_poly(rd, d, M, aD);
+}
+
 // C_L and C_D of one sub-step.
 //  C_D: CD_func passes degrees into a clamp written for radians
 //       (rockets_physics.py:712, aerodynamic_coefficients.py:108-114)
 //  C_L: degrees applied twice (rockets_physics.py:711, aerodynamic_coefficients.py:120-131);
 //       the aoa < -10 branch evaluates (Mach, -10) and is not negated upstream.
-template <typename R>
+template <typename R, int COOP>
 __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R &C_D, int &status,
                                                   const SharedTables *sh) {
     const double M = (double)mach;
@@ -447,8 +483,13 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     if (neg_line) sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[1], g_sd.cl_levels, M, aL, status);
     else sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[0], g_sd.cl_levels, M, aL, status);
     double vL, vD;
-    rbf_eval2<(sizeof(R) == 8 ? 5 : 4)>(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts,
-                                         aD, M, sh->logtab, vL, vD);
+    constexpr int DEG = sizeof(R) == 8 ? 5 : 4;
+    if constexpr (COOP == 1)
+        rbf_eval2<DEG>(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts, aD, M,
+                       sh->logtab, vL, vD);
+    else
+        rbf_eval2_coop<DEG, COOP>(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts, aD,
+                                  M, sh->logtab, vL, vD);
     C_L = zero ? R(0) : (R)(flip ? -vL : vL);
     C_D = (R)vD;
 }
@@ -737,7 +778,7 @@ __device__ __forceinline__ void control_G(const Action<4> &act, const ActPrev &p
 
 // ------------------------------------------------------------------ one Euler sub-step
 // RT = accumulation type of the RBF dot products.
-template <typename R, typename RT, int PHASE, bool WIND>
+template <typename R, typename RT, int PHASE, bool WIND, int COOP = 1>
 __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
                                         const ActPrev &prev, WindState &w, const WindCtx &wc,
                                         unsigned int env_id, Info<R> &info, Control<R> &ctl,
@@ -765,7 +806,7 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     R C_L = R(0), C_D = R(0);
     int status = 0;
     if (a_snd != R(0)) {
-        aero_coefficients<R>(mach, alpha_eff, C_L, C_D, status, sh);
+        aero_coefficients<R, COOP>(mach, alpha_eff, C_L, C_D, status, sh);
     }
     R qdyn = R(0.5) * rho * (speed * speed);
     R drag = qdyn * C_D * c.S_ref;
@@ -989,7 +1030,7 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
 // ------------------------------------------------------------------ one env.step()
 // 4 sub-steps with the same action (and, for G, the same actuator memory), g-load window,
 // truncation -> done -> reward on the new state.  base_environment.py:99-154.
-template <typename R, typename RT, int PHASE, int RTD, bool WIND>
+template <typename R, typename RT, int PHASE, int RTD, bool WIND, int COOP = 1>
 __device__ __forceinline__ void env_step(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
                                          ActPrev &prev, WindState &w, const WindCtx &wc,
                                          unsigned int env_id, GWindow<R> &gw, Info<R> &info,
@@ -999,7 +1040,7 @@ __device__ __forceinline__ void env_step(State &s, const Action<(PHASE == 0 ? 1 
     Control<R> ctl;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k)
-        substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, env_id, info, ctl, sh);
+        substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, env_id, info, ctl, sh);
     if (PHASE == 1) {
         prev.gimbal_deg = ctl.gimbal_deg;
         prev.dl = ctl.dl_cmd;

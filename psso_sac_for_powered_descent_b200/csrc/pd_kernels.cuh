@@ -261,7 +261,7 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
 // One episode per thread from reset to done/truncated: objective_function
 // (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for POLICY_TAPE,
 // LandingBurn.run_closed_loop for POLICY_CLASSICAL.
-template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY>
+template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP>
 __global__ void __launch_bounds__(64)
 rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = PHASE == 0 ? 1 : 4;
@@ -271,7 +271,9 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     // Persistent lanes with a work queue: episode lengths are ragged (P: 101..460 steps,
     // G: 7..27), so a lane that finishes pulls the next episode index instead of idling until
     // the slowest lane of its warp is done.
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    // COOP lanes share one episode (identical state in each; only the RBF sums are split)
+    int e = (blockIdx.x * blockDim.x + threadIdx.x) / COOP;
+    const bool writer = (threadIdx.x & (COOP - 1)) == 0;
     bool active = e < io.n_episodes;
     State s;
     GWindow<R> gw;
@@ -309,7 +311,7 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
             act.f32 = true;
 #pragma unroll
             for (int k = 0; k < A; ++k) act.u[k] = (double)af[k];
-            if (io.act_out) {
+            if (io.act_out && writer) {
 #pragma unroll
                 for (int k = 0; k < A; ++k) io.act_out[((size_t)t * io.n_episodes + e) * A + k] = af[k];
             }
@@ -336,32 +338,37 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
                 Control<R> ctl;
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k)
-                    substep<R, RT, PHASE, WIND>(s, act, prev, w, wc, (unsigned)e, info, ctl, &sh);
+                    substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, (unsigned)e, info, ctl, &sh);
             } else {
                 R g1;
-                env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)e, gw, info, out, g1, &sh);
+                env_step<R, RT, PHASE, RTD, WIND, COOP>(s, act, prev, w, wc, (unsigned)e, gw, info, out, g1, &sh);
             }
             total -= (double)out.reward;
-            if (io.traj) {
+            if (io.traj && writer) {
                 double *p = io.traj + ((size_t)t * io.n_episodes + e) * 11;
                 p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
                 p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
             }
-            if (io.rewards) io.rewards[(size_t)t * io.n_episodes + e] = (double)out.reward;
+            if (io.rewards && writer) io.rewards[(size_t)t * io.n_episodes + e] = (double)out.reward;
             ++t;
             if (out.done || out.truncated) { tid = out.trunc_id; stop = true; }
             else if (t >= io.max_steps) stop = true;
         }
         if (stop) {
-            if (io.ret) io.ret[e] = total;
-            if (io.steps) io.steps[e] = t;
-            if (io.trunc_id) io.trunc_id[e] = tid;
-            if (io.terminal) {
+            if (io.ret && writer) io.ret[e] = total;
+            if (io.steps && writer) io.steps[e] = t;
+            if (io.trunc_id && writer) io.trunc_id[e] = tid;
+            if (io.terminal && writer) {
                 double *p = io.terminal + (size_t)e * 11;
                 p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
                 p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
             }
-            e = atomicAdd(io.queue, 1);
+            if (writer) e = atomicAdd(io.queue, 1);
+            if (COOP > 1) {
+                const int leader = (threadIdx.x & 31) & ~(COOP - 1);
+                const unsigned gmask = (COOP == 32 ? 0xffffffffu : ((1u << COOP) - 1u)) << leader;
+                e = __shfl_sync(gmask, e, leader);
+            }
             active = e < io.n_episodes;
             if (active) begin_episode();
         }
@@ -420,15 +427,21 @@ struct Launch {
     template <int PHASE, int RTD, bool WIND, int POLICY>
     static void roll_t(const RolloutIO &io, const WindCtx &wc, const double *sig, int *status,
                        cudaStream_t st) {
-        // small swarms: one warp per block so that 4 096 episodes still reach 128 SMs; large
-        // ones: a persistent grid (8 blocks of 64 per SM at 128 registers) fed by the work queue
-        int threads = io.n_episodes >= 148 * 64 * 4 ? 64 : 32;
-        int blocks = (io.n_episodes + threads - 1) / threads;
-        const int cap = 148 * 8;
+        // A persistent grid (at most 8 blocks of 64 lanes per SM at 128 registers) fed by the
+        // work queue.  Fewer episodes than ~1/4 of the GPU's lanes: 8 lanes co-operate on each
+        // episode (splits the 100 RBF terms per sub-step), which both fills the SMs and cuts the
+        // per-step latency that bounds a generation by its longest episode.
+        const int threads = 64, cap = 148 * 8;
+        const bool coop = (long long)io.n_episodes * 8 <= (long long)cap * threads / 2 * 3 / 2;
+        const int lanes_per = coop ? 8 : 1;
+        long long lanes = (long long)io.n_episodes * lanes_per;
+        int blocks = (int)((lanes + threads - 1) / threads);
         if (blocks > cap) blocks = cap;
-        cudaMemsetAsync(io.queue, 0, sizeof(int), st);
-        init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads);
-        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY><<<blocks, threads, 0, st>>>(io, wc, sig, status);
+        init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads / lanes_per);
+        if (coop)
+            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, 0, st>>>(io, wc, sig, status);
+        else
+            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, 0, st>>>(io, wc, sig, status);
     }
     static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
                        const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {
