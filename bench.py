@@ -303,6 +303,36 @@ def run_cuda(args):
                "collectives": "1 all_gather(fp64 fitness) + 1 broadcast(best position) per generation",
                "timing": "wall clock between device-synchronised barriers, max over ranks"}
 
+    # ---- SAC data collection (config 4 shape): shared 2-256-256-(1,1) actor on the tensor cores
+    # + fused env step with stochastic wind, 131 072 envs per GPU, auto-reset
+    sac = None
+    if not args.no_sac:
+        import torch.nn as nn
+        torch.manual_seed(0)
+        lin1, lin2, mean_l, lstd_l = nn.Linear(2, 256), nn.Linear(256, 256), nn.Linear(256, 1), nn.Linear(256, 1)
+        actor = dict(w1=lin1.weight, b1=lin1.bias, w2=lin2.weight, b2=lin2.bias, wm=mean_l.weight,
+                     bm=mean_l.bias, ws=lstd_l.weight, bs=lstd_l.bias, max_action=1.0)
+        Bs, Ts = args.sac_envs, args.sac_steps
+        senv = envs.BatchedRocketEnv(Bs, "rl", P, enable_wind=True, stochastic_wind=True,
+                                     horiontal_wind_percentile=50, precision="fp32", auto_reset=True,
+                                     device=local, seed=77 + rank)
+        senv.collect(actor, 3, seed=1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        out = senv.collect(actor, Ts, seed=2)
+        s1.record()
+        barrier()
+        senv.check_status()
+        sms = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        sac = {"envs_per_gpu": Bs, "steps": Ts, "env_steps_per_s": world * Bs * Ts / (sms.item() * 1e-3),
+               "ms_per_step": sms.item() / Ts, "actor": "2-256-256-(1,1), bf16 tcgen05 UMMA + fp32 heads",
+               "wind": "stochastic, percentile 50, Philox gusts", "rtd": "rl",
+               "mean_reward": float(out["rewards"].mean()), "resets": int(out["truncated"].sum() + out["done"].sum())}
+        del senv, out
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -345,7 +375,17 @@ def run_cuda(args):
                         "peak_def": f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz", "sm_mhz_under_load": sm_mhz},
         "cpu_baseline": cpu,
         "pso": pso,
+        "sac_collect": sac,
     }
+    try:      # ncu figures of the same kernel (profiles/, captured by the builder, not live)
+        with open(os.path.join(REPO, "profiles", "step_kernel_ncu.json")) as f:
+            nc = json.load(f)
+        line["roofline"]["traffic"] = nc.get("dram_bytes_per_launch")
+        line["roofline"]["traffic_source"] = nc.get("source")
+        line["fp_roofline"]["fp64_pipe_pct_ncu"] = nc.get("fp64_pipe_pct")
+        line["fp_roofline"]["issue_active_pct_ncu"] = nc.get("issue_active_pct")
+    except Exception:
+        pass
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -366,6 +406,9 @@ def main():
     ap.add_argument("--cpu-steps-per-core", type=int, default=1500)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pso", action="store_true")
+    ap.add_argument("--no-sac", action="store_true")
+    ap.add_argument("--sac-envs", type=int, default=131072)
+    ap.add_argument("--sac-steps", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

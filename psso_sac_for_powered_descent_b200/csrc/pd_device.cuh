@@ -1020,9 +1020,10 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
             float th = (float)s.theta, thd = (float)s.theta_dot, gm = (float)s.gamma;
             o[0] = (R)((double)yf / g_sd.norm_y);
             o[1] = (R)((double)vyf / g_sd.norm_vy);
-            o[2] = (R)tanh(g_sd.k_theta_rl * ((double)th - PD_PI / 2));
-            o[3] = (R)tanh(g_sd.k_thetadot_rl * (double)thd);
-            o[4] = (R)tanh(g_sd.k_theta_rl * ((double)gm - 1.5 * PD_PI));
+            // np.float32 scalar (-, *) Python float stays float32 (NEP 50); math.tanh promotes
+            o[2] = (R)tanh((double)__fmul_rn(g_sf.k_theta_rl, __fsub_rn(th, (float)(PD_PI / 2))));
+            o[3] = (R)tanh((double)__fmul_rn(g_sf.k_thetadot_rl, thd));
+            o[4] = (R)tanh((double)__fmul_rn(g_sf.k_theta_rl, __fsub_rn(gm, (float)(1.5 * PD_PI))));
         }
     }
 }

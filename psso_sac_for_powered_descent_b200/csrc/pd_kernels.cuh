@@ -47,8 +47,12 @@ __device__ __forceinline__ void store_wind(const EnvSoA &e, int i, const WindSta
     e.wctr[i] = w.ctr;
 }
 // rl_wrapped_env_pytorch.augment_action for landing_burn (env_wrapped_rl_pytorch.py:144-157)
-__device__ __forceinline__ double log_compress(double u, double cfac) {
-    return copysign(log(1.0 + cfac * fabs(u)) / log(1.0 + cfac), u);
+// `1 + c*abs(u)` is evaluated in float32 when the action is a float32 ndarray (int * np.float32
+// stays float32 under NEP 50); math.log then works on the promoted double.
+__device__ __forceinline__ double log_compress(double u, double cfac, bool f32) {
+    double arg = f32 ? (double)__fadd_rn(1.0f, __fmul_rn((float)cfac, fabsf((float)u)))
+                     : 1.0 + cfac * fabs(u);
+    return copysign(log(arg) / log(1.0 + cfac), u);
 }
 
 template <int A>
@@ -64,9 +68,9 @@ template <int PHASE, int RTD>
 __device__ __forceinline__ void shape_action(Action<(PHASE == 0 ? 1 : 4)> &a) {
     if constexpr (PHASE == 1 && RTD == 1) {
         // np.array([...python floats...]) -> float64 action
-        a.u[0] = log_compress(a.u[0], 10.0);
-        a.u[2] = log_compress(a.u[2], 5.0);
-        a.u[3] = log_compress(a.u[3], 5.0);
+        a.u[0] = log_compress(a.u[0], 10.0, a.f32);
+        a.u[2] = log_compress(a.u[2], 5.0, a.f32);
+        a.u[3] = log_compress(a.u[3], 5.0, a.f32);
         a.f32 = false;
     }
 }

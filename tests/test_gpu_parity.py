@@ -394,3 +394,108 @@ def test_step_host_matches_step(envs_mod):
         assert np.array_equal(done, d2.cpu().numpy()) and np.array_equal(trunc, t2.cpu().numpy())
         assert torch.equal(e1.trunc_id, i2)
     assert torch.equal(e1.get_state(), e2.get_state())
+
+
+# --------------------------------------------------------------------------- RL rtd, wind, API
+@pytest.mark.parametrize("tag,phase,adim", [("P", P, 1), ("G", G, 4)])
+def test_rl_single_step_vs_oracle(envs_mod, golden, oracle_tables, tag, phase, adim):
+    """type='rl' closures (rtd_rl.py:194-336) on the fixture states: reward, flags, ids, and the
+    fp32-rounded observation of rl_wrapped_env_pytorch; G actions go through augment_action."""
+    from oracle import pd_oracle as O
+    g = golden(f"single_step_{tag}.npz")
+    n = 96
+    env = envs_mod.BatchedRocketEnv(n, "rl", phase, precision="fp64", trajectory_length=1, discount_factor=0.99)
+    env.set_state(g["state"][:n], g["win"][:n], g["nwin"][:n].astype(np.int32), g["aprev"][:n])
+    act = g["act32"][:n]
+    obs, rew, done, trunc, tid = env.step(torch.as_tensor(act).cuda())
+    st = env.get_state().cpu().numpy()
+    rl = O.RlEnv(phase, tables=oracle_tables)
+    for i in range(n):
+        rl.env.reset()
+        rl.env.set_state(g["state"][i], g["win"][i][:g["nwin"][i]], *g["aprev"][i])
+        o, r, d, t, info = rl.step(act[i])
+        assert state_err(st[i], np.array(rl.env.state, float), phase) < 1e-12, i
+        assert (bool(done[i]), bool(trunc[i]), int(tid[i])) == (d, t, rl.env.truncation_id), i
+        assert abs(float(rew[i]) - r) <= 1e-9 * max(1.0, abs(r)), (i, float(rew[i]), r)
+        assert np.max(np.abs(obs[i].cpu().numpy() - o)) < 1e-12, i
+
+
+def test_pso_rollout_with_wind_tape_vs_oracle(envs_mod, oracle_tables):
+    """Persistent rollout kernel with the gust filter on: same noise tape and sigmas as the
+    oracle, per-particle MLP in the loop (fp64 build)."""
+    from oracle import pd_oracle as O
+    rng = np.random.default_rng(21)
+    n = 6
+    pos = rng.uniform(-1.5, 1.5, (n, 249))
+    tape = rng.standard_normal((n, 8 * 700))
+    sig = np.stack([rng.uniform(0.5, 2.25, n), rng.uniform(1.25, 2.0, n)], 1)
+    model = envs_mod.pso_wrapped_env(flight_phase=P, enable_wind=True, stochastic_wind=True,
+                                     horiontal_wind_percentile=50, precision="fp64", max_steps=700)
+    model._b.n_envs = n            # the tape is indexed by episode
+    model._b.set_wind_tape(tape, sig)
+    fit, steps, tid = model.evaluate(pos)
+    model._b.check_status()
+    for i in range(n):
+        ref = O.PsoModel(P, enable_wind=True, stochastic_wind=True, horiontal_wind_percentile=50,
+                         tables=oracle_tables, wind_noise=dict(sigma_u=sig[i, 0], sigma_v=sig[i, 1], tape=tape[i]),
+                         max_steps=700)
+        f = ref.objective_function(pos[i])
+        assert int(steps[i]) == ref.steps, (i, int(steps[i]), ref.steps)
+        assert abs(float(fit[i]) - f) <= 1e-4 * abs(f), (i, float(fit[i]), f)
+
+
+def test_wind_seeds_and_determinism(envs_mod):
+    """Philox gusts: seeds differ, a given (seed, particle, wind-seed) is reproducible, sigma in the
+    reference's ranges (vonkarman.py:62-63)."""
+    rng = np.random.default_rng(4)
+    pos = torch.as_tensor(rng.uniform(-1.5, 1.5, (64, 249)).astype(np.float32)).cuda()
+    m1 = envs_mod.pso_wrapped_env(flight_phase=P, enable_wind=True, stochastic_wind=True, precision="fp32", seed=11)
+    f1, s1, t1 = m1._b.rollout_pso(pos, n_seeds=8)
+    f1b, _, _ = m1._b.rollout_pso(pos, n_seeds=8)
+    assert torch.equal(f1, f1b)
+    m2 = envs_mod.pso_wrapped_env(flight_phase=P, enable_wind=True, stochastic_wind=True, precision="fp32", seed=12)
+    f2, _, _ = m2._b.rollout_pso(pos, n_seeds=8)
+    assert not torch.equal(f1, f2)
+    per_seed = f1.reshape(64, 8)
+    assert float((per_seed.max(1).values - per_seed.min(1).values).max()) > 0.0     # gusts matter
+
+
+def test_scalar_drop_in_api(envs_mod):
+    """rocket_environment_pre_wrap mirror: same call shapes as the reference."""
+    env = envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase=P, enable_wind=False)
+    s0 = env.reset()
+    assert len(s0) == 11 and s0[1] == 30028.385497767023
+    outs = []
+    for a in ((0.25,), [0.25], np.array([0.25]), np.array([[0.25]])):
+        env.reset()
+        s, r, d, t, info = env.step(a)
+        outs.append(s)
+        assert isinstance(r, float) and isinstance(d, bool) and isinstance(t, bool)
+        assert {"mach_number", "dynamic_pressure", "CL", "CD", "g_load_1_sec_window", "action_info"} <= set(info)
+    assert outs[0] == outs[1] == outs[2] == outs[3]
+    env.reset()
+    s32, *_ = env.step(np.array([0.25], dtype=np.float32))      # float32 action: NEP-50 path
+    assert s32 != outs[0] and abs(s32[8] - outs[0][8]) < 1.0
+    with pytest.raises(NotImplementedError):
+        envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase="subsonic", enable_wind=False)
+    with pytest.raises(AssertionError):
+        envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase="nonsense", enable_wind=False)
+    m = envs_mod.pso_wrapped_env(flight_phase=G)
+    assert len(m.bounds) == 372 and "0_weight_0" in m.mock_dictionary_of_opt_params
+
+
+def test_full_size_G_and_cooperative_consistency(envs_mod):
+    """The 8-lane cooperative rollout (small swarms) and the 1-lane work-queue rollout (large
+    swarms) must agree on the same particles (fp64, well within chaotic growth for short episodes)."""
+    rng = np.random.default_rng(8)
+    pos = rng.uniform(-1.5, 1.5, (20000, 372)).astype(np.float32)
+    m = envs_mod.pso_wrapped_env(flight_phase=G, precision="fp64")
+    big = m._b.rollout_pso(torch.as_tensor(pos).cuda())               # 20000 episodes: 1 lane each
+    small = m._b.rollout_pso(torch.as_tensor(pos[:512]).cuda())       # 512 episodes: 8 lanes each
+    m._b.check_status()
+    same = (big[1][:512] == small[1]).float().mean()
+    assert float(same) > 0.9                                          # ill-conditioned G episodes aside
+    ok = (big[1][:512] == small[1])
+    rel = ((big[0][:512] - small[0]).abs() / small[0].abs())[ok]
+    assert float(rel.median()) < 1e-9 and float(rel.max()) < 1e-2
+    assert np.isfinite(big[0].cpu().numpy()).all() and int((big[2] < 0).sum()) == 0
