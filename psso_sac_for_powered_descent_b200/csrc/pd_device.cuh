@@ -392,9 +392,35 @@ __device__ __forceinline__ double rbf_poly(const RbfRow &r, double acc, double M
     return acc + p0.x + p0.y * xh + p1.x * yh;
 }
 
+// log with the table entry already fetched (lets the caller issue all table loads of a batch
+// of terms before the first dependent fma)
+template <int DEG>
+__device__ __forceinline__ double fast_log_t(double x, double2 t) {
+    const double *K = g_sd.log_c;
+    const int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    const double ed = __hiloint2double(0x43300000, hi >> 20) - K[5];
+    const double r = fma(m, t.x, K[6]);
+    double p;
+    if (DEG >= 5) {
+        p = fma(r, K[0], K[1]);
+        p = fma(p, r, K[2]);
+    } else {
+        p = fma(r, K[1], K[2]);
+    }
+    p = fma(p, r, K[3]);
+    p = fma(p * r, r, r);
+    return fma(ed, K[4], t.y + p);
+}
+
 // Values of two interpolants (C_L at (M, aL) from set sidL, C_D at (M, aD) from set sidD) in one
-// flat, uniform 50-trip loop: no per-lane trip counts, 8 + 8 independent chains per trip to hide
-// the fp64 / shared-memory latency at the 3-4 warps per scheduler this workload gives.
+// flat, uniform loop: 12 trips x (4 + 4) terms + a 2 + 2 tail, no per-lane trip counts.
+// The loop is software-pipelined by hand - profiles/r1_step_kernel_final_steady.txt showed 60 %
+// of its stall samples on the two shared-memory gathers (data point, log table) and 14 % on the
+// global load of the index word: (1) index words and coefficients of trip w+1 are fetched
+// during trip w, (2) all 8 point gathers, then all 8 r^2, then all 8 table gathers are issued
+// before the first polynomial.
 template <int DEG>
 __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int sidL,
                                           const double2 *__restrict__ ptsL, double aL,
@@ -403,23 +429,36 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
                                           const double2 *__restrict__ logtab, double &vL, double &vD) {
     const RbfRow rl = rbf_row(rowsL, sidL), rd = rbf_row(rowsD, sidD);
     double l0 = 0.0, l1 = 0.0, d0 = 0.0, d1 = 0.0;
+    unsigned int wl = __ldg(rl.ib), wd = __ldg(rd.ib);
+    double2 cl0 = __ldg(rl.c2), cl1 = __ldg(rl.c2 + 1), cd0 = __ldg(rd.c2), cd1 = __ldg(rd.c2 + 1);
 #pragma unroll 1
     for (int w = 0; w < 12; ++w) {
-        const unsigned int wl = __ldg(rl.ib + w), wd = __ldg(rd.ib + w);
-        const double2 cl0 = __ldg(rl.c2 + 2 * w), cl1 = __ldg(rl.c2 + 2 * w + 1);
-        const double2 cd0 = __ldg(rd.c2 + 2 * w), cd1 = __ldg(rd.c2 + 2 * w + 1);
-        l0 = tps_acc<DEG>(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
-        d0 = tps_acc<DEG>(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
-        l1 = tps_acc<DEG>(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
-        d1 = tps_acc<DEG>(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
-        l0 = tps_acc<DEG>(l0, cl1.x, M, aL, ptsL[(wl >> 16) & 255], logtab);
-        d0 = tps_acc<DEG>(d0, cd1.x, M, aD, ptsD[(wd >> 16) & 255], logtab);
-        l1 = tps_acc<DEG>(l1, cl1.y, M, aL, ptsL[wl >> 24], logtab);
-        d1 = tps_acc<DEG>(d1, cd1.y, M, aD, ptsD[wd >> 24], logtab);
+        double2 pt[8];
+        pt[0] = ptsL[wl & 255]; pt[1] = ptsD[wd & 255];
+        pt[2] = ptsL[(wl >> 8) & 255]; pt[3] = ptsD[(wd >> 8) & 255];
+        pt[4] = ptsL[(wl >> 16) & 255]; pt[5] = ptsD[(wd >> 16) & 255];
+        pt[6] = ptsL[wl >> 24]; pt[7] = ptsD[wd >> 24];
+        const double c[8] = {cl0.x, cd0.x, cl0.y, cd0.y, cl1.x, cd1.x, cl1.y, cd1.y};
+        // prefetch trip w + 1 (trip 12 = the tail: words ib[12], coefficient pair c2[24])
+        wl = __ldg(rl.ib + w + 1); wd = __ldg(rd.ib + w + 1);
+        cl0 = __ldg(rl.c2 + 2 * w + 2); cl1 = __ldg(rl.c2 + 2 * w + 3);
+        cd0 = __ldg(rd.c2 + 2 * w + 2); cd1 = __ldg(rd.c2 + 2 * w + 3);
+        double r2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const double dm = M - pt[i].x, da = ((i & 1) ? aD : aL) - pt[i].y;
+            r2[i] = fma(dm, dm, da * da);
+        }
+        double2 t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = logtab[(__double2hiint(r2[i]) >> 12) & 255];
+        double term[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) term[i] = (c[i] * r2[i]) * fast_log_t<DEG>(r2[i], t[i]);
+        l0 += term[0]; d0 += term[1]; l1 += term[2]; d1 += term[3];
+        l0 += term[4]; d0 += term[5]; l1 += term[6]; d1 += term[7];
     }
     {
-        const unsigned int wl = __ldg(rl.ib + 12), wd = __ldg(rd.ib + 12);
-        const double2 cl0 = __ldg(rl.c2 + 24), cd0 = __ldg(rd.c2 + 24);
         l0 = tps_acc<DEG>(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
         d0 = tps_acc<DEG>(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
         l1 = tps_acc<DEG>(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);

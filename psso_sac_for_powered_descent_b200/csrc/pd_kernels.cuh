@@ -121,8 +121,11 @@ __global__ void observe_kernel(EnvSoA e, R *obs) {
 
 // ------------------------------------------------------------------ fused step kernel
 // physics (4 sub-steps) + g-window + truncation/done/reward + observation + auto-reset.
+#ifndef PD_STEP_MIN_BLOCKS
+#define PD_STEP_MIN_BLOCKS 8
+#endif
 template <typename R, typename RT, int PHASE, int RTD, bool WIND>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, PD_STEP_MIN_BLOCKS)
 step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
