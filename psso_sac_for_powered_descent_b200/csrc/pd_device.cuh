@@ -86,11 +86,17 @@ struct Tables {
     double init[11];
 };
 
-// block-shared staging of the small hot tables (9.4 KB)
+// Block-shared staging of the small hot tables.  Every entry is replicated PD_REP = 8 times,
+// entry i of copy c at [i * 8 + c]; lane l uses copy l & 7.  A 128-bit shared load is served a
+// quarter-warp (8 lanes) at a time, and with this layout the 8 lanes always hit 8 different
+// 16-byte bank groups, whatever (random) entries they gather: 4 wavefronts per request instead
+// of ~11 (the LSU data pipe was the busiest unit of the step kernel at 62 %,
+// profiles/r1_step_kernel_final_steady.txt).  74 KB of dynamic shared memory, one block per SM.
+#define PD_REP 8
 struct SharedTables {
-    double2 logtab[256];
-    double2 cd_pts[192];
-    double2 cl_pts[144];
+    double2 logtab[256 * PD_REP];
+    double2 cd_pts[192 * PD_REP];
+    double2 cl_pts[144 * PD_REP];
 };
 
 // per-TU copies (no relocatable device code): each precision TU uploads its own
@@ -340,7 +346,7 @@ __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__
     const double *K = g_sd.log_c;
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
-    const double2 t = tab[(hi >> 12) & 255];
+    const double2 t = tab[((hi >> 12) & 255) * PD_REP];
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // (double)((hi >> 20) - 1023): biased exponent in the low word of 2^52, minus (2^52 + 1023);
     // x > 0 here, so the sign bit needs no masking
@@ -434,10 +440,10 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
 #pragma unroll 1
     for (int w = 0; w < 12; ++w) {
         double2 pt[8];
-        pt[0] = ptsL[wl & 255]; pt[1] = ptsD[wd & 255];
-        pt[2] = ptsL[(wl >> 8) & 255]; pt[3] = ptsD[(wd >> 8) & 255];
-        pt[4] = ptsL[(wl >> 16) & 255]; pt[5] = ptsD[(wd >> 16) & 255];
-        pt[6] = ptsL[wl >> 24]; pt[7] = ptsD[wd >> 24];
+        pt[0] = ptsL[(wl & 255) * PD_REP]; pt[1] = ptsD[(wd & 255) * PD_REP];
+        pt[2] = ptsL[((wl >> 8) & 255) * PD_REP]; pt[3] = ptsD[((wd >> 8) & 255) * PD_REP];
+        pt[4] = ptsL[((wl >> 16) & 255) * PD_REP]; pt[5] = ptsD[((wd >> 16) & 255) * PD_REP];
+        pt[6] = ptsL[(wl >> 24) * PD_REP]; pt[7] = ptsD[(wd >> 24) * PD_REP];
         const double c[8] = {cl0.x, cd0.x, cl0.y, cd0.y, cl1.x, cd1.x, cl1.y, cd1.y};
         // prefetch trip w + 1 (trip 12 = the tail: words ib[12], coefficient pair c2[24])
         wl = __ldg(rl.ib + w + 1); wd = __ldg(rd.ib + w + 1);
@@ -451,7 +457,7 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
         }
         double2 t[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = logtab[(__double2hiint(r2[i]) >> 12) & 255];
+        for (int i = 0; i < 8; ++i) t[i] = logtab[((__double2hiint(r2[i]) >> 12) & 255) * PD_REP];
         double term[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) term[i] = (c[i] * r2[i]) * fast_log_t<DEG>(r2[i], t[i]);
@@ -459,10 +465,10 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
         l0 += term[4]; d0 += term[5]; l1 += term[6]; d1 += term[7];
     }
     {
-        l0 = tps_acc<DEG>(l0, cl0.x, M, aL, ptsL[wl & 255], logtab);
-        d0 = tps_acc<DEG>(d0, cd0.x, M, aD, ptsD[wd & 255], logtab);
-        l1 = tps_acc<DEG>(l1, cl0.y, M, aL, ptsL[(wl >> 8) & 255], logtab);
-        d1 = tps_acc<DEG>(d1, cd0.y, M, aD, ptsD[(wd >> 8) & 255], logtab);
+        l0 = tps_acc<DEG>(l0, cl0.x, M, aL, ptsL[(wl & 255) * PD_REP], logtab);
+        d0 = tps_acc<DEG>(d0, cd0.x, M, aD, ptsD[(wd & 255) * PD_REP], logtab);
+        l1 = tps_acc<DEG>(l1, cl0.y, M, aL, ptsL[((wl >> 8) & 255) * PD_REP], logtab);
+        d1 = tps_acc<DEG>(d1, cd0.y, M, aD, ptsD[((wd >> 8) & 255) * PD_REP], logtab);
     }
     vL = rbf_poly(rl, l0 + l1, M, aL);
     vD = rbf_poly(rd, d0 + d1, M, aD);
@@ -485,8 +491,8 @@ __device__ __forceinline__ void rbf_eval2_coop(const double *__restrict__ rowsL,
     double l = 0.0, d = 0.0;
 #pragma unroll
     for (int k = sub; k < 50; k += COOP) {
-        l = tps_acc<DEG>(l, __ldg(rl.base + k), M, aL, ptsL[__ldg(ibl + k)], logtab);
-        d = tps_acc<DEG>(d, __ldg(rd.base + k), M, aD, ptsD[__ldg(ibd + k)], logtab);
+        l = tps_acc<DEG>(l, __ldg(rl.base + k), M, aL, ptsL[(int)__ldg(ibl + k) * PD_REP], logtab);
+        d = tps_acc<DEG>(d, __ldg(rd.base + k), M, aD, ptsD[(int)__ldg(ibd + k) * PD_REP], logtab);
     }
     // only the lanes of this group are guaranteed to be here (other groups of the warp may be
     // between episodes), so the shuffles name exactly the group
@@ -523,12 +529,13 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     else sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[0], g_sd.cl_levels, M, aL, status);
     double vL, vD;
     constexpr int DEG = sizeof(R) == 8 ? 5 : 4;
+    const int copy = threadIdx.x & (PD_REP - 1);          // this lane's replica of the tables
     if constexpr (COOP == 1)
-        rbf_eval2<DEG>(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts, aD, M,
-                       sh->logtab, vL, vD);
+        rbf_eval2<DEG>(g_tb.cl.rows, sidL, sh->cl_pts + copy, aL, g_tb.cd.rows, sidD, sh->cd_pts + copy, aD, M,
+                       sh->logtab + copy, vL, vD);
     else
-        rbf_eval2_coop<DEG, COOP>(g_tb.cl.rows, sidL, sh->cl_pts, aL, g_tb.cd.rows, sidD, sh->cd_pts, aD,
-                                  M, sh->logtab, vL, vD);
+        rbf_eval2_coop<DEG, COOP>(g_tb.cl.rows, sidL, sh->cl_pts + copy, aL, g_tb.cd.rows, sidD,
+                                  sh->cd_pts + copy, aD, M, sh->logtab + copy, vL, vD);
     C_L = zero ? R(0) : (R)(flip ? -vL : vL);
     C_D = (R)vD;
 }

@@ -77,10 +77,21 @@ __device__ __forceinline__ void shape_action(Action<(PHASE == 0 ? 1 : 4)> &a) {
 
 // small hot tables -> shared memory; every thread of the block must call this
 __device__ __forceinline__ void stage_tables(SharedTables *sh) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->logtab[i] = g_tb.logtab[i];
-    for (int i = threadIdx.x; i < g_tb.cd.n_points; i += blockDim.x) sh->cd_pts[i] = g_tb.cd.points[i];
-    for (int i = threadIdx.x; i < g_tb.cl.n_points; i += blockDim.x) sh->cl_pts[i] = g_tb.cl.points[i];
+    for (int i = threadIdx.x; i < 256 * PD_REP; i += blockDim.x) sh->logtab[i] = g_tb.logtab[i / PD_REP];
+    for (int i = threadIdx.x; i < g_tb.cd.n_points * PD_REP; i += blockDim.x) sh->cd_pts[i] = g_tb.cd.points[i / PD_REP];
+    for (int i = threadIdx.x; i < g_tb.cl.n_points * PD_REP; i += blockDim.x) sh->cl_pts[i] = g_tb.cl.points[i / PD_REP];
     __syncthreads();
+}
+
+// Block size so that the batch fills the SMs in whole waves of one block per SM:
+// 65 536 envs / 148 SMs -> 448 threads x 147 blocks (14 warps on every SM).
+static inline void big_block_config(long long lanes, int n_sm, int &threads, int &blocks) {
+    long long waves = (lanes + (long long)n_sm * 512 - 1) / ((long long)n_sm * 512);
+    long long per = (lanes + n_sm * waves - 1) / (n_sm * waves);
+    threads = (int)((per + 31) / 32 * 32);
+    if (threads < 64) threads = 64;
+    if (threads > 512) threads = 512;
+    blocks = (int)((lanes + threads - 1) / threads);
 }
 
 // ------------------------------------------------------------------ reset kernel
@@ -125,11 +136,12 @@ __global__ void observe_kernel(EnvSoA e, R *obs) {
 #define PD_STEP_MIN_BLOCKS 8
 #endif
 template <typename R, typename RT, int PHASE, int RTD, bool WIND>
-__global__ void __launch_bounds__(64, PD_STEP_MIN_BLOCKS)
+__global__ void __launch_bounds__(512, 1)
 step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
-    __shared__ SharedTables sh;
+    extern __shared__ __align__(16) unsigned char pd_smem[];
+    SharedTables &sh = *reinterpret_cast<SharedTables *>(pd_smem);
     stage_tables(&sh);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n) return;
@@ -269,11 +281,12 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
 // (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for POLICY_TAPE,
 // LandingBurn.run_closed_loop for POLICY_CLASSICAL.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(512, 1)
 rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
-    __shared__ SharedTables sh;
+    extern __shared__ __align__(16) unsigned char pd_smem[];
+    SharedTables &sh = *reinterpret_cast<SharedTables *>(pd_smem);
     stage_tables(&sh);
     // Persistent lanes with a work queue: episode lengths are ragged (P: 101..460 steps,
     // G: 7..27), so a lane that finishes pulls the next episode index instead of idling until
@@ -414,8 +427,15 @@ struct Launch {
     template <int PHASE, int RTD, bool WIND>
     static void step_t(const EnvSoA &e, const StepIO &io, const WindCtx &wc, const double *sig,
                        int auto_reset, cudaStream_t st) {
-        int threads = 64, blocks = (e.n + threads - 1) / threads;   // 65 536 envs -> 6.9 blocks / SM
-        step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, 0, st>>>(e, io, wc, sig, auto_reset);
+        int threads, blocks;
+        big_block_config(e.n, 148, threads, blocks);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(step_kernel<R, RT, PHASE, RTD, WIND>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedTables));
+            attr = true;
+        }
+        step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, sizeof(SharedTables), st>>>(e, io, wc, sig, auto_reset);
     }
     static void step(int phase, int rtd, int wind, const EnvSoA &e, const StepIO &io,
                      const WindCtx &wc, const double *sig, int auto_reset, cudaStream_t st) {
@@ -438,17 +458,26 @@ struct Launch {
         // work queue.  Fewer episodes than ~1/4 of the GPU's lanes: 8 lanes co-operate on each
         // episode (splits the 100 RBF terms per sub-step), which both fills the SMs and cuts the
         // per-step latency that bounds a generation by its longest episode.
-        const int threads = 64, cap = 148 * 8;
-        const bool coop = (long long)io.n_episodes * 8 <= (long long)cap * threads / 2 * 3 / 2;
+        const int n_sm = 148;
+        const bool coop = (long long)io.n_episodes * 8 <= (long long)n_sm * 512 * 3 / 4;
         const int lanes_per = coop ? 8 : 1;
         long long lanes = (long long)io.n_episodes * lanes_per;
-        int blocks = (int)((lanes + threads - 1) / threads);
-        if (blocks > cap) blocks = cap;
+        int threads, blocks;
+        big_block_config(lanes, n_sm, threads, blocks);
+        if (blocks > n_sm) blocks = n_sm;              // persistent: the queue feeds the rest
         init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads / lanes_per);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedTables));
+            cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedTables));
+            attr = true;
+        }
         if (coop)
-            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, 0, st>>>(io, wc, sig, status);
+            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, sizeof(SharedTables), st>>>(io, wc, sig, status);
         else
-            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, 0, st>>>(io, wc, sig, status);
+            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, sizeof(SharedTables), st>>>(io, wc, sig, status);
     }
     static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
                        const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {
