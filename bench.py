@@ -288,20 +288,37 @@ def run_cuda(args):
         idx, best, best_pos = ev.broadcast_best(fitness, pos[lo:hi], args.particles)
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt, stats["steps"], stats["capped"]], device=dev, dtype=torch.float64)
+        # device-resident optimiser (swarm never leaves HBM): whole generations
+        params = dict(pso_mod.PSO_PARAMS[phase], pop_size=args.particles)
+        sw = pso_mod.DeviceSwarm(model, args.particles, params, n_seeds=args.seeds, seed=5, max_steps=4096)
+        sw.step()
+        barrier()
+        g0 = time.perf_counter()
+        n_gen = 5
+        gsteps = 0.0
+        for _ in range(n_gen):
+            sw.step()
+            gsteps += float(sw.last_steps.sum())
+        barrier()
+        gdt = (time.perf_counter() - g0) / n_gen
+        tt = torch.tensor([dt, stats["steps"], stats["capped"], gdt, gsteps / n_gen], device=dev, dtype=torch.float64)
         if world > 1:
             mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            dt, tot_steps, capped = float(mx[0]), float(sm[1]), int(sm[2])
+            dt, tot_steps, capped, gdt, gsteps = float(mx[0]), float(sm[1]), int(sm[2]), float(mx[3]), float(sm[4])
         else:
-            tot_steps, capped = stats["steps"], stats["capped"]
+            tot_steps, capped, gsteps = stats["steps"], stats["capped"], gsteps / n_gen
         episodes = args.particles * args.seeds
         pso = {"phase": phase, "particles": args.particles, "wind_seeds": args.seeds, "wind": bool(args.pso_wind),
                "fitness_evals_per_s": args.particles / dt, "episodes_per_s": episodes / dt,
                "env_steps_per_s": tot_steps / dt, "ms": dt * 1e3, "mean_episode_steps": tot_steps / episodes,
                "episodes_hitting_step_cap": capped, "best_fitness": best, "best_index": idx,
                "collectives": "1 all_gather(fp64 fitness) + 1 broadcast(best position) per generation",
-               "timing": "wall clock between device-synchronised barriers, max over ranks"}
+               "timing": "wall clock between device-synchronised barriers, max over ranks",
+               "device_swarm": {"ms_per_generation": gdt * 1e3, "fitness_evals_per_s": args.particles / gdt,
+                                "env_steps_per_s": gsteps / gdt,
+                                "what": "evaluate (rollout kernel) + fitness all-gather + sub-swarm best "
+                                        "broadcast + pd_pso_update, swarm resident in HBM"}}
 
     # ---- SAC data collection (config 4 shape): shared 2-256-256-(1,1) actor on the tensor cores
     # + fused env step with stochastic wind, 131 072 envs per GPU, auto-reset

@@ -223,6 +223,18 @@ int pd_collect_shared_actor(PdEnv *env, const PdSharedActor *actor, int n_steps,
 int pd_actor_forward(PdEnv *env, const PdSharedActor *actor, const float *obs, int n, float *act,
                      float *mean_out, void *stream);
 
+/* Device-resident swarm update of one PSO generation for this rank's n particles
+ * (particle_swarm_optimisation.py:431-436 personal bests, :517-521 velocity with the sub-swarm
+ * best and ONE scalar r1, r2 per particle, :112-118 position clamp).  All pointers dev.
+ *   x, v, best [n*P] fp64 (updated in place), best_fit [n], fitness [n] (of x), swarm_of int32[n],
+ *   swarm_best [S*P] (sub-swarm bests, already including this generation),
+ *   weights_out float[n*P] or NULL (fp32 copy of the new x for the next pd_rollout_pso).
+ *   r1, r2 = Philox(seed, generation, index0 + i): independent of the sharding. */
+int pd_pso_update(double *x, double *v, double *best, double *best_fit, const double *fitness,
+                  const int32_t *swarm_of, const double *swarm_best, float *weights_out, int n, int P,
+                  int64_t index0, double w, double c1, double c2, double lo, double hi, uint64_t seed,
+                  int generation, void *stream);
+
 /* The physics constants of a handle live in __constant__ memory shared by all handles of the
  * same precision in the process; every entry point re-uploads them when the active handle
  * changes.  A caller that replays launches captured in a CUDA graph must call pd_activate

@@ -11,6 +11,7 @@
 #include "pd_device.cuh"
 #include "pd_impl.h"
 #include "pd_actor.h"
+#include "pd_pso.h"
 
 using namespace pd;
 
@@ -333,6 +334,21 @@ int pd_set_wind_tape(PdEnv *e, const double *tape, int tape_len, const double *s
     e->tape = tape;
     e->tape_len = tape ? tape_len : 0;
     e->sigma_uv = sigma_uv;
+    return 0;
+}
+
+int pd_pso_update(double *x, double *v, double *best, double *best_fit, const double *fitness,
+                  const int32_t *swarm_of, const double *swarm_best, float *weights_out, int n, int P,
+                  int64_t index0, double w, double c1, double c2, double lo, double hi, uint64_t seed,
+                  int generation, void *stream) {
+    if (!x || !v || !best || !best_fit || !fitness || !swarm_of || !swarm_best || n <= 0 || P <= 0)
+        return fail("pd_pso_update: bad argument");
+    PsoUpdateArgs a;
+    a.x = x; a.v = v; a.best = best; a.best_fit = best_fit; a.fitness = fitness; a.swarm_of = swarm_of;
+    a.swarm_best = swarm_best; a.weights_out = weights_out; a.n = n; a.P = P; a.index0 = index0;
+    a.w = w; a.c1 = c1; a.c2 = c2; a.lo = lo; a.hi = hi; a.seed = seed; a.generation = generation;
+    if (pso_update_launch(a, (cudaStream_t)stream)) return fail("pd_pso_update: launch failed");
+    g_launches++;
     return 0;
 }
 

@@ -351,3 +351,121 @@ class ParticleSubswarmOptimisation:
                        'enable_wind': self.enable_wind, 'stochastic_wind': self.stochastic_wind,
                        'horiontal_wind_percentile': self.horiontal_wind_percentile,
                        'n_seeds': self.n_seeds}, f, indent=1)
+
+
+class DeviceSwarm:
+    """Device-resident sub-swarm PSO for large swarms (BASELINE config 5): positions,
+    velocities and personal bests stay in HBM as fp64, the fitness evaluation is the persistent
+    rollout kernel, the update is `pd_pso_update`, and the only per-generation communication is
+    one all-gather of the fp64 fitness slice plus one broadcast of a sub-swarm best position
+    (only in generations where that sub-swarm improved).
+
+    Particles are block-sharded: rank r owns [lo, hi) = shard_bounds(N, world, r); sub-swarms are
+    index ranges of the global swarm as in `initialize_swarms` (:389-411).  r1, r2 come from
+    Philox keyed by the global particle index, so the optimisation trajectory is identical for
+    every world size.
+    """
+
+    def __init__(self, model, n_particles, pso_params, n_seeds=1, seed=0, max_steps=4096, group=None):
+        import ctypes as C
+        import torch
+        from . import _native as N
+        self.torch, self.C, self.N = torch, C, N
+        self.model, self.n_seeds, self.seed, self.max_steps = model, n_seeds, int(seed), max_steps
+        self.env = model._b
+        self.dev = self.env.device
+        self.lib = N.load_library()
+        p = dict(pso_params)
+        self.params = p
+        self.N_total, self.P = int(n_particles), len(model.bounds)
+        self.S = p['num_sub_swarms']
+        self.lo_b, self.hi_b = float(model.bounds[0][0]), float(model.bounds[0][1])
+        try:
+            import torch.distributed as dist
+            self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        except Exception:
+            self.dist = None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.lo, self.hi = shard_bounds(self.N_total, self.world, self.rank)
+        n = self.hi - self.lo
+        # initial positions: one uniform draw per (particle, parameter), keyed by global index
+        g = torch.Generator(device="cpu")
+        g.manual_seed(self.seed)
+        full = torch.rand(self.N_total, self.P, generator=g, dtype=torch.float64) \
+            if self.N_total * self.P <= 1 << 26 else None
+        if full is not None:
+            x0 = full[self.lo:self.hi]
+        else:       # very large swarms: per-rank stream (still deterministic per world size)
+            g.manual_seed(self.seed * 1000003 + self.rank)
+            x0 = torch.rand(n, self.P, generator=g, dtype=torch.float64)
+        self.x = (self.lo_b + (self.hi_b - self.lo_b) * x0).to(self.dev).contiguous()
+        self.v = torch.zeros_like(self.x)
+        self.best = self.x.clone()
+        self.best_fit = torch.full((n,), float("inf"), dtype=torch.float64, device=self.dev)
+        sub = self.N_total // self.S
+        gidx = torch.arange(self.lo, self.hi, device=self.dev)
+        self.swarm_of = torch.clamp(gidx // max(sub, 1), max=self.S - 1).to(torch.int32).contiguous()
+        self.swarm_of_all = torch.clamp(torch.arange(self.N_total, device=self.dev) // max(sub, 1), max=self.S - 1)
+        self.swarm_best = torch.zeros(self.S, self.P, dtype=torch.float64, device=self.dev)
+        self.swarm_best_fit = torch.full((self.S,), float("inf"), dtype=torch.float64, device=self.dev)
+        self.weights = self.x.to(torch.float32).contiguous()
+        self.generation = 0
+        self.global_best_fitness = float("inf")
+        self.global_best_position = None
+        width = -(-self.N_total // self.world)
+        self._width = width
+        self._send = torch.full((width,), float("inf"), dtype=torch.float64, device=self.dev)
+        self._recv = torch.empty(self.world * width, dtype=torch.float64, device=self.dev)
+
+    def _gather_fitness(self, local):
+        torch = self.torch
+        if self.world == 1:
+            return local
+        self._send.fill_(float("inf"))
+        self._send[:local.numel()] = local
+        self.dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        parts = [self._recv[r * self._width: r * self._width + (shard_bounds(self.N_total, self.world, r)[1]
+                                                               - shard_bounds(self.N_total, self.world, r)[0])]
+                 for r in range(self.world)]
+        return torch.cat(parts)
+
+    def step(self):
+        """One generation; returns the full fitness vector (device tensor)."""
+        torch, C = self.torch, self.C
+        p = self.params
+        fit, steps, tid = self.env.rollout_pso(self.weights, n_seeds=self.n_seeds, max_steps=self.max_steps)
+        local = fit.reshape(-1, self.n_seeds).mean(dim=1)
+        allfit = self._gather_fitness(local)
+        # sub-swarm bests: arg-min per index range, position broadcast from the owner
+        for k in range(self.S):
+            mask = self.swarm_of_all == k
+            masked = torch.where(mask, allfit, torch.full_like(allfit, float("inf")))
+            j = int(torch.argmin(masked))
+            fj = float(masked[j])
+            if fj < float(self.swarm_best_fit[k]):
+                self.swarm_best_fit[k] = fj
+                row = self.swarm_best[k]
+                if self.lo <= j < self.hi:
+                    row.copy_(self.x[j - self.lo])
+                if self.world > 1:
+                    owner = next(r for r in range(self.world)
+                                 if shard_bounds(self.N_total, self.world, r)[0] <= j
+                                 < shard_bounds(self.N_total, self.world, r)[1])
+                    src = self.dist.get_global_rank(self.group, owner) if self.group else owner
+                    self.dist.broadcast(row, src=src, group=self.group)
+        kbest = int(torch.argmin(self.swarm_best_fit))
+        if float(self.swarm_best_fit[kbest]) < self.global_best_fitness:
+            self.global_best_fitness = float(self.swarm_best_fit[kbest])
+            self.global_best_position = self.swarm_best[kbest].clone()
+        w = p['w_start'] - (p['w_start'] - p['w_end']) * self.generation / p['generations']
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        self.N.check(self.lib.pd_pso_update(
+            ptr(self.x), ptr(self.v), ptr(self.best), ptr(self.best_fit), ptr(local.contiguous()),
+            ptr(self.swarm_of), ptr(self.swarm_best), ptr(self.weights), self.hi - self.lo, self.P,
+            self.lo, float(w), float(p['c1']), float(p['c2']), self.lo_b, self.hi_b, self.seed,
+            self.generation, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.generation += 1
+        self.last_steps = steps
+        return allfit

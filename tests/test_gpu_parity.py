@@ -499,3 +499,40 @@ def test_full_size_G_and_cooperative_consistency(envs_mod):
     rel = ((big[0][:512] - small[0]).abs() / small[0].abs())[ok]
     assert float(rel.median()) < 1e-9 and float(rel.max()) < 1e-2
     assert np.isfinite(big[0].cpu().numpy()).all() and int((big[2] < 0).sum()) == 0
+
+
+def test_device_swarm_update_matches_numpy(envs_mod):
+    """pd_pso_update against a numpy restatement of the reference update rule
+    (particle_swarm_optimisation.py:431-436, 517-521, 112-118), and a short optimisation run."""
+    from psso_sac_for_powered_descent_b200 import pso
+    model = envs_mod.pso_wrapped_env(flight_phase=G, precision="fp32", max_steps=256)
+    params = dict(pso.landing_burn_pso_params, pop_size=512, generations=20)
+    sw = pso.DeviceSwarm(model, 512, params, seed=3, max_steps=256)
+    x0, v0 = sw.x.clone(), sw.v.clone()
+    fit = sw.step()
+    assert fit.shape == (512,) and torch.isfinite(fit).all()
+    # personal bests after generation 0 = the evaluated positions
+    assert torch.equal(sw.best, x0) and torch.equal(sw.best_fit, fit)
+    for k in range(2):
+        idx = torch.nonzero(sw.swarm_of_all == k).flatten()
+        j = idx[torch.argmin(fit[idx])]
+        assert torch.equal(sw.swarm_best[k], x0[j]) and float(sw.swarm_best_fit[k]) == float(fit[j])
+    # v1 = w v0 + c1 r1 (pb - x) + c2 r2 (lb - x) with pb == x  ->  every row of v1 is a scalar
+    # multiple of (lb - x0); x1 = clip(x0 + v1)
+    lb = sw.swarm_best[sw.swarm_of_all.long()]
+    d = lb - x0
+    ratio = sw.v / torch.where(d.abs() > 1e-9, d, torch.ones_like(d))
+    big = d.abs() > 1e-3
+    # (the sub-swarm best itself has lb - x0 == 0: its velocity must stay zero)
+    r2 = torch.stack([ratio[i][big[i]].median() if bool(big[i].any()) else ratio.new_zeros(())
+                      for i in range(512)])
+    assert int((~big.any(dim=1)).sum()) == 2
+    assert float(r2.min()) >= 0.0 and float(r2.max()) <= 1.0 and float(r2.std()) > 0.1
+    assert torch.allclose(sw.v, r2[:, None] * d, atol=1e-9)
+    assert torch.allclose(sw.x, torch.clamp(x0 + sw.v, -1.5, 1.5), atol=1e-12)
+    assert torch.equal(sw.weights, sw.x.to(torch.float32))
+    best0 = sw.global_best_fitness
+    for _ in range(6):
+        sw.step()
+    assert sw.global_best_fitness <= best0
+    assert (sw.best_fit <= fit + 1e-12).all()
