@@ -105,6 +105,34 @@ def _cpu_worker(args):
     return done_steps, time.perf_counter() - t0
 
 
+def _cpu_pso_worker(args):
+    """evaluate_worker_function of the reference: a fresh model per particle, one episode."""
+    seed, phase = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)          # one worker per core; avoids intra-op oversubscription
+    from oracle import pd_oracle as O
+    t0 = time.perf_counter()
+    model = O.PsoModel(phase, tables=O.Tables(fast_rbf=False), max_steps=4096)
+    pos = np.random.default_rng(seed).uniform(-1.5, 1.5, model.n_params)
+    f = model.objective_function(pos)
+    return model.steps, time.perf_counter() - t0, f
+
+
+def cpu_pso_rate(phase, per_core=4, cores=None):
+    """PSO fitness evals/s of the oracle port under multiprocessing.Pool(all cores) - the
+    reference's parallel_evaluate structure (a new env per particle, one episode each)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(i, 2, False) for i in range(cores)])
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_pso_worker, [(500 + i, phase) for i in range(cores * per_core)])
+        dt = time.perf_counter() - t0
+    return len(res) / dt, sum(r[0] for r in res) / dt, cores, len(res)
+
+
 def cpu_rate(n_steps_per_core, cores=None, repeats=1):
     """The oracle port (same scipy RBFInterpolator-per-call cost structure as the reference's
     env.step) on `cores` processes; returns env-steps/s aggregate."""
@@ -369,6 +397,13 @@ def run_cuda(args):
                "sample": f"{cores} processes x {args.cpu_steps_per_core} env.step calls of oracle/pd_oracle.py "
                          "(scalar Python port of the reference env, scipy RBFInterpolator per call), "
                          "same phase / rtd / random-action workload"}
+        if pso is not None:
+            ev_s, st_s, c2, n_ep = cpu_pso_rate(args.pso_phase)
+            cpu["pso_fitness_evals_per_s"] = ev_s
+            cpu["pso_env_steps_per_s"] = st_s
+            cpu["pso_sample"] = (f"{n_ep} random particles, Pool({c2}) over the oracle's objective_function with a "
+                                 "fresh model per particle (the reference's evaluate_worker_function structure)")
+            pso["vs_cpu_port"] = pso["fitness_evals_per_s"] / ev_s
     line = {
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,

@@ -14,8 +14,9 @@ following, function by function (paths relative to /root/reference):
 
     isa()                 src/envs/utils/atmosphere_dynamics.py:5-27 + the third-party
                           `ambiance` package (ICAO-1993 ISA; NOT under /root/reference,
-                          version unpinned upstream -> pinned only indirectly through
-                          the golden trajectories)
+                          version unpinned upstream).  PARITY UNPINNED at the ambiance
+                          boundary: its published algorithm is restated here and pinned only
+                          indirectly, through the reference's golden trajectories
     gravity()             src/envs/utils/atmosphere_dynamics.py:29-33
     cd()/cl()             src/envs/utils/aerodynamic_coefficients.py:57-66,105-132 and
                           src/envs/rockets_physics.py:711-712 (degrees passed twice)
