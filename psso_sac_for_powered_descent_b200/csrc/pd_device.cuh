@@ -127,6 +127,10 @@ __device__ __forceinline__ double m_min(double a, double b) { return fmin(a, b);
 __device__ __forceinline__ float m_min(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double m_hypot(double a, double b) { return hypot(a, b); }
 __device__ __forceinline__ float m_hypot(float a, float b) { return hypotf(a, b); }
+// division: IEEE in the parity build; reciprocal-multiply (2 ulp, no slow-path branch) in the
+// fp32 production build, whose tolerance is 1e-5
+__device__ __forceinline__ double m_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float m_div(float a, float b) { return __fdividef(a, b); }
 
 // ------------------------------------------------------------------ per-env registers
 struct State {
@@ -159,7 +163,7 @@ __device__ __forceinline__ void isa(R alt, R &rho, R &p, R &a) {
         return;
     }
     const R RE = R(6356766.0);
-    R H = RE * alt / (RE + alt);
+    R H = m_div(RE * alt, RE + alt);
     int k = 1;
 #pragma unroll
     for (int j = 2; j < 8; ++j)
@@ -172,7 +176,7 @@ __device__ __forceinline__ void isa(R alt, R &rho, R &p, R &a) {
     else
         p = c.isa_pb[k] * m_pow(R(1) + c.isa_boT[k] * dH, c.isa_expo[k]);
     const R Rgas = R(287.05287);
-    rho = p / (Rgas * T);
+    rho = m_div(p, Rgas * T);
     a = m_sqrt(R(1.4 * 287.05287) * T);
 }
 
@@ -195,14 +199,14 @@ __device__ __forceinline__ void cog_inertia(R fill, R &x_cog, R &inertia) {
     R a_ox = c.h_lower + h_ox_t / R(2);
     R a_f = c.h_lower + c.h_ox + h_f_t / R(2);
     R m_p = m_ox_t + m_f_t;
-    R x_prop = (m_ox_t * a_ox + m_f_t * a_f) / m_p;
+    R x_prop = m_div(m_ox_t * a_ox + m_f_t * a_f, m_p);
     R d_ox = a_ox - x_prop;
     R d_f = a_f - x_prop;
     const R twelfth = R(1.0 / 12);
     R I_ox = twelfth * m_ox_t * (h_ox_t * h_ox_t) + m_ox_t * (d_ox * d_ox);
     R I_f = twelfth * m_f_t * (h_f_t * h_f_t) + m_f_t * (d_f * d_f);
     R I_prop = I_ox + I_f;
-    R x_wet = (c.m_dry * c.x_dry + m_p * x_prop) / (c.m_dry + m_ox_t + m_f_t);
+    R x_wet = m_div(c.m_dry * c.x_dry + m_p * x_prop, c.m_dry + m_ox_t + m_f_t);
     R dd = c.x_dry - x_wet;
     R dp = x_prop - x_wet;
     R I_dry_hat = c.I_dry + c.m_dry * (dd * dd);
@@ -375,7 +379,7 @@ __device__ __forceinline__ double tps_acc(double acc, double c2, double M, doubl
 }
 
 // Row of one neighbour set: 64 doubles = 50 coefficients (already halved), 3 polynomial
-// coefficients, shift(2), scale(2), then 50 point-index bytes.
+// coefficients, shift(2), 1/scale(2), then 50 point-index bytes.
 struct RbfRow {
     const double2 *c2;
     const unsigned int *ib;
@@ -392,9 +396,11 @@ __device__ __forceinline__ double rbf_poly(const RbfRow &r, double acc, double M
     const double2 p0 = __ldg(r.c2 + 25);     // c50, c51
     const double2 p1 = __ldg(r.c2 + 26);     // c52, shift_m
     const double2 p2 = __ldg(r.c2 + 27);     // shift_a, scale_m
-    const double sa = __ldg(r.base + 56);
-    const double xh = (M - p1.y) / p2.y;
-    const double yh = (a - p2.x) / sa;
+    const double isa = __ldg(r.base + 56);
+    // the row stores 1/scale (host-side division): two multiplies instead of two fp64 divisions
+    // on the serial tail of every evaluation; moves the result by < 1 ulp of the polynomial part
+    const double xh = (M - p1.y) * p2.y;
+    const double yh = (a - p2.x) * isa;
     return acc + p0.x + p0.y * xh + p1.x * yh;
 }
 
@@ -407,17 +413,14 @@ __device__ __forceinline__ double fast_log_t(double x, double2 t) {
     const int lo = __double2loint(x);
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     const double ed = __hiloint2double(0x43300000, hi >> 20) - K[5];
+    const double s = fma(ed, K[4], t.y);            // e ln2 - log u_j : independent of the polynomial
     const double r = fma(m, t.x, K[6]);
-    double p;
-    if (DEG >= 5) {
-        p = fma(r, K[0], K[1]);
-        p = fma(p, r, K[2]);
-    } else {
-        p = fma(r, K[1], K[2]);
-    }
-    p = fma(p, r, K[3]);
-    p = fma(p * r, r, r);
-    return fma(ed, K[4], t.y + p);
+    // log1p(r) = r + r^2 q(r), Estrin form: dependent depth 3 after r instead of 4-5
+    const double r2 = r * r;
+    double q = fma(r, K[2], K[3]);                  // -1/2 + r/3
+    if (DEG >= 5) q = fma(r2, fma(r, K[0], K[1]), q);   // + r^2 (-1/4 + r/5)
+    else q = fma(r2, K[1], q);                          // - r^2/4
+    return s + fma(r2, q, r);
 }
 
 // Values of two interpolants (C_L at (M, aL) from set sidL, C_D at (M, aD) from set sidD) in one
@@ -834,9 +837,9 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     R rho, p_atm, a_snd;
     isa<R>(y, rho, p_atm, a_snd);
     R speed = m_sqrt(vx * vx + vy * vy);
-    R mach = a_snd != R(0) ? m_min(speed / a_snd, R(10)) : R(0);
+    R mach = a_snd != R(0) ? m_min(m_div(speed, a_snd), R(10)) : R(0);
     R q = R(0.5) * rho * (speed * speed);
-    R fuel = (c.m_prop0 - (R)s.m_prop) / c.m_prop0;
+    R fuel = m_div(c.m_prop0 - (R)s.m_prop, c.m_prop0);
     if (fuel == R(0)) fuel = R(1e-6);
     R x_cog, inertia;
     cog_inertia<R>(R(1) - fuel, x_cog, inertia);
@@ -884,20 +887,20 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     R c_x = c_par * ct + c_perp * st;
     R c_y = c_par * st - c_perp * ct;
     const R RE = R(6371000.0);
-    R gr = RE / (RE + y);
+    R gr = m_div(RE, RE + y);
     R g = R(9.80665) * (gr * gr);
     R fx = aero_x + c_x + f_wind_x;
     R fy = aero_y + c_y;
     R mass = (R)s.mass;
-    R vx_dot = fx / mass;
-    R vy_dot = fy / mass - g;
+    R vx_dot = m_div(fx, mass);
+    R vy_dot = m_div(fy, mass) - g;
     const double dt = g_sd.dt_phys;
     s.vx += (double)(vx_dot * c.dt_phys);
     s.vy += (double)(vy_dot * c.dt_phys);
     s.x += s.vx * dt;
     s.y += s.vy * dt;
     R mz = c_mz + aero_mz;
-    R tdd = mz / inertia;
+    R tdd = m_div(mz, inertia);
     s.theta_dot += (double)(tdd * c.dt_phys);
     s.theta += s.theta_dot * dt;
     double gam = atan2(s.vy, s.vx);

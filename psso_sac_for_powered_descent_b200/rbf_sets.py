@@ -383,7 +383,7 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None
     val = np.asarray(val, float)
     box = np.asarray(boxes, float).reshape(-1)
     tag = hashlib.sha256(mach.tobytes() + aoa.tobytes() + val.tobytes() + box.tobytes()
-                         + repr(grids).encode() + b"v8").hexdigest()[:16]
+                         + repr(grids).encode() + b"v9").hexdigest()[:16]
     if cache_dir:
         path = os.path.join(cache_dir, f"rbf_{tag}.pkl")
         if os.path.exists(path):
@@ -438,6 +438,7 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None
         coeffs[s, 55:57] = scale
         dev = coeffs[s, :57].copy()
         dev[:50] *= 0.5            # r^2 log r = (c/2) r^2 log r^2 ; exact scaling
+        dev[55:57] = 1.0 / dev[55:57]     # device multiplies by 1/scale
         rows[s, :57 * 8] = dev.view(np.uint8)
         rows[s, 57 * 8:57 * 8 + 50] = mine_all[s].astype(np.uint8)
     H = 1

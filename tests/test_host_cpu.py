@@ -183,7 +183,8 @@ def test_device_row_layout(tables):
         assert rows.shape == (tbl.n_sets, 512)
         c = rows[:, :57 * 8].copy().view(np.float64).reshape(tbl.n_sets, 57)
         assert np.array_equal(c[:, :50], 0.5 * tbl.coeffs[:, :50])
-        assert np.array_equal(c[:, 50:57], tbl.coeffs[:, 50:57])
+        assert np.array_equal(c[:, 50:55], tbl.coeffs[:, 50:55])
+        assert np.array_equal(c[:, 55:57], 1.0 / tbl.coeffs[:, 55:57])
         idx = rows[:, 57 * 8:57 * 8 + 50]
         assert idx.max() < len(tbl.mach_sorted)
         for s in (0, tbl.n_sets // 2, tbl.n_sets - 1):
