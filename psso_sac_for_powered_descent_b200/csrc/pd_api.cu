@@ -244,6 +244,23 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
         const double *d = nullptr;
         if (dev_copy(e, tab.data(), tab.size(), &d)) { pd_destroy(e); return 1; }
         e->tb.logtab = reinterpret_cast<const double2 *>(d);
+        // SharedTables image: every entry replicated PD_REP times (entry i of copy c at i*PD_REP + c),
+        // pulled into shared memory by one TMA bulk copy per block (pd_kernels.cuh: stage_tables)
+        std::vector<double> img(pd::PD_SH_IMAGE_BYTES / sizeof(double), 0.0);
+        size_t o = 0;
+        auto put = [&](const double *src, int n_src, int n_slots) {
+            for (int i = 0; i < n_slots; ++i)
+                for (int c = 0; c < PD_REP; ++c) {
+                    img[o++] = i < n_src ? src[2 * i] : 0.0;
+                    img[o++] = i < n_src ? src[2 * i + 1] : 0.0;
+                }
+        };
+        put(tab.data(), 256, 256);
+        put(p->cd.points, p->cd.n_points, 256);
+        put(p->cl.points, p->cl.n_points, 144);
+        const double *di = nullptr;
+        if (dev_copy(e, img.data(), img.size(), &di)) { pd_destroy(e); return 1; }
+        e->tb.sh_image = di;
     }
     to_float(e->sd, e->sf);
     e->tb.n_ca = p->n_gf_ca;

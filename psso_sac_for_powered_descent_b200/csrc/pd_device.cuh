@@ -79,6 +79,7 @@ struct RbfDev {
 struct Tables {
     RbfDev cd, cl;
     const double2 *logtab;              // [256] (1/c_j rounded, -log of that), see fast_log
+    const void *sh_image;               // SharedTables image (host-replicated), source of the TMA bulk copy
     const double *ca_x, *ca_y, *ca_s;   // grid fin C_a segments (x_lo, y_lo, slope)
     const double *cn_x, *cn_y, *cn_s;
     int n_ca, n_cn;
@@ -92,12 +93,23 @@ struct Tables {
 // 16-byte bank groups, whatever (random) entries they gather: 4 wavefronts per request instead
 // of ~11 (the LSU data pipe was the busiest unit of the step kernel at 62 %,
 // profiles/r1_step_kernel_final_steady.txt).  74 KB of dynamic shared memory, one block per SM.
+// The replicated image is built once on the host (pd_create) and pulled into shared memory by
+// ONE TMA bulk copy per block (cp.async.bulk + mbarrier) while the threads load their env state:
+// the per-launch staging loop it replaces cost ~5 % of the step kernel (STS stalls in the
+// prologue, gpurun_out/prof_step_r1f).
 #define PD_REP 8
+// Each table starts on a 32 KB boundary of the shared window (the kernels round the dynamic
+// shared base up), so a gather address is base | (field & 0x7F80): one shift + one LOP3 per
+// lookup instead of shift + mask + scaled add.
 struct SharedTables {
-    double2 logtab[256 * PD_REP];
-    double2 cd_pts[192 * PD_REP];
+    double2 logtab[256 * PD_REP];       // 32 KB
+    double2 cd_pts[256 * PD_REP];       // 32 KB slot, 192 used
     double2 cl_pts[144 * PD_REP];
+    unsigned long long bar;             // mbarrier of the bulk copy (not part of the image)
 };
+constexpr unsigned PD_SH_ALIGN = 32768;
+constexpr unsigned PD_SH_BYTES = sizeof(SharedTables) + PD_SH_ALIGN;      // dynamic shared memory per block
+constexpr unsigned PD_SH_IMAGE_BYTES = (256 + 256 + 144) * PD_REP * 16;
 
 // per-TU copies (no relocatable device code): each precision TU uploads its own
 static __constant__ Scalars<double> g_sd;
@@ -404,17 +416,26 @@ __device__ __forceinline__ double rbf_poly(const RbfRow &r, double acc, double M
     return acc + p0.x + p0.y * xh + p1.x * yh;
 }
 
+__device__ __forceinline__ unsigned sh_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds_d2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
 // log with the table entry already fetched (lets the caller issue all table loads of a batch
 // of terms before the first dependent fma)
 template <int DEG>
 __device__ __forceinline__ double fast_log_t(double x, double2 t) {
     const double *K = g_sd.log_c;
     const int hi = __double2hiint(x);
-    const int lo = __double2loint(x);
-    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    // r = m u_j - 1 with m = x 2^-e: the power of two goes into u_j (integer subtract on its high
+    // word, exact), so m is never assembled: r = fma(x, u_j 2^-e, -1)
+    const int eb = hi & 0x7FF00000;
+    const double us = __hiloint2double(__double2hiint(t.x) - eb + 0x3FF00000, __double2loint(t.x));
     const double ed = __hiloint2double(0x43300000, hi >> 20) - K[5];
     const double s = fma(ed, K[4], t.y);            // e ln2 - log u_j : independent of the polynomial
-    const double r = fma(m, t.x, K[6]);
+    const double r = fma(x, us, K[6]);
     // log1p(r) = r + r^2 q(r), Estrin form: dependent depth 3 after r instead of 4-5
     const double r2 = r * r;
     double q = fma(r, K[2], K[3]);                  // -1/2 + r/3
@@ -440,13 +461,16 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
     double l0 = 0.0, l1 = 0.0, d0 = 0.0, d1 = 0.0;
     unsigned int wl = __ldg(rl.ib), wd = __ldg(rd.ib);
     double2 cl0 = __ldg(rl.c2), cl1 = __ldg(rl.c2 + 1), cd0 = __ldg(rd.c2), cd1 = __ldg(rd.c2 + 1);
+    // 32-bit shared-window addresses of this lane's replica; the tables are 32 KB aligned, so an
+    // entry address is base | (index << 7)
+    const unsigned bL = sh_addr(ptsL), bD = sh_addr(ptsD), bT = sh_addr(logtab);
 #pragma unroll 1
     for (int w = 0; w < 12; ++w) {
         double2 pt[8];
-        pt[0] = ptsL[(wl & 255) * PD_REP]; pt[1] = ptsD[(wd & 255) * PD_REP];
-        pt[2] = ptsL[((wl >> 8) & 255) * PD_REP]; pt[3] = ptsD[((wd >> 8) & 255) * PD_REP];
-        pt[4] = ptsL[((wl >> 16) & 255) * PD_REP]; pt[5] = ptsD[((wd >> 16) & 255) * PD_REP];
-        pt[6] = ptsL[(wl >> 24) * PD_REP]; pt[7] = ptsD[(wd >> 24) * PD_REP];
+        pt[0] = lds_d2(bL | ((wl << 7) & 0x7F80u)); pt[1] = lds_d2(bD | ((wd << 7) & 0x7F80u));
+        pt[2] = lds_d2(bL | ((wl >> 1) & 0x7F80u)); pt[3] = lds_d2(bD | ((wd >> 1) & 0x7F80u));
+        pt[4] = lds_d2(bL | ((wl >> 9) & 0x7F80u)); pt[5] = lds_d2(bD | ((wd >> 9) & 0x7F80u));
+        pt[6] = lds_d2(bL | ((wl >> 17) & 0x7F80u)); pt[7] = lds_d2(bD | ((wd >> 17) & 0x7F80u));
         const double c[8] = {cl0.x, cd0.x, cl0.y, cd0.y, cl1.x, cd1.x, cl1.y, cd1.y};
         // prefetch trip w + 1 (trip 12 = the tail: words ib[12], coefficient pair c2[24])
         wl = __ldg(rl.ib + w + 1); wd = __ldg(rd.ib + w + 1);
@@ -460,12 +484,14 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
         }
         double2 t[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = logtab[((__double2hiint(r2[i]) >> 12) & 255) * PD_REP];
-        double term[8];
+        for (int i = 0; i < 8; ++i) t[i] = lds_d2(bT | (((unsigned)__double2hiint(r2[i]) >> 5) & 0x7F80u));
+        double lg[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) term[i] = (c[i] * r2[i]) * fast_log_t<DEG>(r2[i], t[i]);
-        l0 += term[0]; d0 += term[1]; l1 += term[2]; d1 += term[3];
-        l0 += term[4]; d0 += term[5]; l1 += term[6]; d1 += term[7];
+        for (int i = 0; i < 8; ++i) lg[i] = fast_log_t<DEG>(r2[i], t[i]);
+        l0 = fma(c[0] * r2[0], lg[0], l0); d0 = fma(c[1] * r2[1], lg[1], d0);
+        l1 = fma(c[2] * r2[2], lg[2], l1); d1 = fma(c[3] * r2[3], lg[3], d1);
+        l0 = fma(c[4] * r2[4], lg[4], l0); d0 = fma(c[5] * r2[5], lg[5], d0);
+        l1 = fma(c[6] * r2[6], lg[6], l1); d1 = fma(c[7] * r2[7], lg[7], d1);
     }
     {
         l0 = tps_acc<DEG>(l0, cl0.x, M, aL, ptsL[(wl & 255) * PD_REP], logtab);

@@ -75,22 +75,55 @@ __device__ __forceinline__ void shape_action(Action<(PHASE == 0 ? 1 : 4)> &a) {
     }
 }
 
-// small hot tables -> shared memory; every thread of the block must call this
+// small hot tables -> shared memory.  stage_tables: every thread of the block calls it (one
+// __syncthreads); thread 0 then starts one TMA bulk copy of the host-replicated image.
+// wait_tables: every thread that goes on to read the tables calls it once, as late as possible
+// (state / window / action loads are issued in between).
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ SharedTables *aligned_tables(unsigned char *raw) {
+    const unsigned a = smem_addr(raw);
+    return reinterpret_cast<SharedTables *>(raw + (((a + PD_SH_ALIGN - 1) & ~(PD_SH_ALIGN - 1)) - a));
+}
 __device__ __forceinline__ void stage_tables(SharedTables *sh) {
-    for (int i = threadIdx.x; i < 256 * PD_REP; i += blockDim.x) sh->logtab[i] = g_tb.logtab[i / PD_REP];
-    for (int i = threadIdx.x; i < g_tb.cd.n_points * PD_REP; i += blockDim.x) sh->cd_pts[i] = g_tb.cd.points[i / PD_REP];
-    for (int i = threadIdx.x; i < g_tb.cl.n_points * PD_REP; i += blockDim.x) sh->cl_pts[i] = g_tb.cl.points[i / PD_REP];
+    const unsigned bar = smem_addr(&sh->bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PD_SH_IMAGE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(sh)), "l"(g_tb.sh_image), "r"(PD_SH_IMAGE_BYTES), "r"(bar) : "memory");
+    }
+}
+__device__ __forceinline__ void wait_tables(SharedTables *sh) {
+    const unsigned bar = smem_addr(&sh->bar);
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(0) : "memory");
+    }
 }
 
+// One block per SM, at most PD_MAX_BLOCK = 448 threads: 65 536 registers / 448 = 146, so ptxas may
+// use 144 registers per thread and keeps the loop invariants of the RBF sums (clamped angles,
+// table bases) in registers instead of rematerialising ~50 instructions per trip (128-register
+// build, gpurun_out/prof_step_r1f).
+#ifndef PD_MAX_BLOCK
+#define PD_MAX_BLOCK 448
+#endif
 // Block size so that the batch fills the SMs in whole waves of one block per SM:
 // 65 536 envs / 148 SMs -> 448 threads x 147 blocks (14 warps on every SM).
 static inline void big_block_config(long long lanes, int n_sm, int &threads, int &blocks) {
-    long long waves = (lanes + (long long)n_sm * 512 - 1) / ((long long)n_sm * 512);
+    long long waves = (lanes + (long long)n_sm * PD_MAX_BLOCK - 1) / ((long long)n_sm * PD_MAX_BLOCK);
     long long per = (lanes + n_sm * waves - 1) / (n_sm * waves);
     threads = (int)((per + 31) / 32 * 32);
     if (threads < 64) threads = 64;
-    if (threads > 512) threads = 512;
+    if (threads > PD_MAX_BLOCK) threads = PD_MAX_BLOCK;
     blocks = (int)((lanes + threads - 1) / threads);
 }
 
@@ -136,12 +169,12 @@ __global__ void observe_kernel(EnvSoA e, R *obs) {
 #define PD_STEP_MIN_BLOCKS 8
 #endif
 template <typename R, typename RT, int PHASE, int RTD, bool WIND>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
     extern __shared__ __align__(16) unsigned char pd_smem[];
-    SharedTables &sh = *reinterpret_cast<SharedTables *>(pd_smem);
+    SharedTables &sh = *aligned_tables(pd_smem);
     stage_tables(&sh);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n) return;
@@ -163,6 +196,7 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     info.rbf_status = 0;
     Rtd<R> out;
     R g1;
+    wait_tables(&sh);
     env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
     if (info.rbf_status) atomicOr(e.status, info.rbf_status);
     R obs[O];
@@ -281,13 +315,14 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
 // (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for POLICY_TAPE,
 // LandingBurn.run_closed_loop for POLICY_CLASSICAL.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = PHASE == 0 ? 1 : 4;
     constexpr int O = PHASE == 0 ? 2 : 5;
     extern __shared__ __align__(16) unsigned char pd_smem[];
-    SharedTables &sh = *reinterpret_cast<SharedTables *>(pd_smem);
+    SharedTables &sh = *aligned_tables(pd_smem);
     stage_tables(&sh);
+    wait_tables(&sh);
     // Persistent lanes with a work queue: episode lengths are ragged (P: 101..460 steps,
     // G: 7..27), so a lane that finishes pulls the next episode index instead of idling until
     // the slowest lane of its warp is done.
@@ -432,10 +467,10 @@ struct Launch {
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(step_kernel<R, RT, PHASE, RTD, WIND>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedTables));
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
             attr = true;
         }
-        step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, sizeof(SharedTables), st>>>(e, io, wc, sig, auto_reset);
+        step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, PD_SH_BYTES, st>>>(e, io, wc, sig, auto_reset);
     }
     static void step(int phase, int rtd, int wind, const EnvSoA &e, const StepIO &io,
                      const WindCtx &wc, const double *sig, int auto_reset, cudaStream_t st) {
@@ -459,7 +494,7 @@ struct Launch {
         // episode (splits the 100 RBF terms per sub-step), which both fills the SMs and cuts the
         // per-step latency that bounds a generation by its longest episode.
         const int n_sm = 148;
-        const bool coop = (long long)io.n_episodes * 8 <= (long long)n_sm * 512 * 3 / 4;
+        const bool coop = (long long)io.n_episodes * 8 <= (long long)n_sm * PD_MAX_BLOCK * 3 / 4;
         const int lanes_per = coop ? 8 : 1;
         long long lanes = (long long)io.n_episodes * lanes_per;
         int threads, blocks;
@@ -469,15 +504,15 @@ struct Launch {
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedTables));
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
             cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedTables));
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
             attr = true;
         }
         if (coop)
-            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, sizeof(SharedTables), st>>>(io, wc, sig, status);
+            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
         else
-            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, sizeof(SharedTables), st>>>(io, wc, sig, status);
+            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
     }
     static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
                        const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {

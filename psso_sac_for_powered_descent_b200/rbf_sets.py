@@ -330,6 +330,29 @@ def _sets_of_queries(tbl, M, A):
     return lo, hi
 
 
+def pack_keys(lo, hi):
+    """Vectorised pack_key for [n, L] bound arrays -> uint64[n]."""
+    lo = np.asarray(lo, np.uint64)
+    hi = np.asarray(hi, np.uint64)
+    empty = lo == hi
+    a = np.where(empty, np.uint64(0), lo & np.uint64(63))
+    b = np.where(empty, np.uint64(0), hi & np.uint64(63))
+    key = np.full(lo.shape[0], np.uint64(1) << np.uint64(63), np.uint64)
+    for l in range(lo.shape[1]):
+        key |= (a[:, l] << np.uint64(12 * l)) | (b[:, l] << np.uint64(12 * l + 6))
+    return key
+
+
+def pack_hints(lo, hi):
+    """Vectorised pack_hint for [n, L] bound arrays -> uint64[n]."""
+    lo = np.asarray(lo, np.uint64) & np.uint64(63)
+    hi = np.asarray(hi, np.uint64) & np.uint64(63)
+    h = np.zeros(lo.shape[0], np.uint64)
+    for l in range(lo.shape[1]):
+        h |= (lo[:, l] << np.uint64(12 * l)) | (hi[:, l] << np.uint64(12 * l + 6))
+    return h
+
+
 def pack_hint(lo, hi):
     h = 0
     for l in range(len(lo)):
@@ -342,15 +365,15 @@ def build_grid(tbl, box, nm, na) -> QueryGrid:
     m0, m1, a0, a1 = box
     dm = (m1 - m0) / nm
     da = (a1 - a0) / na if na > 1 else max(a1 - a0, 1e-9)
-    key_of = {}
-    for sid in range(tbl.n_sets):
-        key_of[pack_key(tbl.set_lo[sid], tbl.set_hi[sid])] = sid
+    set_keys = pack_keys(tbl.set_lo, tbl.set_hi)
+    order = np.argsort(set_keys)
+    sorted_keys = set_keys[order]
 
     def ids(M, A):
         lo, hi = _sets_of_queries(tbl, M, A)
-        out = np.empty(len(M), np.int64)
-        for i in range(len(M)):
-            out[i] = key_of.get(pack_key(lo[i], hi[i]), -1)
+        k = pack_keys(lo, hi)
+        pos = np.minimum(np.searchsorted(sorted_keys, k), len(sorted_keys) - 1)
+        out = np.where(sorted_keys[pos] == k, order[pos], -1).astype(np.int64)
         return out, lo, hi
     # corners (na+1) x (nm+1)
     cm = m0 + dm * np.arange(nm + 1)
@@ -368,7 +391,7 @@ def build_grid(tbl, box, nm, na) -> QueryGrid:
     cells = np.where(pure, zid2, 0).astype(np.int32).ravel()
     imp = np.nonzero(~pure.ravel())[0]
     cells[imp] = -(np.arange(len(imp), dtype=np.int32) + 1)
-    imp_hint = np.array([pack_hint(zlo[i], zhi[i]) for i in imp], np.uint64)
+    imp_hint = pack_hints(zlo[imp], zhi[imp]) if len(imp) else np.zeros(0, np.uint64)
     imp_id = zid[imp].astype(np.int32)
     return QueryGrid(float(m0), float(dm), int(nm), float(a0), float(da), int(len(aa)), cells,
                      imp_hint, imp_id)
@@ -472,7 +495,13 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None
 CD_BOXES = [(-0.02, 10.02, -0.2, 0.2)]
 CL_BOXES = [(-0.02, 10.02, -0.01, 10.01), (-0.02, 10.02, -10.01, -9.99)]
 _LIM = 0.17453292519943295 * (1 + 1e-9)
-# device lookup grids: (box, n_mach, n_aoa).  Mach is clamped to [0, 10] upstream; beyond the
-# last data point (Mach 5.51) the neighbour set no longer changes.
+# device lookup grids: (box, n_mach, n_aoa).  Mach is clamped to [0, 10] upstream.  The grids must
+# cover that whole range: beyond the last data point (Mach 5.51) the 50-NN set still changes
+# (cross-level distance orderings keep flipping as Mach grows), so no column can stand in for the
+# tail.  C_L 2-D grid: 4096 x 512 cells (8 MB, L2-resident) are 83 % pure against 73 % for
+# 1024 x 256, +3 % step throughput on B200 (fewer lanes take the exact walk).
 CD_GRIDS = [((0.0, 10.0, -_LIM, _LIM), 2048, 8)]
-CL_GRIDS = [((0.0, 10.0, 0.0, 10.0), 1024, 256), ((0.0, 10.0, -10.0 - 1e-9, -10.0 + 1e-9), 2048, 1)]
+CL_GRIDS = [((0.0, 10.0, 0.0, 10.0), 4096, 512), ((0.0, 10.0, -10.0 - 1e-9, -10.0 + 1e-9), 2048, 1)]
+if os.environ.get("PD_CL_GRID"):      # experiment knob: "mach_max,n_mach,n_aoa"
+    _mm, _nm, _na = os.environ["PD_CL_GRID"].split(",")
+    CL_GRIDS[0] = ((0.0, float(_mm), 0.0, 10.0), int(_nm), int(_na))
