@@ -5,10 +5,18 @@ legs may import this module; the product package never does (it fails loudly whe
 its CUDA extension is missing instead of falling back to this).
 
 It is a scalar, pure-Python/numpy/scipy restatement of the reference's algorithm
-for the two working landing phases
+for the two landing phases that work in PSO and RL mode
 
     P = 'landing_burn_pure_throttle'   (1 action, dt_phys 0.025 x 4)
     G = 'landing_burn'                 (4 actions, dt_phys 0.1 x 4)
+
+and for the four further phases that work upstream in RL mode only (their PSO closures
+have the wrong arity, rtd_pso.py:38-157; 'flip_over_boostbackburn' raises TypeError in
+RL mode too, rtd_rl.py:132, and 'landing_burn_ACS' is broken in compile_physics)
+
+    S = 'subsonic', U = 'supersonic'   (2 actions: gimbal, throttle; dt 0.1 x 1)
+    B = 'ballistic_arc_descent'        (1 action: RCS; dt 0.1 x 1)
+    C = 'landing_burn_pure_throttle_Pcontrol'  (1 action: reference speed; dt 0.1 x 1)
 
 following, function by function (paths relative to /root/reference):
 
@@ -24,6 +32,9 @@ following, function by function (paths relative to /root/reference):
     acs()                 src/envs/utils/acs_model.py:13-86
     cog_inertia()         src/RocketSizing/functions/rocket_dimensions.py:167-196
     control_P()/control_G()  src/envs/rockets_physics.py:340-400 / 168-269
+    control_ascent()/control_rcs()/control_C()  rockets_physics.py:17-56 / 149-166 / 402-451
+    cog_inertia_full()    src/RocketSizing/functions/rocket_dimensions.py:199-241
+    ascent / ballistic / P-control rtd   src/envs/rl/rtd_rl.py:11-114, 147-188, 353-534
     substep()             src/envs/rockets_physics.py:455-646
     wind                  src/envs/wind/{full_wind_model.py:35-49, vonkarman.py:9-96,
                           HorizontalWindSpeed.py:44-114}
@@ -61,6 +72,29 @@ DEFAULT_SNAPSHOT = os.path.join(
 
 PHASE_P = "landing_burn_pure_throttle"
 PHASE_G = "landing_burn"
+PHASE_S = "subsonic"
+PHASE_U = "supersonic"
+PHASE_B = "ballistic_arc_descent"
+PHASE_C = "landing_burn_pure_throttle_Pcontrol"
+RL_ONLY_PHASES = (PHASE_S, PHASE_U, PHASE_B, PHASE_C)
+
+# Mach-scheduled truncation thresholds / reward weights of the ascent phases
+# (rtd_rl.py:544-575): [mach, max_x_error, max_vy_error, max_vx_error, max_alpha_deg,
+#  alpha_w, x_w, vy_w, vx_w]
+SUBSONIC_HYPER = [
+    [0.0, 50, 10, 10, 0.5, 100, 100, 100, 100], [0.1, 50, 15, 10, 10, 100, 100, 100, 100],
+    [0.2, 50, 20, 5, 2, 100, 100, 100, 100], [0.3, 50, 20, 5, 2, 100, 100, 100, 100],
+    [0.4, 50, 20, 5, 2, 100, 100, 100, 100], [0.5, 50, 20, 5, 2, 100, 100, 100, 100],
+    [0.6, 50, 20, 5, 1.75, 100, 100, 100, 100], [0.7, 50, 20, 5, 1.75, 100, 100, 100, 100],
+    [0.8, 50, 20, 5, 1.75, 100, 100, 100, 100], [0.9, 50, 20, 5, 1.75, 100, 100, 100, 100],
+    [1.0, 50, 20, 5, 1.75, 100, 100, 100, 100], [1.1, 50, 20, 5, 1.75, 100, 100, 100, 100]]
+SUPERSONIC_HYPER = [
+    [1.0, 100, 50, 9, 8, 100, 100, 100, 100], [1.1, 100, 60, 20, 8, 100, 100, 100, 100],
+    [1.5, 100, 60, 20, 8, 100, 100, 100, 100], [1.75, 100, 60, 30, 8, 100, 100, 100, 100],
+    [2.0, 100, 60, 40, 8, 100, 100, 100, 100], [2.25, 100, 60, 50, 8, 100, 100, 100, 100],
+    [2.5, 100, 60, 60, 8, 100, 100, 100, 100], [2.75, 100, 60, 70, 8, 100, 100, 100, 100],
+    [3.0, 100, 60, 80, 8, 100, 100, 100, 100], [3.25, 100, 60, 90, 8, 100, 100, 100, 100],
+    [3.5, 100, 60, 100, 8, 100, 100, 100, 100], [3.75, 100, 60, 100, 8, 100, 100, 100, 100]]
 
 # ---------------------------------------------------------------------------
 # ISA (ambiance restatement)
@@ -278,6 +312,17 @@ class Tables:
         self.initial_state = [np.float64(v) for v in p["initial_state"]]
         self.norm_vals = np.array(p["norm_vals"])
         self.inertia = {k: np.float64(v) for k, v in p["inertia"].items()}
+        o = p.get("other_phases") or {}
+        self.other = o
+        if o:
+            self.inertia_full = {k: np.float64(v) for k, v in o["inertia_full"].items()}
+            self.cop_full = o["cop_d0_full"] * o["cop_length_full"]
+            self.initial_states = {k: [np.float64(v) for v in st] for k, st in o["initial_states"].items()}
+            rt = o["ref_traj_ascent"]
+            # reference_trajectory_interpolation.py:14-16 (only x, vx, vy are consumed)
+            self.ref_x = interp1d(rt["y"], rt["x"], kind="linear", fill_value="extrapolate")
+            self.ref_vx = interp1d(rt["y"], rt["vx"], kind="linear", fill_value="extrapolate")
+            self.ref_vy = interp1d(rt["y"], rt["vy"], kind="linear", fill_value="extrapolate")
 
     # -- aero -----------------------------------------------------------
     def cd(self, mach, alpha_rad):
@@ -331,6 +376,26 @@ class Tables:
         I_prop_hat = I_prop + (m_ox_t + m_f_t) * (x_prop - x_wet) ** 2
         return x_wet, I_dry_hat + I_prop_hat
 
+    def cog_inertia_full(self, fill):
+        """full_rocket_inertia (rocket_dimensions.py:199-241), the ascent phases' closure."""
+        c = self.inertia_full
+        h_ox = c["h_1_ox"] * fill
+        h_f = c["h_1_f"] * fill
+        m_ox = c["m_1_ox"] * fill
+        m_f = c["m_1_f"] * fill
+        m_prop = m_ox + m_f
+        x_prop = (m_ox * (c["h_lower_1"] + h_ox / 2)
+                  + c["m_1_f"] * (c["h_lower_1"] + h_ox + h_f / 2)) / (m_ox + m_f)
+        I_ox = 1 / 12 * m_ox * h_ox ** 2 + m_ox * (c["h_lower_1"] + h_ox / 2 - x_prop) ** 2
+        I_f = 1 / 12 * m_f * h_f ** 2 + m_f * (c["h_lower_1"] + h_ox + h_f / 2 - x_prop) ** 2
+        I_prop = I_ox + I_f
+        x_rocket = (c["m_s_1"] * c["x_dry_1"] + (c["m_2"] + c["m_pay"]) * (c["x_wet_2_initial"] + c["h_1"])
+                    + m_prop * x_prop) / (c["m_s_1"] + c["m_2"] + c["m_pay"] + m_prop)
+        I_rocket = c["I_dry_1"] + c["m_s_1"] * (c["x_dry_1"] - x_rocket) ** 2 \
+            + c["I_wet_2_initial"] + c["m_2"] * (c["x_wet_2_initial"] - x_rocket) ** 2 \
+            + I_prop + m_prop * (x_prop - x_rocket) ** 2
+        return x_rocket, I_rocket
+
     def acs(self, alpha_eff, theta, q, mach, x_cog, cmd_left_deg, cmd_right_deg,
             prev_left, prev_right, dt):
         p = self.p
@@ -372,13 +437,17 @@ def _unpack_action_G(actions):
 
 
 class OracleEnv:
-    """Scalar env == rocket_environment_pre_wrap for phases P and G, type 'pso' | 'rl'."""
+    """Scalar env == rocket_environment_pre_wrap: phases P and G with type 'pso' | 'rl',
+    phases S, U, B, C with type 'rl' (their PSO closures are broken upstream)."""
 
     def __init__(self, flight_phase=PHASE_P, type="pso", enable_wind=False,
                  stochastic_wind=False, horiontal_wind_percentile=50, tables=None,
                  wind_noise=None, fast_rbf=False, trajectory_length=1, discount_factor=0.99):
-        assert flight_phase in (PHASE_P, PHASE_G)
+        assert flight_phase in (PHASE_P, PHASE_G) + RL_ONLY_PHASES
         assert type in ("pso", "rl")
+        if flight_phase in RL_ONLY_PHASES and type != "rl":
+            raise TypeError(f"{flight_phase}: the reference's pso closures have the wrong arity "
+                            "(rtd_pso.py:38-157); only type='rl' works upstream")
         self.trajectory_length = trajectory_length
         self.discount_factor = discount_factor
         self.T = tables or Tables(fast_rbf=fast_rbf)
@@ -387,25 +456,50 @@ class OracleEnv:
         self.dt = 0.1
         p = self.T.p
         n_gim = int(p["n_engines_gimballed"])
+        self.n_sub = 4
         if flight_phase == PHASE_P:
             self.n_eng = n_gim
             self.nominal_throttle = (0 * 0.4) / n_gim
             self.dt_phys = 0.025
             self.dt_act = 0.025
-        else:
+        elif flight_phase == PHASE_G:
             self.n_eng = n_gim + 2
             self.nominal_throttle = (3 * 0.4) / n_gim
             self.dt_phys = 0.1        # landing_burn integrates with the env dt ...
             self.dt_act = 0.025       # ... but filters its actuators with dt_temp
+        else:
+            # one Euler step of the env dt, no sub-stepping (rockets_physics.py:727-801, 959-997)
+            self.n_sub = 1
+            self.n_eng = n_gim
+            self.nominal_throttle = 0.5 if flight_phase in (PHASE_S, PHASE_U) else (0 * 0.4) / n_gim
+            self.dt_phys = 0.1
+            self.dt_act = 0.1
+        self.ascent = flight_phase in (PHASE_S, PHASE_U)
         self.enable_wind = enable_wind
         if enable_wind:
             self.wind = OracleWind(p["wind_table"], self.dt, stochastic_wind,
                                    horiontal_wind_percentile, noise=wind_noise)
         else:
             self.wind = None
-        self.state_initial = list(self.T.initial_state)
-        self.y_0 = self.state_initial[1]
-        self.mass_0 = self.state_initial[8]
+        if flight_phase in (PHASE_S, PHASE_U, PHASE_B):
+            self.state_initial = list(self.T.initial_states[flight_phase])
+        else:
+            self.state_initial = list(self.T.initial_state)
+        # the landing closures take y_0 / mass_0 from load_landing_burn_initial_state()
+        self.y_0 = self.T.initial_state[1]
+        self.mass_0 = self.T.initial_state[8]
+        if self.ascent:
+            hyper = SUBSONIC_HYPER if flight_phase == PHASE_S else SUPERSONIC_HYPER
+            cols = list(zip(*hyper))
+            f = lambda k: interp1d(cols[0], cols[k], kind="linear", fill_value="extrapolate")
+            (self.f_max_x, self.f_max_vy, self.f_max_vx, self.f_max_alpha, self.f_w_alpha,
+             self.f_w_x, self.f_w_vy, self.f_w_vx) = [f(k) for k in range(1, 9)]
+            if flight_phase == PHASE_S:
+                self.terminal_mach = 1.0
+            else:       # rtd_rl.py:582-588
+                xt, yt, vxt, vyt, mt = self.T.other["ref_traj_ascent_terminal"]
+                _, _, a_t = isa(yt)
+                self.terminal_mach = math.sqrt(vxt ** 2 + vyt ** 2) / a_t
         self.truncation_id = 0
         self.last = {}
         self.reset()
@@ -471,6 +565,46 @@ class OracleEnv:
         return (t_par + f_par, t_perp + f_perp, m_z + a_mz, mass_flow, throttle,
                 (gimbal_deg, d_cmd_l, d_cmd_r))
 
+    def _control_ascent(self, actions, p_atm, d_thrust_cg):
+        """force_moment_decomposer_ascent, rockets_physics.py:17-56 (gimbal +-7 deg, nominal 0.5)."""
+        p = self.T.p
+        u0, u1 = actions
+        gimbal_rad = u0 * math.radians(7.0)
+        nn = (u1 + 1) / 2
+        throttle = nn * (1 - self.nominal_throttle) + self.nominal_throttle
+        t_full = p["thrust_per_engine"] + (p["nozzle_exit_pressure"] - p_atm) * p["nozzle_exit_area"]
+        n_g = int(p["n_engines_gimballed"])
+        n_ng = int(self.T.other["n_engines_stage1"]) - n_g
+        thrust_g = t_full * n_g * throttle
+        thrust_ng = t_full * n_ng * throttle
+        t_par = thrust_ng + thrust_g * math.cos(gimbal_rad)
+        t_perp = -thrust_g * math.sin(gimbal_rad)
+        m_z = -thrust_g * math.sin(gimbal_rad) * d_thrust_cg
+        total = np.sqrt(t_par ** 2 + t_perp ** 2)
+        n_tot = total / t_full
+        mass_flow = (p["thrust_per_engine"] / p["v_exhaust"]) * n_tot
+        return t_par, t_perp, m_z, mass_flow, throttle, None
+
+    def _control_rcs(self, action, x_cog):
+        """RCS, rockets_physics.py:149-166."""
+        o = self.T.other
+        thruster_force = o["max_rcs_force_per_thruster"] * action
+        m_z = (-thruster_force * (x_cog - o["d_base_rcs_bottom"])
+               + thruster_force * (o["d_base_rcs_top"] - x_cog))
+        if not (type(m_z) == np.float64 or type(m_z) == float):
+            m_z = m_z[0]
+        return 0, 0, m_z, 0, None, None
+
+    def _control_C(self, actions_v_ref, p_atm, theta, alpha_eff, q, x_cog, mach, speed):
+        """force_moment_decomposer_landing_burn_throttle_PID, rockets_physics.py:402-451."""
+        if actions_v_ref.ndim == 2:
+            v_ref = actions_v_ref[0][0]
+        else:
+            v_ref = actions_v_ref[0]
+        error = v_ref - speed
+        nn = np.clip(error * -0.08, 0, 1)
+        return self._control_P([2 * (nn - 0.5)], p_atm, theta, alpha_eff, q, x_cog, mach)
+
     def substep(self, state, actions):
         T = self.T
         x, y, vx, vy, theta, theta_dot, gamma, alpha, mass, m_prop, time = state
@@ -484,13 +618,17 @@ class OracleEnv:
         fuel_frac = (T.m_prop0 - m_prop) / T.m_prop0
         if fuel_frac == 0.0:
             fuel_frac = 1e-6
-        x_cog, inertia = T.cog_inertia(1 - fuel_frac)
-        d_thrust_cg = x_cog + T.p["engine_height"]
+        if self.ascent:
+            x_cog, inertia = T.cog_inertia_full(1 - fuel_frac)
+            d_thrust_cg = x_cog + T.other["engine_height_full"]
+        else:
+            x_cog, inertia = T.cog_inertia(1 - fuel_frac)
+            d_thrust_cg = x_cog + T.p["engine_height"]
         if vy < 0:
             alpha_eff = gamma - theta - math.pi
         else:
             alpha_eff = alpha
-        d_cp_cg = x_cog - T.cop
+        d_cp_cg = x_cog - (T.cop_full if self.ascent else T.cop)
         if self.wind is not None:
             ug, vg = self.wind(y)
         else:
@@ -519,9 +657,17 @@ class OracleEnv:
         if self.flight_phase == PHASE_P:
             c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_P(
                 actions, p_atm, theta, alpha_eff, q, x_cog, mach)
-        else:
+        elif self.flight_phase == PHASE_G:
             c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_G(
                 actions, p_atm, d_thrust_cg, theta, alpha_eff, q, x_cog, mach)
+        elif self.ascent:
+            c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_ascent(
+                actions, p_atm, d_thrust_cg)
+        elif self.flight_phase == PHASE_B:
+            c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_rcs(actions, x_cog)
+        else:
+            c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_C(
+                actions, p_atm, theta, alpha_eff, q, x_cog, mach, speed)
         # NaN guards: an if/elif chain, only the first NaN is cleared
         if math.isnan(c_par):
             c_par = 0.0
@@ -561,7 +707,7 @@ class OracleEnv:
 
     def step(self, actions):
         state = self.state
-        for _ in range(4):
+        for _ in range(self.n_sub):
             state, info = self.substep(state, actions)
         self.state = state
         if self.flight_phase == PHASE_G:
@@ -587,9 +733,25 @@ class OracleEnv:
         return state, reward, done, truncated, info
 
     # -- reward / truncation / done ---------------------------------------
+    @staticmethod
+    def _mach_rtd(y, vx, vy):
+        _, _, a = isa(y)
+        speed = math.sqrt(vx ** 2 + vy ** 2)
+        return speed / a if (speed != 0 and a != 0) else 0
+
     def _done(self, s):
         x, y, vx, vy = s[:4]
         speed = math.sqrt(vx ** 2 + vy ** 2)
+        if self.ascent:                     # rtd_rl.py:35-51
+            if any(math.isnan(v) for v in s):
+                return False
+            return bool(s[9] >= 0 and self._mach_rtd(y, vx, vy) > self.terminal_mach)
+        if self.flight_phase == PHASE_B:    # rtd_rl.py:148-158
+            rho, _, _ = isa(y)
+            q = 0.5 * rho * speed ** 2
+            return bool(q > 10000 and abs(s[6] - s[4] - math.pi) < math.radians(3))
+        if self.flight_phase == PHASE_C:    # rtd_rl.py:356-367
+            return bool(y > 0 and y < 5 and speed < 1)
         if self.type == "pso" and self.flight_phase == PHASE_G:
             dist = math.sqrt(x ** 2 + y ** 2)
             return bool(dist > 0 and dist < 1 and speed < 2.5)
@@ -606,6 +768,44 @@ class OracleEnv:
             a_eff = abs(gamma - theta - math.pi)
         else:
             a_eff = abs(theta - gamma)
+        if self.ascent:                     # rtd_rl.py:53-88
+            if any(math.isnan(v) for v in s):
+                return True, 0
+            xr, vxr, vyr = self.T.ref_x(y), self.T.ref_vx(y), self.T.ref_vy(y)
+            mach = self._mach_rtd(y, vx, vy)
+            if m_prop <= 0:
+                return True, 1
+            elif mach > self.terminal_mach + 0.09:
+                return True, 2
+            elif abs(x - xr) > self.f_max_x(mach):
+                return True, 3
+            elif y < 0:
+                return True, 4
+            elif abs(alpha) > math.radians(self.f_max_alpha(mach)):
+                return True, 5
+            elif abs(vx - vxr) > self.f_max_vx(mach):
+                return True, 6
+            elif abs(vy - vyr) > self.f_max_vy(mach):
+                return True, 7
+            return False, 0
+        if self.flight_phase == PHASE_B:    # rtd_rl.py:160-170
+            if q > 10000 - 2000 and abs(gamma - theta - math.pi) > math.radians(5):
+                return True, 1
+            return False, 0
+        if self.flight_phase == PHASE_C:    # rtd_rl.py:369-401
+            if y < -10:
+                return True, 1
+            elif m_prop <= 0:
+                return True, 2
+            elif theta > math.pi + math.radians(2):
+                return True, 3
+            elif q > 65000:
+                return True, 4
+            elif g1 > 6.0:
+                return True, 5
+            elif vy > 0.0:
+                return True, 6
+            return False, 0
         if self.type == "pso" and self.flight_phase == PHASE_P:
             if y < 0.0:
                 return True, 1
@@ -686,7 +886,55 @@ class OracleEnv:
                 elif done:
                     reward = m_prop
             return reward
+        if self.ascent:                     # rtd_rl.py:90-120
+            if any(math.isnan(v) for v in s):
+                return 0
+            mach = self._mach_rtd(y, vx, vy)
+            reward = 0
+            xr, vxr, vyr = self.T.ref_x(y), self.T.ref_vx(y), self.T.ref_vy(y)
+            if y < 0:
+                return 0
+            reward += math.exp(-4 * (vx - vxr) ** 2 / self.f_max_vx(mach) ** 2) * self.f_w_vx(mach)
+            reward += math.exp(-4 * (vy - vyr) ** 2 / self.f_max_vy(mach) ** 2) * self.f_w_vy(mach)
+            reward += math.exp(-4 * (x - xr) ** 2 / self.f_max_x(mach) ** 2) * self.f_w_x(mach)
+            reward += math.exp(-4 * math.degrees(alpha) ** 2 / self.f_max_alpha(mach) ** 2) * self.f_w_alpha(mach)
+            if done:
+                reward += 2.5
+            reward /= 10 ** 4
+            return reward
+        if self.flight_phase == PHASE_B:    # rtd_rl.py:172-181
+            reward = (math.pi - abs(gamma - theta - math.pi)) / math.pi
+            if done:
+                reward += 3.5
+            reward /= 100
+            return reward
         rho, _, _ = isa(y)
+        if self.flight_phase == PHASE_C:    # rtd_rl.py:478-531 (the second definition wins)
+            speed = math.hypot(vx, vy)
+            q = 0.5 * rho * speed ** 2
+            v_ref = actions[0][0] if actions.ndim == 2 else actions[0]
+            reward = 0.0
+            if q > 60_000.0:
+                q_ex = (q - 60_000.0) / (65_000.0 - 60_000.0)
+                reward -= 1.0 * min(q_ex ** 2, 1.0)
+            g1 = info["g_load_1_sec_window"]
+            if g1 > 5.5:
+                g_ex = (g1 - 5.5) / (6.0 - 5.5)
+                reward -= 1.0 * min(g_ex ** 2, 1.0)
+            prog = (self.y_0 - y) / self.y_0
+            vel_tracking = max(0.0, 1.0 - abs(speed - v_ref) / 10.0)
+            w_prog = 0.5 if (q <= 60_000.0 and g1 <= 5.5) else 0.5 * 0.1
+            reward += w_prog * prog * vel_tracking
+            if y < 100.0:
+                reward += 0.5 * max(0.0, 1.0 - abs(vy - 0.0) / 50.0)
+            reward += 0.01 * (1 - self.discount_factor)
+            if done and not truncated:
+                reward += 5.0
+                mass_used = self.y_0 * 0.0 + (self.mass_0 - mass)
+                reward -= min(0.1 * mass_used, 1.0)
+            elif truncated:
+                reward -= min(4.0 * (y / self.y_0) * (abs(vy) / 100.0), 5.0)
+            return np.clip(reward, -10.0, 10.0)
         if self.flight_phase == PHASE_P:
             speed = math.hypot(vx, vy)
             q = 0.5 * rho * speed ** 2
@@ -808,9 +1056,16 @@ class RlEnv:
                              horiontal_wind_percentile, tables, wind_noise, fast_rbf,
                              trajectory_length, discount_factor)
         self.flight_phase = flight_phase
-        self.state_dim, self.action_dim = (2, 1) if flight_phase == PHASE_P else (5, 4)
+        self.state_dim, self.action_dim = {PHASE_P: (2, 1), PHASE_G: (5, 4), PHASE_S: (8, 2),
+                                           PHASE_U: (8, 2), PHASE_B: (4, 1), PHASE_C: (1, 1)}[flight_phase]
+        if flight_phase == PHASE_C:
+            vx0, vy0 = self.env.T.initial_state[2], self.env.T.initial_state[3]
+            self.speed0 = math.sqrt(vx0 ** 2 + vy0 ** 2)
 
     def augment_action(self, a):
+        if self.flight_phase == PHASE_C:        # env_wrapped_rl_pytorch.py:158-164
+            u0 = a[0] if a.ndim == 2 else a
+            return np.array([(u0 + 1) / 2 * self.speed0])
         if self.flight_phase != PHASE_G:
             return a
         u0, u1, u2, u3 = a[0] if a.ndim == 2 else a
@@ -822,6 +1077,16 @@ class RlEnv:
         s = np.asarray(state, dtype=np.float32).reshape(-1)
         x, y, vx, vy, theta, theta_dot, gamma = s[:7]
         nv = self.env.T.norm_vals
+        if self.flight_phase in (PHASE_S, PHASE_U, PHASE_B):    # env_wrapped_rl_pytorch.py:169-177
+            alpha, mass = s[7], s[8]
+            if self.flight_phase == PHASE_B:
+                o = np.array([theta, theta_dot, gamma, alpha])
+            else:
+                o = np.array([x, y, vx, vy, theta, theta_dot, alpha, mass])
+            o /= np.array(self.env.T.other["norm_vals"][self.flight_phase])
+            return o
+        if self.flight_phase == PHASE_C:
+            return np.array([(1 - y / nv[0]) * 2 - 1])
         if self.flight_phase == PHASE_P:
             return np.array([(1 - y / nv[0]) * 2 - 1, (1 - vy / nv[1]) * 2 - 1])
         k = float(np.arctanh(0.75) / math.radians(5))

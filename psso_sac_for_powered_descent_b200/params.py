@@ -37,7 +37,8 @@ STATE_FIELDS = ("x", "y", "vx", "vy", "theta", "theta_dot", "gamma", "alpha", "m
                 "mass_propellant", "time")
 
 # Hard-coded knobs of compile_physics (rockets_physics.py:803-836, 909-934).
-PHASES = ("landing_burn_pure_throttle", "landing_burn")
+PHASES = ("landing_burn_pure_throttle", "landing_burn", "subsonic", "supersonic",
+          "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol")
 
 
 @dataclass
@@ -79,6 +80,11 @@ class RocketParams:
     gf_cn_val: List[float] = field(default_factory=list)
     # wind percentile table: name -> {"wind_speed": [...], "altitude_km": [...]}
     wind_table: Dict[str, Dict[str, List[float]]] = field(default_factory=dict)
+    # flight phases outside the two landing burns (subsonic, supersonic, ballistic_arc_descent,
+    # landing_burn_pure_throttle_Pcontrol): stage-1 engine count, RCS geometry, the full-rocket
+    # inertia closure (x_cog_inertia_subrocket_0_lambda), per-phase initial states and
+    # normalisation vectors, the ascent reference trajectory (tools/extract_params.py)
+    other_phases: Dict = field(default_factory=dict)
 
     # ------------------------------------------------------------------ derived
     @property

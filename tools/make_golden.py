@@ -263,6 +263,119 @@ def rl_sequence(phase, tag, n_steps, seed=1):
     print("rl_sequence", tag, len(R), "steps, last reward", R[-1], "trunc", T[-1], env.truncation_id())
 
 
+S_, U_, B_, C_ = "subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol"
+
+
+def rl_sequence_other(phase, tag, n_steps, seed=11, mode="random"):
+    """RL-wrapper sequences of the phases outside the landing burns.
+    mode 'csv': replay the reference's own recorded controller actions (float32, as a torch
+    policy would hand them over); 'random'; 'track' (phase C: follow the v_opt(y) profile)."""
+    import pandas as pd
+    from src.envs.rl.env_wrapped_rl_pytorch import rl_wrapped_env_pytorch
+    rng = np.random.default_rng(seed)
+    env = quiet(rl_wrapped_env_pytorch, flight_phase=phase, enable_wind=False, trajectory_length=1000,
+                discount_factor=0.99)
+    act_dim = env.action_dim
+    csv_states = np.zeros((0, 11))
+    if mode == "csv":
+        f = {S_: "subsonic_state_action_ascent_control.csv",
+             U_: "supersonic_state_action_ascent_control.csv"}[phase]
+        g = pd.read_csv("data/reference_trajectory/ascent_controls/" + f)
+        tape = g[["u0", "u1"]].values.astype(np.float32)
+        cols = ["x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "theta[rad]", "theta_dot[rad/s]", "gamma[rad]",
+                "alpha[rad]", "mass[kg]", "mass_propellant[kg]", "time[s]"]
+        csv_states = g[cols].values
+        n_steps = min(n_steps, len(tape))
+    obs0 = env.reset()
+    O, R, D, T, A, S = [np.array(obs0, float)], [], [], [], [], []
+    a_opt, b_opt = -7.445479767703873e-07, 0.056435801747276214
+    for k in range(n_steps):
+        if mode == "csv":
+            a = tape[k]
+        elif mode == "track":
+            y = float(env.env.state[1])
+            a = np.array([np.clip(2 * (a_opt * y * y + b_opt * y) / env.speed0 - 1, -1, 1)], np.float32)
+        else:
+            a = rng.uniform(-1, 1, act_dim).astype(np.float32)
+        o, r, d, t, info = quiet(env.step, a)
+        O.append(np.array(o, float)); R.append(r); D.append(d); T.append(t); A.append(a)
+        S.append([float(v) for v in env.env.state])
+        if d or t:
+            break
+    np.savez_compressed(os.path.join(OUT, f"rl_sequence_{tag}.npz"), actions=np.array(A),
+                        obs=np.array(O), rewards=np.array(R), done=np.array(D),
+                        truncated=np.array(T), states=np.array(S), trunc_id=env.truncation_id(),
+                        csv_states=csv_states, obs_dtype=str(np.asarray(o).dtype))
+    print("rl_sequence", tag, len(R), "steps, last reward", R[-1], "done", D[-1], "trunc", T[-1],
+          env.truncation_id())
+    return np.array(S)
+
+
+def single_step_other(phase, tag, pool, n=96, seed=21):
+    """(state, g-window, action) -> one step of the reference base env (type='rl'), float64 and
+    float32 action arrays (NEP-50 paths of the ascent / RCS / P-control decomposers)."""
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    rng = np.random.default_rng(seed)
+    env = quiet(rocket_environment_pre_wrap, type="rl", flight_phase=phase, enable_wind=False,
+                trajectory_length=1000, discount_factor=0.99)
+    act_dim = {S_: 2, U_: 2, B_: 1, C_: 1}[phase]
+    rows = dict(state=[], win=[], nwin=[], act32=[], act64=[], o64=[], o32=[])
+    for i in range(n):
+        s = np.array(pool[rng.integers(len(pool))], float)
+        if i % 3 == 1:
+            s = s * (1 + 0.01 * rng.standard_normal(11))
+            s[6] = math.atan2(s[3], s[2]) % (2 * math.pi)
+            s[7] = s[4] - s[6]
+        elif i % 3 == 2 and phase == C_:
+            s[1] = rng.uniform(-12.0, 150.0); s[3] = -rng.uniform(0.1, 60.0); s[2] = rng.uniform(-2, 2)
+            s[6] = math.atan2(s[3], s[2]) % (2 * math.pi)
+            s[7] = s[4] - s[6]
+        nwin = int(rng.integers(0, 11))
+        win = list(rng.uniform(0.0, 0.7 if i % 5 else 7.0, nwin))
+        if phase == C_:
+            a32 = rng.uniform(0.0, 1100.0, act_dim).astype(np.float32)     # v_ref [m/s]
+        else:
+            a32 = rng.uniform(-1, 1, act_dim).astype(np.float32)
+        outs = {}
+        for key, a in (("o64", a32.astype(np.float64)), ("o32", a32)):
+            quiet(env.reset)
+            env.state = [np.float64(v) for v in s]
+            env.previous_state = env.state
+            env.g_loads_window = list(win)
+            ns, r, d, t, info = quiet(env.step, a)
+            outs[key] = [float(v) for v in ns] + [float(r), float(d), float(t), float(env.truncation_id),
+                                                  info["mach_number"], info["dynamic_pressure"],
+                                                  info["CL"], info["CD"], info["x_cog"], info["inertia"],
+                                                  float(info["mass_flow"]), info["g_load_1_sec_window"]]
+        w = np.zeros(10); w[:nwin] = win
+        rows["state"].append(s); rows["win"].append(w); rows["nwin"].append(nwin)
+        rows["act32"].append(a32); rows["act64"].append(a32.astype(np.float64))
+        rows["o64"].append(outs["o64"]); rows["o32"].append(outs["o32"])
+    cols = ["x", "y", "vx", "vy", "theta", "theta_dot", "gamma", "alpha", "mass", "m_prop", "time",
+            "reward", "done", "truncated", "trunc_id", "mach", "q", "CL", "CD", "x_cog", "inertia",
+            "mass_flow", "g1"]
+    np.savez_compressed(os.path.join(OUT, f"single_step_{tag}.npz"),
+                        **{k: np.array(v) for k, v in rows.items()}, out_cols=cols)
+    o = np.array(rows["o64"])
+    print("single_step", tag, n, "done", int(o[:, 12].sum()), "trunc ids",
+          np.unique(o[:, 14], return_counts=True))
+
+
+def ascent_csv():
+    """The reference's own committed ascent controller recordings (actions + states per 0.1 s
+    step) - golden vectors written on the author's machine, copied verbatim."""
+    import pandas as pd
+    cols = ["x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "theta[rad]", "theta_dot[rad/s]", "gamma[rad]",
+            "alpha[rad]", "mass[kg]", "mass_propellant[kg]", "time[s]"]
+    out = {}
+    for tag, f in (("S", "subsonic"), ("U", "supersonic")):
+        g = pd.read_csv(f"data/reference_trajectory/ascent_controls/{f}_state_action_ascent_control.csv")
+        out[f"actions_{tag}"] = g[["u0", "u1"]].values
+        out[f"states_{tag}"] = g[cols].values
+    np.savez_compressed(os.path.join(OUT, "ascent_csv.npz"), **out)
+    print("ascent_csv", {k: v.shape for k, v in out.items()})
+
+
 def wind_sequence(n_steps=260, seed=3):
     from src.envs.base_environment import rocket_environment_pre_wrap
     rng = np.random.default_rng(seed)
@@ -340,7 +453,18 @@ def aero_probe(seed=5, n=400):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     load_reference()
-    which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero"]
+    which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero", "other"]
+    if "other" in which:
+        ascent_csv()
+        pool = rl_sequence_other(S_, "S", 400, mode="csv")
+        single_step_other(S_, "S", pool)
+        pool = rl_sequence_other(U_, "U", 600, mode="csv")
+        single_step_other(U_, "U", pool)
+        pool = rl_sequence_other(B_, "B", 500, mode="random")
+        single_step_other(B_, "B", pool)
+        pool = rl_sequence_other(C_, "C", 400, mode="random")
+        pool2 = rl_sequence_other(C_, "C2", 2500, mode="track")
+        single_step_other(C_, "C", np.concatenate([pool, pool2]))
     if "aero" in which:
         aero_probe()
     if "tape" in which:
