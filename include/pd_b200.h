@@ -36,7 +36,14 @@ extern "C" {
 #define PD_RBF_ROW_BYTES 512
 #define PD_DBG_DIM 16
 
-enum { PD_PHASE_PURE_THROTTLE = 0, PD_PHASE_GIMBALLED = 1 };   /* flight_phase strings   */
+/* flight_phase strings (src/envs/base_environment.py:21).  0/1 work with type 'pso' and 'rl';
+ * 2..5 with type 'rl' only, as upstream (their pso closures have the wrong arity,
+ * src/envs/pso/rtd_pso.py:38-157).  'flip_over_boostbackburn' (TypeError in rtd_rl.py:132) and
+ * 'landing_burn_ACS' (broken in compile_physics, rockets_physics.py:867-889) do not run upstream
+ * and are not offered. */
+enum { PD_PHASE_PURE_THROTTLE = 0, PD_PHASE_GIMBALLED = 1, PD_PHASE_SUBSONIC = 2,
+       PD_PHASE_SUPERSONIC = 3, PD_PHASE_BALLISTIC_ARC = 4, PD_PHASE_PCONTROL = 5,
+       PD_N_PHASES = 6 };
 enum { PD_RTD_PSO = 0, PD_RTD_RL = 1 };                        /* type = 'pso' | 'rl'     */
 enum { PD_FP64 = 0, PD_FP32 = 1 };                             /* compute precision build */
 enum { PD_ACT_F64 = 0, PD_ACT_F32 = 1 };                       /* dtype of the action     */
@@ -73,6 +80,27 @@ typedef struct {
     PdRbfGrid grids[2];
 } PdRbfTable;
 
+/* Constants of the flight phases outside the two landing burns (host pointers, copied by
+ * pd_create): force_moment_decomposer_ascent (rockets_physics.py:17-56, 727-752), RCS
+ * (:149-166, 782-801), full_rocket_inertia closure cells
+ * (src/RocketSizing/functions/rocket_dimensions.py:199-241), per-phase initial states
+ * (src/envs/load_initial_states.py:5-54) and normalisation vectors
+ * (src/envs/utils/input_normalisation.py:5-71), the ascent reference trajectory
+ * (src/envs/utils/reference_trajectory_interpolation.py:5-35). */
+typedef struct {
+    int32_t n_engines_stage1;             /* 'Number of engines stage 1' */
+    int32_t n_ref;                        /* reference-trajectory rows */
+    double max_rcs_force_per_thruster, d_base_rcs_bottom, d_base_rcs_top;
+    /* m_s_1, x_dry_1, I_dry_1, m_2, m_pay, x_wet_2_initial, I_wet_2_initial, h_1, h_1_ox, h_1_f,
+     * m_1_ox, m_1_f, h_lower_1 */
+    double inertia_full[13];
+    double engine_height_full, cop_full;
+    double initial_state[3][PD_STATE_DIM]; /* subsonic, supersonic, ballistic_arc_descent */
+    double norm_vals[3][8];               /* same order; ballistic uses the first 4 */
+    const double *ref_y, *ref_x, *ref_vx, *ref_vy;   /* host [n_ref], raw csv order */
+    double ref_terminal[5];               /* last row: x, y, vx, vy, mass */
+} PdOtherPhases;
+
 /* Constants the reference loads in compile_physics (src/envs/rockets_physics.py:707-957),
  * module import side effects (rockets_physics.py:12-14, acs_model.py:10-11),
  * load_landing_burn_initial_state (src/envs/load_initial_states.py:56-62) and
@@ -99,6 +127,7 @@ typedef struct {
     const double *wind_alt_km, *wind_speed;   /* host */
     double vk_Adu[4], vk_Bdu[2], vk_Adv[4], vk_Bdv[2];
     PdRbfTable cd, cl;
+    const PdOtherPhases *other;           /* host; required for PD_PHASE_SUBSONIC .. PD_PHASE_PCONTROL */
 } PdParams;
 
 /* rocket_environment_pre_wrap.__init__ kwargs (src/envs/base_environment.py:12-20) + batch */
@@ -113,6 +142,12 @@ typedef struct {
     int32_t device;
     uint64_t seed;            /* Philox key for gust noise / sigma draws */
     double rl_reward_scale;   /* (1-g)/(1-g^L) of rtd_rl.py:266 (phase G, rl only) */
+    double discount_factor;   /* rtd_rl.py:496 ALIVE_BONUS = 0.01 (1-g) (P-control phase, rl only) */
+    int32_t raw_actions;      /* type 'rl' only.  0: pd_step takes the policy's action and applies
+                                 rl_wrapped_env_pytorch.augment_action (log-compression for
+                                 landing_burn, reference-speed scaling for P-control) in the kernel;
+                                 1: actions are already what rocket_environment_pre_wrap.step expects */
+    int32_t _pad;
 } PdConfig;
 
 typedef struct PdEnv PdEnv;
@@ -128,7 +163,8 @@ int pd_destroy(PdEnv *env);
 int pd_reset(PdEnv *env, const uint8_t *mask, void *stream);
 
 /* .step(actions)  (base_environment.py:99-154) for every env of the batch.
- *   actions   dev [n_envs * A], double or float per action_dtype (A = 1 | 4).  A float32
+ *   actions   dev [n_envs * A], double or float per action_dtype (A = 1, 4, 2, 2, 1, 1 for
+ *             phases 0..5).  A float32
  *             action reproduces NumPy's NEP-50 float32 contamination of throttle, thrust and
  *             mass flow in the fp64 build (SURVEY.md 8a "dtype rule").
  *   obs       dev [n_envs * O] pso: pso_wrapper.augment_state (env_wrapped_ea.py:97-123);

@@ -15,12 +15,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpd_b200.so")
 CACHE_DIR = os.path.join(HERE, "_cache")
 
-PHASES = {"landing_burn_pure_throttle": 0, "landing_burn": 1}
+PHASES = {"landing_burn_pure_throttle": 0, "landing_burn": 1, "subsonic": 2, "supersonic": 3,
+          "ballistic_arc_descent": 4, "landing_burn_pure_throttle_Pcontrol": 5}
+RL_ONLY_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol")
 RTD = {"pso": 0, "rl": 1}
 PRECISION = {"fp64": 0, "fp32": 1}
-OBS_DIM = {0: 2, 1: 5}
-ACT_DIM = {0: 1, 1: 4}
+OBS_DIM = {0: 2, 1: 5, 2: 8, 3: 8, 4: 4, 5: 1}
+ACT_DIM = {0: 1, 1: 4, 2: 2, 3: 2, 4: 1, 5: 1}
 N_PARAMS = {0: 249, 1: 372}
+INERTIA_FULL_ORDER = ("m_s_1", "x_dry_1", "I_dry_1", "m_2", "m_pay", "x_wet_2_initial", "I_wet_2_initial",
+                      "h_1", "h_1_ox", "h_1_f", "m_1_ox", "m_1_f", "h_lower_1")
 
 
 class PdRbfGrid(C.Structure):
@@ -35,6 +39,16 @@ class PdRbfTable(C.Structure):
                 ("n_grids", C.c_int32), ("mach_sorted", C.c_void_p), ("points", C.c_void_p),
                 ("rows", C.c_void_p), ("hash_keys", C.c_void_p), ("hash_vals", C.c_void_p),
                 ("grids", PdRbfGrid * 2)]
+
+
+class PdOtherPhases(C.Structure):
+    _fields_ = [("n_engines_stage1", C.c_int32), ("n_ref", C.c_int32),
+                ("max_rcs_force_per_thruster", C.c_double), ("d_base_rcs_bottom", C.c_double),
+                ("d_base_rcs_top", C.c_double), ("inertia_full", C.c_double * 13),
+                ("engine_height_full", C.c_double), ("cop_full", C.c_double),
+                ("initial_state", (C.c_double * 11) * 3), ("norm_vals", (C.c_double * 8) * 3),
+                ("ref_y", C.c_void_p), ("ref_x", C.c_void_p), ("ref_vx", C.c_void_p), ("ref_vy", C.c_void_p),
+                ("ref_terminal", C.c_double * 5)]
 
 
 class PdParams(C.Structure):
@@ -55,14 +69,15 @@ class PdParams(C.Structure):
                 ("wind_alt_km", C.c_void_p), ("wind_speed", C.c_void_p),
                 ("vk_Adu", C.c_double * 4), ("vk_Bdu", C.c_double * 2),
                 ("vk_Adv", C.c_double * 4), ("vk_Bdv", C.c_double * 2),
-                ("cd", PdRbfTable), ("cl", PdRbfTable)]
+                ("cd", PdRbfTable), ("cl", PdRbfTable), ("other", C.POINTER(PdOtherPhases))]
 
 
 class PdConfig(C.Structure):
     _fields_ = [("phase", C.c_int32), ("rtd", C.c_int32), ("precision", C.c_int32),
                 ("enable_wind", C.c_int32), ("stochastic_wind", C.c_int32),
                 ("auto_reset", C.c_int32), ("n_envs", C.c_int32), ("device", C.c_int32),
-                ("seed", C.c_uint64), ("rl_reward_scale", C.c_double)]
+                ("seed", C.c_uint64), ("rl_reward_scale", C.c_double), ("discount_factor", C.c_double),
+                ("raw_actions", C.c_int32), ("_pad", C.c_int32)]
 
 
 class PdSharedActor(C.Structure):
@@ -271,4 +286,28 @@ def make_params(p: RocketParams, percentile=50):
     cd, cl = aero_tables(p)
     c.cd = _rbf_struct(cd, keep)
     c.cl = _rbf_struct(cl, keep)
+    o = getattr(p, "other_phases", None)
+    if o:
+        t = PdOtherPhases()
+        t.n_engines_stage1 = int(o["n_engines_stage1"])
+        t.max_rcs_force_per_thruster = o["max_rcs_force_per_thruster"]
+        t.d_base_rcs_bottom, t.d_base_rcs_top = o["d_base_rcs_bottom"], o["d_base_rcs_top"]
+        for i, k in enumerate(INERTIA_FULL_ORDER):
+            t.inertia_full[i] = o["inertia_full"][k]
+        t.engine_height_full = o["engine_height_full"]
+        t.cop_full = o["cop_d0_full"] * o["cop_length_full"]
+        for r, ph in enumerate(("subsonic", "supersonic", "ballistic_arc_descent")):
+            for i in range(11):
+                t.initial_state[r][i] = o["initial_states"][ph][i]
+            for i, v in enumerate(o["norm_vals"][ph]):
+                t.norm_vals[r][i] = v
+        rt = o["ref_traj_ascent"]
+        arrs = [np.ascontiguousarray(rt[k], np.float64) for k in ("y", "x", "vx", "vy")]
+        keep.extend(arrs)
+        t.n_ref = len(arrs[0])
+        t.ref_y, t.ref_x, t.ref_vx, t.ref_vy = [a.ctypes.data for a in arrs]
+        for i in range(5):
+            t.ref_terminal[i] = o["ref_traj_ascent_terminal"][i]
+        keep.append(t)
+        c.other = C.pointer(t)
     return c, keep

@@ -349,6 +349,9 @@ int actor_launch(int O, int A, const ActorArgs &p, const float *obs, float *act,
                  int use_tc, int n_sm, cudaStream_t st) {
     if (O == 2 && A == 1) return launch_t<2, 1>(p, obs, act, mean_out, B, use_tc, n_sm, st);
     if (O == 5 && A == 4) return launch_t<5, 4>(p, obs, act, mean_out, B, use_tc, n_sm, st);
+    if (O == 8 && A == 2) return launch_t<8, 2>(p, obs, act, mean_out, B, use_tc, n_sm, st);   // ascent
+    if (O == 4 && A == 1) return launch_t<4, 1>(p, obs, act, mean_out, B, use_tc, n_sm, st);   // ballistic arc
+    if (O == 1 && A == 1) return launch_t<1, 1>(p, obs, act, mean_out, B, use_tc, n_sm, st);   // P-control
     return 1;
 }
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/pd_b200.h"
 #include "pd_device.cuh"
@@ -141,6 +142,22 @@ static void to_float(const Scalars<double> &a, Scalars<R> &b) {
     for (size_t i = 0; i < sizeof(a) / sizeof(double); ++i) dst[i] = (R)src[i];
 }
 
+// ICAO-1993 ISA speed of sound on the host (terminal Mach of the supersonic phase); the same
+// layer table as the device isa()
+static double host_speed_of_sound(double alt) {
+    static const double L[8][3] = {{-5.0e3, 320.65, -6.5e-3}, {0.0e3, 288.15, -6.5e-3}, {11.0e3, 216.65, 0.0},
+                                   {20.0e3, 216.65, 1.0e-3},  {32.0e3, 228.65, 2.8e-3}, {47.0e3, 270.65, 0.0},
+                                   {51.0e3, 270.65, -2.8e-3}, {71.0e3, 214.65, -2.0e-3}};
+    if (alt < 0) alt = 0;
+    const double RE = 6356766.0;
+    const double H = RE * alt / (RE + alt);
+    int k = 0;
+    for (int j = 0; j < 8; ++j)
+        if (H >= L[j][0]) k = j;
+    const double T = L[k][1] + L[k][2] * (H - L[k][0]);
+    return sqrt(1.4 * 287.05287 * T);
+}
+
 static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double> &s) {
     memset(&s, 0, sizeof(s));
     const double d2r = PD_PI / 180.0, r2d = 180.0 / PD_PI;
@@ -153,9 +170,13 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
         s.n_eng = n_gim;
         s.nominal = (0 * 0.4) / n_gim;
         s.dt_phys = 0.025;
-    } else {                                         // rockets_physics.py:803-836
+    } else if (cfg.phase == PD_PHASE_GIMBALLED) {    // rockets_physics.py:803-836
         s.n_eng = n_gim + 2;
         s.nominal = (3 * 0.4) / n_gim;
+        s.dt_phys = 0.1;
+    } else {                                         // one Euler step of the env dt, :727-801, 959-997
+        s.n_eng = n_gim;
+        s.nominal = (cfg.phase == PD_PHASE_SUBSONIC || cfg.phase == PD_PHASE_SUPERSONIC) ? 0.5 : (0 * 0.4) / n_gim;
         s.dt_phys = 0.1;
     }
     s.dt_act = 0.025;
@@ -170,8 +191,50 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
     s.m_dry = p.inertia[4]; s.m_f = p.inertia[5]; s.m_ox = p.inertia[6]; s.x_dry = p.inertia[7];
     s.engine_height = p.engine_height;
     s.cop = p.cop;
-    s.max_gimbal_rad = 5 * d2r;
+    const bool ascent = cfg.phase == PD_PHASE_SUBSONIC || cfg.phase == PD_PHASE_SUPERSONIC;
+    s.max_gimbal_rad = (ascent ? 7.0 : 5) * d2r;     // math.radians(7.0) :739 / math.radians(5) :831
     s.max_gimbal_deg = (5 * d2r) * r2d;
+    s.alive_bonus = 0.01 * (1 - cfg.discount_factor);
+    s.speed0 = sqrt(p.initial_state[2] * p.initial_state[2] + p.initial_state[3] * p.initial_state[3]);
+    if (p.other) {
+        const PdOtherPhases &o = *p.other;
+        s.n_eng_ng = o.n_engines_stage1 - n_gim;
+        for (int i = 0; i < 13; ++i) s.fi[i] = o.inertia_full[i];
+        s.rcs_force = o.max_rcs_force_per_thruster;
+        s.d_rcs_bottom = o.d_base_rcs_bottom;
+        s.d_rcs_top = o.d_base_rcs_top;
+        if (ascent) {
+            s.engine_height = o.engine_height_full;
+            s.cop = o.cop_full;
+        }
+        const int row = cfg.phase == PD_PHASE_SUBSONIC ? 0 : cfg.phase == PD_PHASE_SUPERSONIC ? 1 : 2;
+        for (int i = 0; i < 8; ++i) s.norm8[i] = o.norm_vals[row][i] != 0.0 ? o.norm_vals[row][i] : 1.0;
+        // Mach schedules of rtd_rl.py:544-575: max_x, max_vy, max_vx, max_alpha_deg
+        static const double SUB[12][5] = {
+            {0.0, 50, 10, 10, 0.5}, {0.1, 50, 15, 10, 10}, {0.2, 50, 20, 5, 2}, {0.3, 50, 20, 5, 2},
+            {0.4, 50, 20, 5, 2}, {0.5, 50, 20, 5, 2}, {0.6, 50, 20, 5, 1.75}, {0.7, 50, 20, 5, 1.75},
+            {0.8, 50, 20, 5, 1.75}, {0.9, 50, 20, 5, 1.75}, {1.0, 50, 20, 5, 1.75}, {1.1, 50, 20, 5, 1.75}};
+        static const double SUP[12][5] = {
+            {1.0, 100, 50, 9, 8}, {1.1, 100, 60, 20, 8}, {1.5, 100, 60, 20, 8}, {1.75, 100, 60, 30, 8},
+            {2.0, 100, 60, 40, 8}, {2.25, 100, 60, 50, 8}, {2.5, 100, 60, 60, 8}, {2.75, 100, 60, 70, 8},
+            {3.0, 100, 60, 80, 8}, {3.25, 100, 60, 90, 8}, {3.5, 100, 60, 100, 8}, {3.75, 100, 60, 100, 8}};
+        const double (*H)[5] = cfg.phase == PD_PHASE_SUPERSONIC ? SUP : SUB;
+        for (int j = 0; j < 12; ++j) {
+            s.hyp_m[j] = H[j][0];
+            for (int r = 0; r < 4; ++r) s.hyp_v[r][j] = H[j][r + 1];
+        }
+        for (int r = 0; r < 4; ++r) {
+            for (int j = 0; j + 1 < 12; ++j)
+                s.hyp_s[r][j] = (s.hyp_v[r][j + 1] - s.hyp_v[r][j]) / (s.hyp_m[j + 1] - s.hyp_m[j]);
+            s.hyp_s[r][11] = s.hyp_s[r][10];
+        }
+        if (cfg.phase == PD_PHASE_SUBSONIC) {
+            s.terminal_mach = 1.0;
+        } else {        // rtd_rl.py:582-588: Mach of the reference trajectory's last row
+            const double yt = o.ref_terminal[1], vxt = o.ref_terminal[2], vyt = o.ref_terminal[3];
+            s.terminal_mach = sqrt(vxt * vxt + vyt * vyt) / host_speed_of_sound(yt);
+        }
+    }
     s.max_defl_rad = 20 * d2r;
     s.norm_y = p.norm_vals[0]; s.norm_vy = p.norm_vals[1];
     s.norm_x = p.norm_vals[5]; s.norm_vx = p.norm_vals[6];
@@ -217,7 +280,12 @@ uint64_t pd_launch_count(void) { return g_launches.load(); }
 int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     if (!cfg || !p || !out) return fail("pd_create: null argument");
     if (cfg->n_envs <= 0) return fail("pd_create: n_envs must be positive");
-    if (cfg->phase != 0 && cfg->phase != 1) return fail("pd_create: unknown flight phase");
+    if (cfg->phase < 0 || cfg->phase >= PD_N_PHASES) return fail("pd_create: unknown flight phase");
+    if (cfg->phase > PD_PHASE_GIMBALLED && cfg->rtd != PD_RTD_RL)
+        return fail("pd_create: this flight phase only works with type='rl' upstream (its pso "
+                    "closures have the wrong arity, rtd_pso.py:38-157)");
+    if (cfg->phase > PD_PHASE_GIMBALLED && cfg->phase != PD_PHASE_PCONTROL && !p->other)
+        return fail("pd_create: PdParams.other is required for this flight phase");
     if (cfg->rtd != 0 && cfg->rtd != 1) return fail("pd_create: unknown rtd type");
     if (p->n_wind > 16) return fail("pd_create: wind profile longer than 16 points");
     int ndev = 0;
@@ -267,6 +335,30 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     e->tb.n_cn = p->n_gf_cn;
     e->tb.n_wind = p->n_wind;
     for (int k = 0; k < 11; ++k) e->tb.init[k] = p->initial_state[k];
+    if (cfg->phase >= PD_PHASE_SUBSONIC && cfg->phase <= PD_PHASE_BALLISTIC_ARC)
+        for (int k = 0; k < 11; ++k) e->tb.init[k] = p->other->initial_state[cfg->phase - PD_PHASE_SUBSONIC][k];
+    if (p->other && p->other->n_ref >= 2 && (cfg->phase == PD_PHASE_SUBSONIC || cfg->phase == PD_PHASE_SUPERSONIC)) {
+        // scipy interp1d sorts by x with a stable sort (reference_trajectory_interpolation.py:14-16)
+        const PdOtherPhases &o = *p->other;
+        const int n = o.n_ref;
+        std::vector<int> ord(n);
+        for (int i = 0; i < n; ++i) ord[i] = i;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return o.ref_y[a] < o.ref_y[b]; });
+        std::vector<double> y(n), v(n), sl(n);
+        for (int i = 0; i < n; ++i) y[i] = o.ref_y[ord[i]];
+        if (dev_copy(e, y.data(), (size_t)n, &e->tb.ref_y)) { pd_destroy(e); return 1; }
+        const double *src[3] = {o.ref_x, o.ref_vx, o.ref_vy};
+        for (int c = 0; c < 3; ++c) {
+            for (int i = 0; i < n; ++i) v[i] = src[c][ord[i]];
+            for (int i = 0; i + 1 < n; ++i) sl[i] = (v[i + 1] - v[i]) / (y[i + 1] - y[i]);
+            sl[n - 1] = sl[n - 2];
+            if (dev_copy(e, v.data(), (size_t)n, &e->tb.ref_v[c]) || dev_copy(e, sl.data(), (size_t)n, &e->tb.ref_s[c])) {
+                pd_destroy(e);
+                return 1;
+            }
+        }
+        e->tb.n_ref = n;
+    }
     const size_t B = (size_t)cfg->n_envs;
     EnvSoA &s = e->soa;
     s.n = cfg->n_envs;
@@ -318,6 +410,7 @@ int pd_step(PdEnv *e, const void *actions, int action_dtype, void *obs, void *re
     if (activate(e)) return 1;
     StepIO io;
     io.actions = actions; io.action_dtype = action_dtype; io.obs = obs; io.reward = reward;
+    io.raw_actions = e->cfg.raw_actions;
     io.next_obs = next_obs; io.done = done; io.truncated = truncated; io.trunc_id = trunc_id;
     io.dbg = dbg;
     e->impl->step(e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
@@ -404,6 +497,7 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
     if (n_params != expect) return fail("pd_rollout_pso: n_params does not match the phase's actor");
     if (n_particles <= 0 || n_seeds <= 0 || max_steps <= 0) return fail("pd_rollout_pso: bad sizes");
     if (e->cfg.rtd != PD_RTD_PSO) return fail("pd_rollout_pso: handle was not created with type='pso'");
+    if (e->cfg.phase > PD_PHASE_GIMBALLED) return fail("pd_rollout_pso: landing phases only");
     if (activate(e)) return 1;
     if (ensure_wT(e, (size_t)n_particles * n_params)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -484,7 +578,7 @@ static int actor_args(PdEnv *e, const PdSharedActor *a, ActorArgs &p, int &use_t
 int pd_actor_forward(PdEnv *e, const PdSharedActor *actor, const float *obs, int n, float *act,
                      float *mean_out, void *stream) {
     if (!e || !actor || !obs || !act || n <= 0) return fail("pd_actor_forward: bad argument");
-    const int O = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 2 : 5, A = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 1 : 4;
+    const int O = pd::phase_odim(e->cfg.phase), A = pd::phase_adim(e->cfg.phase);
     ActorArgs p;
     int use_tc = 0;
     if (actor_args(e, actor, p, use_tc, (cudaStream_t)stream)) return 1;
@@ -502,7 +596,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
     if (!e->cfg.auto_reset) return fail("pd_collect_shared_actor: handle must be created with auto_reset");
     if (activate(e)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const int O = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 2 : 5, A = e->cfg.phase == PD_PHASE_PURE_THROTTLE ? 1 : 4;
+    const int O = pd::phase_odim(e->cfg.phase), A = pd::phase_adim(e->cfg.phase);
     const size_t B = (size_t)e->cfg.n_envs;
     if (!e->obs_carry) {
         CK(cudaMalloc(&e->obs_carry, B * O * sizeof(float)));
@@ -527,7 +621,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
                         cudaGetErrorString(cudaGetLastError()));
         g_launches++;
         StepIO io;
-        io.actions = act_t; io.action_dtype = PD_ACT_F32;
+        io.actions = act_t; io.action_dtype = PD_ACT_F32; io.raw_actions = 0;
         io.obs = next_obs_out ? next_obs_out + (size_t)t * B * O : nullptr;
         io.reward = rew_out ? rew_out + (size_t)t * B : nullptr;
         io.done = done_out ? done_out + (size_t)t * B : nullptr;

@@ -17,6 +17,10 @@
 //   substep()        src/envs/rockets_physics.py:455-646
 //   wind             src/envs/wind/full_wind_model.py:35-43, vonkarman.py:33-36
 //   rtd_*()          src/envs/pso/rtd_pso.py:172-317, src/envs/rl/rtd_rl.py:194-336
+// Phases outside the landing burns (RL mode only, as upstream):
+//   control_ascent() rockets_physics.py:17-56 ; control_rcs() :149-166 ; control_C() :402-451
+//   cog_inertia_full()  src/RocketSizing/functions/rocket_dimensions.py:199-241
+//   rtd ascent / ballistic / P-control   src/envs/rl/rtd_rl.py:11-114, 147-188, 353-534
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,6 +30,16 @@
 #define PD_TWO_PI 6.283185307179586
 
 namespace pd {
+
+// ------------------------------------------------------------------ flight phases
+// 0 landing_burn_pure_throttle, 1 landing_burn, 2 subsonic, 3 supersonic,
+// 4 ballistic_arc_descent, 5 landing_burn_pure_throttle_Pcontrol
+__host__ __device__ constexpr int phase_adim(int ph) { return ph == 1 ? 4 : ((ph == 2 || ph == 3) ? 2 : 1); }
+__host__ __device__ constexpr int phase_odim(int ph) {
+    return ph == 0 ? 2 : ph == 1 ? 5 : (ph == 2 || ph == 3) ? 8 : ph == 4 ? 4 : 1;
+}
+__host__ __device__ constexpr int phase_nsub(int ph) { return ph <= 1 ? 4 : 1; }
+__host__ __device__ constexpr bool phase_ascent(int ph) { return ph == 2 || ph == 3; }
 
 // ------------------------------------------------------------------ constants
 template <typename R>
@@ -50,6 +64,17 @@ struct Scalars {
     // fast_log constants, read as constant-bank operands (64-bit immediates would cost a pair
     // of UMOVs per use): 1/5, -1/4, 1/3, -1/2, ln 2, 2^52 + 1023, -1
     R log_c[8];
+    // ---- phases 2..5
+    R n_eng_ng;                     // non-gimballed engines (ascent)
+    R fi[13];                       // full_rocket_inertia cells: m_s_1, x_dry_1, I_dry_1, m_2, m_pay,
+                                    // x_wet_2_initial, I_wet_2_initial, h_1, h_1_ox, h_1_f, m_1_ox,
+                                    // m_1_f, h_lower_1
+    R rcs_force, d_rcs_bottom, d_rcs_top;
+    R norm8[8];                     // obs normalisation of phases 2..4
+    R speed0, terminal_mach, alive_bonus;
+    // Mach-scheduled ascent thresholds (rtd_rl.py:544-575): grid, 4 value rows (max_x, max_vy,
+    // max_vx, max_alpha_deg) and their segment slopes; the reward weights are 100 everywhere
+    R hyp_m[12], hyp_v[4][12], hyp_s[4][12];
 };
 
 // Uniform (Mach, AoA) lookup grid over one query box.  cells >= 0: the grid cell lies
@@ -80,6 +105,9 @@ struct Tables {
     RbfDev cd, cl;
     const double2 *logtab;              // [256] (1/c_j rounded, -log of that), see fast_log
     const void *sh_image;               // SharedTables image (host-replicated), source of the TMA bulk copy
+    // ascent reference trajectory, sorted by altitude: x(y), vx(y), vy(y) values and slopes
+    const double *ref_y, *ref_v[3], *ref_s[3];
+    int n_ref;
     const double *ca_x, *ca_y, *ca_s;   // grid fin C_a segments (x_lo, y_lo, slope)
     const double *cn_x, *cn_y, *cn_s;
     int n_ca, n_cn;
@@ -225,6 +253,32 @@ __device__ __forceinline__ void cog_inertia(R fill, R &x_cog, R &inertia) {
     R I_prop_hat = I_prop + m_p * (dp * dp);
     x_cog = x_wet;
     inertia = I_dry_hat + I_prop_hat;
+}
+
+// full_rocket_inertia (rocket_dimensions.py:199-241): the ascent phases' closure.  Note the
+// upstream asymmetries kept as they are: the fuel column sits on the *current* oxidiser height,
+// and x_prop weights it with the full fuel mass m_1_f.
+template <typename R>
+__device__ __forceinline__ void cog_inertia_full(R fill, R &x_cog, R &inertia) {
+    const R *f = SC<R>().fi;
+    const R m_s_1 = f[0], x_dry_1 = f[1], I_dry_1 = f[2], m_2 = f[3], m_pay = f[4], x_wet_2 = f[5],
+            I_wet_2 = f[6], h_1 = f[7], h_1_ox = f[8], h_1_f = f[9], m_1_ox = f[10], m_1_f = f[11],
+            h_lower_1 = f[12];
+    R h_ox = h_1_ox * fill, h_f = h_1_f * fill, m_ox = m_1_ox * fill, m_f = m_1_f * fill;
+    R m_prop = m_ox + m_f;
+    R a_ox = h_lower_1 + h_ox / R(2);
+    R a_f = h_lower_1 + h_ox + h_f / R(2);
+    R x_prop = m_div(m_ox * a_ox + m_1_f * a_f, m_ox + m_f);
+    const R twelfth = R(1.0 / 12);
+    R d_ox = a_ox - x_prop, d_f = a_f - x_prop;
+    R I_ox = twelfth * m_ox * (h_ox * h_ox) + m_ox * (d_ox * d_ox);
+    R I_f = twelfth * m_f * (h_f * h_f) + m_f * (d_f * d_f);
+    R I_prop = I_ox + I_f;
+    R x_r = m_div(m_s_1 * x_dry_1 + (m_2 + m_pay) * (x_wet_2 + h_1) + m_prop * x_prop,
+                  m_s_1 + m_2 + m_pay + m_prop);
+    R d1 = x_dry_1 - x_r, d2 = x_wet_2 - x_r, d3 = x_prop - x_r;
+    x_cog = x_r;
+    inertia = I_dry_1 + m_s_1 * (d1 * d1) + I_wet_2 + m_2 * (d2 * d2) + I_prop + m_prop * (d3 * d3);
 }
 
 // ------------------------------------------------------------------ local TPS RBF
@@ -715,6 +769,8 @@ struct Control {
     R par, perp, mz, mass_flow_dt;   // mass_flow * dt_phys, rounded as the reference rounds it
     R mass_flow, throttle;
     double gimbal_deg, dl_cmd, dr_cmd;
+    bool f32_forces;                 // par / perp are np.float32 upstream (ascent, float32 action):
+                                     // the body->inertial rotation then runs in float32 too
 };
 
 // ACS (grid fins), acs_model.py:13-86.  d_cmd_* = delta_command_*_rad =
@@ -851,10 +907,97 @@ __device__ __forceinline__ void control_G(const Action<4> &act, const ActPrev &p
     o.mz = m_z + a_mz;
 }
 
+// subsonic / supersonic: force_moment_decomposer_ascent, rockets_physics.py:17-56 with
+// max_gimbal 7 deg, nominal throttle 0.5, 16 gimballed + 26 fixed engines (:727-739).
+// float32 action (fp64 build): gimbal angle, throttle, both thrusts, the parallel /
+// perpendicular sums, total thrust and mass flow are float32; math.cos / math.sin return
+// Python floats that NumPy casts back to float32; the moment is float32 * np.float64.
+template <typename R>
+__device__ __forceinline__ void control_ascent(const Action<2> &act, R p_atm, R d_thrust_cg, Control<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    R t_full = c.T_e + (c.p_e - p_atm) * c.A_e;
+    if (sizeof(R) == 8 && act.f32) {
+        float grad = __fmul_rn((float)act.u[0], g_sf.max_gimbal_rad);
+        double sgd, cgd;
+        sincos((double)grad, &sgd, &cgd);
+        float sg = (float)sgd, cg = (float)cgd;
+        float thr = f32_throttle((float)act.u[1]);
+        float thrust_g = __fmul_rn((float)((double)t_full * (double)c.n_eng), thr);
+        float thrust_ng = __fmul_rn((float)((double)t_full * (double)c.n_eng_ng), thr);
+        float fpar = __fadd_rn(thrust_ng, __fmul_rn(thrust_g, cg));
+        float fperp = __fmul_rn(-thrust_g, sg);
+        o.mz = (R)((double)__fmul_rn(-thrust_g, sg) * (double)d_thrust_cg);
+        float total = __fsqrt_rn(__fadd_rn(__fmul_rn(fpar, fpar), __fmul_rn(fperp, fperp)));
+        float n_tot = __fdiv_rn(total, (float)t_full);
+        float mf = __fmul_rn(g_sf.te_over_vex, n_tot);
+        o.par = (R)fpar;
+        o.perp = (R)fperp;
+        o.mass_flow = (R)mf;
+        o.mass_flow_dt = (R)__fmul_rn(mf, g_sf.dt_phys);
+        o.throttle = (R)thr;
+        o.f32_forces = true;         // no np.float64 ACS term is added here, unlike the landing burns
+    } else {
+        R grad = (R)act.u[0] * c.max_gimbal_rad;
+        R sg, cg;
+        m_sincos(grad, &sg, &cg);
+        R u1 = (R)act.u[1];
+        R throttle = (u1 + R(1)) / R(2) * c.one_minus_nominal + c.nominal;
+        R thrust_g = t_full * c.n_eng * throttle;
+        R thrust_ng = t_full * c.n_eng_ng * throttle;
+        R t_par = thrust_ng + thrust_g * cg;
+        R t_perp = -thrust_g * sg;
+        o.mz = -thrust_g * sg * d_thrust_cg;
+        R total = m_sqrt(t_par * t_par + t_perp * t_perp);
+        R n_tot = total / t_full;
+        R mf = c.te_over_vex * n_tot;
+        o.par = t_par;
+        o.perp = t_perp;
+        o.mass_flow = mf;
+        o.mass_flow_dt = mf * c.dt_phys;
+        o.throttle = throttle;
+    }
+}
+
+// ballistic_arc_descent: RCS, rockets_physics.py:149-166.  Pure couple, no force, no mass flow.
+// float32 action: the thruster force is float32, the moment arms are np.float64.
+template <typename R>
+__device__ __forceinline__ void control_rcs(const Action<1> &act, R x_cog, Control<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    R F;
+    if (sizeof(R) == 8 && act.f32) F = (R)__fmul_rn(g_sf.rcs_force, (float)act.u[0]);
+    else F = c.rcs_force * (R)act.u[0];
+    o.mz = -F * (x_cog - c.d_rcs_bottom) + F * (c.d_rcs_top - x_cog);
+    o.par = R(0); o.perp = R(0);
+    o.mass_flow = R(0); o.mass_flow_dt = R(0); o.throttle = R(0);
+}
+
+// landing_burn_pure_throttle_Pcontrol: force_moment_decomposer_landing_burn_throttle_PID,
+// rockets_physics.py:402-451.  action = reference speed; Kp = -0.08; the inner throttle
+// command is handed on as a *list*, which upstream unpacks with float(): whatever the dtype of
+// v_ref, the thrust chain after it runs in float64.
+template <typename R>
+__device__ __forceinline__ void control_C(const Action<1> &act, R speed, R p_atm, R alpha_eff, R q,
+                                          R x_cog, R mach, Control<R> &o) {
+    Action<1> inner;
+    inner.f32 = false;
+    if (sizeof(R) == 8 && act.f32) {
+        float err = __fsub_rn((float)act.u[0], (float)speed);
+        float nn = __fmul_rn(err, -0.08f);
+        nn = nn < 0.f ? 0.f : (nn > 1.f ? 1.f : nn);
+        inner.u[0] = (double)__fmul_rn(2.0f, __fsub_rn(nn, 0.5f));
+    } else {
+        R err = (R)act.u[0] - speed;
+        R nn = err * R(-0.08);
+        nn = nn < R(0) ? R(0) : (nn > R(1) ? R(1) : nn);
+        inner.u[0] = (double)(R(2) * (nn - R(0.5)));
+    }
+    control_P<R>(inner, p_atm, alpha_eff, q, x_cog, mach, o);
+}
+
 // ------------------------------------------------------------------ one Euler sub-step
 // RT = accumulation type of the RBF dot products.
 template <typename R, typename RT, int PHASE, bool WIND, int COOP = 1>
-__device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
+__device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)> &act,
                                         const ActPrev &prev, WindState &w, const WindCtx &wc,
                                         unsigned int env_id, Info<R> &info, Control<R> &ctl,
                                         const SharedTables *sh) {
@@ -868,7 +1011,8 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     R fuel = m_div(c.m_prop0 - (R)s.m_prop, c.m_prop0);
     if (fuel == R(0)) fuel = R(1e-6);
     R x_cog, inertia;
-    cog_inertia<R>(R(1) - fuel, x_cog, inertia);
+    if constexpr (phase_ascent(PHASE)) cog_inertia_full<R>(R(1) - fuel, x_cog, inertia);
+    else cog_inertia<R>(R(1) - fuel, x_cog, inertia);
     R d_thrust_cg = x_cog + c.engine_height;
     R alpha_eff = s.vy < 0.0 ? (R)(s.gamma - s.theta - PD_PI) : (R)s.alpha;
     R d_cp_cg = x_cog - c.cop;
@@ -901,10 +1045,17 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     R aero_x = a_par * ct + a_perp * st;
     R aero_y = a_par * st - a_perp * ct;
     R aero_mz = a_perp * d_cp_cg;
+    ctl.f32_forces = false;
     if constexpr (PHASE == 0)
         control_P<R>(act, p_atm, alpha_eff, q, x_cog, mach, ctl);
-    else
+    else if constexpr (PHASE == 1)
         control_G<R>(act, prev, p_atm, d_thrust_cg, alpha_eff, q, x_cog, mach, ctl);
+    else if constexpr (phase_ascent(PHASE))
+        control_ascent<R>(act, p_atm, d_thrust_cg, ctl);
+    else if constexpr (PHASE == 4)
+        control_rcs<R>(act, x_cog, ctl);
+    else
+        control_C<R>(act, speed, p_atm, alpha_eff, q, x_cog, mach, ctl);
     R c_par = ctl.par, c_perp = ctl.perp, c_mz = ctl.mz;
     // NaN guards are an if/elif chain upstream: only the first NaN is cleared
     if (c_par != c_par) c_par = R(0);
@@ -912,11 +1063,22 @@ __device__ __forceinline__ void substep(State &s, const Action<(PHASE == 0 ? 1 :
     else if (c_mz != c_mz) c_mz = R(0);
     R c_x = c_par * ct + c_perp * st;
     R c_y = c_par * st - c_perp * ct;
+    R fx = aero_x + c_x + f_wind_x;
+    R fy = aero_y + c_y;
+    if (sizeof(R) == 8 && ctl.f32_forces) {
+        // rockets_physics.py:608-616 with np.float32 control forces: math.cos/sin(theta) are cast
+        // to float32, and so is the aerodynamic force - a Python float (weak) here, since the
+        // RBF coefficients come back as Python floats - before the float32 sum; the wind force
+        // (np.float64) then promotes the total
+        const float pf = (float)c_par, qf = (float)c_perp, cf = (float)ct, sf = (float)st;
+        const float cxf = __fadd_rn(__fmul_rn(pf, cf), __fmul_rn(qf, sf));
+        const float cyf = __fsub_rn(__fmul_rn(pf, sf), __fmul_rn(qf, cf));
+        fx = (R)__fadd_rn((float)aero_x, cxf) + f_wind_x;
+        fy = (R)__fadd_rn((float)aero_y, cyf);
+    }
     const R RE = R(6371000.0);
     R gr = m_div(RE, RE + y);
     R g = R(9.80665) * (gr * gr);
-    R fx = aero_x + c_x + f_wind_x;
-    R fy = aero_y + c_y;
     R mass = (R)s.mass;
     R vx_dot = m_div(fx, mass);
     R vy_dot = m_div(fy, mass) - g;
@@ -983,6 +1145,135 @@ __device__ __forceinline__ R overshoot(double x, double y) {
     if (x < 0.0) return (R)(-x);
     if (y < 0.0) return (R)(-y);
     return R(0);
+}
+
+// scipy interp1d(kind='linear', fill_value='extrapolate') on a sorted grid with precomputed
+// segment slopes: idx = clip(searchsorted(x, v, 'left'), 1, n-1); y = s[idx-1] (v - x[idx-1]) + y[idx-1]
+__device__ __forceinline__ double interp_global(const double *x, const double *y, const double *sl, int n, double v) {
+    const int lo = seg_index(x, n, v);
+    return __ldg(sl + lo) * (v - __ldg(x + lo)) + __ldg(y + lo);
+}
+template <typename R>
+__device__ __forceinline__ R hyper(int row, R mach) {
+    const Scalars<R> &c = SC<R>();
+    int a = 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) a += (c.hyp_m[j] < mach) ? 1 : 0;
+    const int idx = a < 1 ? 1 : (a > 11 ? 11 : a);
+    const int lo = idx - 1;
+    return c.hyp_s[row][lo] * (mach - c.hyp_m[lo]) + c.hyp_v[row][lo];
+}
+
+// subsonic / supersonic closures, rtd_rl.py:11-114 (NaN states: truncated with id 0, reward 0)
+template <typename R>
+__device__ __forceinline__ void rtd_ascent(const State &s, Rtd<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    const bool nan = (s.x != s.x) || (s.y != s.y) || (s.vx != s.vx) || (s.vy != s.vy) ||
+                     (s.theta != s.theta) || (s.theta_dot != s.theta_dot) || (s.gamma != s.gamma) ||
+                     (s.alpha != s.alpha) || (s.mass != s.mass) || (s.m_prop != s.m_prop) || (s.time != s.time);
+    if (nan) { o.reward = R(0); o.done = 0; o.truncated = 1; o.trunc_id = 0; return; }
+    R rho, p_atm, a_snd;
+    isa<R>((R)s.y, rho, p_atm, a_snd);
+    R vx = (R)s.vx, vy = (R)s.vy;
+    R speed = m_sqrt(vx * vx + vy * vy);
+    R mach = (speed != R(0) && a_snd != R(0)) ? speed / a_snd : R(0);
+    const R xr = (R)interp_global(g_tb.ref_y, g_tb.ref_v[0], g_tb.ref_s[0], g_tb.n_ref, s.y);
+    const R vxr = (R)interp_global(g_tb.ref_y, g_tb.ref_v[1], g_tb.ref_s[1], g_tb.n_ref, s.y);
+    const R vyr = (R)interp_global(g_tb.ref_y, g_tb.ref_v[2], g_tb.ref_s[2], g_tb.n_ref, s.y);
+    const R max_x = hyper<R>(0, mach), max_vy = hyper<R>(1, mach), max_vx = hyper<R>(2, mach),
+            max_al = hyper<R>(3, mach);
+    R ex = (R)s.x - xr, evx = vx - vxr, evy = vy - vyr;
+    int tr = 0, id = 0;
+    if (s.m_prop <= 0.0) { tr = 1; id = 1; }
+    else if (mach > c.terminal_mach + R(0.09)) { tr = 1; id = 2; }
+    else if (m_abs(ex) > max_x) { tr = 1; id = 3; }
+    else if (s.y < 0.0) { tr = 1; id = 4; }
+    else if ((R)fabs(s.alpha) > max_al * R(PD_PI / 180.0)) { tr = 1; id = 5; }
+    else if (m_abs(evx) > max_vx) { tr = 1; id = 6; }
+    else if (m_abs(evy) > max_vy) { tr = 1; id = 7; }
+    const int dn = (s.m_prop >= 0.0 && mach > c.terminal_mach) ? 1 : 0;
+    R reward = R(0);
+    if (!(s.y < 0.0)) {
+        const R adeg = (R)s.alpha * R(180.0 / PD_PI);
+        reward += m_exp(R(-4) * (evx * evx) / (max_vx * max_vx)) * R(100);
+        reward += m_exp(R(-4) * (evy * evy) / (max_vy * max_vy)) * R(100);
+        reward += m_exp(R(-4) * (ex * ex) / (max_x * max_x)) * R(100);
+        reward += m_exp(R(-4) * (adeg * adeg) / (max_al * max_al)) * R(100);
+        if (dn) reward += R(2.5);
+        reward /= R(10000);
+    }
+    o.reward = reward; o.done = dn; o.truncated = tr; o.trunc_id = id;
+}
+
+// ballistic_arc_descent closures, rtd_rl.py:147-188
+template <typename R>
+__device__ __forceinline__ void rtd_ballistic(const State &s, Rtd<R> &o) {
+    R vx = (R)s.vx, vy = (R)s.vy;
+    R speed = m_sqrt(vx * vx + vy * vy);
+    R q = R(0.5) * isa_rho<R>((R)s.y) * (speed * speed);
+    const double ae = fabs(s.gamma - s.theta - PD_PI);
+    const int dn = (q > R(10000) && ae < 3.0 * (PD_PI / 180.0)) ? 1 : 0;
+    const int tr = (q > R(10000 - 2000) && ae > 5.0 * (PD_PI / 180.0)) ? 1 : 0;
+    R reward = (R)((PD_PI - ae) / PD_PI);
+    if (dn) reward += R(3.5);
+    o.reward = reward / R(100); o.done = dn; o.truncated = tr; o.trunc_id = tr;
+}
+
+// landing_burn_pure_throttle_Pcontrol closures, rtd_rl.py:353-401 and the second (winning)
+// reward definition :478-531.  v_ref / vref_f32: the action as the base env received it.
+template <typename R>
+__device__ __forceinline__ void rtd_pcontrol(const State &s, R g1, double v_ref, bool vref_f32, Rtd<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    R vx = (R)s.vx, vy = (R)s.vy;
+    R speed = m_sqrt(vx * vx + vy * vy);
+    R rho = isa_rho<R>((R)s.y);
+    R q = R(0.5) * rho * (speed * speed);
+    const double theta_lim = PD_PI + 2.0 * (PD_PI / 180.0);
+    int tr = 0, id = 0;
+    if (s.y < -10.0) { tr = 1; id = 1; }
+    else if (s.m_prop <= 0.0) { tr = 1; id = 2; }
+    else if (s.theta > theta_lim) { tr = 1; id = 3; }
+    else if (q > R(65000)) { tr = 1; id = 4; }
+    else if (g1 > R(6.0)) { tr = 1; id = 5; }
+    else if (s.vy > 0.0) { tr = 1; id = 6; }
+    const int dn = (s.y > 0.0 && s.y < 5.0 && speed < R(1)) ? 1 : 0;
+    R sp = m_hypot(vx, vy);
+    R qq = R(0.5) * rho * (sp * sp);
+    R r = R(0);
+    if (qq > R(60000)) {
+        R e = (qq - R(60000)) / R(5000);
+        r -= m_min(e * e, R(1));
+    }
+    if (g1 > R(5.5)) {
+        R e = (g1 - R(5.5)) / R(0.5);
+        r -= m_min(e * e, R(1));
+    }
+    R prog = (R)((g_sd.y0 - s.y) / g_sd.y0);
+    R track;
+    if (sizeof(R) == 8 && vref_f32) {
+        // np.float32 arithmetic: abs(speed - v_ref) / 10.0, 1.0 - ..., then max(0.0, .)
+        float t = __fsub_rn(1.0f, __fdiv_rn(fabsf(__fsub_rn((float)sp, (float)v_ref)), 10.0f));
+        track = t > 0.f ? (R)t : R(0);
+    } else {
+        R t = R(1) - m_abs(sp - (R)v_ref) / R(10);
+        track = t > R(0) ? t : R(0);
+    }
+    R wp = (qq <= R(60000) && g1 <= R(5.5)) ? R(0.5) : R(0.5 * 0.1);
+    r += wp * prog * track;
+    if (s.y < 100.0) {
+        R sl = R(1) - m_abs(vy) / R(50);
+        r += R(0.5) * (sl > R(0) ? sl : R(0));
+    }
+    r += c.alive_bonus;
+    if (dn && !tr) {
+        r += R(5);
+        R used = (R)(g_sd.y0 * 0.0 + (g_sd.mass0 - s.mass));
+        r -= m_min(R(0.1) * used, R(1));
+    } else if (tr) {
+        r -= m_min(R(4) * (R)(s.y / g_sd.y0) * (m_abs(vy) / R(100)), R(5));
+    }
+    r = r < R(-10) ? R(-10) : (r > R(10) ? R(10) : r);
+    o.reward = r; o.done = dn; o.truncated = tr; o.trunc_id = id;
 }
 
 template <typename R, int PHASE, int RTD>
@@ -1074,6 +1365,23 @@ __device__ __forceinline__ void rtd_eval(const State &s, R g1, R u0, Rtd<R> &o) 
 template <typename R, int PHASE, int RTD>
 __device__ __forceinline__ void observe(const State &s, R *o) {
     const Scalars<R> &c = SC<R>();
+    if constexpr (PHASE >= 2) {
+        // env_wrapped_rl_pytorch.py:169-177, 199-201: the state is rounded to float32; phases 2..4
+        // divide a float32 array in place by the float64 normalisation vector (float64 divide,
+        // float32 result); P-control forms (1 - y/norm)*2 - 1 in float64
+        if constexpr (phase_ascent(PHASE)) {
+            const double v[8] = {s.x, s.y, s.vx, s.vy, s.theta, s.theta_dot, s.alpha, s.mass};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = (R)(float)((double)(float)v[k] / g_sd.norm8[k]);
+        } else if constexpr (PHASE == 4) {
+            const double v[4] = {s.theta, s.theta_dot, s.gamma, s.alpha};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = (R)(float)((double)(float)v[k] / g_sd.norm8[k]);
+        } else {
+            o[0] = (R)((1.0 - (double)(float)s.y / g_sd.norm_y) * 2 - 1);
+        }
+        return;
+    }
     if (RTD == 0) {
         if (PHASE == 0) {
             o[0] = (R)s.y / c.norm_y;
@@ -1107,7 +1415,7 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
 // 4 sub-steps with the same action (and, for G, the same actuator memory), g-load window,
 // truncation -> done -> reward on the new state.  base_environment.py:99-154.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, int COOP = 1>
-__device__ __forceinline__ void env_step(State &s, const Action<(PHASE == 0 ? 1 : 4)> &act,
+__device__ __forceinline__ void env_step(State &s, const Action<phase_adim(PHASE)> &act,
                                          ActPrev &prev, WindState &w, const WindCtx &wc,
                                          unsigned int env_id, GWindow<R> &gw, Info<R> &info,
                                          Rtd<R> &out, R &g1_out, const SharedTables *sh) {
@@ -1115,7 +1423,7 @@ __device__ __forceinline__ void env_step(State &s, const Action<(PHASE == 0 ? 1 
     R v_p = m_sqrt(vxp * vxp + vyp * vyp);
     Control<R> ctl;
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < phase_nsub(PHASE); ++k)
         substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, env_id, info, ctl, sh);
     if (PHASE == 1) {
         prev.gimbal_deg = ctl.gimbal_deg;
@@ -1127,9 +1435,17 @@ __device__ __forceinline__ void env_step(State &s, const Action<(PHASE == 0 ? 1 
     R g_load = m_abs(v - v_p) / R(0.1) * R(1) / R(9.81);
     R g1 = gwindow_push<R>(gw, g_load);
     g1_out = g1;
-    R u0 = (R)act.u[0];
-    if (sizeof(R) == 8 && act.f32) u0 = (R)(float)act.u[0];
-    rtd_eval<R, PHASE, RTD>(s, g1, u0, out);
+    if constexpr (phase_ascent(PHASE)) {
+        rtd_ascent<R>(s, out);
+    } else if constexpr (PHASE == 4) {
+        rtd_ballistic<R>(s, out);
+    } else if constexpr (PHASE == 5) {
+        rtd_pcontrol<R>(s, g1, act.u[0], act.f32, out);
+    } else {
+        R u0 = (R)act.u[0];
+        if (sizeof(R) == 8 && act.f32) u0 = (R)(float)act.u[0];
+        rtd_eval<R, PHASE, RTD>(s, g1, u0, out);
+    }
 }
 
 __device__ __forceinline__ void state_reset(State &s) {

@@ -28,6 +28,7 @@ struct EnvSoA {
 struct StepIO {
     const void *actions;
     int action_dtype;
+    int raw_actions;       // skip the RL wrapper's augment_action
     void *obs, *reward, *next_obs;
     uint8_t *done, *truncated;
     int32_t *trunc_id;

@@ -65,7 +65,13 @@ __device__ __forceinline__ void read_action(const void *actions, int dtype, size
 }
 
 template <int PHASE, int RTD>
-__device__ __forceinline__ void shape_action(Action<(PHASE == 0 ? 1 : 4)> &a) {
+__device__ __forceinline__ void shape_action(Action<phase_adim(PHASE)> &a) {
+    if constexpr (PHASE == 5 && RTD == 1) {
+        // rl_wrapped_env_pytorch.augment_action (env_wrapped_rl_pytorch.py:158-164):
+        // v_ref = (u0 + 1)/2 * speed0, float32 arithmetic for a float32 action
+        if (a.f32) a.u[0] = (double)__fmul_rn(__fdiv_rn(__fadd_rn((float)a.u[0], 1.0f), 2.0f), g_sf.speed0);
+        else a.u[0] = (a.u[0] + 1.0) / 2.0 * g_sd.speed0;
+    }
     if constexpr (PHASE == 1 && RTD == 1) {
         // np.array([...python floats...]) -> float64 action
         a.u[0] = log_compress(a.u[0], 10.0, a.f32);
@@ -152,7 +158,7 @@ __global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const do
 // observation of the current state (first step of a collection run)
 template <typename R, int PHASE, int RTD>
 __global__ void observe_kernel(EnvSoA e, R *obs) {
-    constexpr int O = PHASE == 0 ? 2 : 5;
+    constexpr int O = phase_odim(PHASE);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n) return;
     State s;
@@ -171,8 +177,8 @@ __global__ void observe_kernel(EnvSoA e, R *obs) {
 template <typename R, typename RT, int PHASE, int RTD, bool WIND>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
-    constexpr int A = PHASE == 0 ? 1 : 4;
-    constexpr int O = PHASE == 0 ? 2 : 5;
+    constexpr int A = phase_adim(PHASE);
+    constexpr int O = phase_odim(PHASE);
     extern __shared__ __align__(16) unsigned char pd_smem[];
     SharedTables &sh = *aligned_tables(pd_smem);
     stage_tables(&sh);
@@ -191,7 +197,7 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     if (WIND) load_wind(e, i, w);
     Action<A> act;
     read_action<A>(io.actions, io.action_dtype, (size_t)i, act);
-    shape_action<PHASE, RTD>(act);
+    if (!io.raw_actions) shape_action<PHASE, RTD>(act);
     Info<R> info;
     info.rbf_status = 0;
     Rtd<R> out;
@@ -317,8 +323,8 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
-    constexpr int A = PHASE == 0 ? 1 : 4;
-    constexpr int O = PHASE == 0 ? 2 : 5;
+    constexpr int A = phase_adim(PHASE);
+    constexpr int O = phase_odim(PHASE);
     extern __shared__ __align__(16) unsigned char pd_smem[];
     SharedTables &sh = *aligned_tables(pd_smem);
     stage_tables(&sh);
@@ -483,7 +489,16 @@ struct Launch {
             case 4: step_t<1, 0, false>(e, io, wc, sig, auto_reset, st); break;
             case 5: step_t<1, 0, true>(e, io, wc, sig, auto_reset, st); break;
             case 6: step_t<1, 1, false>(e, io, wc, sig, auto_reset, st); break;
-            default: step_t<1, 1, true>(e, io, wc, sig, auto_reset, st); break;
+            case 7: step_t<1, 1, true>(e, io, wc, sig, auto_reset, st); break;
+            // phases 2..5 exist with the rl closures only (pd_create rejects type 'pso')
+            case 10: step_t<2, 1, false>(e, io, wc, sig, auto_reset, st); break;
+            case 11: step_t<2, 1, true>(e, io, wc, sig, auto_reset, st); break;
+            case 14: step_t<3, 1, false>(e, io, wc, sig, auto_reset, st); break;
+            case 15: step_t<3, 1, true>(e, io, wc, sig, auto_reset, st); break;
+            case 18: step_t<4, 1, false>(e, io, wc, sig, auto_reset, st); break;
+            case 19: step_t<4, 1, true>(e, io, wc, sig, auto_reset, st); break;
+            case 22: step_t<5, 1, false>(e, io, wc, sig, auto_reset, st); break;
+            default: step_t<5, 1, true>(e, io, wc, sig, auto_reset, st); break;
         }
     }
     template <int PHASE, int RTD, bool WIND, int POLICY>
@@ -516,6 +531,7 @@ struct Launch {
     }
     static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
                        const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {
+        if (phase > 1) return 1;    // whole-episode rollouts: the two landing phases
         if (policy == 0) {          // per-particle MLP: pso rtd only
             int key = phase * 2 + (wind ? 1 : 0);
             switch (key) {
@@ -558,7 +574,11 @@ static void impl_observe(int phase, int rtd, const EnvSoA &e, void *obs, cudaStr
         case 0: observe_kernel<R, 0, 0><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
         case 1: observe_kernel<R, 0, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
         case 2: observe_kernel<R, 1, 0><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        default: observe_kernel<R, 1, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        case 3: observe_kernel<R, 1, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        case 5: observe_kernel<R, 2, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        case 7: observe_kernel<R, 3, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        case 9: observe_kernel<R, 4, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        default: observe_kernel<R, 5, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
     }
 }
 

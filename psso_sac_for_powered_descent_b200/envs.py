@@ -24,7 +24,12 @@ import torch
 from . import _native as N
 from .params import RocketParams
 
-WORKING_PHASES = ("landing_burn_pure_throttle", "landing_burn")
+# landing_burn_pure_throttle / landing_burn: type 'pso' and 'rl'.  subsonic, supersonic,
+# ballistic_arc_descent, landing_burn_pure_throttle_Pcontrol: type 'rl' only - upstream their pso
+# closures have the wrong arity (rtd_pso.py:38-157 vs base_environment.py:150-152 -> TypeError).
+# flip_over_boostbackburn (TypeError in rl mode too, rtd_rl.py:132) and landing_burn_ACS (broken in
+# compile_physics, rockets_physics.py:867-889) do not run upstream and are not offered.
+WORKING_PHASES = tuple(N.PHASES)
 ALL_PHASES = ["subsonic", "supersonic", "flip_over_boostbackburn", "ballistic_arc_descent",
               "landing_burn", "landing_burn_ACS", "landing_burn_pure_throttle",
               "landing_burn_pure_throttle_Pcontrol"]
@@ -49,15 +54,23 @@ class BatchedRocketEnv:
     def __init__(self, n_envs, type="pso", flight_phase="landing_burn_pure_throttle",
                  enable_wind=False, stochastic_wind=False, horiontal_wind_percentile=50,
                  trajectory_length=1, discount_factor=0.99, precision="fp32", auto_reset=False,
-                 device=None, seed=0, params: RocketParams | None = None):
+                 device=None, seed=0, params: RocketParams | None = None, raw_actions=False):
+        """raw_actions (type 'rl'): False = `step` takes the policy's action and applies
+        rl_wrapped_env_pytorch.augment_action inside the kernel (landing_burn log-compression,
+        P-control reference-speed scaling); True = actions are what
+        rocket_environment_pre_wrap.step expects."""
         assert flight_phase in ALL_PHASES
         if flight_phase not in WORKING_PHASES:
             raise NotImplementedError(
-                f"flight phase {flight_phase!r} is outside the B200 hot path "
-                "(landing_burn_pure_throttle, landing_burn); see DESIGN.md")
+                f"flight phase {flight_phase!r} does not run in the reference either "
+                "(flip_over_boostbackburn: rtd_rl.py:132 TypeError; landing_burn_ACS: "
+                "rockets_physics.py:867-889); see DESIGN.md")
         assert type in ("rl", "pso", "supervisory")
         if type == "supervisory":
             raise NotImplementedError("supervisory rtd closures are outside the hot path")
+        if flight_phase in N.RL_ONLY_PHASES and type != "rl":
+            raise TypeError(f"{flight_phase}: only type='rl' works upstream (the pso closures of this "
+                            "phase have the wrong arity, rtd_pso.py:38-157)")
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedRocketEnv needs a CUDA device (no CPU fallback)")
         if enable_wind:
@@ -74,7 +87,7 @@ class BatchedRocketEnv:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else device.index or 0)
         self.obs_dim, self.act_dim = N.OBS_DIM[self.phase_id], N.ACT_DIM[self.phase_id]
-        self.n_actor_params = N.N_PARAMS[self.phase_id]
+        self.n_actor_params = N.N_PARAMS.get(self.phase_id)
         self.dt = 0.1
         self.enable_wind = bool(enable_wind)
         cfg = N.PdConfig()
@@ -84,6 +97,8 @@ class BatchedRocketEnv:
         cfg.seed = int(seed)
         g, L = discount_factor, trajectory_length
         cfg.rl_reward_scale = (1 - g) / (1 - g ** L) if (g is not None and L) else 1.0
+        cfg.discount_factor = g if g is not None else 0.99
+        cfg.raw_actions = int(bool(raw_actions))
         self._cparams, self._keep = N.make_params(self.params, horiontal_wind_percentile)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -359,15 +374,18 @@ class rocket_environment_pre_wrap:
 
     def __init__(self, type="rl", flight_phase="subsonic", enable_wind=True, stochastic_wind=True,
                  horiontal_wind_percentile=50, trajectory_length=100, discount_factor=0.99,
-                 precision="fp64", seed=0):
+                 precision="fp64", seed=0, _wrapped=False):
         assert flight_phase in ALL_PHASES
         assert type in ["rl", "pso", "supervisory"]
         self.flight_phase, self.type, self.dt = flight_phase, type, 0.1
         self.enable_wind = enable_wind
+        # the base env takes its actions as they are; the RL wrapper (_wrapped) hands over the
+        # policy's action and lets the kernel apply augment_action
         self._b = BatchedRocketEnv(1, type, flight_phase, enable_wind, stochastic_wind,
                                    horiontal_wind_percentile, trajectory_length, discount_factor,
-                                   precision=precision, seed=seed)
-        self.state_initial = list(self._b.params.initial_state)
+                                   precision=precision, seed=seed, raw_actions=not _wrapped)
+        op = self._b.params.other_phases.get("initial_states", {}) if self._b.params.other_phases else {}
+        self.state_initial = list(op.get(flight_phase, self._b.params.initial_state))
         self.wind_generator = self._b if enable_wind else None
         self._dbg = torch.zeros(1, 16, dtype=torch.float64, device=self._b.device)
         self.truncation_id = 0
@@ -466,8 +484,9 @@ class pso_wrapped_env:
 
 
 class rl_wrapped_env_pytorch:
-    """rl_wrapped_env_pytorch (env_wrapped_rl_pytorch.py:68-205) for the landing phases:
-    float32-rounded observation, G action log-compression, state_dim/action_dim."""
+    """rl_wrapped_env_pytorch (env_wrapped_rl_pytorch.py:68-205): float32-rounded observation,
+    G action log-compression, P-control reference-speed scaling (both inside the step kernel),
+    state_dim/action_dim."""
 
     def __init__(self, flight_phase="subsonic", enable_wind=False, stochastic_wind=True,
                  horiontal_wind_percentile=50, trajectory_length=None, discount_factor=None,
@@ -476,7 +495,8 @@ class rl_wrapped_env_pytorch:
         self.flight_phase = flight_phase
         self.env = rocket_environment_pre_wrap("rl", flight_phase, enable_wind, stochastic_wind,
                                                horiontal_wind_percentile, trajectory_length,
-                                               discount_factor, precision=precision, seed=seed)
+                                               discount_factor, precision=precision, seed=seed,
+                                               _wrapped=True)
         self.enable_wind = enable_wind
         self.state_dim, self.action_dim = self.env._b.obs_dim, self.env._b.act_dim
 
@@ -492,6 +512,13 @@ class rl_wrapped_env_pytorch:
     def _obs_from_state(self, state):
         s = np.asarray(state, dtype=np.float32)
         nv = np.array(self.env._b.params.norm_vals)     # np.float64 scalars, as upstream
+        if self.flight_phase in ("subsonic", "supersonic", "ballistic_arc_descent"):
+            idx = [4, 5, 6, 7] if self.flight_phase == "ballistic_arc_descent" else [0, 1, 2, 3, 4, 5, 7, 8]
+            o = s[idx].copy()
+            o /= np.array(self.env._b.params.other_phases["norm_vals"][self.flight_phase])
+            return o
+        if self.flight_phase == "landing_burn_pure_throttle_Pcontrol":
+            return np.array([(1 - s[1] / nv[0]) * 2 - 1])
         if self.flight_phase == "landing_burn_pure_throttle":
             return np.array([(1 - s[1] / nv[0]) * 2 - 1, (1 - s[3] / nv[1]) * 2 - 1])
         k = float(np.arctanh(0.75) / math.radians(5))
@@ -511,6 +538,8 @@ class rl_wrapped_env_pytorch:
             a = a[0]
         state, reward, done, truncated, info = self.env.step(a)
         obs = self.env._obs.to(torch.float64).cpu().numpy()
+        if self.flight_phase in ("subsonic", "supersonic", "ballistic_arc_descent"):
+            obs = obs.astype(np.float32)        # upstream hands back a float32 array for these phases
         return obs, float(reward), bool(done), bool(truncated), info
 
     def __getattr__(self, name):

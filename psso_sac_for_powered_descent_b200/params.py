@@ -150,9 +150,12 @@ class RocketParams:
 
         if closure_cells is None:
             snap = cls.default()
+            so = snap.other_phases
             closure_cells = dict(inertia=snap.inertia, engine_height=snap.engine_height,
                                  cop_length=snap.cop_length, cop_d0=snap.cop_d0,
-                                 v_opt_a=snap.v_opt_a, v_opt_b=snap.v_opt_b)
+                                 v_opt_a=snap.v_opt_a, v_opt_b=snap.v_opt_b,
+                                 inertia_full=so["inertia_full"], engine_height_full=so["engine_height_full"],
+                                 cop_length_full=so["cop_length_full"], cop_d0_full=so["cop_d0_full"])
         p.inertia = {k: float(v) for k, v in closure_cells["inertia"].items()}
         p.engine_height = float(closure_cells["engine_height"])
         p.cop_length = float(closure_cells["cop_length"])
@@ -192,7 +195,56 @@ class RocketParams:
         p.gf_cn_val = [float(v) for v in cn[1].values]
 
         p.wind_table = _parse_wind_table(os.path.join(root, "data/Wind/horizontal_wind.csv"))
+        p.other_phases = _other_phases(root, sizing, closure_cells, traj)
         return p
+
+
+_STATE_COLS = ("x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "theta[rad]", "theta_dot[rad/s]", "gamma[rad]",
+               "alpha[rad]", "mass[kg]", "mass_propellant[kg]", "time[s]")
+
+
+def _other_phases(root, sizing, cc, ballistic_traj):
+    """Constants of subsonic / supersonic / ballistic_arc_descent, parsed the way the reference
+    parses them: load_initial_states.py:5-54, input_normalisation.py:5-71,
+    reference_trajectory_interpolation.py:5-35, rockets_physics.py:727-801."""
+    import pandas as pd
+    fl = lambda v: [float(x) for x in v]
+    asc = os.path.join(root, "data/reference_trajectory/ascent_controls")
+    sub = pd.read_csv(os.path.join(asc, "subsonic_state_action_ascent_control.csv"))
+    sup = pd.read_csv(os.path.join(asc, "supersonic_state_action_ascent_control.csv"))
+    flip = pd.read_csv(os.path.join(root, "data/reference_trajectory/flip_over_and_boostbackburn_controls/"
+                                          "state_action_flip_over_and_boostbackburn_control.csv"))
+    ref = pd.read_csv(os.path.join(asc, "reference_trajectory_ascent_control.csv"))
+    init_sub = np.array([0, 1.5, 0, 0, np.pi / 2, 0, 0, 0,
+                         float(sizing["Initial mass (subrocket 0)"]) * 1000,
+                         float(sizing["Actual propellant mass stage 1"]) * 1000, 0])
+
+    def ascent_norm(d, add):
+        st = d[["x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "theta[rad]", "theta_dot[rad/s]", "alpha[rad]",
+                "mass[kg]"]].values
+        m = np.max(np.abs(st), axis=0)
+        return [m[0] + add[0], m[1] + add[1], m[2] + add[2], m[3] + add[3], m[4] + math.radians(add[4]),
+                m[5] * 2.5, m[6] + math.radians(3), m[7]]
+    bs = ballistic_traj[["theta[rad]", "theta_dot[rad/s]", "alpha[rad]", "gamma[rad]"]].values
+    bm = np.max(np.abs(bs), axis=0)
+    states = ref[["x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "mass[kg]"]].values
+    return dict(
+        n_engines_stage1=int(sizing["Number of engines stage 1"]),
+        max_rcs_force_per_thruster=float(sizing["max_RCS_force_per_thruster"]),
+        d_base_rcs_bottom=float(sizing["d_base_rcs_bottom"]),
+        d_base_rcs_top=float(sizing["d_base_rcs_top"]),
+        inertia_full={k: float(v) for k, v in cc["inertia_full"].items()},
+        engine_height_full=float(cc["engine_height_full"]),
+        cop_length_full=float(cc["cop_length_full"]), cop_d0_full=float(cc["cop_d0_full"]),
+        initial_states=dict(subsonic=fl(init_sub), supersonic=fl(sub.iloc[-1][list(_STATE_COLS)]),
+                            ballistic_arc_descent=fl(flip.iloc[-1][list(_STATE_COLS)])),
+        norm_vals=dict(subsonic=fl(ascent_norm(sub, (100, 500, 5, 50, 2))),
+                       supersonic=fl(ascent_norm(sup, (2500, 5000, 100, 150, 5))),
+                       ballistic_arc_descent=fl([bm[0] + math.radians(5), bm[1] * 2.5,
+                                                 bm[3] + math.radians(5), bm[2] + math.radians(5)])),
+        ref_traj_ascent=dict(y=fl(ref["y[m]"].values), x=fl(ref["x[m]"].values),
+                             vx=fl(ref["vx[m/s]"].values), vy=fl(ref["vy[m/s]"].values)),
+        ref_traj_ascent_terminal=fl(states[-1]))
 
 
 def _parse_v2_table(path):

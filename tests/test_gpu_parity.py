@@ -476,8 +476,10 @@ def test_scalar_drop_in_api(envs_mod):
     env.reset()
     s32, *_ = env.step(np.array([0.25], dtype=np.float32))      # float32 action: NEP-50 path
     assert s32 != outs[0] and abs(s32[8] - outs[0][8]) < 1.0
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):          # upstream: pso closures of this phase have the wrong arity
         envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase="subsonic", enable_wind=False)
+    with pytest.raises(NotImplementedError):    # does not run upstream either
+        envs_mod.rocket_environment_pre_wrap(type="rl", flight_phase="landing_burn_ACS", enable_wind=False)
     with pytest.raises(AssertionError):
         envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase="nonsense", enable_wind=False)
     m = envs_mod.pso_wrapped_env(flight_phase=G)
