@@ -35,6 +35,7 @@ extern "C" {
 #define PD_RBF_NEIGHBOURS 50
 #define PD_RBF_ROW_BYTES 512
 #define PD_DBG_DIM 16
+#define PD_INFO_DIM 48     /* PD_DBG_DIM + 32 (pd_set_info_mode) */
 
 /* flight_phase strings (src/envs/base_environment.py:21).  0/1 work with type 'pso' and 'rl';
  * 2..5 with type 'rl' only, as upstream (their pso closures have the wrong arity,
@@ -180,6 +181,16 @@ int pd_reset(PdEnv *env, const uint8_t *mask, void *stream);
 int pd_step(PdEnv *env, const void *actions, int action_dtype, void *obs, void *reward,
             uint8_t *done, uint8_t *truncated, int32_t *trunc_id, void *next_obs, double *dbg,
             void *stream);
+
+/* Width of pd_step's `dbg` rows.  full = 0 (default): PD_DBG_DIM values.  full = 1 (PD_FP64 build,
+ * wind disabled): PD_INFO_DIM values - the 16 above followed by the remaining primitives of the
+ * reference's `info` dict (rockets_physics.py:649-702) of the last sub-step: drag, lift, d_cp_cg,
+ * d_thrust_cg, fuel_percentage_consumed, control_force_parallel, control_force_perpendicular,
+ * control_force_x, control_force_y, aero_force_x, aero_force_y, g, control_moment_z,
+ * aero_moment_z, moments_z, theta_dot_dot, vx_dot, vy_dot, F_wind_x, gimbal_angle_deg,
+ * delta_command_left_rad, delta_command_right_rad, mach_number_max, 9 reserved zeros.  A separate
+ * diagnostic instantiation of the step kernel; the throughput kernels are unaffected. */
+int pd_set_info_mode(PdEnv *env, int full);
 
 /* AoS state access (dev double[n_envs*11]); g_window dev double[n_envs*10] + n_window dev
  * int32[n_envs]; act_prev dev double[n_envs*3] = gimbal_angle_deg_prev,

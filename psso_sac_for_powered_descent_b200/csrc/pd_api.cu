@@ -52,6 +52,7 @@ struct PdEnv {
     bool obs_valid = false;
     unsigned int collect_step = 0;
     int n_sm = 148;
+    bool info_full = false;          // pd_set_info_mode
 };
 
 // the __constant__ blocks are per precision TU and per process: re-upload on handle switch
@@ -393,6 +394,14 @@ static WindCtx wind_ctx(const PdEnv *e) {
     return wc;
 }
 
+int pd_set_info_mode(PdEnv *e, int full) {
+    if (!e) return fail("pd_set_info_mode: null handle");
+    if (full && (e->cfg.precision != PD_FP64 || e->cfg.enable_wind))
+        return fail("pd_set_info_mode: the full info row needs the PD_FP64 build without wind");
+    e->info_full = full != 0;
+    return 0;
+}
+
 int pd_reset(PdEnv *e, const uint8_t *mask, void *stream) {
     if (!e) return fail("pd_reset: null handle");
     if (activate(e)) return 1;
@@ -411,6 +420,7 @@ int pd_step(PdEnv *e, const void *actions, int action_dtype, void *obs, void *re
     StepIO io;
     io.actions = actions; io.action_dtype = action_dtype; io.obs = obs; io.reward = reward;
     io.raw_actions = e->cfg.raw_actions;
+    io.dbg_full = (dbg && e->info_full) ? 1 : 0;
     io.next_obs = next_obs; io.done = done; io.truncated = truncated; io.trunc_id = trunc_id;
     io.dbg = dbg;
     e->impl->step(e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
@@ -621,7 +631,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
                         cudaGetErrorString(cudaGetLastError()));
         g_launches++;
         StepIO io;
-        io.actions = act_t; io.action_dtype = PD_ACT_F32; io.raw_actions = 0;
+        io.actions = act_t; io.action_dtype = PD_ACT_F32; io.raw_actions = 0; io.dbg_full = 0;
         io.obs = next_obs_out ? next_obs_out + (size_t)t * B * O : nullptr;
         io.reward = rew_out ? rew_out + (size_t)t * B : nullptr;
         io.done = done_out ? done_out + (size_t)t * B : nullptr;

@@ -187,10 +187,26 @@ struct WindState {
     unsigned int ctr;              // draws consumed (tape position / Philox counter)
 };
 
-template <typename R>
-struct Info {                      // values of the last sub-step (reference `info` dict)
+// values of the last sub-step (reference `info` dict, rockets_physics.py:649-702).  FULL adds
+// the remaining primitives of that dict (forces, moments, accelerations, actuator outputs); it is
+// only instantiated for the fp64 diagnostic kernels so the production kernels keep their
+// register budget.
+#define PD_INFO_X 32
+template <typename R, bool FULL = false>
+struct Info {
     R mach, q, CL, CD, rho, p_atm, a, x_cog, inertia, mass_flow, throttle, alpha_eff, ug, vg;
     int rbf_status;
+};
+template <typename R>
+struct Info<R, true> {
+    R mach, q, CL, CD, rho, p_atm, a, x_cog, inertia, mass_flow, throttle, alpha_eff, ug, vg;
+    int rbf_status;
+    // 0 drag, 1 lift, 2 d_cp_cg, 3 d_thrust_cg, 4 fuel_percentage_consumed, 5 control_force_parallel,
+    // 6 control_force_perpendicular, 7 control_force_x, 8 control_force_y, 9 aero_force_x,
+    // 10 aero_force_y, 11 g, 12 control_moment_z, 13 aero_moment_z, 14 moments_z, 15 theta_dot_dot,
+    // 16 vx_dot, 17 vy_dot, 18 F_wind_x, 19 gimbal_angle_deg, 20 delta_command_left_rad,
+    // 21 delta_command_right_rad, 22 mach_number_max (Qmax = 65 kPa landing phases, 30 kPa others)
+    R x[PD_INFO_X];
 };
 
 // ------------------------------------------------------------------ ISA
@@ -996,10 +1012,10 @@ __device__ __forceinline__ void control_C(const Action<1> &act, R speed, R p_atm
 
 // ------------------------------------------------------------------ one Euler sub-step
 // RT = accumulation type of the RBF dot products.
-template <typename R, typename RT, int PHASE, bool WIND, int COOP = 1>
+template <typename R, typename RT, int PHASE, bool WIND, int COOP = 1, bool FULL = false>
 __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)> &act,
                                         const ActPrev &prev, WindState &w, const WindCtx &wc,
-                                        unsigned int env_id, Info<R> &info, Control<R> &ctl,
+                                        unsigned int env_id, Info<R, FULL> &info, Control<R> &ctl,
                                         const SharedTables *sh) {
     const Scalars<R> &c = SC<R>();
     R y = (R)s.y, vx = (R)s.vx, vy = (R)s.vy;
@@ -1104,6 +1120,20 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
     info.mass_flow = ctl.mass_flow; info.throttle = ctl.throttle; info.alpha_eff = alpha_eff;
     info.ug = ug; info.vg = vg;
     info.rbf_status |= status;
+    if constexpr (FULL) {
+        R *x = info.x;
+        x[0] = drag; x[1] = lift; x[2] = d_cp_cg; x[3] = d_thrust_cg; x[4] = fuel;
+        x[5] = c_par; x[6] = c_perp; x[7] = c_x; x[8] = c_y; x[9] = aero_x; x[10] = aero_y;
+        x[11] = g; x[12] = c_mz; x[13] = aero_mz; x[14] = mz; x[15] = tdd; x[16] = vx_dot;
+        x[17] = vy_dot; x[18] = f_wind_x;
+        x[19] = PHASE == 1 ? (R)ctl.gimbal_deg : (phase_ascent(PHASE) ? (R)(act.u[0] * g_sd.max_gimbal_rad * (180.0 / PD_PI)) : R(0));
+        x[20] = PHASE == 1 ? (R)ctl.dl_cmd : R(0);
+        x[21] = PHASE == 1 ? (R)ctl.dr_cmd : R(0);
+        const R qmax = PHASE <= 1 || PHASE == 5 ? R(65000) : R(30000);
+        x[22] = a_snd != R(0) ? m_sqrt(R(2) * qmax / rho) * R(1) / a_snd : R(200);
+#pragma unroll
+        for (int k = 23; k < PD_INFO_X; ++k) x[k] = R(0);
+    }
 }
 
 // ------------------------------------------------------------------ g-load window
@@ -1414,17 +1444,17 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
 // ------------------------------------------------------------------ one env.step()
 // 4 sub-steps with the same action (and, for G, the same actuator memory), g-load window,
 // truncation -> done -> reward on the new state.  base_environment.py:99-154.
-template <typename R, typename RT, int PHASE, int RTD, bool WIND, int COOP = 1>
+template <typename R, typename RT, int PHASE, int RTD, bool WIND, int COOP = 1, bool FULL = false>
 __device__ __forceinline__ void env_step(State &s, const Action<phase_adim(PHASE)> &act,
                                          ActPrev &prev, WindState &w, const WindCtx &wc,
-                                         unsigned int env_id, GWindow<R> &gw, Info<R> &info,
+                                         unsigned int env_id, GWindow<R> &gw, Info<R, FULL> &info,
                                          Rtd<R> &out, R &g1_out, const SharedTables *sh) {
     R vxp = (R)s.vx, vyp = (R)s.vy;
     R v_p = m_sqrt(vxp * vxp + vyp * vyp);
     Control<R> ctl;
 #pragma unroll 1
     for (int k = 0; k < phase_nsub(PHASE); ++k)
-        substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, env_id, info, ctl, sh);
+        substep<R, RT, PHASE, WIND, COOP, FULL>(s, act, prev, w, wc, env_id, info, ctl, sh);
     if (PHASE == 1) {
         prev.gimbal_deg = ctl.gimbal_deg;
         prev.dl = ctl.dl_cmd;

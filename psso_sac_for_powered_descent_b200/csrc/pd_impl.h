@@ -29,6 +29,7 @@ struct StepIO {
     const void *actions;
     int action_dtype;
     int raw_actions;       // skip the RL wrapper's augment_action
+    int dbg_full;          // dbg rows are PD_INFO_DIM wide (fp64 build, no wind)
     void *obs, *reward, *next_obs;
     uint8_t *done, *truncated;
     int32_t *trunc_id;

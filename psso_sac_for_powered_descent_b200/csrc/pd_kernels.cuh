@@ -174,7 +174,7 @@ __global__ void observe_kernel(EnvSoA e, R *obs) {
 #ifndef PD_STEP_MIN_BLOCKS
 #define PD_STEP_MIN_BLOCKS 8
 #endif
-template <typename R, typename RT, int PHASE, int RTD, bool WIND>
+template <typename R, typename RT, int PHASE, int RTD, bool WIND, bool FULL = false>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
     constexpr int A = phase_adim(PHASE);
@@ -198,12 +198,12 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     Action<A> act;
     read_action<A>(io.actions, io.action_dtype, (size_t)i, act);
     if (!io.raw_actions) shape_action<PHASE, RTD>(act);
-    Info<R> info;
+    Info<R, FULL> info;
     info.rbf_status = 0;
     Rtd<R> out;
     R g1;
     wait_tables(&sh);
-    env_step<R, RT, PHASE, RTD, WIND>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
+    env_step<R, RT, PHASE, RTD, WIND, 1, FULL>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
     if (info.rbf_status) atomicOr(e.status, info.rbf_status);
     R obs[O];
     observe<R, PHASE, RTD>(s, obs);
@@ -216,7 +216,11 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     if (io.truncated) io.truncated[i] = (uint8_t)out.truncated;
     if (io.trunc_id) io.trunc_id[i] = out.trunc_id;
     if (io.dbg) {
-        double *d = io.dbg + (size_t)i * 16;
+        double *d = io.dbg + (size_t)i * (FULL ? 16 + PD_INFO_X : 16);
+        if constexpr (FULL) {
+#pragma unroll
+            for (int k = 0; k < PD_INFO_X; ++k) d[16 + k] = (double)info.x[k];
+        }
         d[0] = info.mach; d[1] = info.q; d[2] = info.CL; d[3] = info.CD; d[4] = info.rho;
         d[5] = info.p_atm; d[6] = info.a; d[7] = info.x_cog; d[8] = info.inertia;
         d[9] = info.mass_flow; d[10] = info.throttle; d[11] = info.alpha_eff; d[12] = g1;
@@ -470,6 +474,20 @@ struct Launch {
                        int auto_reset, cudaStream_t st) {
         int threads, blocks;
         big_block_config(e.n, 148, threads, blocks);
+        if constexpr (sizeof(R) == 8 && !WIND) {
+            // full-info diagnostic variant (fp64, no wind): the scalar drop-in env and the
+            // trajectory export use it; never on the throughput path
+            if (io.dbg_full) {
+                static bool attr_f = false;
+                if (!attr_f) {
+                    cudaFuncSetAttribute(step_kernel<R, RT, PHASE, RTD, WIND, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
+                    attr_f = true;
+                }
+                step_kernel<R, RT, PHASE, RTD, WIND, true><<<blocks, threads, PD_SH_BYTES, st>>>(e, io, wc, sig, auto_reset);
+                return;
+            }
+        }
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(step_kernel<R, RT, PHASE, RTD, WIND>,

@@ -387,7 +387,13 @@ class rocket_environment_pre_wrap:
         op = self._b.params.other_phases.get("initial_states", {}) if self._b.params.other_phases else {}
         self.state_initial = list(op.get(flight_phase, self._b.params.initial_state))
         self.wind_generator = self._b if enable_wind else None
-        self._dbg = torch.zeros(1, 16, dtype=torch.float64, device=self._b.device)
+        # the complete `info` dict of the reference (rockets_physics.py:649-702) needs the fp64
+        # diagnostic kernel (no wind); otherwise the 16-value subset
+        self._full_info = precision == "fp64" and not enable_wind
+        if self._full_info:
+            N.check(self._b.lib.pd_set_info_mode(self._b._h, 1))
+        self._dbg = torch.zeros(1, 48 if self._full_info else 16, dtype=torch.float64,
+                                device=self._b.device)
         self.truncation_id = 0
         self.reset()
 
@@ -408,8 +414,51 @@ class rocket_environment_pre_wrap:
                     atmospheric_pressure=d[5], speed_of_sound=d[6], x_cog=d[7], inertia=d[8],
                     mass_flow=d[9], action_info=dict(throttle=d[10]), alpha_effective=d[11],
                     g_load_1_sec_window=d[12], ug=d[13], vg=d[14], state=self.state, actions=actions)
+        if self._full_info:
+            info.update(_full_info_dict(self.flight_phase, d, self.state, self.previous_state, actions,
+                                        self._b.params))
         self._obs = obs[0]
         return self.state, float(rew[0]), bool(done[0]), bool(trunc[0]), info
+
+
+def _full_info_dict(phase, d, state, prev_state, actions, p):
+    """The rest of the reference's `info` dict (rockets_physics.py:649-702) from the primitives
+    the diagnostic kernel exports (include/pd_b200.h: pd_set_info_mode)."""
+    x = d[16:]
+    (drag, lift, d_cp_cg, d_thrust_cg, fuel, c_par, c_perp, c_x, c_y, aero_x, aero_y, g, c_mz, aero_mz,
+     mz, tdd, vx_dot, vy_dot, f_wind_x, gimbal_deg, dl_cmd, dr_cmd, mach_max) = x[:23]
+    gamma, mass = state[6], state[8]
+    acc = {
+        "acceleration_x_component_control": c_x / mass,
+        "acceleration_y_component_control": c_y / mass,
+        "acceleration_x_component_drag": -drag * math.cos(gamma) / mass,
+        "acceleration_y_component_drag": -drag / mass * math.sin(gamma) / mass,     # sic, :654
+        "acceleration_x_component_lift": -lift * math.cos(math.pi - gamma) / mass,
+        "acceleration_y_component_lift": lift * math.sin(math.pi - gamma) / mass,
+        "acceleration_x_component_gravity": 0,
+        "acceleration_y_component_gravity": -g,
+        "acceleration_x_component": vx_dot,
+        "acceleration_y_component": vy_dot,
+        "acceleration_x_component_wind": f_wind_x / mass,
+        "acceleration_y_component_wind": 0.0,
+    }
+    mom = {"control_moment_z": c_mz, "aero_moment_z": aero_mz, "moments_z": mz, "theta_dot_dot": tdd,
+           "M_wind_z": 0.0}
+    throttle = d[10]
+    if phase in ("subsonic", "supersonic"):
+        action_info = {"gimbal_angle_deg": gimbal_deg, "throttle": throttle}
+    elif phase == "ballistic_arc_descent":
+        action_info = {"RCS_throttle": actions}
+    elif phase == "landing_burn":
+        action_info = {"throttle": throttle, "delta_command_left_rad": dl_cmd,
+                       "delta_command_right_rad": dr_cmd, "gimbal_angle_deg": gimbal_deg}
+    else:
+        action_info = {"throttle": throttle}
+    return dict(acceleration_dict=acc, moment_dict=mom, mach_number_max=mach_max, drag=drag, lift=lift,
+                d_cp_cg=d_cp_cg, d_thrust_cg=d_thrust_cg, fuel_percentage_consumed=fuel,
+                control_force_parallel=c_par, control_force_perpendicular=c_perp, control_force_x=c_x,
+                control_force_y=c_y, aero_force_x=aero_x, aero_force_y=aero_y, gravity_force_y=-g * mass,
+                action_info=action_info)
 
 
 class simple_actor_spec:

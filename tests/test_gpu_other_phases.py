@@ -229,3 +229,40 @@ def test_batched_fp32_rollout_and_collect(envs_mod, phase):
     assert out["obs"].shape == (8, Bn, O) and out["actions"].shape == (8, Bn, A)
     assert torch.isfinite(out["rewards"]).all() and torch.isfinite(out["next_obs"]).all()
     assert float(out["actions"].abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("tag,phase,typ", [("P", "landing_burn_pure_throttle", "pso"), ("G", "landing_burn", "pso"),
+                                           ("U", U, "rl"), ("B", B, "rl")])
+def test_full_info_dict_vs_reference(envs_mod, golden, tag, phase, typ):
+    """rocket_environment_pre_wrap.step returns the reference's complete `info` dict
+    (rockets_physics.py:649-702: forces, moments, acceleration_dict, moment_dict, action_info)
+    from the fp64 diagnostic kernel (pd_set_info_mode)."""
+    g = golden("info_full.npz")
+    keys, acc_keys, mom_keys = list(g["keys"]), list(g["acc_keys"]), list(g["mom_keys"])
+    env = envs_mod.rocket_environment_pre_wrap(type=typ, flight_phase=phase, enable_wind=False,
+                                               trajectory_length=1000, discount_factor=0.99)
+    A, V, AI = g[f"actions_{tag}"], g[f"values_{tag}"], g[f"action_info_{tag}"]
+    # C_L / aero moment / pitch acceleration carry the ~5e4 cancellation factor of the
+    # thin-plate-spline sum: 2e-9; everything else 1e-10 relative to max(|ref|, floor)
+    loose = {"CL", "CD", "lift", "drag", "aero_force_x", "aero_force_y", "aero_moment_z", "moments_z",
+             "theta_dot_dot", "acceleration_x_component_lift", "acceleration_y_component_lift",
+             "acceleration_x_component_drag", "acceleration_y_component_drag",
+             "acceleration_x_component", "acceleration_y_component"}
+    # free-running episode: the gimballed landing burn amplifies rounding ~10x per step
+    for k in range(min(len(A), 4 if tag == "G" else 8)):
+        s, r, d, t, info = env.step(A[k])
+        got = [info[n] for n in keys] + [info["acceleration_dict"][n] for n in acc_keys] + \
+              [info["moment_dict"][n] for n in mom_keys]
+        for name, a, b in zip(keys + acc_keys + mom_keys, got, V[k]):
+            tol = 2e-8 if name in loose else 1e-10
+            scale = max(abs(b), 1e-3 * max(1.0, float(np.max(np.abs(V[:, (keys + acc_keys + mom_keys).index(name)])))))
+            assert abs(float(a) - b) <= tol * scale, (k, name, float(a), b)
+        ai = info["action_info"]
+        ref_ai = AI[k]
+        if "throttle" in ai:
+            assert abs(ai["throttle"] - ref_ai[0]) < 1e-12
+        if "gimbal_angle_deg" in ai:
+            assert abs(ai["gimbal_angle_deg"] - ref_ai[1]) < 1e-10
+        if "delta_command_left_rad" in ai:
+            assert abs(ai["delta_command_left_rad"] - ref_ai[2]) < 1e-12
+            assert abs(ai["delta_command_right_rad"] - ref_ai[3]) < 1e-12

@@ -361,6 +361,51 @@ def single_step_other(phase, tag, pool, n=96, seed=21):
           np.unique(o[:, 14], return_counts=True))
 
 
+INFO_FULL_KEYS = ["mach_number", "mach_number_max", "CL", "CD", "drag", "lift", "d_cp_cg", "d_thrust_cg",
+                  "x_cog", "inertia", "dynamic_pressure", "mass_flow", "fuel_percentage_consumed",
+                  "control_force_parallel", "control_force_perpendicular", "control_force_x",
+                  "control_force_y", "aero_force_x", "aero_force_y", "gravity_force_y",
+                  "atmospheric_pressure", "air_density", "speed_of_sound", "ug", "vg", "alpha_effective",
+                  "g_load_1_sec_window"]
+ACC_KEYS = ["acceleration_x_component_control", "acceleration_y_component_control",
+            "acceleration_x_component_drag", "acceleration_y_component_drag",
+            "acceleration_x_component_lift", "acceleration_y_component_lift",
+            "acceleration_x_component_gravity", "acceleration_y_component_gravity",
+            "acceleration_x_component", "acceleration_y_component", "acceleration_x_component_wind",
+            "acceleration_y_component_wind"]
+MOM_KEYS = ["control_moment_z", "aero_moment_z", "moments_z", "theta_dot_dot", "M_wind_z"]
+
+
+def info_full(n_steps=25, seed=31):
+    """The complete per-step `info` dict of the reference (rockets_physics.py:649-702) along short
+    episodes of four phases: pins the trajectory / info export."""
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    rng = np.random.default_rng(seed)
+    out = {}
+    for tag, phase, typ, adim in (("P", P, "pso", 1), ("G", G, "pso", 4), ("U", U_, "rl", 2), ("B", B_, "rl", 1)):
+        env = quiet(rocket_environment_pre_wrap, type=typ, flight_phase=phase, enable_wind=False,
+                    trajectory_length=1000, discount_factor=0.99)
+        quiet(env.reset)
+        A, V, ACT = [], [], []
+        for k in range(n_steps):
+            a = (0.3 * rng.uniform(-1, 1, adim)).astype(np.float64)
+            s, r, d, t, info = quiet(env.step, a)
+            row = [float(info[k_]) for k_ in INFO_FULL_KEYS]
+            row += [float(info["acceleration_dict"][k_]) for k_ in ACC_KEYS]
+            row += [float(info["moment_dict"][k_]) for k_ in MOM_KEYS]
+            ai = info["action_info"]
+            ACT.append([float(ai.get("throttle", 0.0) or 0.0), float(ai.get("gimbal_angle_deg", 0.0)),
+                        float(ai.get("delta_command_left_rad", 0.0)), float(ai.get("delta_command_right_rad", 0.0))])
+            A.append(a); V.append(row)
+            if d or t:
+                break
+        out[f"actions_{tag}"] = np.array(A); out[f"values_{tag}"] = np.array(V)
+        out[f"action_info_{tag}"] = np.array(ACT)
+    np.savez_compressed(os.path.join(OUT, "info_full.npz"), keys=INFO_FULL_KEYS, acc_keys=ACC_KEYS,
+                        mom_keys=MOM_KEYS, **out)
+    print("info_full", {k: v.shape for k, v in out.items() if k.startswith("values")})
+
+
 def ascent_csv():
     """The reference's own committed ascent controller recordings (actions + states per 0.1 s
     step) - golden vectors written on the author's machine, copied verbatim."""
@@ -453,7 +498,9 @@ def aero_probe(seed=5, n=400):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     load_reference()
-    which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero", "other"]
+    which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero", "other", "info"]
+    if "info" in which:
+        info_full()
     if "other" in which:
         ascent_csv()
         pool = rl_sequence_other(S_, "S", 400, mode="csv")
