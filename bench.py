@@ -381,6 +381,32 @@ def run_cuda(args):
                "mean_reward": float(out["rewards"].mean()), "resets": int(out["truncated"].sum() + out["done"].sum())}
         del senv, out
 
+    # ---- the four further flight phases, RL closures, same fused step kernel
+    phases = None
+    if not args.no_phases:
+        phases = {}
+        for ph in ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol"):
+            penv = envs.BatchedRocketEnv(B, "rl", ph, precision=args.precision, auto_reset=True, device=local,
+                                         trajectory_length=1000, discount_factor=0.99, seed=5 + rank)
+            ptape = torch.rand(40, B, penv.act_dim, device=dev, generator=gen, dtype=torch.float32) * 2 - 1
+            with torch.cuda.stream(stream):
+                penv.reset()
+                for k in range(10):
+                    penv.step(ptape[k])
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                p0.record(stream)
+                for k in range(10, 40):
+                    penv.step(ptape[k])
+                p1.record(stream)
+                barrier()
+                penv.check_status()
+            pms = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+            phases[ph] = {"env_steps_per_s": world * B * 30 / (pms.item() * 1e-3), "us_per_step": pms.item() / 30 * 1e3}
+            del penv, ptape
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -431,6 +457,7 @@ def run_cuda(args):
         "cpu_baseline": cpu,
         "pso": pso,
         "sac_collect": sac,
+        "other_phases": phases,
     }
     try:      # ncu figures of the same kernel (profiles/, captured by the builder, not live)
         with open(os.path.join(REPO, "profiles", "step_kernel_ncu.json")) as f:
@@ -462,6 +489,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pso", action="store_true")
     ap.add_argument("--no-sac", action="store_true")
+    ap.add_argument("--no-phases", action="store_true")
     ap.add_argument("--sac-envs", type=int, default=131072)
     ap.add_argument("--sac-steps", type=int, default=40)
     args = ap.parse_args()
