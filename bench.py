@@ -266,7 +266,7 @@ def run_cuda(args):
 
     # ---- end-to-end through the public host-facing call: numpy actions in, numpy results out,
     # every step (BatchedRocketEnv.step_host: H2D copy + fused step + ONE D2H copy, CUDA graph)
-    host_tape = tape.cpu().numpy()
+    host_tape = tape.cpu().pin_memory()       # the host's actions live in pinned memory
     Ke = min(K, 300)
     env.reset()
     torch.cuda.synchronize(dev)
@@ -309,7 +309,8 @@ def run_cuda(args):
             return fit.reshape(len(p), args.seeds).mean(dim=1).cpu().numpy()
         ev = pso_mod.ShardedEvaluator(local_eval)
         lo, hi = pso_mod.shard_bounds(args.particles, world, rank)
-        ev(pos)                                                     # warm-up (weights upload, caches)
+        fw = ev(pos)                                                # warm-up (weights upload, caches,
+        ev.broadcast_best(fw, pos[lo:hi], args.particles)           # NCCL channels of both collectives)
         barrier()
         t0 = time.perf_counter()
         fitness = ev(pos)

@@ -165,8 +165,10 @@ class BatchedRocketEnv:
         [n_envs, A]; returns numpy views (obs, reward, done, truncated, trunc_id) of a pinned
         host buffer, valid until the next call (trunc_id is only refreshed by
         `self.trunc_id.cpu()`).  One host->device copy, the fused step kernel and one
-        device->host copy, replayed from a CUDA graph."""
-        a = torch.as_tensor(actions)
+        device->host copy; kernel + read-back are replayed from a CUDA graph.  A CPU tensor that
+        already lives in pinned memory is copied to the device straight from where it is (no
+        staging copy)."""
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(actions)
         if a.dtype not in (torch.float32, torch.float64):
             a = a.to(torch.float64)
         a = a.reshape(self.n_envs, self.act_dim)
@@ -186,10 +188,9 @@ class BatchedRocketEnv:
                           v("trunc_id", torch.int32, (B,)))
             with torch.cuda.stream(h["stream"]):
                 def body():
-                    h["act_dev"].copy_(h["act_pin"], non_blocking=True)
                     self.step(h["act_dev"])
                     h["out_pin"][:n_copy].copy_(self._out[:n_copy], non_blocking=True)
-                h["act_pin"].zero_()
+                h["act_dev"].zero_()
                 N.check(self.lib.pd_activate(self._h))      # not allowed inside a capture
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
@@ -198,9 +199,14 @@ class BatchedRocketEnv:
                 h["graph"] = g
             self._host = h
         h = self._host
-        h["act_pin"].copy_(a)
+        if a.is_pinned() and a.is_contiguous():
+            src = a
+        else:
+            h["act_pin"].copy_(a)
+            src = h["act_pin"]
         N.check(self.lib.pd_activate(self._h))
         with torch.cuda.stream(h["stream"]):
+            h["act_dev"].copy_(src, non_blocking=True)
             h["graph"].replay()
         h["stream"].synchronize()
         return h["views"]
