@@ -337,22 +337,36 @@ class BatchedRocketEnv:
         N.check(self.lib.pd_actor_forward(self._h, C.byref(a), _ptr(obs), n, _ptr(act), _ptr(mean), _stream()))
         return (act, mean) if want_mean else act
 
-    def collect(self, actor, n_steps, deterministic=False, seed=0, fp32_path=False, next_obs=True):
+    def collect(self, actor, n_steps, deterministic=False, seed=0, fp32_path=False, next_obs=True,
+                into=None):
         """n_steps of [shared-actor inference -> fused env step with auto-reset] on the whole
         batch (the loop body of sac_pytorch_powered_descent.py:160-183).  Returns step-major
-        tensors obs, actions, rewards, done, truncated (, next_obs)."""
+        tensors obs, actions, rewards, done, truncated (, next_obs).  `into`: a
+        replay.DeviceReplayBuffer - the kernels then write the transitions straight into its
+        storage and the returned tensors are views of it."""
         a, keep = self._actor_struct(actor, deterministic, seed, fp32_path)
         B, T, dev = self.n_envs, n_steps, self.device
-        out = dict(obs=torch.empty(T, B, self.obs_dim, dtype=torch.float32, device=dev),
-                   actions=torch.empty(T, B, self.act_dim, dtype=torch.float32, device=dev),
-                   rewards=torch.empty(T, B, dtype=torch.float32, device=dev),
-                   done=torch.empty(T, B, dtype=torch.uint8, device=dev),
-                   truncated=torch.empty(T, B, dtype=torch.uint8, device=dev))
-        if next_obs:
-            out["next_obs"] = torch.empty(T, B, self.obs_dim, dtype=torch.float32, device=dev)
+        if into is not None:
+            if (into.state_dim, into.action_dim) != (self.obs_dim, self.act_dim) or into.device != dev:
+                raise ValueError("replay buffer does not match this env's dims / device")
+            start, v = into.reserve(T * B)
+            out = dict(obs=v["obs"].view(T, B, self.obs_dim), actions=v["actions"].view(T, B, self.act_dim),
+                       rewards=v["rewards"].view(T, B), done=v["done"].view(T, B),
+                       truncated=torch.empty(T, B, dtype=torch.uint8, device=dev),
+                       next_obs=v["next_obs"].view(T, B, self.obs_dim))
+        else:
+            out = dict(obs=torch.empty(T, B, self.obs_dim, dtype=torch.float32, device=dev),
+                       actions=torch.empty(T, B, self.act_dim, dtype=torch.float32, device=dev),
+                       rewards=torch.empty(T, B, dtype=torch.float32, device=dev),
+                       done=torch.empty(T, B, dtype=torch.uint8, device=dev),
+                       truncated=torch.empty(T, B, dtype=torch.uint8, device=dev))
+            if next_obs:
+                out["next_obs"] = torch.empty(T, B, self.obs_dim, dtype=torch.float32, device=dev)
         N.check(self.lib.pd_collect_shared_actor(self._h, C.byref(a), T, _ptr(out["obs"]), _ptr(out["actions"]),
                                                  _ptr(out["rewards"]), _ptr(out["done"]), _ptr(out["truncated"]),
                                                  _ptr(out.get("next_obs")), _stream()))
+        if into is not None:
+            into.commit(start, T * B)
         return out
 
 

@@ -266,3 +266,40 @@ def test_full_info_dict_vs_reference(envs_mod, golden, tag, phase, typ):
         if "delta_command_left_rad" in ai:
             assert abs(ai["delta_command_left_rad"] - ref_ai[2]) < 1e-12
             assert abs(ai["delta_command_right_rad"] - ref_ai[3]) < 1e-12
+
+
+def test_collect_into_device_replay_buffer(envs_mod):
+    """collect(into=buffer): the collection kernels write straight into the ring storage; the
+    result equals a plain collect() with the same seeds and feeds a SAC-style critic update."""
+    import torch.nn as nn
+    from psso_sac_for_powered_descent_b200.replay import DeviceReplayBuffer
+    P = "landing_burn_pure_throttle"
+    Bn, T = 2048, 6
+    torch.manual_seed(0)
+    l1, l2, m, s = nn.Linear(2, 256), nn.Linear(256, 256), nn.Linear(256, 1), nn.Linear(256, 1)
+    actor = dict(w1=l1.weight, b1=l1.bias, w2=l2.weight, b2=l2.bias, wm=m.weight, bm=m.bias,
+                 ws=s.weight, bs=s.bias, max_action=1.0)
+    outs = []
+    for use_buf in (False, True):
+        env = envs_mod.BatchedRocketEnv(Bn, "rl", P, precision="fp32", auto_reset=True, seed=11,
+                                        trajectory_length=1000, discount_factor=0.99)
+        env.reset()
+        buf = DeviceReplayBuffer(4 * T * Bn, env.obs_dim, env.act_dim, device=env.device) if use_buf else None
+        o = env.collect(actor, T, seed=5, into=buf)
+        env.check_status()
+        outs.append((o, buf))
+    a, (b, buf) = outs[0][0], outs[1]
+    for k in ("obs", "actions", "rewards", "next_obs", "done"):
+        assert torch.equal(a[k].reshape(-1), b[k].reshape(-1)), k
+    assert len(buf) == T * Bn and buf.position == T * Bn
+    assert torch.equal(buf.states[:T * Bn], a["obs"].reshape(-1, 2))
+    assert torch.equal(buf.dones[:T * Bn, 0], a["done"].reshape(-1).float())
+    # the consumer side of SACPyTorch.update (sac_pytorch.py:430-436): sample, .to(device), a TD target
+    st, ac, rw, ns, dn = buf.sample(512)
+    st, ac, rw, ns, dn = [t.to(env.device) for t in (st, ac, rw, ns, dn)]
+    critic = nn.Sequential(nn.Linear(3, 64), nn.ReLU(), nn.Linear(64, 1)).to(env.device)
+    q = critic(torch.cat([st, ac], 1))
+    target = rw + 0.99 * (1 - dn) * critic(torch.cat([ns, ac], 1)).detach()
+    loss = ((q - target) ** 2).mean()
+    loss.backward()
+    assert torch.isfinite(loss)

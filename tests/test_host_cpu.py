@@ -33,15 +33,16 @@ def test_struct_layouts_match_header_sizes():
     import subprocess
     import tempfile
     from psso_sac_for_powered_descent_b200 import _native as N
-    src = '#include <stdio.h>\n#include "pd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", ' \
-          'sizeof(PdRbfGrid), sizeof(PdRbfTable), sizeof(PdParams), sizeof(PdConfig), sizeof(PdSharedActor));}'
+    src = '#include <stdio.h>\n#include "pd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", ' \
+          'sizeof(PdRbfGrid), sizeof(PdRbfTable), sizeof(PdParams), sizeof(PdConfig), sizeof(PdSharedActor), ' \
+          'sizeof(PdOtherPhases));}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), os.path.join(d, "p.c"),
                                "-o", os.path.join(d, "p")])
         sizes = list(map(int, subprocess.check_output([os.path.join(d, "p")]).split()))
     assert sizes == [ctypes.sizeof(N.PdRbfGrid), ctypes.sizeof(N.PdRbfTable), ctypes.sizeof(N.PdParams),
-                     ctypes.sizeof(N.PdConfig), ctypes.sizeof(N.PdSharedActor)]
+                     ctypes.sizeof(N.PdConfig), ctypes.sizeof(N.PdSharedActor), ctypes.sizeof(N.PdOtherPhases)]
 
 
 def test_no_cpu_fallback():
@@ -310,3 +311,37 @@ def test_sharded_evaluation_world2_gloo(tmp_path):
     # the optimiser itself: both ranks end in the same state as a single process would
     assert float(r0["gbest"]) == float(r1["gbest"])
     assert np.array_equal(r0["gpos"], r1["gpos"])
+
+
+def test_device_replay_buffer_interface_cpu():
+    """replay.DeviceReplayBuffer keeps the reference ReplayBuffer's interface
+    (src/agents/sac_pytorch.py:12-47) and hands out contiguous ring slots."""
+    import torch
+    from psso_sac_for_powered_descent_b200.replay import DeviceReplayBuffer
+    buf = DeviceReplayBuffer(10, 2, 1, device="cpu")
+    assert len(buf) == 0 and (buf.capacity, buf.state_dim, buf.action_dim) == (10, 2, 1)
+    for k in range(3):
+        buf.add(state=np.array([k, -k], np.float32), action=np.array([0.5]), reward=float(k),
+                next_state=[k + 1, -k - 1], done=1.0 if k == 2 else 0.0)
+    assert len(buf) == 3 and buf.position == 3
+    assert buf.dones[:3, 0].tolist() == [0.0, 0.0, 1.0]
+    start, v = buf.reserve(4)
+    assert start == 3 and v["obs"].shape == (4, 2) and v["done"].dtype == torch.uint8
+    v["obs"].fill_(7.0); v["actions"].fill_(0.25); v["rewards"].fill_(-1.0); v["next_obs"].fill_(8.0)
+    v["done"].copy_(torch.tensor([0, 1, 0, 0], dtype=torch.uint8))
+    buf.commit(start, 4)
+    assert len(buf) == 7 and buf.position == 7
+    assert buf.states[3:7].eq(7.0).all() and buf.dones[3:7, 0].tolist() == [0.0, 1.0, 0.0, 0.0]
+    # a block that does not fit the tail starts again at slot 0
+    start, v = buf.reserve(5)
+    assert start == 0
+    buf.commit(start, 5)
+    assert buf.position == 5 and len(buf) == 7
+    s, a, r, ns, d = buf.sample(16)
+    assert s.shape == (16, 2) and a.shape == (16, 1) and r.shape == (16, 1) and ns.shape == (16, 2)
+    assert d.shape == (16, 1) and s.dtype == torch.float32
+    n0 = buf.add_batch(torch.ones(2, 3, 2), torch.zeros(2, 3, 1), torch.ones(2, 3), torch.ones(2, 3, 2),
+                       torch.zeros(2, 3, dtype=torch.uint8))
+    assert n0 == 0 and buf.position == 6       # 5 + 6 > 10: wrapped
+    with pytest.raises(ValueError):
+        buf.reserve(11)
