@@ -401,19 +401,28 @@ __device__ __noinline__ int rbf_walk(const RbfDev &T, const double *levels_d, do
 }
 
 // Stateless set lookup: grid cell -> set id; only cells cut by a Voronoi edge take the walk.
-template <int NL>
-__device__ __forceinline__ int rbf_locate(const RbfDev &T, const RbfGrid &G, const double *levels_d,
-                                          double M, double a, int &status) {
+// Split in two so that a caller can put the cell loads of several lookups in flight before it
+// consumes the first one (each is an L2 round trip on the critical path of a sub-step).
+__device__ __forceinline__ const int *rbf_cell_ptr(const RbfGrid &G, double M, double a) {
     int im = (int)((M - G.m0) * G.inv_dm);
     int ia = (int)((a - G.a0) * G.inv_da);
     im = max(0, min(im, G.nm - 1));
     ia = max(0, min(ia, G.na - 1));
-    int cell = __ldg(G.cells + ia * G.nm + im);
+    return G.cells + ia * G.nm + im;
+}
+template <int NL>
+__device__ __forceinline__ int rbf_resolve(const RbfDev &T, const RbfGrid &G, const double *levels_d,
+                                           double M, double a, int cell, int &status) {
     if (cell >= 0) return cell;
     const int k = -cell - 1;
     int sid = __ldg(G.imp_id + k);
     status |= rbf_walk<NL>(T, levels_d, M, a, __ldg(G.imp_hint + k), sid);
     return sid;
+}
+template <int NL>
+__device__ __forceinline__ int rbf_locate(const RbfDev &T, const RbfGrid &G, const double *levels_d,
+                                          double M, double a, int &status) {
+    return rbf_resolve<NL>(T, G, levels_d, M, a, __ldg(rbf_cell_ptr(G, M, a)), status);
 }
 
 // Natural log of a positive normal double, ~1 ulp, ~18 instructions (CUDA's log() costs ~130
@@ -622,10 +631,12 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     const bool neg_line = aoa < -10.0;
     const double aL = neg_line ? -10.0 : fmin(fmax(fabs(aoa), 1e-6), 10.0);
     const bool flip = !neg_line && aoa < 0.0;
-    const int sidD = rbf_locate<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, M, aD, status);
-    int sidL;
-    if (neg_line) sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[1], g_sd.cl_levels, M, aL, status);
-    else sidL = rbf_locate<5>(g_tb.cl, g_tb.cl.grid[0], g_sd.cl_levels, M, aL, status);
+    // both grid-cell loads in flight before either is consumed
+    const RbfGrid &GL = neg_line ? g_tb.cl.grid[1] : g_tb.cl.grid[0];
+    const int cellD = __ldg(rbf_cell_ptr(g_tb.cd.grid[0], M, aD));
+    const int cellL = __ldg(rbf_cell_ptr(GL, M, aL));
+    const int sidD = rbf_resolve<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, M, aD, cellD, status);
+    const int sidL = rbf_resolve<5>(g_tb.cl, GL, g_sd.cl_levels, M, aL, cellL, status);
     double vL, vD;
     constexpr int DEG = sizeof(R) == 8 ? 5 : 4;
     const int copy = threadIdx.x & (PD_REP - 1);          // this lane's replica of the tables
