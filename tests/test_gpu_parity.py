@@ -538,3 +538,38 @@ def test_device_swarm_update_matches_numpy(envs_mod):
         sw.step()
     assert sw.global_best_fitness <= best0
     assert (sw.best_fit <= fit + 1e-12).all()
+
+
+@pytest.mark.parametrize("n", [1, 33, 449, 1000])
+def test_ragged_batch_sizes_bitwise(envs_mod, golden, n):
+    """Batch sizes that do not fill a warp / a block / a wave: every env's result is bit-identical
+    to the same env stepped inside the 192-env fixture batch (no cross-lane dependence)."""
+    g = golden("single_step_P.npz")
+    ref_env = _load_fixture_batch(envs_mod, g, P, "fp64")
+    act = torch.as_tensor(g["act32"]).cuda()
+    ref_env.step(act)
+    ref_state = ref_env.get_state().cpu().numpy()
+    ref_rew = ref_env.reward.cpu().numpy().copy()
+    idx = np.arange(n) % len(g["state"])
+    env = envs_mod.BatchedRocketEnv(n, "pso", P, precision="fp64")
+    env.set_state(g["state"][idx], g["win"][idx], g["nwin"][idx].astype(np.int32), g["aprev"][idx])
+    obs, rew, done, trunc, tid = env.step(act[torch.as_tensor(idx).cuda()])
+    env.check_status()
+    assert np.array_equal(env.get_state().cpu().numpy(), ref_state[idx])
+    assert np.array_equal(rew.cpu().numpy(), ref_rew[idx])
+
+
+def test_config4_batch_on_one_gpu(envs_mod):
+    """BASELINE config 4's full batch (1 048 576 envs, RL closures, stochastic wind) fits and steps
+    on a single B200; auto-reset keeps every lane inside the aero tables."""
+    n = 1 << 20
+    env = envs_mod.BatchedRocketEnv(n, "rl", P, enable_wind=True, stochastic_wind=True,
+                                    horiontal_wind_percentile=50, precision="fp32", auto_reset=True, seed=1)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for k in range(12):
+        obs, rew, done, trunc, tid = env.step(torch.rand(n, 1, device="cuda", generator=gen) * 2 - 1)
+    env.check_status()
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    st = env.get_state()
+    assert float(st[:, 1].max()) <= 30028.385497767023 + 1e-6 and float(st[:, 9].min()) > 0
