@@ -188,7 +188,9 @@ int pd_step(PdEnv *env, const void *actions, int action_dtype, void *obs, void *
  * d_thrust_cg, fuel_percentage_consumed, control_force_parallel, control_force_perpendicular,
  * control_force_x, control_force_y, aero_force_x, aero_force_y, g, control_moment_z,
  * aero_moment_z, moments_z, theta_dot_dot, vx_dot, vy_dot, F_wind_x, gimbal_angle_deg,
- * delta_command_left_rad, delta_command_right_rad, mach_number_max, 9 reserved zeros.  A separate
+ * delta_command_left_rad, delta_command_right_rad, mach_number_max, pitch angle at the start of
+ * the sub-step, grid-fin C_a(M), C_n_alpha(M), filtered left / right fin deflection (the inputs of
+ * acs_info, src/envs/utils/acs_model.py:62-84), 4 reserved zeros.  A separate
  * diagnostic instantiation of the step kernel; the throughput kernels are unaffected. */
 int pd_set_info_mode(PdEnv *env, int full);
 

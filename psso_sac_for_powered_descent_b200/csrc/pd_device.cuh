@@ -205,7 +205,9 @@ struct Info<R, true> {
     // 6 control_force_perpendicular, 7 control_force_x, 8 control_force_y, 9 aero_force_x,
     // 10 aero_force_y, 11 g, 12 control_moment_z, 13 aero_moment_z, 14 moments_z, 15 theta_dot_dot,
     // 16 vx_dot, 17 vy_dot, 18 F_wind_x, 19 gimbal_angle_deg, 20 delta_command_left_rad,
-    // 21 delta_command_right_rad, 22 mach_number_max (Qmax = 65 kPa landing phases, 30 kPa others)
+    // 21 delta_command_right_rad, 22 mach_number_max (Qmax = 65 kPa landing phases, 30 kPa others),
+    // 23 pitch angle at the start of the sub-step, 24 C_a(M), 25 C_n_alpha(M) [per degree],
+    // 26 / 27 filtered left / right fin deflection [rad] (acs_info, acs_model.py:62-84)
     R x[PD_INFO_X];
 };
 
@@ -1030,6 +1032,7 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
                                         const SharedTables *sh) {
     const Scalars<R> &c = SC<R>();
     R y = (R)s.y, vx = (R)s.vx, vy = (R)s.vy;
+    const double theta_pre = s.theta;
     R rho, p_atm, a_snd;
     isa<R>(y, rho, p_atm, a_snd);
     R speed = m_sqrt(vx * vx + vy * vy);
@@ -1142,8 +1145,13 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
         x[21] = PHASE == 1 ? (R)ctl.dr_cmd : R(0);
         const R qmax = PHASE <= 1 || PHASE == 5 ? R(65000) : R(30000);
         x[22] = a_snd != R(0) ? m_sqrt(R(2) * qmax / rho) * R(1) / a_snd : R(200);
+        x[23] = (R)theta_pre;
+        x[24] = gridfin_ca<R>(mach);
+        x[25] = gridfin_cn_alpha<R>(mach);
+        x[26] = PHASE == 1 ? (R)(prev.dl + g_sd.dt_act * ((-prev.dl + ctl.dl_cmd) / 0.5)) : R(0);
+        x[27] = PHASE == 1 ? (R)(prev.dr + g_sd.dt_act * ((-prev.dr + ctl.dr_cmd) / 0.5)) : R(0);
 #pragma unroll
-        for (int k = 23; k < PD_INFO_X; ++k) x[k] = R(0);
+        for (int k = 28; k < PD_INFO_X; ++k) x[k] = R(0);
     }
 }
 

@@ -447,6 +447,7 @@ def _full_info_dict(phase, d, state, prev_state, actions, p):
     x = d[16:]
     (drag, lift, d_cp_cg, d_thrust_cg, fuel, c_par, c_perp, c_x, c_y, aero_x, aero_y, g, c_mz, aero_mz,
      mz, tdd, vx_dot, vy_dot, f_wind_x, gimbal_deg, dl_cmd, dr_cmd, mach_max) = x[:23]
+    x = list(x) + [0.0] * 8
     gamma, mass = state[6], state[8]
     acc = {
         "acceleration_x_component_control": c_x / mass,
@@ -465,15 +466,41 @@ def _full_info_dict(phase, d, state, prev_state, actions, p):
     mom = {"control_moment_z": c_mz, "aero_moment_z": aero_mz, "moments_z": mz, "theta_dot_dot": tdd,
            "M_wind_z": 0.0}
     throttle = d[10]
+    acs_info = None
+    if phase in ("landing_burn", "landing_burn_pure_throttle", "landing_burn_pure_throttle_Pcontrol"):
+        # acs_model.py:39-84 from the exported C_a, C_n_alpha, filtered deflections and pitch angle
+        theta0, Ca, cna, dl, dr = x[23:28]
+        a_eff, q, x_cog = d[11], d[1], d[7]
+        qS = q * p.grid_fin_area
+        al, ar = a_eff - dl, a_eff - dr
+        Cn_L, Cn_R = cna * math.degrees(al), cna * math.degrees(ar)
+        f_perp = qS * (Cn_R * math.cos(dr) - Cn_L * math.cos(dl) - Ca * (math.sin(dl) - math.sin(dr)))
+        f_par = qS * (Ca * (2 + math.cos(dl) + math.cos(dr)) - Cn_L * math.sin(dl) + Cn_R * math.sin(dr))
+        m_z = -(p.d_base_grid_fin - x_cog) * f_perp + p.rocket_radius * qS * (
+            Ca * (math.sin(dr) - math.sin(dl)) - Cn_L * math.cos(dl) + Cn_R * math.cos(dr))
+        acs_info = {
+            "alpha_local_left_rad": al, "alpha_local_right_rad": ar, "C_n_L": Cn_L, "C_a_L": Ca,
+            "C_n_R": Cn_R, "C_a_R": Ca, "F_n_L": Cn_L * qS, "F_a_L": Ca * qS, "F_n_R": Cn_R * qS,
+            "F_a_R": Ca * qS,
+            "F_perpendicular_L": qS * (Cn_L * math.cos(dl) - Ca * math.sin(dl)),
+            "F_perpendicular_R": qS * (Cn_R * math.cos(dr) - Ca * math.sin(dr)),
+            "F_perpendicular": f_perp,
+            "F_parallel_L": qS * (Ca * math.cos(dl) + Cn_L * math.sin(dl)),
+            "F_parallel_R": qS * (Ca * math.cos(dr) + Cn_R * math.sin(dr)),
+            "F_parallel": f_par,
+            "Fx": f_par * math.cos(theta0) + f_perp * math.sin(theta0),
+            "Fy": f_par * math.sin(theta0) - f_perp * math.cos(theta0),
+            "Mz": m_z, "d_fin_cg": p.d_base_grid_fin - x_cog, "delta_left_rad": dl, "delta_right_rad": dr}
     if phase in ("subsonic", "supersonic"):
         action_info = {"gimbal_angle_deg": gimbal_deg, "throttle": throttle}
     elif phase == "ballistic_arc_descent":
         action_info = {"RCS_throttle": actions}
     elif phase == "landing_burn":
         action_info = {"throttle": throttle, "delta_command_left_rad": dl_cmd,
-                       "delta_command_right_rad": dr_cmd, "gimbal_angle_deg": gimbal_deg}
+                       "delta_command_right_rad": dr_cmd, "gimbal_angle_deg": gimbal_deg,
+                       "acs_info": acs_info}
     else:
-        action_info = {"throttle": throttle}
+        action_info = {"throttle": throttle, "acs_info": acs_info}
     return dict(acceleration_dict=acc, moment_dict=mom, mach_number_max=mach_max, drag=drag, lift=lift,
                 d_cp_cg=d_cp_cg, d_thrust_cg=d_thrust_cg, fuel_percentage_consumed=fuel,
                 control_force_parallel=c_par, control_force_perpendicular=c_perp, control_force_x=c_x,

@@ -353,6 +353,88 @@ class ParticleSubswarmOptimisation:
                        'n_seeds': self.n_seeds}, f, indent=1)
 
 
+    # ------------------------------------------------------------------ trajectory export
+    def collect_trajectory_data(self, individual, max_steps=8192):
+        """One episode of `individual` with everything the reference records per step
+        (particle_swarm_optimisation.py:759-785): observations ('states'), actions, rewards and the
+        complete `info` dict.  Runs closed-loop in a single fp64 diagnostic env lane
+        (envs.rocket_environment_pre_wrap, pd_set_info_mode) with the per-particle MLP evaluated on
+        the host in float32 (simple_actor.forward, env_wrapped_ea.py:18-44) - a one-episode export
+        path, not the throughput path (that is pd_rollout_pso)."""
+        from .envs import rocket_environment_pre_wrap
+        layers = self._unpack_actor(np.asarray(individual, dtype=np.float64))
+        env = rocket_environment_pre_wrap(type="pso", flight_phase=self.flight_phase, enable_wind=False,
+                                          precision="fp64")
+        data = {'states': [], 'actions': [], 'rewards': [], 'info': []}
+        state = env.reset()
+        for _ in range(max_steps):
+            obs = self._augment_state(state)
+            h = np.asarray(obs, dtype=np.float32)
+            for i, (W, b) in enumerate(layers):
+                h = W @ h + b
+                h = np.tanh(h) if i == len(layers) - 1 else np.maximum(h, np.float32(0))
+            action = h.astype(np.float32)
+            state, r, d, t, info = env.step(action)
+            data['states'].append(obs)
+            data['actions'].append(action.tolist())
+            data['rewards'].append(r)
+            data['info'].append(info)
+            if d or t:
+                break
+        return data
+
+    def _unpack_actor(self, individual):
+        """named_parameters() order: per layer weight (out x in, row-major) then bias
+        (env_wrapped_ea.py:46-59)."""
+        i, o, n = (2, 1, 3) if self.flight_phase == 'landing_burn_pure_throttle' else (5, 4, 4)
+        shapes = [(8, i)] + [(8, 8)] * n + [(o, 8)]
+        layers, k = [], 0
+        for (a, b) in shapes:
+            W = individual[k:k + a * b].astype(np.float32).reshape(a, b); k += a * b
+            bias = individual[k:k + a].astype(np.float32); k += a
+            layers.append((W, bias))
+        assert k == len(individual), "individual does not match the phase's actor"
+        return layers
+
+    def _augment_state(self, state):
+        """pso_wrapper.augment_state (env_wrapped_ea.py:97-123)."""
+        import math
+        nv = self.model._b.params.norm_vals if hasattr(self.model, "_b") else None
+        if nv is None:
+            from .params import RocketParams
+            nv = RocketParams.default().norm_vals
+        x, y, vx, vy, theta = state[:5]
+        if self.flight_phase == 'landing_burn_pure_throttle':
+            return [y / nv[0], vy / nv[1]]
+        k = float(np.arctanh(0.75) / math.radians(25))
+        return [x / nv[5], y / nv[0], vx / nv[6], vy / nv[1], math.tanh(k * (theta - math.pi / 2))]
+
+    def save_trajectory_data(self, trajectory_data, trajectory_dir=None):
+        """states.csv / actions.csv / rewards.csv / info_data.csv with the reference's layout
+        (particle_swarm_optimisation.py:787-809: nested dicts flattened with '_'-joined keys)."""
+        import pandas as pd
+        d = trajectory_dir or f'{self.base_save_dir}/trajectory_data'
+        os.makedirs(d, exist_ok=True)
+        pd.DataFrame(trajectory_data['states']).to_csv(f'{d}/states.csv', index=False)
+        pd.DataFrame(trajectory_data['actions']).to_csv(f'{d}/actions.csv', index=False)
+        pd.DataFrame(trajectory_data['rewards'], columns=['reward']).to_csv(f'{d}/rewards.csv', index=False)
+        if trajectory_data['info']:
+            flat_data = []
+            for info in trajectory_data['info']:
+                flat = {}
+
+                def flatten(dct, prefix=''):
+                    for key, value in dct.items():
+                        if isinstance(value, dict):
+                            flatten(value, f"{prefix}{key}_")
+                        else:
+                            flat[f"{prefix}{key}"] = value
+                flatten(info)
+                flat_data.append(flat)
+            pd.DataFrame(flat_data).to_csv(f'{d}/info_data.csv', index=False)
+        return d
+
+
 class DeviceSwarm:
     """Device-resident sub-swarm PSO for large swarms (BASELINE config 5): positions,
     velocities and personal bests stay in HBM as fp64, the fitness evaluation is the persistent

@@ -303,3 +303,66 @@ def test_collect_into_device_replay_buffer(envs_mod):
     loss = ((q - target) ** 2).mean()
     loss.backward()
     assert torch.isfinite(loss)
+
+
+def test_info_export_vs_reference_stored_csv(envs_mod, golden):
+    """The reference's own committed info_data.csv of its saved best P actor (author's machine,
+    particle_swarm_optimisation.py:787-809), 67 numeric columns incl. acceleration_dict /
+    moment_dict / acs_info: the stored actions replayed through the fp64 diagnostic lane."""
+    g = golden("stored_info_P.npz")
+    cols, V, A = list(g["columns"]), g["values"], g["actions"]
+    env = envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase="landing_burn_pure_throttle",
+                                               enable_wind=False)
+
+    def flat(dct, prefix="", out=None):
+        out = {} if out is None else out
+        for k, v in dct.items():
+            if isinstance(v, dict):
+                flat(v, f"{prefix}{k}_", out)
+            else:
+                out[f"{prefix}{k}"] = v
+        return out
+    # upstream's MLP (another torch build) produced these actions; replaying them keeps the
+    # trajectories together to ~1e-9 over the first steps; alpha_effective (gamma - theta - pi,
+    # ~1e-2) and everything multiplied by it carries the 1e-9 * 1e2 conditioning
+    tight = 1e-7
+    loose = {"alpha_effective", "CL", "lift", "aero_force_x", "aero_force_y", "moment_dict_aero_moment_z",
+             "moment_dict_moments_z", "moment_dict_theta_dot_dot", "acceleration_dict_acceleration_x_component_lift",
+             "acceleration_dict_acceleration_y_component_lift", "acceleration_dict_acceleration_x_component",
+             "action_info_acs_info_alpha_local_left_rad", "action_info_acs_info_alpha_local_right_rad",
+             "action_info_acs_info_C_n_L", "action_info_acs_info_C_n_R", "action_info_acs_info_F_n_L",
+             "action_info_acs_info_F_n_R", "action_info_acs_info_F_perpendicular_L",
+             "action_info_acs_info_F_perpendicular_R", "action_info_acs_info_F_perpendicular",
+             "action_info_acs_info_Fx", "action_info_acs_info_Fy", "action_info_acs_info_Mz",
+             "control_force_perpendicular", "moment_dict_control_moment_z"}
+    scale = np.maximum(np.max(np.abs(V[:40]), axis=0), 1e-12)
+    for k in range(40):
+        s, r, d, t, info = env.step(A[k].astype(np.float32))
+        f = flat(info)
+        for j, name in enumerate(cols):
+            assert name in f, name
+            tol = 5e-4 if name in loose else tight
+            assert abs(float(f[name]) - V[k, j]) <= tol * max(abs(V[k, j]), 1e-3 * scale[j]) + 1e-9 * scale[j], (
+                k, name, float(f[name]), V[k, j])
+
+
+def test_collect_and_save_trajectory_data(envs_mod, golden, tmp_path):
+    """ParticleSubswarmOptimisation.collect_trajectory_data / save_trajectory_data: the saved best
+    actor's episode (823 steps) with the reference's four CSV files and column names."""
+    import pandas as pd
+    from psso_sac_for_powered_descent_b200 import pso
+    g = golden("pso_best_actor_P.npz")
+    gi = golden("stored_info_P.npz")
+    opt = pso.ParticleSubswarmOptimisation("landing_burn_pure_throttle", pso_params=dict(
+        pso.PSO_PARAMS["landing_burn_pure_throttle"], pop_size=8, num_sub_swarms=2), seed=0,
+        base_save_dir=str(tmp_path))
+    data = opt.collect_trajectory_data(g["weights"])
+    assert len(data["states"]) == int(g["steps"]) == 823
+    assert abs(-sum(data["rewards"]) - float(g["fitness"])) <= 1e-3 * abs(float(g["fitness"]))
+    d = opt.save_trajectory_data(data)
+    info = pd.read_csv(f"{d}/info_data.csv")
+    assert set(gi["all_columns"]) <= set(info.columns)
+    st = pd.read_csv(f"{d}/states.csv").values
+    assert st.shape == (823, 2)
+    assert np.max(np.abs(st[:50] - g["stored_states"][:50])) < 1e-6
+    assert pd.read_csv(f"{d}/actions.csv").shape == (823, 1) and pd.read_csv(f"{d}/rewards.csv").shape == (823, 1)

@@ -406,6 +406,21 @@ def info_full(n_steps=25, seed=31):
     print("info_full", {k: v.shape for k, v in out.items() if k.startswith("values")})
 
 
+def stored_info_csv(n_rows=120):
+    """The reference's own committed per-step `info_data.csv` of its saved best P actor (written on
+    the author's machine by save_trajectory_data, particle_swarm_optimisation.py:787-809): numeric
+    columns of the first rows, with the stored actions that produced them."""
+    import pandas as pd
+    d = "data/pso_saves/landing_burn_pure_throttle/PSO_different_starting_point/trajectory_data/"
+    info = pd.read_csv(d + "info_data.csv")
+    acts = pd.read_csv(d + "actions.csv").values[:n_rows]
+    cols = [c for c in info.columns if info[c].dtype.kind == "f" or info[c].dtype.kind == "i"]
+    np.savez_compressed(os.path.join(OUT, "stored_info_P.npz"), columns=np.array(cols),
+                        values=info[cols].values[:n_rows].astype(float), actions=acts.astype(float),
+                        all_columns=np.array(list(info.columns)))
+    print("stored_info", len(cols), "numeric columns of", len(info.columns), "rows", n_rows)
+
+
 def ascent_csv():
     """The reference's own committed ascent controller recordings (actions + states per 0.1 s
     step) - golden vectors written on the author's machine, copied verbatim."""
@@ -501,6 +516,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero", "other", "info"]
     if "info" in which:
         info_full()
+        stored_info_csv()
     if "other" in which:
         ascent_csv()
         pool = rl_sequence_other(S_, "S", 400, mode="csv")
