@@ -187,8 +187,18 @@ constexpr int TILE_M = 128;
 constexpr uint32_t A_BYTES = TILE_M * ACT_H * 2;        // 64 KB: 4 K-blocks x 16 KB
 constexpr uint32_t B_BYTES = ACT_H * ACT_H * 2;         // 128 KB: 4 K-blocks x 32 KB
 
+// 256 threads = two halves of 4 warps.  Row (env) of a thread = tid & 127; half h = tid >> 7
+// takes K blocks {2h, 2h+1} of layer 1 and accumulator columns [128h, 128h + 128) of the epilogue
+// (a warp may only touch TMEM lanes 32 (warp % 4) .. +31, so the two halves share lanes and split
+// columns).  The fp32 accumulator is double-buffered in TMEM (2 x 256 of the 512 columns): the
+// 16 UMMAs of tile i are issued asynchronously and run on the tensor core while all 8 warps do the
+// epilogue of tile i-1; only then does the CTA wait for tile i's commit (its A tile may not be
+// overwritten earlier).  Per tile the CTA therefore pays layer 1 + epilogue, each at half the
+// former per-thread work, and no longer the MMA latency.
+constexpr int ACT_THREADS = 256;
+
 template <int O, int A>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(ACT_THREADS, 1)
 actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ act, float *mean_out,
                 int B, int n_tiles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -200,9 +210,11 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
     float *s_b2 = s_b1 + ACT_H;
     float *s_wm = s_b2 + ACT_H;                          // [A][256]
     float *s_ws = s_wm + A * ACT_H;
-    uint64_t *bars = (uint64_t *)(s_ws + A * ACT_H);     // [0] W2 landed, [1] MMA done
+    float *s_part = s_ws + A * ACT_H;                    // [128][2A] head partial sums of half 1
+    uint64_t *bars = (uint64_t *)(s_part + TILE_M * 2 * A);   // [0] W2 landed, [1] MMA done
     uint32_t *s_tmem = (uint32_t *)(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (TILE_M - 1), half = tid >> 7;
     const uint32_t bar_w2 = smem_u32(bars), bar_mma = smem_u32(bars + 1);
 
     if (tid == 0) {
@@ -210,14 +222,14 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
         mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {      // one warp allocates 256 TMEM columns (fp32 accumulator 128 x 256)
+    if (warp == 0) {      // one warp allocates all 512 TMEM columns: two 128 x 256 fp32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(s_tmem)), "n"(256) : "memory");
+                     ::"r"(smem_u32(s_tmem)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < ACT_H * O; i += 128) s_w1[i] = p.w1[i];
-    for (int i = tid; i < ACT_H; i += 128) { s_b1[i] = p.b1[i]; s_b2[i] = p.b2[i]; }
-    for (int i = tid; i < A * ACT_H; i += 128) { s_wm[i] = p.wm[i]; s_ws[i] = p.ws[i]; }
+    for (int i = tid; i < ACT_H * O; i += ACT_THREADS) s_w1[i] = p.w1[i];
+    for (int i = tid; i < ACT_H; i += ACT_THREADS) { s_b1[i] = p.b1[i]; s_b2[i] = p.b2[i]; }
+    for (int i = tid; i < A * ACT_H; i += ACT_THREADS) { s_wm[i] = p.wm[i]; s_ws[i] = p.ws[i]; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -233,15 +245,63 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
     uint32_t mma_phase = 0;
     bool w2_ready = false;
 
+    // epilogue of one finished tile: bias + ReLU on this half's 128 accumulator columns, partial
+    // head dot products, combine the halves through shared memory, sample
+    auto epilogue = [&](int tile, uint32_t buf) {
+        float mean[A], lstd[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) { mean[a] = 0.f; lstd[a] = 0.f; }
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256 + half * 128;
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + cb * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = half * 128 + cb * 32 + j;
+                const float h2 = fmaxf(__uint_as_float(v[j]) + s_b2[n], 0.f);
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    mean[a] = fmaf(s_wm[a * ACT_H + n], h2, mean[a]);
+                    lstd[a] = fmaf(s_ws[a * ACT_H + n], h2, lstd[a]);
+                }
+            }
+        }
+        if (half == 1) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) { s_part[row * 2 * A + a] = mean[a]; s_part[row * 2 * A + A + a] = lstd[a]; }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();      // partial sums visible; all TMEM reads of this buffer are done
+        if (half == 0) {
+            const int env = tile * TILE_M + row;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                mean[a] += s_part[row * 2 * A + a] + p.bm[a];
+                lstd[a] += s_part[row * 2 * A + A + a] + p.bs[a];
+            }
+            if (env < B) head_and_sample<A>(p, mean, lstd, (unsigned)env, act, mean_out);
+        }
+    };
+
+    int prev_tile = -1;
+    uint32_t buf = 0;
+    // the observations of the next tile are fetched while this tile's epilogue runs
+    float o_next[O];
+    {
+        const int env0 = blockIdx.x * TILE_M + row;
+#pragma unroll
+        for (int k = 0; k < O; ++k) o_next[k] = (blockIdx.x < n_tiles && env0 < B) ? obs[(size_t)env0 * O + k] : 0.f;
+    }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int env = tile * TILE_M + tid;
         float o[O];
 #pragma unroll
-        for (int k = 0; k < O; ++k) o[k] = env < B ? obs[(size_t)env * O + k] : 0.f;
-        // layer 1 -> bf16 -> swizzled A tile (row = tid)
-        const uint32_t row_off = (uint32_t)(tid >> 3) * 1024 + (uint32_t)(tid & 7) * 128;
+        for (int k = 0; k < O; ++k) o[k] = o_next[k];
+        // layer 1 -> bf16 -> swizzled A tile (row = tid & 127), this half's two K blocks
+        const uint32_t row_off = (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128;
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kq = 0; kq < 2; ++kq) {
+            const int kb = half * 2 + kq;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 uint32_t packed[4];
@@ -259,7 +319,7 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
                     __nv_bfloat162 b2v = __floats2bfloat162_rn(h[0], h[1]);
                     packed[j] = *reinterpret_cast<uint32_t *>(&b2v);
                 }
-                uint8_t *dst = sA + kb * 16384 + row_off + ((c ^ (tid & 7)) * 16);
+                uint8_t *dst = sA + kb * 16384 + row_off + ((c ^ (row & 7)) * 16);
                 *reinterpret_cast<uint4 *>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
         }
@@ -276,48 +336,36 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
                 for (int k = 0; k < 4; ++k) {      // UMMA_K = 16 bf16 = 32 bytes inside the 128 B atom
                     uint64_t ad = umma_desc_sw128(smem_u32(sA) + kb * 16384 + k * 32);
                     uint64_t bd = umma_desc_sw128(smem_u32(sB) + kb * 32768 + k * 32);
-                    umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_base + buf * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
                 }
             }
             umma_commit(bar_mma);
         }
         w2_ready = true;
-        mbar_wait(bar_mma, mma_phase);
+        {
+            const int nt = tile + gridDim.x, envn = nt * TILE_M + row;
+#pragma unroll
+            for (int k = 0; k < O; ++k) o_next[k] = (nt < n_tiles && envn < B) ? obs[(size_t)envn * O + k] : 0.f;
+        }
+        // the previous tile's epilogue runs while the tensor core works on this tile
+        if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1u);
+        mbar_wait(bar_mma, mma_phase);      // tile done: the A tile may be rewritten
         mma_phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // epilogue: thread tid owns TMEM lane tid (warp w may touch lanes 32w..32w+31)
-        float mean[A], lstd[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) { mean[a] = p.bm[a]; lstd[a] = p.bs[a]; }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(lane_base + cb * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = cb * 32 + j;
-                const float h2 = fmaxf(__uint_as_float(v[j]) + s_b2[n], 0.f);
-#pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    mean[a] = fmaf(s_wm[a * ACT_H + n], h2, mean[a]);
-                    lstd[a] = fmaf(s_ws[a * ACT_H + n], h2, lstd[a]);
-                }
-            }
-        }
-        if (env < B) head_and_sample<A>(p, mean, lstd, (unsigned)env, act, mean_out);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();      // all TMEM reads done before the next tile's MMAs overwrite it
+        prev_tile = tile;
+        buf ^= 1u;
     }
+    if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1u);
     if (!w2_ready && tid == 0) mbar_wait(bar_w2, 0);      // never leave with a TMA in flight
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }
 
 size_t actor_tc_smem_bytes(int O, int A) {
-    return 1024 + A_BYTES + B_BYTES + sizeof(float) * (ACT_H * O + 3 * ACT_H + 2 * A * ACT_H) + 64;
+    return 1024 + A_BYTES + B_BYTES + sizeof(float) * (ACT_H * O + 3 * ACT_H + 2 * A * ACT_H + TILE_M * 2 * A) + 64;
 }
 
 int actor_prep_w2(const float *w2, void *img, cudaStream_t st) {
@@ -338,7 +386,7 @@ static int launch_t(const ActorArgs &p, const float *obs, float *act, float *mea
         }
         int n_tiles = (B + TILE_M - 1) / TILE_M;
         int grid = n_tiles < n_sm ? n_tiles : n_sm;
-        actor_tc_kernel<O, A><<<grid, 128, smem, st>>>(p, obs, act, mean_out, B, n_tiles);
+        actor_tc_kernel<O, A><<<grid, ACT_THREADS, smem, st>>>(p, obs, act, mean_out, B, n_tiles);
     } else {
         actor_fp32_kernel<O, A><<<(B + 127) / 128, 128, 0, st>>>(p, obs, act, mean_out, B);
     }
