@@ -366,3 +366,27 @@ def test_collect_and_save_trajectory_data(envs_mod, golden, tmp_path):
     assert st.shape == (823, 2)
     assert np.max(np.abs(st[:50] - g["stored_states"][:50])) < 1e-6
     assert pd.read_csv(f"{d}/actions.csv").shape == (823, 1) and pd.read_csv(f"{d}/rewards.csv").shape == (823, 1)
+
+
+@pytest.mark.parametrize("key,dt", [("f32", torch.float32), ("f64", torch.float64)])
+def test_supersonic_with_wind_tape(envs_mod, golden, key, dt):
+    """Supersonic ascent with the stochastic gust filter on an explicit noise tape (the reference
+    run with the same tape): the ascent decomposer's float32 force sums meet the np.float64 wind
+    force here (float32 actions), pure float64 otherwise."""
+    g = golden("wind_sequence_U.npz")
+    env = envs_mod.BatchedRocketEnv(1, "rl", U, enable_wind=True, stochastic_wind=True,
+                                    horiontal_wind_percentile=int(g["percentile"]), precision="fp64",
+                                    trajectory_length=1000, discount_factor=0.99)
+    env.set_wind_tape(g["tape"][None, :], [[float(g["sigma_u"]), float(g["sigma_v"])]])
+    env.reset()
+    dbg = torch.zeros(1, 16, dtype=torch.float64, device="cuda")
+    S, UG, R, FL = g[f"states_{key}"], g[f"ug_vg_{key}"], g[f"rewards_{key}"], g[f"flags_{key}"]
+    acts = torch.as_tensor(g["actions"]).to(dt).cuda()
+    for k in range(len(S)):
+        obs, rew, done, trunc, tid = env.step(acts[k].reshape(1, 2), dbg=dbg)
+        st = env.get_state()[0].cpu().numpy()
+        assert float(state_err(st, S[k], U)) < (1e-12 if k < 3 else 1e-9), k
+        assert np.max(np.abs(dbg[0, 13:15].cpu().numpy() - UG[k])) < 1e-9 * max(1.0, abs(UG[k][0]))
+        assert abs(float(rew[0]) - R[k]) < 1e-9
+        assert (float(done[0]), float(trunc[0]), float(tid[0])) == tuple(FL[k])
+    env.check_status()

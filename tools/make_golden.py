@@ -472,6 +472,45 @@ def wind_sequence(n_steps=260, seed=3):
           "last ug", UG[-1])
 
 
+def wind_sequence_ascent(n_steps=80, seed=13):
+    """Supersonic ascent with stochastic wind (gust filter active below 15 km) driven by an explicit
+    noise tape; recorded controller actions as float32 and as float64 (the float32 force sums of
+    the ascent decomposer meet the np.float64 wind force here)."""
+    import pandas as pd
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    rng = np.random.default_rng(seed)
+    tape = rng.standard_normal(2 * n_steps + 16)
+    sig_u, sig_v = 1.9, 1.6
+    g = pd.read_csv("data/reference_trajectory/ascent_controls/supersonic_state_action_ascent_control.csv")
+    acts = g[["u0", "u1"]].values[:n_steps]
+    out = {}
+    for key, dt in (("f32", np.float32), ("f64", np.float64)):
+        nt = NoiseTapeWind(tape, sig_u, sig_v)
+        nt.install()
+        try:
+            env = quiet(rocket_environment_pre_wrap, type="rl", flight_phase=U_, enable_wind=True,
+                        stochastic_wind=True, horiontal_wind_percentile=50, trajectory_length=1000,
+                        discount_factor=0.99)
+            nt.pos = 0
+            quiet(env.reset)
+            nt.pos = 0
+            S, UG, R, FL = [], [], [], []
+            for k in range(n_steps):
+                s, r, d, t, info = quiet(env.step, acts[k].astype(dt))
+                S.append([float(v) for v in s]); UG.append([float(info["ug"]), float(info["vg"])])
+                R.append(float(r)); FL.append([float(d), float(t), float(env.truncation_id)])
+                if d or t:
+                    break
+        finally:
+            nt.uninstall()
+        out[f"states_{key}"] = np.array(S); out[f"ug_vg_{key}"] = np.array(UG)
+        out[f"rewards_{key}"] = np.array(R); out[f"flags_{key}"] = np.array(FL)
+        out[f"tape_used_{key}"] = nt.pos
+    np.savez_compressed(os.path.join(OUT, "wind_sequence_U.npz"), tape=tape, sigma_u=sig_u, sigma_v=sig_v,
+                        actions=acts, percentile=50, **out)
+    print("wind_sequence_U", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 def classical():
     from src.classical_controls.landing_burn_pure_throttle import LandingBurn
     lb = quiet(LandingBurn, test_case="control")
@@ -545,5 +584,7 @@ if __name__ == "__main__":
         rl_sequence(G, "G", 12)
     if "wind" in which:
         wind_sequence()
+    if "windU" in which or "wind" in which:
+        wind_sequence_ascent()
     if "classical" in which:
         classical()
