@@ -303,9 +303,9 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     rc = rc || upload_segments(e, p->gf_cn_mach, p->gf_cn_val, p->n_gf_cn, &e->tb.cn_x, &e->tb.cn_y, &e->tb.cn_s);
     if (rc) { pd_destroy(e); return 1; }
     {   // fast_log table: u_j = double(1/c_j), c_j = 1 + (j + 0.5)/256; second word -log(u_j)
-        std::vector<double> tab(512);
-        for (int j = 0; j < 256; ++j) {
-            long double cj = 1.0L + ((long double)j + 0.5L) / 256.0L;
+        std::vector<double> tab(2 * PD_LOG_N);
+        for (int j = 0; j < PD_LOG_N; ++j) {
+            long double cj = 1.0L + ((long double)j + 0.5L) / (long double)PD_LOG_N;
             double u = (double)(1.0L / cj);
             tab[2 * j] = u;
             tab[2 * j + 1] = (double)(-logl((long double)u));
@@ -324,7 +324,7 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
                     img[o++] = i < n_src ? src[2 * i + 1] : 0.0;
                 }
         };
-        put(tab.data(), 256, 256);
+        put(tab.data(), PD_LOG_N, PD_LOG_N);
         put(p->cd.points, p->cd.n_points, 256);
         put(p->cl.points, p->cl.n_points, 144);
         const double *di = nullptr;

@@ -129,15 +129,24 @@ struct Tables {
 // Each table starts on a 32 KB boundary of the shared window (the kernels round the dynamic
 // shared base up), so a gather address is base | (field & 0x7F80): one shift + one LOP3 per
 // lookup instead of shift + mask + scaled add.
+// PD_LOG_BITS = mantissa bits that index the log table.  8 (256 entries, degree 5 / 4) is the
+// default.  9 (512 entries, |r| < 2^-10, one polynomial degree and one DFMA per term less) was
+// measured 1.5 % SLOWER on B200 (80.0 vs 78.8 us per 65 536-env step): the larger image costs more
+// to stage per launch than the saved FP64 instruction buys - the kernel is not FP64-bound.
+#ifndef PD_LOG_BITS
+#define PD_LOG_BITS 8
+#endif
+#define PD_LOG_N (1 << PD_LOG_BITS)
 struct SharedTables {
-    double2 logtab[256 * PD_REP];       // 32 KB
+    double2 logtab[PD_LOG_N * PD_REP];  // 32 KB (256 entries)
     double2 cd_pts[256 * PD_REP];       // 32 KB slot, 192 used
     double2 cl_pts[144 * PD_REP];
     unsigned long long bar;             // mbarrier of the bulk copy (not part of the image)
 };
-constexpr unsigned PD_SH_ALIGN = 32768;
+constexpr unsigned PD_SH_ALIGN = PD_LOG_N * PD_REP * 16;                  // the largest table's span
 constexpr unsigned PD_SH_BYTES = sizeof(SharedTables) + PD_SH_ALIGN;      // dynamic shared memory per block
-constexpr unsigned PD_SH_IMAGE_BYTES = (256 + 256 + 144) * PD_REP * 16;
+constexpr unsigned PD_SH_IMAGE_BYTES = (PD_LOG_N + 256 + 144) * PD_REP * 16;
+constexpr unsigned PD_LOG_MASK = (PD_LOG_N - 1) << 7;                     // byte-offset field of a table index
 
 // per-TU copies (no relocatable device code): each precision TU uploads its own
 static __constant__ Scalars<double> g_sd;
@@ -443,7 +452,7 @@ __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__
     const double *K = g_sd.log_c;
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
-    const double2 t = tab[((hi >> 12) & 255) * PD_REP];
+    const double2 t = tab[((hi >> (20 - PD_LOG_BITS)) & (PD_LOG_N - 1)) * PD_REP];
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // (double)((hi >> 20) - 1023): biased exponent in the low word of 2^52, minus (2^52 + 1023);
     // x > 0 here, so the sign bit needs no masking
@@ -453,10 +462,13 @@ __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__
     if (DEG >= 5) {
         p = fma(r, K[0], K[1]);
         p = fma(p, r, K[2]);
-    } else {
+        p = fma(p, r, K[3]);
+    } else if (DEG == 4) {
         p = fma(r, K[1], K[2]);
+        p = fma(p, r, K[3]);
+    } else {
+        p = fma(r, K[2], K[3]);
     }
-    p = fma(p, r, K[3]);
     p = fma(p * r, r, r);
     return fma(ed, K[4], t.y + p);
 }
@@ -521,7 +533,7 @@ __device__ __forceinline__ double fast_log_t(double x, double2 t) {
     const double r2 = r * r;
     double q = fma(r, K[2], K[3]);                  // -1/2 + r/3
     if (DEG >= 5) q = fma(r2, fma(r, K[0], K[1]), q);   // + r^2 (-1/4 + r/5)
-    else q = fma(r2, K[1], q);                          // - r^2/4
+    else if (DEG == 4) q = fma(r2, K[1], q);            // - r^2/4
     return s + fma(r2, q, r);
 }
 
@@ -565,7 +577,7 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
         }
         double2 t[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = lds_d2(bT | (((unsigned)__double2hiint(r2[i]) >> 5) & 0x7F80u));
+        for (int i = 0; i < 8; ++i) t[i] = lds_d2(bT | (((unsigned)__double2hiint(r2[i]) >> (13 - PD_LOG_BITS)) & PD_LOG_MASK));
         double lg[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) lg[i] = fast_log_t<DEG>(r2[i], t[i]);
@@ -640,7 +652,7 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     const int sidD = rbf_resolve<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, M, aD, cellD, status);
     const int sidL = rbf_resolve<5>(g_tb.cl, GL, g_sd.cl_levels, M, aL, cellL, status);
     double vL, vD;
-    constexpr int DEG = sizeof(R) == 8 ? 5 : 4;
+    constexpr int DEG = (sizeof(R) == 8 ? 5 : 4) - (PD_LOG_BITS >= 9 ? 1 : 0);
     const int copy = threadIdx.x & (PD_REP - 1);          // this lane's replica of the tables
     if constexpr (COOP == 1)
         rbf_eval2<DEG>(g_tb.cl.rows, sidL, sh->cl_pts + copy, aL, g_tb.cd.rows, sidD, sh->cd_pts + copy, aD, M,
