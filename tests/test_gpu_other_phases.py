@@ -124,7 +124,7 @@ def test_pcontrol_wrapper_sequence_fp64(envs_mod, golden, tag):
     """P-control episodes through the RL wrapper (kernel-side v_ref scaling, reward with the
     float32 tracking term).  One 0.1 s Euler step per env step makes the pitch channel of this
     phase violently unstable - a 5e-14 difference in theta_dot after step 0 is 1e-10 after 5
-    steps and O(1) after 100 (measured, tools/gpu_debug.py), in ANY implementation including the
+    steps and O(1) after 100 (measured, tools/sequence_divergence.py), in ANY implementation including the
     reference on another BLAS - so: a free-running prefix, then every step restarted from the
     reference's own previous state (g-load window carried on the device)."""
     phase = C

@@ -1,4 +1,6 @@
-"""Ad-hoc GPU debug: per-step divergence of an RL-wrapper sequence against its fixture."""
+"""Per-step divergence of a free-running RL-wrapper episode (fp64 build) from its reference fixture:
+    python tools/sequence_divergence.py C landing_burn_pure_throttle_Pcontrol
+Shows how fast a 1e-14 rounding difference grows through the pitch channel of each phase."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
