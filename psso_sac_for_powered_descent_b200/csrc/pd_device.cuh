@@ -421,19 +421,27 @@ __device__ __forceinline__ const int *rbf_cell_ptr(const RbfGrid &G, double M, d
     ia = max(0, min(ia, G.na - 1));
     return G.cells + ia * G.nm + im;
 }
+// pts: this lane's replica of the table's (Mach, AoA) points in shared memory.
+// Impure cells come in two kinds (rbf_sets._resolve_single_edge_cells): cut by exactly one
+// order-50 Voronoi edge - bit 63 of the hint; the two sets differ by one swap p <-> q and the
+// query belongs to the first iff it is not farther from p than from q: two gathers and six FP64
+// operations, no divergence worth the name - or anything else (< 1 % of the cells): the walk.
 template <int NL>
 __device__ __forceinline__ int rbf_resolve(const RbfDev &T, const RbfGrid &G, const double *levels_d,
-                                           double M, double a, int cell, int &status) {
+                                           const double2 *__restrict__ pts, double M, double a, int cell,
+                                           int &status) {
     if (cell >= 0) return cell;
     const int k = -cell - 1;
     int sid = __ldg(G.imp_id + k);
-    status |= rbf_walk<NL>(T, levels_d, M, a, __ldg(G.imp_hint + k), sid);
+    const unsigned long long hint = __ldg(G.imp_hint + k);
+    if (hint >> 63) {
+        const double2 P = pts[(int)((hint >> 8) & 255) * PD_REP], Q = pts[(int)(hint & 255) * PD_REP];
+        const double px = M - P.x, py = a - P.y, qx = M - Q.x, qy = a - Q.y;
+        const double dp = fma(px, px, py * py), dq = fma(qx, qx, qy * qy);
+        return dp <= dq ? sid : (int)((hint >> 16) & 0xFFFF);
+    }
+    status |= rbf_walk<NL>(T, levels_d, M, a, hint, sid);
     return sid;
-}
-template <int NL>
-__device__ __forceinline__ int rbf_locate(const RbfDev &T, const RbfGrid &G, const double *levels_d,
-                                          double M, double a, int &status) {
-    return rbf_resolve<NL>(T, G, levels_d, M, a, __ldg(rbf_cell_ptr(G, M, a)), status);
 }
 
 // Natural log of a positive normal double, ~1 ulp, ~18 instructions (CUDA's log() costs ~130
@@ -649,11 +657,11 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     const RbfGrid &GL = neg_line ? g_tb.cl.grid[1] : g_tb.cl.grid[0];
     const int cellD = __ldg(rbf_cell_ptr(g_tb.cd.grid[0], M, aD));
     const int cellL = __ldg(rbf_cell_ptr(GL, M, aL));
-    const int sidD = rbf_resolve<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, M, aD, cellD, status);
-    const int sidL = rbf_resolve<5>(g_tb.cl, GL, g_sd.cl_levels, M, aL, cellL, status);
+    const int copy = threadIdx.x & (PD_REP - 1);          // this lane's replica of the tables
+    const int sidD = rbf_resolve<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, sh->cd_pts + copy, M, aD, cellD, status);
+    const int sidL = rbf_resolve<5>(g_tb.cl, GL, g_sd.cl_levels, sh->cl_pts + copy, M, aL, cellL, status);
     double vL, vD;
     constexpr int DEG = (sizeof(R) == 8 ? 5 : 4) - (PD_LOG_BITS >= 9 ? 1 : 0);
-    const int copy = threadIdx.x & (PD_REP - 1);          // this lane's replica of the tables
     if constexpr (COOP == 1)
         rbf_eval2<DEG>(g_tb.cl.rows, sidL, sh->cl_pts + copy, aL, g_tb.cd.rows, sidD, sh->cd_pts + copy, aD, M,
                        sh->logtab + copy, vL, vD);

@@ -27,6 +27,7 @@ Design (B200-first, not a translation of scipy):
 from __future__ import annotations
 
 import hashlib
+import math
 import os
 from dataclasses import dataclass
 
@@ -393,8 +394,81 @@ def build_grid(tbl, box, nm, na) -> QueryGrid:
     cells[imp] = -(np.arange(len(imp), dtype=np.int32) + 1)
     imp_hint = pack_hints(zlo[imp], zhi[imp]) if len(imp) else np.zeros(0, np.uint64)
     imp_id = zid[imp].astype(np.int32)
+    if len(imp):
+        _resolve_single_edge_cells(tbl, ids, imp, cid, zid2, m0, dm, a0, da, nm, imp_hint, imp_id)
     return QueryGrid(float(m0), float(dm), int(nm), float(a0), float(da), int(len(aa)), cells,
                      imp_hint, imp_id)
+
+
+EDGE_FLAG = np.uint64(1) << np.uint64(63)
+
+
+def _resolve_single_edge_cells(tbl, ids, imp, cid, zid2, m0, dm, a0, da, nm, imp_hint, imp_id):
+    """Impure grid cells that are cut by exactly ONE order-50 Voronoi edge need no search on the
+    device: the two sets differ by one swap (S2 = S1 - {p} + {q}), the edge is the bisector of p
+    and q, and the query belongs to S1 iff it is not farther from p than from q.  Such a cell is
+    re-encoded in place: imp_id = S1, imp_hint = bit 63 | S2 << 16 | p << 8 | q (p, q = point
+    slots).  Proof obligation per cell (all checked here with the brute-force 50-NN): the five
+    samples (corners + centre) show only S1 and S2, each on its side of the bisector, and the two
+    points where the bisector crosses the cell boundary, nudged to either side, show S1 / S2 -
+    every vertex of the two convex polygons the bisector cuts the cell into lies in the (convex)
+    Voronoi cell of its set, hence so do the polygons."""
+    L = len(tbl.levels)
+    S, NP = tbl.n_sets, len(tbl.mach_sorted)
+    member = np.zeros((S, NP), bool)
+    lo_all, hi_all = np.asarray(tbl.set_lo, np.int64), np.asarray(tbl.set_hi, np.int64)
+    for l in range(L):
+        idx = np.arange(tbl.level_off[l + 1] - tbl.level_off[l])[None, :]
+        member[:, tbl.level_off[l]:tbl.level_off[l + 1]] = (idx >= lo_all[:, l:l + 1]) & (idx < hi_all[:, l:l + 1])
+    ia, im = np.divmod(imp, nm)
+    five = np.stack([cid[ia, im], cid[ia, im + 1], cid[ia + 1, im], cid[ia + 1, im + 1], zid2[ia, im]], 1)
+    s1, s2 = five.min(1), five.max(1)
+    cand = ((five == s1[:, None]) | (five == s2[:, None])).all(1) & (s1 != s2)
+    k = np.nonzero(cand)[0]
+    if len(k) == 0:
+        return
+    d1 = member[s1[k]] & ~member[s2[k]]
+    d2 = member[s2[k]] & ~member[s1[k]]
+    single = (d1.sum(1) == 1) & (d2.sum(1) == 1)
+    k, d1, d2 = k[single], d1[single], d2[single]
+    p, q = d1.argmax(1), d2.argmax(1)
+    pts = np.asarray(tbl.points, float).reshape(-1, 2)
+    P, Q = pts[p], pts[q]
+    nrm = Q - P
+    c = 0.5 * ((Q ** 2).sum(1) - (P ** 2).sum(1))
+    x0, y0 = m0 + dm * im[k], a0 + da * ia[k]
+    corners = np.stack([np.stack([x0, y0], 1), np.stack([x0 + dm, y0], 1), np.stack([x0, y0 + da], 1),
+                        np.stack([x0 + dm, y0 + da], 1), np.stack([x0 + 0.5 * dm, y0 + 0.5 * da], 1)], 1)
+    side = (corners * nrm[:, None, :]).sum(2) - c[:, None]            # < 0: nearer p -> S1
+    want = np.where(side < 0, s1[k][:, None], s2[k][:, None])
+    ok = (side != 0).all(1) & (want == five[k]).all(1)
+    # the two boundary crossings: rectangle edges in order 00-01, 01-11, 11-10, 10-00
+    order = [(0, 1), (1, 3), (3, 2), (2, 0)]
+    cross = np.stack([(side[:, a] < 0) != (side[:, b] < 0) for a, b in order], 1)
+    ok &= cross.sum(1) == 2
+    k, p, q, nrm, corners, side, cross = k[ok], p[ok], q[ok], nrm[ok], corners[ok], side[ok], cross[ok]
+    if len(k) == 0:
+        return
+    X = []
+    for e, (a, b) in enumerate(order):
+        t = side[:, a] / (side[:, a] - side[:, b] + (side[:, a] == side[:, b]))
+        X.append(corners[:, a] + (corners[:, b] - corners[:, a]) * t[:, None])
+    X = np.stack(X, 1)                                                 # [n, 4 edges, 2]
+    first = cross.argmax(1)
+    second = 3 - cross[:, ::-1].argmax(1)
+    n_hat = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    eps = 1e-6 * math.hypot(dm, da)
+    good = np.ones(len(k), bool)
+    for sel in (first, second):
+        x = X[np.arange(len(k)), sel]
+        for sgn, sid in ((-1.0, s1[k]), (1.0, s2[k])):
+            y = x + sgn * eps * n_hat
+            got, _, _ = ids(y[:, 0], y[:, 1])
+            good &= got == sid
+    k, p, q = k[good], p[good], q[good]
+    imp_id[k] = s1[k].astype(np.int32)
+    imp_hint[k] = EDGE_FLAG | (s2[k].astype(np.uint64) << np.uint64(16)) | (p.astype(np.uint64) << np.uint64(8)) \
+        | q.astype(np.uint64)
 
 
 def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None) -> LocalRbfTable:
@@ -406,7 +480,7 @@ def build_table(mach, aoa, val, boxes, cache_dir=None, grid=(64, 24), grids=None
     val = np.asarray(val, float)
     box = np.asarray(boxes, float).reshape(-1)
     tag = hashlib.sha256(mach.tobytes() + aoa.tobytes() + val.tobytes() + box.tobytes()
-                         + repr(grids).encode() + b"v9").hexdigest()[:16]
+                         + repr(grids).encode() + b"v10").hexdigest()[:16]
     if cache_dir:
         path = os.path.join(cache_dir, f"rbf_{tag}.pkl")
         if os.path.exists(path):
