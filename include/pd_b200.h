@@ -52,7 +52,11 @@ enum { PD_POLICY_MLP = 0, PD_POLICY_TAPE = 1, PD_POLICY_CLASSICAL = 2 };
 
 /* Uniform (Mach, AoA) lookup grid over one query region of a local RBF table.
  * cells[ia*nm+im] >= 0 : set id valid for the whole grid cell;
- * cells < 0            : -(k+1) indexes (imp_hint, imp_id): candidate set to walk from. */
+ * cells < 0            : -(k+1) indexes (imp_hint, imp_id).  imp_hint bit 63 set: the cell is cut
+ *                        by exactly one Voronoi edge; imp_id = first set, bits 16..31 = second set,
+ *                        bits 8..15 / 0..7 = point slots p / q; the query belongs to the first set iff
+ *                        it is not farther from p than from q.  Bit 63 clear: imp_hint = packed
+ *                        per-level [lo, hi) of the candidate set imp_id to walk from. */
 typedef struct {
     double m0, dm, a0, da;
     int32_t nm, na;
