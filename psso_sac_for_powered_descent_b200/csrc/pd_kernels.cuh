@@ -202,6 +202,7 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     info.rbf_status = 0;
     Rtd<R> out;
     R g1;
+    const int ep_steps_in = e.ep_steps[i];      // issued with the other state loads, consumed at the end
     wait_tables(&sh);
     env_step<R, RT, PHASE, RTD, WIND, 1, FULL>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
     if (info.rbf_status) atomicOr(e.status, info.rbf_status);
@@ -227,7 +228,7 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
         d[13] = info.ug; d[14] = info.vg; d[15] = (double)info.rbf_status;
     }
     e.trunc_id[i] = out.trunc_id;
-    int ep_steps = e.ep_steps[i] + 1;
+    int ep_steps = ep_steps_in + 1;
     if (auto_reset && (out.done || out.truncated)) {
         state_reset(s);
         gw.n = 0;
