@@ -90,7 +90,7 @@ class PdSharedActor(C.Structure):
 EXPORTS = ["pd_last_error", "pd_version", "pd_create", "pd_destroy", "pd_reset", "pd_step",
            "pd_get_state", "pd_set_state", "pd_set_wind_tape", "pd_rollout_pso", "pd_rollout_policy",
            "pd_collect_shared_actor", "pd_actor_forward", "pd_pso_update", "pd_activate", "pd_check_status", "pd_launch_count",
-           "pd_set_info_mode"]
+           "pd_set_info_mode", "pd_set_rollout_handoff"]
 
 _lib = None
 
@@ -123,6 +123,7 @@ def load_library():
     lib.pd_check_status.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.pd_activate.argtypes = [vp]
     lib.pd_set_info_mode.argtypes = [vp, i32]
+    lib.pd_set_rollout_handoff.argtypes = [vp, i32]
     lib.pd_pso_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_int64, C.c_double,
                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, i32, vp]
     for name in EXPORTS:

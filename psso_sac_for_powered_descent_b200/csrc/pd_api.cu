@@ -45,6 +45,11 @@ struct PdEnv {
     size_t wT_cap = 0;
     int *roll_status = nullptr;
     int *roll_queue = nullptr;
+    double *cont_d = nullptr;        // straggler hand-off records (pd_rollout_pso)
+    int *cont_i = nullptr;
+    int *cont_count = nullptr;
+    int cont_cap = 0;
+    int handoff_steps = 256;         // pd_set_rollout_handoff
     // shared-actor collection
     void *w2_img = nullptr;          // bf16 smem image of W2
     const float *w2_src = nullptr;   // which W2 the image was built from
@@ -275,7 +280,7 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
 extern "C" {
 
 const char *pd_last_error(void) { return g_err.c_str(); }
-int pd_version(void) { return 110; }
+int pd_version(void) { return 120; }
 uint64_t pd_launch_count(void) { return g_launches.load(); }
 
 int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
@@ -381,6 +386,8 @@ int pd_destroy(PdEnv *e) {
         if (g_active[p] == e) g_active[p] = nullptr;
     for (void *a : e->allocs) cudaFree(a);
     if (e->wT) cudaFree(e->wT);
+    if (e->cont_d) cudaFree(e->cont_d);
+    if (e->cont_i) cudaFree(e->cont_i);
     delete e;
     return 0;
 }
@@ -392,6 +399,13 @@ static WindCtx wind_ctx(const PdEnv *e) {
     wc.seed = e->cfg.seed;
     wc.stochastic = e->cfg.stochastic_wind;
     return wc;
+}
+
+int pd_set_rollout_handoff(PdEnv *e, int steps) {
+    if (!e) return fail("pd_set_rollout_handoff: null handle");
+    if (steps < 0) return fail("pd_set_rollout_handoff: steps must be >= 0 (0 = off)");
+    e->handoff_steps = steps;
+    return 0;
 }
 
 int pd_set_info_mode(PdEnv *e, int full) {
@@ -523,6 +537,21 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
     io.ret = fitness; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
     io.traj = traj; io.act_out = actions_out; io.rewards = rewards;
     io.queue = e->roll_queue;
+    if (e->handoff_steps > 0 && io.n_episodes > 148 * 448 * 3 / 4 / 8) {
+        // continuation records for the straggler hand-off (used when one lane runs one episode)
+        if (e->cont_cap < io.n_episodes) {
+            if (e->cont_d) { cudaFree(e->cont_d); cudaFree(e->cont_i); e->cont_d = nullptr; e->cont_i = nullptr; }
+            CK(cudaMalloc(&e->cont_d, (size_t)PD_CONT_D * io.n_episodes * sizeof(double)));
+            CK(cudaMalloc(&e->cont_i, (size_t)PD_CONT_I * io.n_episodes * sizeof(int)));
+            e->cont_cap = io.n_episodes;
+        }
+        if (!e->cont_count) {
+            CK(cudaMalloc(&e->cont_count, sizeof(int)));
+            e->allocs.push_back(e->cont_count);
+        }
+        io.handoff_steps = e->handoff_steps;
+        io.cont_d = e->cont_d; io.cont_i = e->cont_i; io.cont_count = e->cont_count; io.cont_cap = e->cont_cap;
+    }
     if (e->impl->rollout(PD_POLICY_MLP, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
                          e->sigma_uv, e->roll_status, st))
         return fail("pd_rollout_pso: unsupported configuration");

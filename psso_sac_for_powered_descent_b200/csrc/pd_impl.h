@@ -47,7 +47,18 @@ struct RolloutIO {
     double *terminal, *traj, *rewards;
     float *act_out;        // [max_steps][n_episodes][A] actions applied (MLP policy)
     int *queue;            // work-queue head (next episode index to hand out)
+    // Straggler hand-off (per-particle MLP policy, large swarms): the first pass gives up
+    // episodes that are still running after handoff_steps and appends their complete state to
+    // the continuation records; a second, 8-lane cooperative pass finishes them at ~2.5x lower
+    // per-step latency (a generation is otherwise bounded by its longest episode).
+    int handoff_steps;     // 0 = off
+    double *cont_d;        // [PD_CONT_D][cont_cap]
+    int *cont_i;           // [PD_CONT_I][cont_cap]: episode, t, g-window count, wind draw counter
+    int *cont_count;       // [1]
+    int cont_cap;
 };
+#define PD_CONT_D 32
+#define PD_CONT_I 4
 
 struct Impl {
     int (*upload)(const Scalars<double> *, const Scalars<float> *, const Tables *);

@@ -325,7 +325,10 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
 // One episode per thread from reset to done/truncated: objective_function
 // (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for POLICY_TAPE,
 // LandingBurn.run_closed_loop for POLICY_CLASSICAL.
-template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP>
+// MODE 0: whole episodes.  MODE 1: first pass of the straggler hand-off (episodes still running
+// after io.handoff_steps are written to the continuation records instead of being finished).
+// MODE 2: second pass, episodes = continuation records.
+template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE = 0>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = phase_adim(PHASE);
@@ -338,9 +341,11 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     // G: 7..27), so a lane that finishes pulls the next episode index instead of idling until
     // the slowest lane of its warp is done.
     // COOP lanes share one episode (identical state in each; only the RBF sums are split)
-    int e = (blockIdx.x * blockDim.x + threadIdx.x) / COOP;
+    int e = (blockIdx.x * blockDim.x + threadIdx.x) / COOP;      // MODE 2: record index
     const bool writer = (threadIdx.x & (COOP - 1)) == 0;
-    bool active = e < io.n_episodes;
+    const int n_work = MODE == 2 ? min(*io.cont_count, io.cont_cap) : io.n_episodes;
+    bool active = e < n_work;
+    int eid = e;                                                  // episode the lane works on
     State s;
     GWindow<R> gw;
     ActPrev prev;
@@ -351,16 +356,34 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     int t = 0;
     size_t col = 0;
     auto begin_episode = [&]() {
-        state_reset(s);
-        gw.n = 0;
+        if constexpr (MODE == 2) {
+            const size_t cap = (size_t)io.cont_cap;
+            const double *d = io.cont_d + e;
+            const int *ci = io.cont_i + e;
+            eid = ci[0]; t = ci[cap]; gw.n = ci[2 * cap]; w.ctr = (unsigned)ci[3 * cap];
+            s.x = d[0]; s.y = d[cap]; s.vx = d[2 * cap]; s.vy = d[3 * cap]; s.theta = d[4 * cap];
+            s.theta_dot = d[5 * cap]; s.gamma = d[6 * cap]; s.alpha = d[7 * cap]; s.mass = d[8 * cap];
+            s.m_prop = d[9 * cap]; s.time = d[10 * cap];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
-        prev.gimbal_deg = prev.dl = prev.dr = 0.0;
-        if (WIND) wind_reset(w, wc, (unsigned)e, 1u, sigma_uv);
-        info.q = R(0);
-        total = 0.0;
-        t = 0;
-        col = (size_t)(e / io.n_seeds);
+            for (int k = 0; k < 10; ++k) gw.w[k] = (R)d[(11 + k) * cap];
+            prev.gimbal_deg = d[21 * cap]; prev.dl = d[22 * cap]; prev.dr = d[23 * cap];
+            w.xu0 = d[24 * cap]; w.xu1 = d[25 * cap]; w.xv0 = d[26 * cap]; w.xv1 = d[27 * cap];
+            w.sigma_u = d[28 * cap]; w.sigma_v = d[29 * cap];
+            total = d[30 * cap];
+            info.q = R(0);
+        } else {
+            eid = e;
+            state_reset(s);
+            gw.n = 0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
+            prev.gimbal_deg = prev.dl = prev.dr = 0.0;
+            if (WIND) wind_reset(w, wc, (unsigned)eid, 1u, sigma_uv);
+            info.q = R(0);
+            total = 0.0;
+            t = 0;
+        }
+        col = (size_t)(eid / io.n_seeds);
     };
     if (active) begin_episode();
     while (__any_sync(0xffffffffu, active)) {
@@ -379,10 +402,10 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
             for (int k = 0; k < A; ++k) act.u[k] = (double)af[k];
             if (io.act_out && writer) {
 #pragma unroll
-                for (int k = 0; k < A; ++k) io.act_out[((size_t)t * io.n_episodes + e) * A + k] = af[k];
+                for (int k = 0; k < A; ++k) io.act_out[((size_t)t * io.n_episodes + eid) * A + k] = af[k];
             }
         } else if constexpr (POLICY == 1) {
-            read_action<A>(io.actions, io.action_dtype, (size_t)t * io.n_episodes + e, act);
+            read_action<A>(io.actions, io.action_dtype, (size_t)t * io.n_episodes + eid, act);
             shape_action<PHASE, RTD>(act);
         } else {
             // classical P controller on v_ref(y) (landing_burn_pure_throttle.py:261-339)
@@ -404,28 +427,54 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
                 Control<R> ctl;
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k)
-                    substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, (unsigned)e, info, ctl, &sh);
+                    substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, (unsigned)eid, info, ctl, &sh);
             } else {
                 R g1;
-                env_step<R, RT, PHASE, RTD, WIND, COOP>(s, act, prev, w, wc, (unsigned)e, gw, info, out, g1, &sh);
+                env_step<R, RT, PHASE, RTD, WIND, COOP>(s, act, prev, w, wc, (unsigned)eid, gw, info, out, g1, &sh);
             }
             total -= (double)out.reward;
             if (io.traj && writer) {
-                double *p = io.traj + ((size_t)t * io.n_episodes + e) * 11;
+                double *p = io.traj + ((size_t)t * io.n_episodes + eid) * 11;
                 p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
                 p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
             }
-            if (io.rewards && writer) io.rewards[(size_t)t * io.n_episodes + e] = (double)out.reward;
+            if (io.rewards && writer) io.rewards[(size_t)t * io.n_episodes + eid] = (double)out.reward;
             ++t;
             if (out.done || out.truncated) { tid = out.trunc_id; stop = true; }
             else if (t >= io.max_steps) stop = true;
         }
+        bool handoff = false;
+        if constexpr (MODE == 1) {
+            if (!stop && t >= io.handoff_steps) {
+                // still running: append the complete episode state to the continuation records
+                const int r = atomicAdd(io.cont_count, 1);
+                if (r < io.cont_cap) {
+                    const size_t cap = (size_t)io.cont_cap;
+                    double *d = io.cont_d + r;
+                    int *ci = io.cont_i + r;
+                    ci[0] = eid; ci[cap] = t; ci[2 * cap] = gw.n; ci[3 * cap] = (int)w.ctr;
+                    d[0] = s.x; d[cap] = s.y; d[2 * cap] = s.vx; d[3 * cap] = s.vy; d[4 * cap] = s.theta;
+                    d[5 * cap] = s.theta_dot; d[6 * cap] = s.gamma; d[7 * cap] = s.alpha; d[8 * cap] = s.mass;
+                    d[9 * cap] = s.m_prop; d[10 * cap] = s.time;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) d[(11 + k) * cap] = (double)gw.w[k];
+                    d[21 * cap] = prev.gimbal_deg; d[22 * cap] = prev.dl; d[23 * cap] = prev.dr;
+                    d[24 * cap] = w.xu0; d[25 * cap] = w.xu1; d[26 * cap] = w.xv0; d[27 * cap] = w.xv1;
+                    d[28 * cap] = w.sigma_u; d[29 * cap] = w.sigma_v;
+                    d[30 * cap] = total;
+                    handoff = true;
+                    stop = true;
+                }
+            }
+        }
         if (stop) {
-            if (io.ret && writer) io.ret[e] = total;
-            if (io.steps && writer) io.steps[e] = t;
-            if (io.trunc_id && writer) io.trunc_id[e] = tid;
-            if (io.terminal && writer) {
-                double *p = io.terminal + (size_t)e * 11;
+            if (!handoff) {
+            if (io.ret && writer) io.ret[eid] = total;
+            if (io.steps && writer) io.steps[eid] = t;
+            if (io.trunc_id && writer) io.trunc_id[eid] = tid;
+            }
+            if (io.terminal && writer && !handoff) {
+                double *p = io.terminal + (size_t)eid * 11;
                 p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
                 p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
             }
@@ -435,7 +484,7 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
                 const unsigned gmask = (COOP == 32 ? 0xffffffffu : ((1u << COOP) - 1u)) << leader;
                 e = __shfl_sync(gmask, e, leader);
             }
-            active = e < io.n_episodes;
+            active = e < n_work;
             if (active) begin_episode();
         }
     }
@@ -543,10 +592,31 @@ struct Launch {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
             attr = true;
         }
-        if (coop)
+        if (coop) {
             rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
-        else
-            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
+            return;
+        }
+        if constexpr (POLICY == 0) {
+            if (io.handoff_steps > 0 && io.handoff_steps < io.max_steps && io.cont_d && io.cont_i && io.cont_count) {
+                // two passes: one lane per episode up to handoff_steps, then the stragglers (about
+                // 1 % of a random swarm) 8 lanes each
+                static bool attr2 = false;
+                if (!attr2) {
+                    cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
+                    cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
+                    attr2 = true;
+                }
+                cudaMemsetAsync(io.cont_count, 0, sizeof(int), st);
+                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
+                const int b2 = n_sm, t2 = PD_MAX_BLOCK;
+                init_queue_kernel<<<1, 1, 0, st>>>(io.queue, b2 * t2 / 8);
+                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2><<<b2, t2, PD_SH_BYTES, st>>>(io, wc, sig, status);
+                return;
+            }
+        }
+        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
     }
     static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
                        const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {

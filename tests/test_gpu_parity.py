@@ -573,3 +573,32 @@ def test_config4_batch_on_one_gpu(envs_mod):
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     st = env.get_state()
     assert float(st[:, 1].max()) <= 30028.385497767023 + 1e-6 and float(st[:, 9].min()) > 0
+
+
+def test_rollout_straggler_handoff(envs_mod):
+    """pd_set_rollout_handoff: episodes still running after N steps are finished by a second,
+    8-lane cooperative pass.  Episodes that end before the hand-off are bit-identical to the
+    one-pass rollout; handed-off ones resume from their exact state (same step count and fitness
+    unless the different summation order of the cooperative RBF sums flips a chaotic episode)."""
+    from psso_sac_for_powered_descent_b200 import _native as N
+    n = 16384
+    rng = np.random.default_rng(7)
+    pos = torch.as_tensor(rng.uniform(-1.5, 1.5, (n, 249)).astype(np.float32)).cuda()
+    res = {}
+    for steps in (0, 300):
+        env = envs_mod.BatchedRocketEnv(1, "pso", P, precision="fp64")
+        N.check(env.lib.pd_set_rollout_handoff(env._h, steps))
+        fit, st, tid, term = env.rollout_pso(pos, max_steps=1500, terminal=True)
+        env.check_status()
+        res[steps] = (fit.cpu().numpy(), st.cpu().numpy(), tid.cpu().numpy(), term.cpu().numpy())
+    f0, s0, t0, x0 = res[0]
+    f1, s1, t1, x1 = res[300]
+    early = s0 < 300
+    assert early.sum() > 0.5 * n and (~early).sum() > 100
+    assert np.array_equal(f0[early], f1[early]) and np.array_equal(s0[early], s1[early])
+    assert np.array_equal(t0[early], t1[early]) and np.array_equal(x0[early], x1[early])
+    late = ~early
+    assert np.isfinite(f1[late]).all() and (s1[late] >= 300).all()
+    same = s0[late] == s1[late]
+    assert same.mean() > 0.9
+    assert np.max(np.abs(f0[late][same] - f1[late][same]) / np.maximum(np.abs(f0[late][same]), 1.0)) < 1e-6
