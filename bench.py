@@ -317,6 +317,28 @@ def run_cuda(args):
         idx, best, best_pos = ev.broadcast_best(fitness, pos[lo:hi], args.particles)
         barrier()
         dt = time.perf_counter() - t0
+        # north_star's swarm size: 65 536 particles through the same sharded evaluation
+        big = None
+        if args.particles < 65536 and not args.no_pso_scale:
+            pos_big = rngp.uniform(-1.5, 1.5, (65536, n_par))
+            ev(pos_big)
+            barrier()
+            b0 = time.perf_counter()
+            fb = ev(pos_big)
+            barrier()
+            bdt = time.perf_counter() - b0
+            tb = torch.tensor([bdt, stats["steps"]], device=dev, dtype=torch.float64)
+            if world > 1:
+                mb = tb.clone(); dist.all_reduce(mb, op=dist.ReduceOp.MAX)
+                sb = tb.clone(); dist.all_reduce(sb, op=dist.ReduceOp.SUM)
+                bdt, bsteps = float(mb[0]), float(sb[1])
+            else:
+                bsteps = stats["steps"]
+            big = {"particles": 65536, "wind_seeds": args.seeds, "fitness_evals_per_s": 65536 / bdt, "ms": bdt * 1e3,
+                   "env_steps_per_s": bsteps / bdt, "mean_episode_steps": bsteps / (65536 * args.seeds),
+                   "what": "host list of positions in, fitness list out (ShardedEvaluator): weights upload, "
+                           "rollout with straggler hand-off, fitness all-gather"}
+            del pos_big, fb
         # device-resident optimiser (swarm never leaves HBM): whole generations
         params = dict(pso_mod.PSO_PARAMS[phase], pop_size=args.particles)
         sw = pso_mod.DeviceSwarm(model, args.particles, params, n_seeds=args.seeds, seed=5, max_steps=4096)
@@ -344,6 +366,7 @@ def run_cuda(args):
                "episodes_hitting_step_cap": capped, "best_fitness": best, "best_index": idx,
                "collectives": "1 all_gather(fp64 fitness) + 1 broadcast(best position) per generation",
                "timing": "wall clock between device-synchronised barriers, max over ranks",
+               "at_65536_particles": big,
                "device_swarm": {"ms_per_generation": gdt * 1e3, "fitness_evals_per_s": args.particles / gdt,
                                 "env_steps_per_s": gsteps / gdt,
                                 "what": "evaluate (rollout kernel) + fitness all-gather + sub-swarm best "
@@ -431,6 +454,8 @@ def run_cuda(args):
             cpu["pso_sample"] = (f"{n_ep} random particles, Pool({c2}) over the oracle's objective_function with a "
                                  "fresh model per particle (the reference's evaluate_worker_function structure)")
             pso["vs_cpu_port"] = pso["fitness_evals_per_s"] / ev_s
+            if pso.get("at_65536_particles"):
+                pso["at_65536_particles"]["vs_cpu_port"] = pso["at_65536_particles"]["fitness_evals_per_s"] / ev_s
     line = {
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
@@ -491,6 +516,7 @@ def main():
     ap.add_argument("--no-pso", action="store_true")
     ap.add_argument("--no-sac", action="store_true")
     ap.add_argument("--no-phases", action="store_true")
+    ap.add_argument("--no-pso-scale", action="store_true")
     ap.add_argument("--sac-envs", type=int, default=131072)
     ap.add_argument("--sac-steps", type=int, default=40)
     args = ap.parse_args()
