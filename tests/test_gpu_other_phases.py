@@ -204,13 +204,15 @@ def test_scalar_rl_wrapper_dropin(envs_mod, golden, phase):
         assert (d, t) == (bool(g["done"][k]), bool(g["truncated"][k]))
 
 
-@pytest.mark.parametrize("phase", [S, B, C])
-def test_batched_fp32_rollout_and_collect(envs_mod, phase):
+@pytest.mark.parametrize("phase,wind", [(S, False), (B, False), (C, False), (U, True), (B, True), (C, True)])
+def test_batched_fp32_rollout_and_collect(envs_mod, phase, wind):
     """Production build: a batch with auto-reset runs random actions and the shared-actor
-    collection loop without leaving the aero tables; rewards and observations stay finite."""
+    collection loop (with and without the stochastic wind model) without leaving the aero
+    tables; rewards and observations stay finite."""
     import torch.nn as nn
     Bn = 4096
-    env = envs_mod.BatchedRocketEnv(Bn, "rl", phase, precision="fp32", auto_reset=True,
+    env = envs_mod.BatchedRocketEnv(Bn, "rl", phase, precision="fp32", auto_reset=True, enable_wind=wind,
+                                    stochastic_wind=wind, horiontal_wind_percentile=75,
                                     trajectory_length=1000, discount_factor=0.99, seed=3)
     env.reset()
     gen = torch.Generator(device="cuda").manual_seed(0)
