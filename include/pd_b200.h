@@ -45,7 +45,9 @@ extern "C" {
 enum { PD_PHASE_PURE_THROTTLE = 0, PD_PHASE_GIMBALLED = 1, PD_PHASE_SUBSONIC = 2,
        PD_PHASE_SUPERSONIC = 3, PD_PHASE_BALLISTIC_ARC = 4, PD_PHASE_PCONTROL = 5,
        PD_N_PHASES = 6 };
-enum { PD_RTD_PSO = 0, PD_RTD_RL = 1 };                        /* type = 'pso' | 'rl'     */
+/* type = 'pso' | 'rl' | 'supervisory' (src/envs/supervisory/rtd_supervisory_mock.py: done /
+ * truncation per phase, reward 0; pd_step only, actions as the base env takes them) */
+enum { PD_RTD_PSO = 0, PD_RTD_RL = 1, PD_RTD_SUPERVISORY = 2 };
 enum { PD_FP64 = 0, PD_FP32 = 1 };                             /* compute precision build */
 enum { PD_ACT_F64 = 0, PD_ACT_F32 = 1 };                       /* dtype of the action     */
 enum { PD_POLICY_MLP = 0, PD_POLICY_TAPE = 1, PD_POLICY_CLASSICAL = 2 };

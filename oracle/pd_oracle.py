@@ -444,8 +444,8 @@ class OracleEnv:
                  stochastic_wind=False, horiontal_wind_percentile=50, tables=None,
                  wind_noise=None, fast_rbf=False, trajectory_length=1, discount_factor=0.99):
         assert flight_phase in (PHASE_P, PHASE_G) + RL_ONLY_PHASES
-        assert type in ("pso", "rl")
-        if flight_phase in RL_ONLY_PHASES and type != "rl":
+        assert type in ("pso", "rl", "supervisory")
+        if flight_phase in RL_ONLY_PHASES and type == "pso":
             raise TypeError(f"{flight_phase}: the reference's pso closures have the wrong arity "
                             "(rtd_pso.py:38-157); only type='rl' works upstream")
         self.trajectory_length = trajectory_length
@@ -739,9 +739,47 @@ class OracleEnv:
         speed = math.sqrt(vx ** 2 + vy ** 2)
         return speed / a if (speed != 0 and a != 0) else 0
 
+    # -- type 'supervisory': src/envs/supervisory/rtd_supervisory_mock.py:6-104 (reward 0)
+    def _sup_done(self, s):
+        x, y, vx, vy, theta, theta_dot, gamma = s[:7]
+        rho, _, a = isa(y)
+        speed = math.sqrt(vx ** 2 + vy ** 2)
+        if self.flight_phase == PHASE_S:
+            return bool(speed / a > 1.1)
+        if self.flight_phase == PHASE_U:
+            return bool(y > self.T.other["ref_traj_ascent_terminal"][1])
+        if self.flight_phase == PHASE_B:
+            return bool(0.5 * rho * speed ** 2 > 65000 and abs(gamma - theta - math.pi) < math.radians(3))
+        return bool(y < 1)
+
+    def _sup_truncated(self, s, info):
+        x, y, vx, vy, theta, theta_dot, gamma, alpha, mass, m_prop, time = s
+        rho, _, _ = isa(y)
+        speed = math.sqrt(vx ** 2 + vy ** 2)
+        q = 0.5 * rho * speed ** 2
+        if self.ascent:
+            return (True, 1) if m_prop <= 0 else (False, 0)
+        if self.flight_phase == PHASE_B:
+            return (True, 1) if (q > 35000 and abs(gamma - theta - math.pi) > math.radians(3)) else (False, 0)
+        if y < -10:
+            return True, 1
+        elif m_prop <= 0:
+            return True, 2
+        elif theta > math.pi + math.radians(2):
+            return True, 3
+        elif q > 65000:
+            return True, 4
+        elif info["g_load_1_sec_window"] > 6.0:
+            return True, 5      # upstream's print in this branch raises NameError ('acceleration')
+        elif vy > 0.0:
+            return True, 6
+        return False, 0
+
     def _done(self, s):
         x, y, vx, vy = s[:4]
         speed = math.sqrt(vx ** 2 + vy ** 2)
+        if self.type == "supervisory":
+            return self._sup_done(s)
         if self.ascent:                     # rtd_rl.py:35-51
             if any(math.isnan(v) for v in s):
                 return False
@@ -768,6 +806,8 @@ class OracleEnv:
             a_eff = abs(gamma - theta - math.pi)
         else:
             a_eff = abs(theta - gamma)
+        if self.type == "supervisory":
+            return self._sup_truncated(s, info)
         if self.ascent:                     # rtd_rl.py:53-88
             if any(math.isnan(v) for v in s):
                 return True, 0
@@ -867,6 +907,8 @@ class OracleEnv:
     def _reward(self, s, done, truncated, actions, info):
         x, y, vx, vy, theta, theta_dot, gamma, alpha, mass, m_prop, time = s
         speed = math.sqrt(vx ** 2 + vy ** 2)
+        if self.type == "supervisory":
+            return 0
         if self.type == "pso":
             reward = 0
             if self.flight_phase == PHASE_P:

@@ -18,7 +18,7 @@ CACHE_DIR = os.path.join(HERE, "_cache")
 PHASES = {"landing_burn_pure_throttle": 0, "landing_burn": 1, "subsonic": 2, "supersonic": 3,
           "ballistic_arc_descent": 4, "landing_burn_pure_throttle_Pcontrol": 5}
 RL_ONLY_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol")
-RTD = {"pso": 0, "rl": 1}
+RTD = {"pso": 0, "rl": 1, "supervisory": 2}
 PRECISION = {"fp64": 0, "fp32": 1}
 OBS_DIM = {0: 2, 1: 5, 2: 8, 3: 8, 4: 4, 5: 1}
 ACT_DIM = {0: 1, 1: 4, 2: 2, 3: 2, 4: 1, 5: 1}

@@ -206,6 +206,7 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
         const PdOtherPhases &o = *p.other;
         s.n_eng_ng = o.n_engines_stage1 - n_gim;
         for (int i = 0; i < 13; ++i) s.fi[i] = o.inertia_full[i];
+        s.sup_terminal_alt = o.ref_terminal[1];
         s.rcs_force = o.max_rcs_force_per_thruster;
         s.d_rcs_bottom = o.d_base_rcs_bottom;
         s.d_rcs_top = o.d_base_rcs_top;
@@ -287,12 +288,12 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     if (!cfg || !p || !out) return fail("pd_create: null argument");
     if (cfg->n_envs <= 0) return fail("pd_create: n_envs must be positive");
     if (cfg->phase < 0 || cfg->phase >= PD_N_PHASES) return fail("pd_create: unknown flight phase");
-    if (cfg->phase > PD_PHASE_GIMBALLED && cfg->rtd != PD_RTD_RL)
+    if (cfg->phase > PD_PHASE_GIMBALLED && cfg->rtd == PD_RTD_PSO)
         return fail("pd_create: this flight phase only works with type='rl' upstream (its pso "
                     "closures have the wrong arity, rtd_pso.py:38-157)");
     if (cfg->phase > PD_PHASE_GIMBALLED && cfg->phase != PD_PHASE_PCONTROL && !p->other)
         return fail("pd_create: PdParams.other is required for this flight phase");
-    if (cfg->rtd != 0 && cfg->rtd != 1) return fail("pd_create: unknown rtd type");
+    if (cfg->rtd < 0 || cfg->rtd > PD_RTD_SUPERVISORY) return fail("pd_create: unknown rtd type");
     if (p->n_wind > 16) return fail("pd_create: wind profile longer than 16 points");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -392,6 +393,9 @@ int pd_destroy(PdEnv *e) {
     return 0;
 }
 
+// the supervisory closures ride on the rl kernels (StepIO.supervisory overrides their verdict)
+static int kernel_rtd(const PdEnv *e) { return e->cfg.rtd == PD_RTD_SUPERVISORY ? PD_RTD_RL : e->cfg.rtd; }
+
 static WindCtx wind_ctx(const PdEnv *e) {
     WindCtx wc;
     wc.tape = e->tape;
@@ -433,11 +437,12 @@ int pd_step(PdEnv *e, const void *actions, int action_dtype, void *obs, void *re
     if (activate(e)) return 1;
     StepIO io;
     io.actions = actions; io.action_dtype = action_dtype; io.obs = obs; io.reward = reward;
-    io.raw_actions = e->cfg.raw_actions;
+    io.raw_actions = e->cfg.raw_actions || e->cfg.rtd == PD_RTD_SUPERVISORY;
     io.dbg_full = (dbg && e->info_full) ? 1 : 0;
+    io.supervisory = e->cfg.rtd == PD_RTD_SUPERVISORY;
     io.next_obs = next_obs; io.done = done; io.truncated = truncated; io.trunc_id = trunc_id;
     io.dbg = dbg;
-    e->impl->step(e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
+    e->impl->step(e->cfg.phase, kernel_rtd(e), e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
                   e->cfg.auto_reset, (cudaStream_t)stream);
     g_launches++;
     CK(cudaGetLastError());
@@ -566,6 +571,8 @@ int pd_rollout_policy(PdEnv *e, int policy, const void *actions, int action_dtyp
     if (!e) return fail("pd_rollout_policy: null handle");
     if (policy != PD_POLICY_TAPE && policy != PD_POLICY_CLASSICAL) return fail("pd_rollout_policy: policy");
     if (policy == PD_POLICY_TAPE && !actions) return fail("pd_rollout_policy: tape policy needs actions");
+    if (policy == PD_POLICY_TAPE && e->cfg.rtd == PD_RTD_SUPERVISORY)
+        return fail("pd_rollout_policy: type 'supervisory' is served by pd_step only");
     if (n_episodes <= 0 || max_steps <= 0) return fail("pd_rollout_policy: bad sizes");
     if (activate(e)) return 1;
     RolloutIO io;
@@ -633,6 +640,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
     if (!e || !actor || !act_out || n_steps <= 0) return fail("pd_collect_shared_actor: bad argument");
     if (e->cfg.precision != PD_FP32) return fail("pd_collect_shared_actor: needs the PD_FP32 build (float obs)");
     if (!e->cfg.auto_reset) return fail("pd_collect_shared_actor: handle must be created with auto_reset");
+    if (e->cfg.rtd != PD_RTD_RL) return fail("pd_collect_shared_actor: handle must be created with type='rl'");
     if (activate(e)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     const int O = pd::phase_odim(e->cfg.phase), A = pd::phase_adim(e->cfg.phase);
@@ -642,7 +650,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
         e->allocs.push_back(e->obs_carry);
     }
     if (!e->obs_valid) {
-        e->impl->observe(e->cfg.phase, e->cfg.rtd, e->soa, e->obs_carry, st);
+        e->impl->observe(e->cfg.phase, kernel_rtd(e), e->soa, e->obs_carry, st);
         g_launches++;
         e->obs_valid = true;
     }
@@ -660,7 +668,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
                         cudaGetErrorString(cudaGetLastError()));
         g_launches++;
         StepIO io;
-        io.actions = act_t; io.action_dtype = PD_ACT_F32; io.raw_actions = 0; io.dbg_full = 0;
+        io.actions = act_t; io.action_dtype = PD_ACT_F32; io.raw_actions = 0; io.dbg_full = 0; io.supervisory = 0;
         io.obs = next_obs_out ? next_obs_out + (size_t)t * B * O : nullptr;
         io.reward = rew_out ? rew_out + (size_t)t * B : nullptr;
         io.done = done_out ? done_out + (size_t)t * B : nullptr;
@@ -669,7 +677,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
         io.dbg = nullptr;
         // post-reset observation feeds the next action
         io.next_obs = (obs_out && t + 1 < n_steps) ? (void *)(obs_out + (size_t)(t + 1) * B * O) : (void *)e->obs_carry;
-        e->impl->step(e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
+        e->impl->step(e->cfg.phase, kernel_rtd(e), e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
                       e->cfg.auto_reset, st);
         g_launches++;
     }

@@ -72,6 +72,7 @@ struct Scalars {
     R rcs_force, d_rcs_bottom, d_rcs_top;
     R norm8[8];                     // obs normalisation of phases 2..4
     R speed0, terminal_mach, alive_bonus;
+    R sup_terminal_alt;             // supervisory closures: last altitude of the supersonic recording
     // Mach-scheduled ascent thresholds (rtd_rl.py:544-575): grid, 4 value rows (max_x, max_vy,
     // max_vx, max_alpha_deg) and their segment slopes; the reward weights are 100 everywhere
     R hyp_m[12], hyp_v[4][12], hyp_s[4][12];
@@ -1358,6 +1359,40 @@ __device__ __forceinline__ void rtd_pcontrol(const State &s, R g1, double v_ref,
     }
     r = r < R(-10) ? R(-10) : (r > R(10) ? R(10) : r);
     o.reward = r; o.done = dn; o.truncated = tr; o.trunc_id = id;
+}
+
+// type = 'supervisory' closures, src/envs/supervisory/rtd_supervisory_mock.py:6-104: done and
+// truncation per phase, reward 0.  (Upstream's g-load branch raises NameError when it fires;
+// here it truncates with id 5.)
+template <typename R, int PHASE>
+__device__ __forceinline__ void rtd_supervisory(const State &s, R g1, Rtd<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    R rho, p_atm, a_snd;
+    isa<R>((R)s.y, rho, p_atm, a_snd);
+    R vx = (R)s.vx, vy = (R)s.vy;
+    R speed = m_sqrt(vx * vx + vy * vy);
+    R q = R(0.5) * rho * (speed * speed);
+    const double ae = fabs(s.gamma - s.theta - PD_PI);
+    int dn = 0, tr = 0, id = 0;
+    if constexpr (PHASE == 2) {
+        dn = speed / a_snd > R(1.1);
+        if (s.m_prop <= 0.0) { tr = 1; id = 1; }
+    } else if constexpr (PHASE == 3) {
+        dn = s.y > (double)g_sd.sup_terminal_alt;
+        if (s.m_prop <= 0.0) { tr = 1; id = 1; }
+    } else if constexpr (PHASE == 4) {
+        dn = q > R(65000) && ae < 3.0 * (PD_PI / 180.0);
+        if (q > R(35000) && ae > 3.0 * (PD_PI / 180.0)) { tr = 1; id = 1; }
+    } else {
+        dn = s.y < 1.0;
+        if (s.y < -10.0) { tr = 1; id = 1; }
+        else if (s.m_prop <= 0.0) { tr = 1; id = 2; }
+        else if (s.theta > PD_PI + 2.0 * (PD_PI / 180.0)) { tr = 1; id = 3; }
+        else if (q > R(65000)) { tr = 1; id = 4; }
+        else if (g1 > R(6.0)) { tr = 1; id = 5; }
+        else if (s.vy > 0.0) { tr = 1; id = 6; }
+    }
+    o.reward = R(0); o.done = dn; o.truncated = tr; o.trunc_id = id;
 }
 
 template <typename R, int PHASE, int RTD>

@@ -30,6 +30,7 @@ struct StepIO {
     int action_dtype;
     int raw_actions;       // skip the RL wrapper's augment_action
     int dbg_full;          // dbg rows are PD_INFO_DIM wide (fp64 build, no wind)
+    int supervisory;       // type = 'supervisory': replace the rl closures' verdict (rtd_supervisory_mock.py)
     void *obs, *reward, *next_obs;
     uint8_t *done, *truncated;
     int32_t *trunc_id;

@@ -205,6 +205,9 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     const int ep_steps_in = e.ep_steps[i];      // issued with the other state loads, consumed at the end
     wait_tables(&sh);
     env_step<R, RT, PHASE, RTD, WIND, 1, FULL>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
+    if constexpr (RTD == 1) {
+        if (io.supervisory) rtd_supervisory<R, PHASE>(s, g1, out);
+    }
     if (info.rbf_status) atomicOr(e.status, info.rbf_status);
     R obs[O];
     observe<R, PHASE, RTD>(s, obs);

@@ -66,9 +66,7 @@ class BatchedRocketEnv:
                 "(flip_over_boostbackburn: rtd_rl.py:132 TypeError; landing_burn_ACS: "
                 "rockets_physics.py:867-889); see DESIGN.md")
         assert type in ("rl", "pso", "supervisory")
-        if type == "supervisory":
-            raise NotImplementedError("supervisory rtd closures are outside the hot path")
-        if flight_phase in N.RL_ONLY_PHASES and type != "rl":
+        if flight_phase in N.RL_ONLY_PHASES and type == "pso":
             raise TypeError(f"{flight_phase}: only type='rl' works upstream (the pso closures of this "
                             "phase have the wrong arity, rtd_pso.py:38-157)")
         if not torch.cuda.is_available():

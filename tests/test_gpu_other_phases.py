@@ -392,3 +392,27 @@ def test_supersonic_with_wind_tape(envs_mod, golden, key, dt):
         assert abs(float(rew[0]) - R[k]) < 1e-9
         assert (float(done[0]), float(trunc[0]), float(tid[0])) == tuple(FL[k])
     env.check_status()
+
+
+@pytest.mark.parametrize("tag,phase", [("P", "landing_burn_pure_throttle"), ("G", "landing_burn"), ("S", S), ("U", U),
+                                       ("B", B), ("C", C)])
+def test_supervisory_closures(envs_mod, golden, tag, phase):
+    """type='supervisory' (src/envs/supervisory/rtd_supervisory_mock.py): the rl step kernels with
+    the supervisory verdict - state 1e-12, done / truncated / id exact, reward 0."""
+    g, f = golden("supervisory_step.npz"), golden(f"single_step_{tag}.npz")
+    idx, ref = g[f"idx_{tag}"], g[f"out_{tag}"]
+    n = len(idx)
+    env = envs_mod.BatchedRocketEnv(n, "supervisory", phase, precision="fp64")
+    aprev = f["aprev"][idx] if "aprev" in f.files else np.zeros((n, 3))
+    env.set_state(f["state"][idx], f["win"][idx], f["nwin"][idx].astype(np.int32), aprev)
+    obs, rew, done, trunc, tid = env.step(torch.as_tensor(f["act64"][idx]).cuda())
+    env.check_status()
+    st = env.get_state().cpu().numpy()
+    ok = ~np.isnan(ref[:, 0])                 # nan rows: upstream raises NameError in its g-load branch
+    fl = FLOOR.get(phase, np.array([1e3, 1e3, 1e2, 1e2, 2.0, 10.0, 1.0, 2.0, 1e5, 1e5, 1e2]))
+    err = np.max(np.abs(st[ok] - ref[ok, :11]) / np.maximum(np.abs(ref[ok, :11]), fl), axis=1)
+    assert err.max() < 1e-12
+    assert float(rew.abs().max()) == 0.0
+    assert np.array_equal(done.cpu().numpy()[ok].astype(float), ref[ok, 12])
+    assert np.array_equal(trunc.cpu().numpy().astype(float), ref[:, 13])
+    assert np.array_equal(tid.cpu().numpy().astype(float), ref[:, 14])

@@ -421,6 +421,36 @@ def stored_info_csv(n_rows=120):
     print("stored_info", len(cols), "numeric columns of", len(info.columns), "rows", n_rows)
 
 
+def supervisory_steps(n=64, seed=41):
+    """type='supervisory' closures (rtd_supervisory_mock.py): one reference step from states of the
+    existing single-step fixtures, all six working phases."""
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    rng = np.random.default_rng(seed)
+    out = {}
+    for tag, phase in (("P", P), ("G", G), ("S", S_), ("U", U_), ("B", B_), ("C", C_)):
+        g = np.load(os.path.join(OUT, f"single_step_{tag}.npz"), allow_pickle=True)
+        env = quiet(rocket_environment_pre_wrap, type="supervisory", flight_phase=phase, enable_wind=False)
+        idx = rng.choice(len(g["state"]), size=min(n, len(g["state"])), replace=False)
+        rows = []
+        for i in idx:
+            quiet(env.reset)
+            env.state = [np.float64(v) for v in g["state"][i]]
+            env.previous_state = env.state
+            env.g_loads_window = [float(v) for v in g["win"][i][:g["nwin"][i]]]
+            if phase == G:
+                env.gimbal_angle_deg_prev, env.delta_command_left_rad_prev, env.delta_command_right_rad_prev = \
+                    [float(v) for v in g["aprev"][i]]
+            try:
+                ns, r, d, t, info = quiet(env.step, g["act64"][i])
+                rows.append([float(v) for v in ns] + [float(r), float(d), float(t), float(env.truncation_id)])
+            except NameError:      # upstream bug: the g-load branch prints an undefined name
+                rows.append([np.nan] * 11 + [0.0, np.nan, 1.0, 5.0])
+        out[f"idx_{tag}"] = idx; out[f"out_{tag}"] = np.array(rows)
+    np.savez_compressed(os.path.join(OUT, "supervisory_step.npz"), **out)
+    print("supervisory", {k: v.shape for k, v in out.items() if k.startswith("out")},
+          {k: np.nansum(v[:, 13]) for k, v in out.items() if k.startswith("out")})
+
+
 def ascent_csv():
     """The reference's own committed ascent controller recordings (actions + states per 0.1 s
     step) - golden vectors written on the author's machine, copied verbatim."""
@@ -553,6 +583,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     load_reference()
     which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero", "other", "info"]
+    if "sup" in which:
+        supervisory_steps()
     if "info" in which:
         info_full()
         stored_info_csv()
