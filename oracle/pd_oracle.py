@@ -1148,6 +1148,38 @@ class RlEnv:
         return self.obs(state), float(reward), bool(done), bool(truncated), info
 
 
+class SupervisoryEnv:
+    """supervisory_wrapper (src/envs/supervisory/env_wrapped_supervisory.py:6-116): base env with the
+    supervisory closures, float64 observation over the caller's scales, wind always off."""
+
+    def __init__(self, input_normalisation_values, flight_phase=PHASE_S, tables=None, fast_rbf=False):
+        self.env = OracleEnv(flight_phase, "supervisory", False, False, 95, tables, None, fast_rbf)
+        self.flight_phase = flight_phase
+        self.nv = input_normalisation_values[:2] if flight_phase == PHASE_P else input_normalisation_values
+        self._rl = RlEnv.__new__(RlEnv)              # borrows augment_action (same shaping, :58-104)
+        self._rl.flight_phase = flight_phase
+        if flight_phase == PHASE_C:
+            vx0, vy0 = self.env.T.initial_state[2], self.env.T.initial_state[3]
+            self._rl.speed0 = math.sqrt(vx0 ** 2 + vy0 ** 2)
+
+    def obs(self, state):                            # :35-56
+        x, y, vx, vy, theta, theta_dot, gamma, alpha, mass = state[:9]
+        if self.flight_phase in (PHASE_S, PHASE_U, PHASE_G):
+            return np.array([x, y, vx, vy, theta, theta_dot, alpha, mass]) / self.nv
+        if self.flight_phase == PHASE_B:
+            return np.array([theta, theta_dot, gamma, alpha]) / self.nv
+        if self.flight_phase == PHASE_P:
+            return np.array([(1 - y / self.nv[0]) * 2 - 1, (1 - vy / self.nv[1]) * 2 - 1])
+        return np.array([(1 - y / self.nv[0]) * 2 - 1])
+
+    def reset(self):
+        return self.obs(self.env.reset())
+
+    def step(self, action):                          # :106-111 (no ndim squeeze here)
+        state, reward, done, truncated, info = self.env.step(self._rl.augment_action(np.array(action)))
+        return self.obs(state), reward, done, truncated, info
+
+
 def classical_rollout(tables=None, fast_rbf=False, max_steps=50000):
     """LandingBurn(test_case='control').run_closed_loop(): P controller on v_ref(y),
     physics only (no rtd), float64 2-D action."""

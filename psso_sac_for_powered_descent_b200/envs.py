@@ -644,3 +644,61 @@ class rl_wrapped_env_pytorch:
 
     def close(self):
         pass
+
+
+class supervisory_wrapper:
+    """supervisory_wrapper (src/envs/supervisory/env_wrapped_supervisory.py:6-116): the base env with
+    type='supervisory' (reward 0, rtd_supervisory_mock.py verdicts), float64 observation scaled by
+    the caller's `input_normalisation_values`, action shaping on the host in float64 (the base env
+    then takes the action as it is).  As upstream, the wind arguments are accepted and ignored."""
+
+    _SLICES = {"subsonic": [0, 1, 2, 3, 4, 5, 7, 8], "supersonic": [0, 1, 2, 3, 4, 5, 7, 8],
+               "landing_burn": [0, 1, 2, 3, 4, 5, 7, 8], "ballistic_arc_descent": [4, 5, 6, 7]}
+
+    def __init__(self, input_normalisation_values, flight_phase="subsonic", enable_wind=False,
+                 stochastic_wind=False, horiontal_wind_percentile=95, precision="fp64", seed=0):
+        assert flight_phase in ["subsonic", "supersonic", "flip_over_boostbackburn", "ballistic_arc_descent",
+                                "landing_burn", "landing_burn_pure_throttle",
+                                "landing_burn_pure_throttle_Pcontrol"]
+        self.flight_phase = flight_phase
+        self.input_normalisation_values = input_normalisation_values
+        if flight_phase == "landing_burn_pure_throttle":
+            self.input_normalisation_values = input_normalisation_values[:2]
+        self.enable_wind, self.stochastic_wind, self.horiontal_wind_percentile = False, False, 95
+        self.env = rocket_environment_pre_wrap("supervisory", flight_phase, False, False, 95,
+                                               precision=precision, seed=seed)
+        self.initial_mass = self.env.reset()[-2]
+        if flight_phase == "landing_burn_pure_throttle_Pcontrol":
+            vx0, vy0 = self.env._b.params.initial_state[2:4]
+            self.speed0 = math.sqrt(vx0 ** 2 + vy0 ** 2)
+
+    def truncation_id(self):
+        return self.env.truncation_id
+
+    def augment_state(self, state):
+        nv = self.input_normalisation_values
+        if self.flight_phase in self._SLICES:
+            return np.array([state[i] for i in self._SLICES[self.flight_phase]]) / nv
+        if self.flight_phase == "landing_burn_pure_throttle":
+            return np.array([(1 - state[1] / nv[0]) * 2 - 1, (1 - state[3] / nv[1]) * 2 - 1])
+        return np.array([(1 - state[1] / nv[0]) * 2 - 1])
+
+    def augment_action(self, actions):
+        if self.flight_phase == "landing_burn":
+            u = actions[0] if actions.ndim == 2 else actions
+
+            def squash(v, c):
+                return math.copysign(math.log(1 + c * abs(v)) / math.log(1 + c), v)
+            shaped = [squash(u[0], 10), u[1], squash(u[2], 5), squash(u[3], 5)]
+            actions = np.array([shaped]) if actions.ndim == 2 else np.array(shaped)
+        if self.flight_phase == "landing_burn_pure_throttle_Pcontrol":
+            u0 = actions[0] if actions.ndim == 2 else actions
+            actions = np.array([(u0 + 1) / 2 * self.speed0])
+        return actions
+
+    def step(self, action):
+        state, reward, done, truncated, info = self.env.step(self.augment_action(np.array(action)))
+        return self.augment_state(state), reward, done, truncated, info
+
+    def reset(self):
+        return self.augment_state(self.env.reset())

@@ -416,3 +416,22 @@ def test_supervisory_closures(envs_mod, golden, tag, phase):
     assert np.array_equal(done.cpu().numpy()[ok].astype(float), ref[ok, 12])
     assert np.array_equal(trunc.cpu().numpy().astype(float), ref[:, 13])
     assert np.array_equal(tid.cpu().numpy().astype(float), ref[:, 14])
+
+
+@pytest.mark.parametrize("tag,phase", [("P", "landing_burn_pure_throttle"), ("G", "landing_burn"), ("S", S), ("U", U),
+                                       ("B", B), ("C", C)])
+def test_supervisory_wrapper(envs_mod, golden, tag, phase):
+    """envs.supervisory_wrapper against the reference's supervisory_wrapper (reset + steps)."""
+    g = golden("supervisory_wrapper.npz")
+    env = envs_mod.supervisory_wrapper(g[f"nv_{tag}"], flight_phase=phase, enable_wind=True)
+    assert env.enable_wind is False               # upstream ignores the wind arguments
+    ref = g[f"obs_{tag}"]
+    assert np.allclose(env.reset(), ref[0], rtol=1e-15, atol=0)
+    for k, a in enumerate(g[f"act_{tag}"]):
+        o, r, d, t, _ = env.step(a)
+        # free-running sequence: the single-step 1e-12 grows through the gimbal / pitch-rate loop of G
+        err = np.abs(np.reshape(o, -1) - ref[k + 1]) / np.maximum(np.abs(ref[k + 1]), 1e-3)
+        assert err.max() < (1e-7 if tag == "G" else 1e-9), (k, err)
+        assert [float(r), float(d), float(t), float(env.truncation_id())] == list(g[f"flags_{tag}"][k])
+    with pytest.raises(ValueError):               # the stock 7-vector does not broadcast upstream either
+        envs_mod.supervisory_wrapper(np.ones(7), flight_phase="landing_burn").reset()

@@ -451,6 +451,38 @@ def supervisory_steps(n=64, seed=41):
           {k: np.nansum(v[:, 13]) for k, v in out.items() if k.startswith("out")})
 
 
+def supervisory_wrapper_sequences(n_steps=8, seed=43):
+    """supervisory_wrapper (env_wrapped_supervisory.py): reset observation + a few steps per phase with
+    the reference's own normalisation values (an 8-vector of ones-free made-up scales for landing_burn,
+    whose stock 7-vector does not broadcast upstream)."""
+    from src.envs.supervisory.env_wrapped_supervisory import supervisory_wrapper
+    from src.envs.utils.input_normalisation import find_input_normalisation_vals
+    rng = np.random.default_rng(seed)
+    out = {}
+    for tag, phase, adim in (("P", P, 1), ("G", G, 4), ("S", S_, 2), ("U", U_, 2), ("B", B_, 1), ("C", C_, 1)):
+        nv = quiet(find_input_normalisation_vals, phase)
+        if phase == G:
+            nv = np.array([6e3, 4e4, 300.0, 1200.0, 2.0, 0.1, 3.5, 2e6])
+        env = quiet(supervisory_wrapper, nv, flight_phase=phase)
+        obs = [quiet(env.reset)]
+        acts = rng.uniform(-1, 1, size=(n_steps, adim))
+        if phase in (S_, U_):
+            acts[:, 1] = rng.uniform(0.2, 1.0, size=n_steps)
+        flags = []
+        for a in acts:
+            o, r, d, t, _ = quiet(env.step, a if adim > 1 else a)
+            obs.append(np.asarray(o, dtype=np.float64).reshape(-1))
+            flags.append([float(r), float(d), float(t), float(env.truncation_id())])
+            if d or t:
+                break
+        out[f"nv_{tag}"] = np.asarray(nv, dtype=np.float64)
+        out[f"act_{tag}"] = acts[:len(flags)]
+        out[f"obs_{tag}"] = np.array([np.asarray(o, dtype=np.float64).reshape(-1) for o in obs])
+        out[f"flags_{tag}"] = np.array(flags)
+    np.savez_compressed(os.path.join(OUT, "supervisory_wrapper.npz"), **out)
+    print("supervisory_wrapper", {k: v.shape for k, v in out.items() if k.startswith("obs")})
+
+
 def ascent_csv():
     """The reference's own committed ascent controller recordings (actions + states per 0.1 s
     step) - golden vectors written on the author's machine, copied verbatim."""
@@ -585,6 +617,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["tape", "ss", "pso", "best", "rl", "wind", "classical", "aero", "other", "info"]
     if "sup" in which:
         supervisory_steps()
+    if "supw" in which:
+        supervisory_wrapper_sequences()
     if "info" in which:
         info_full()
         stored_info_csv()
