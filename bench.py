@@ -265,7 +265,8 @@ def run_cuda(args):
     del flush
 
     # ---- end-to-end through the public host-facing call: numpy actions in, numpy results out,
-    # every step (BatchedRocketEnv.step_host: H2D copy + fused step + ONE D2H copy, CUDA graph)
+    # every step (BatchedRocketEnv.step_host: the step kernel reads the actions from and stores its
+    # results to mapped pinned host memory - the same bytes over PCIe, no staging copies)
     host_tape = tape.cpu().pin_memory()       # the host's actions live in pinned memory
     Ke = min(K, 300)
     env.reset()
@@ -469,7 +470,11 @@ def run_cuda(args):
                          "measured with a 256 MB L2 flush between launches",
                    "launch": "K step launches captured in one CUDA graph"},
         "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": Ke},
+                "d2h_bytes_per_step": d2h, "steps": Ke,
+                "transport": {"zc_all": "step kernel reads the pinned host actions and stores its results to "
+                                        "pinned host memory directly (mapped, same bytes over PCIe)",
+                              "zc_out": "H2D copy of the actions, results stored to mapped pinned memory",
+                              "copy": "H2D copy, kernel, one D2H copy (CUDA graph)"}[env._host["mode"]]},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

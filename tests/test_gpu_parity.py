@@ -380,15 +380,18 @@ def test_collect_shared_actor_matches_stepwise(envs_mod):
     assert float(a.abs().max()) <= 1.0 and float(a.std()) > 1e-3
 
 
-def test_step_host_matches_step(envs_mod):
-    """Host-facing graph-replayed step (numpy in / numpy out) == device step."""
+@pytest.mark.parametrize("mode", ["zc_all", "zc_out", "copy"])
+def test_step_host_matches_step(envs_mod, mode, monkeypatch):
+    """Host-facing step (numpy in / numpy out; mapped pinned memory or explicit copies + CUDA
+    graph) == device step."""
+    monkeypatch.setenv("PD_HOST_STEP", mode)
     B = 1024
     e1 = envs_mod.BatchedRocketEnv(B, "pso", P, precision="fp32", auto_reset=True)
     e2 = envs_mod.BatchedRocketEnv(B, "pso", P, precision="fp32", auto_reset=True)
     rng = np.random.default_rng(2)
     for t in range(5):
         a = rng.uniform(-1, 1, (B, 1)).astype(np.float32)
-        obs, rew, done, trunc, tid = e1.step_host(a)
+        obs, rew, done, trunc, tid = e1.step_host(torch.as_tensor(a).pin_memory() if t % 2 else a)
         o2, r2, d2, t2, i2 = e2.step(torch.as_tensor(a).cuda())     # interleaved handles: re-activation
         assert np.array_equal(obs, o2.cpu().numpy()) and np.array_equal(rew, r2.cpu().numpy())
         assert np.array_equal(done, d2.cpu().numpy()) and np.array_equal(trunc, t2.cpu().numpy())
