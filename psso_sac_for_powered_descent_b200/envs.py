@@ -15,6 +15,7 @@ include/pd_b200.h; torch is used for device memory and streams only.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 import os
@@ -166,7 +167,8 @@ class BatchedRocketEnv:
         host buffer, valid until the next call (trunc_id is only refreshed by
         `self.trunc_id.cpu()`).  The step kernel reads the actions from, and stores its results to,
         mapped pinned host memory (the same bytes cross PCIe, without staging copies or extra
-        launches: 106 us against 125 us per 65 536-env step on B200); a CPU tensor that already
+        launches, one ctypes call with cached pointers: 90 us against 125 us per 65 536-env step on
+        B200); a CPU tensor that already
         lives in pinned memory is read where it is.  PD_HOST_STEP=copy selects explicit copies
         (H2D copy, then kernel + one D2H copy replayed from a CUDA graph), PD_HOST_STEP=zc_out
         keeps the H2D copy only."""
@@ -195,7 +197,15 @@ class BatchedRocketEnv:
             pinned_out = (pv("obs", self.dtype, (B, self.obs_dim)), pv("reward", self.dtype, (B,)),
                           pv("done", torch.uint8, (B,)), pv("truncated", torch.uint8, (B,)))
             h["mode"], h["pinned_out"] = mode, pinned_out
-            with torch.cuda.stream(h["stream"]):
+            h["act_code"] = 1 if a.dtype == torch.float32 else 0
+            h["ptrs"] = tuple(_ptr(t) for t in pinned_out) + (_ptr(self.trunc_id), _ptr(self.next_obs), None,
+                                                              h["stream"].cuda_stream)
+            with torch.cuda.stream(h["stream"]) if mode != "zc_all" else contextlib.nullcontext():
+                if mode == "zc_all":
+                    N.check(self.lib.pd_activate(self._h))
+                    self._host = h
+                    return self.step_host(actions)
+
                 def body():
                     if mode == "copy":
                         self.step(h["act_dev"])
@@ -211,6 +221,18 @@ class BatchedRocketEnv:
                 h["graph"] = g
             self._host = h
         h = self._host
+        if h["mode"] == "zc_all":
+            # lean path: one ctypes call with cached pointers on the handle's own stream
+            if not (a.is_pinned() and a.is_contiguous()):
+                h["act_pin"].copy_(a)
+                a = h["act_pin"]
+            if torch.cuda.current_device() != self.device.index:
+                with torch.cuda.device(self.device):
+                    N.check(self.lib.pd_step(self._h, a.data_ptr(), h["act_code"], *h["ptrs"]))
+            else:
+                N.check(self.lib.pd_step(self._h, a.data_ptr(), h["act_code"], *h["ptrs"]))
+            h["stream"].synchronize()
+            return h["views"]
         if a.is_pinned() and a.is_contiguous():
             src = a
         else:
@@ -218,11 +240,8 @@ class BatchedRocketEnv:
             src = h["act_pin"]
         N.check(self.lib.pd_activate(self._h))
         with torch.cuda.stream(h["stream"]):
-            if h["mode"] == "zc_all":
-                self.step(src, _out=h["pinned_out"])
-            else:
-                h["act_dev"].copy_(src, non_blocking=True)
-                h["graph"].replay()
+            h["act_dev"].copy_(src, non_blocking=True)
+            h["graph"].replay()
         h["stream"].synchronize()
         return h["views"]
 
