@@ -580,8 +580,11 @@ __device__ __forceinline__ void rbf_eval2(const double *__restrict__ rowsL, int 
     // 32-bit shared-window addresses of this lane's replica; the tables are 32 KB aligned, so an
     // entry address is base | (index << 7)
     const unsigned bL = sh_addr(ptsL), bD = sh_addr(ptsD), bT = sh_addr(logtab);
+#ifndef PD_EXP_SUM_TRIPS
+#define PD_EXP_SUM_TRIPS 12      // experiments only: fewer trips = wrong sums, measures the loop's share
+#endif
 #pragma unroll 1
-    for (int w = 0; w < 12; ++w) {
+    for (int w = 0; w < PD_EXP_SUM_TRIPS; ++w) {
         double2 pt[8];
         pt[0] = lds_d2(bL | ((wl << 7) & 0x7F80u)); pt[1] = lds_d2(bD | ((wd << 7) & 0x7F80u));
         pt[2] = lds_d2(bL | ((wl >> 1) & 0x7F80u)); pt[3] = lds_d2(bD | ((wd >> 1) & 0x7F80u));
