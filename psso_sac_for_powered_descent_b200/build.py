@@ -30,8 +30,19 @@ def _sources():
     return deps
 
 
+STAMP = os.path.join(BUILD, "flags.txt")
+
+
+def _flags_changed():
+    """Objects and library are only valid for the flags they were compiled with (PD_EXTRA_NVCC_FLAGS)."""
+    try:
+        return open(STAMP).read() != " ".join(FLAGS)
+    except OSError:
+        return True
+
+
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or _flags_changed():
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(d) > t for d in _sources())
@@ -56,6 +67,10 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     os.makedirs(BUILD, exist_ok=True)
+    if _flags_changed():
+        for f in os.listdir(BUILD):
+            if f.endswith(".o"):
+                os.remove(os.path.join(BUILD, f))
     units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u))]
     with ThreadPoolExecutor(max_workers=len(units)) as ex:
         res = list(ex.map(_compile, units))
@@ -64,6 +79,8 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(STAMP, "w") as f:
+        f.write(" ".join(FLAGS))
     if verbose:
         for _, log in res:
             sys.stderr.write(log)
