@@ -183,7 +183,10 @@ int pd_reset(PdEnv *env, const uint8_t *mask, void *stream);
  *   next_obs  dev or NULL: observation after the auto-reset (== obs where no reset happened)
  *   dbg       dev double[n_envs * PD_DBG_DIM] or NULL: last sub-step's info values
  *             (mach, q, CL, CD, rho, p_atm, a, x_cog, inertia, mass_flow, throttle,
- *              alpha_eff, g_load_1_sec_window, ug, vg, rbf_status) */
+ *              alpha_eff, g_load_1_sec_window, ug, vg, rbf_status)
+ * "dev" pointers may also be mapped pinned host memory (cudaHostAlloc / torch pin_memory, same
+ * address under UVA): each action is read once and each result stored once, coalesced, so a
+ * host caller needs no staging copies (BatchedRocketEnv.step_host does exactly that). */
 int pd_step(PdEnv *env, const void *actions, int action_dtype, void *obs, void *reward,
             uint8_t *done, uint8_t *truncated, int32_t *trunc_id, void *next_obs, double *dbg,
             void *stream);
