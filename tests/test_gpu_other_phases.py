@@ -435,3 +435,24 @@ def test_supervisory_wrapper(envs_mod, golden, tag, phase):
         assert [float(r), float(d), float(t), float(env.truncation_id())] == list(g[f"flags_{tag}"][k])
     with pytest.raises(ValueError):               # the stock 7-vector does not broadcast upstream either
         envs_mod.supervisory_wrapper(np.ones(7), flight_phase="landing_burn").reset()
+
+
+@pytest.mark.parametrize("tag,phase", [("P", "landing_burn_pure_throttle"), ("S", S), ("B", B)])
+def test_supervisory_closures_fp32_build(envs_mod, golden, tag, phase):
+    """Production (fp32) build with type='supervisory': state 1e-5, reward 0, verdicts equal to the
+    reference except for rows sitting on a threshold."""
+    g, f = golden("supervisory_step.npz"), golden(f"single_step_{tag}.npz")
+    idx, ref = g[f"idx_{tag}"], g[f"out_{tag}"]
+    n = len(idx)
+    env = envs_mod.BatchedRocketEnv(n, "supervisory", phase, precision="fp32")
+    env.set_state(f["state"][idx], f["win"][idx], f["nwin"][idx].astype(np.int32), np.zeros((n, 3)))
+    obs, rew, done, trunc, tid = env.step(torch.as_tensor(f["act64"][idx]).cuda())
+    env.check_status()
+    st = env.get_state().cpu().numpy()
+    ok = ~np.isnan(ref[:, 0])
+    fl = FLOOR.get(phase, np.array([1e3, 1e3, 1e2, 1e2, 2.0, 10.0, 1.0, 2.0, 1e5, 1e5, 1e2]))
+    err = np.max(np.abs(st[ok] - ref[ok, :11]) / np.maximum(np.abs(ref[ok, :11]), fl), axis=1)
+    assert err.max() < 1e-5
+    assert float(rew.abs().max()) == 0.0
+    same = (trunc.cpu().numpy().astype(float) == ref[:, 13]) & (tid.cpu().numpy().astype(float) == ref[:, 14])
+    assert same.mean() >= 0.97
