@@ -62,6 +62,8 @@ def main():
                 n = int(r[hdrs.index("Instructions Executed")]); sm = int(r[hdrs.index("# Samples")])
             except Exception:
                 continue
+            if not r[hdrs.index("Line No")].strip():
+                continue                  # SASS rows of the mixed listing: already counted on their CUDA line
             k = (cur_file, r[hdrs.index("Line No")])
             tot[k] += n; samp[k] += sm; text[k] = r[hdrs.index("Source")][:100]
             for c in hdrs:
@@ -71,7 +73,7 @@ def main():
                     except Exception:
                         pass
     T, S = sum(tot.values()) or 1, sum(samp.values()) or 1
-    lines.append(f"top source lines of the first profiled launch (instructions {T}, samples {S}); blank line = inlined CUDA math library code")
+    lines.append(f"top source lines of the first profiled launch (instructions {T}, samples {S})")
     for k, v in tot.most_common(25):
         lines.append(f"  {k[0]:18s}:{k[1]:>5s}  inst {100*v/T:5.1f}%  samples {100*samp[k]/S:5.1f}%  {text[k]}")
     lines.append("")
