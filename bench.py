@@ -233,7 +233,6 @@ def run_cuda(args):
         l0 = lib.pd_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        _native.check(lib.pd_activate(env._h))
         e0.record(stream)
         graph.replay()
         e1.record(stream)

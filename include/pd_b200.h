@@ -225,7 +225,9 @@ int pd_set_wind_tape(PdEnv *env, const double *tape, int tape_len, const double 
  *   weights   dev float[n_particles * n_params], named_parameters() order
  *             (weight row-major then bias per layer, env_wrapped_ea.py:46-59)
  *   n_seeds   episodes per particle (wind seeds); episode e = particle * n_seeds + seed
- *   max_steps step cap (the reference has none; capped episodes report trunc_id = -1)
+ *   max_steps step cap (the reference has none).  A capped episode reports trunc_id = -1 and is
+ *             scored as a truncation at its final state (the closures' truncated-branch reward:
+ *             rtd_pso.py:222-229 / 300-316), so that a stalling policy never outranks a crash
  *   fitness   dev double[n_particles*n_seeds] = -sum(reward)
  *   steps, trunc_id  dev int32[...] or NULL;  terminal_state dev double[... * 11] or NULL
  *   traj / actions_out / rewards: optional per-step trace, step-major
@@ -302,14 +304,20 @@ int pd_pso_update(double *x, double *v, double *best, double *best_fit, const do
                   int64_t index0, double w, double c1, double c2, double lo, double hi, uint64_t seed,
                   int generation, void *stream);
 
-/* The physics constants of a handle live in __constant__ memory shared by all handles of the
- * same precision in the process; every entry point re-uploads them when the active handle
- * changes.  A caller that replays launches captured in a CUDA graph must call pd_activate
- * before the replay if another handle was used since the capture. */
-int pd_activate(PdEnv *env);
+/* Gust-noise stream of the next pd_rollout_pso / pd_rollout_policy calls.  The Philox counter of
+ * an episode's noise is (index0 * n_seeds + local episode, draw, episode word = generation + 1):
+ * index0 = GLOBAL index of this rank's first particle (block-sharded swarms: the windy fitness of a
+ * particle then does not depend on the rank layout), generation = PSO generation (fresh gusts every
+ * generation, as upstream draws fresh noise on every reset: src/envs/wind/vonkarman.py:86-96).
+ * Default (0, 0).  The physics constants of a handle travel as a __grid_constant__ kernel parameter
+ * of every launch: there is no process-global constant state, handles on different streams or
+ * devices are independent, and a captured CUDA graph stays valid whatever other handles do. */
+int pd_set_rollout_stream(PdEnv *env, int64_t index0, uint32_t generation);
 
 /* Sticky device status (synchronises): 0 = ok; bit 0 = an aero-table query fell outside the
- * enumerated neighbour-set table, bit 1 = neighbour search did not converge. */
+ * enumerated neighbour-set table, bit 1 = neighbour search did not converge.  Cannot happen for
+ * finite states (the enumeration covers the whole clamped query box); a lane that hits it has its
+ * C_L / C_D set to NaN, so the env turns NaN instead of continuing on a wrong interpolant. */
 int pd_check_status(PdEnv *env, int32_t *status);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */

@@ -12,7 +12,7 @@ from .params import RocketParams
 from . import rbf_sets
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpd_b200.so")
+LIB_PATH = os.environ.get("PD_LIB_PATH") or os.path.join(HERE, "libpd_b200.so")
 CACHE_DIR = os.path.join(HERE, "_cache")
 
 PHASES = {"landing_burn_pure_throttle": 0, "landing_burn": 1, "subsonic": 2, "supersonic": 3,
@@ -89,7 +89,7 @@ class PdSharedActor(C.Structure):
 
 EXPORTS = ["pd_last_error", "pd_version", "pd_create", "pd_destroy", "pd_reset", "pd_step",
            "pd_get_state", "pd_set_state", "pd_set_wind_tape", "pd_rollout_pso", "pd_rollout_policy",
-           "pd_collect_shared_actor", "pd_actor_forward", "pd_pso_update", "pd_activate", "pd_check_status", "pd_launch_count",
+           "pd_collect_shared_actor", "pd_actor_forward", "pd_pso_update", "pd_set_rollout_stream", "pd_check_status", "pd_launch_count",
            "pd_set_info_mode", "pd_set_rollout_handoff"]
 
 _lib = None
@@ -121,7 +121,7 @@ def load_library():
     lib.pd_collect_shared_actor.argtypes = [vp, C.POINTER(PdSharedActor), i32, vp, vp, vp, vp, vp, vp, vp]
     lib.pd_actor_forward.argtypes = [vp, C.POINTER(PdSharedActor), vp, i32, vp, vp, vp]
     lib.pd_check_status.argtypes = [vp, C.POINTER(C.c_int32)]
-    lib.pd_activate.argtypes = [vp]
+    lib.pd_set_rollout_stream.argtypes = [vp, C.c_int64, C.c_uint32]
     lib.pd_set_info_mode.argtypes = [vp, i32]
     lib.pd_set_rollout_handoff.argtypes = [vp, i32]
     lib.pd_pso_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_int64, C.c_double,

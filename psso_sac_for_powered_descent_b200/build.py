@@ -15,8 +15,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libpd_b200.so")
-BUILD = os.path.join(HERE, "build")
+# PD_LIB_PATH / PD_BUILD_DIR: experiment builds (tools/, -D knobs via PD_EXTRA_NVCC_FLAGS) that live
+# next to the production library instead of replacing it
+OUT = os.environ.get("PD_LIB_PATH") or os.path.join(HERE, "libpd_b200.so")
+BUILD = os.environ.get("PD_BUILD_DIR") or os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + \

@@ -34,9 +34,13 @@ struct PdEnv {
     PdConfig cfg;
     const Impl *impl;
     EnvSoA soa;
-    Scalars<double> sd;
-    Scalars<float> sf;
-    Tables tb;
+    KParams kp;                      // per-handle constants: a __grid_constant__ parameter of every launch
+    Scalars<double> &sd = kp.sd;
+    Scalars<float> &sf = kp.sf;
+    Tables &tb = kp.tb;
+    LaunchCtx lc() const { return LaunchCtx{&kp, n_sm, cfg.device}; }
+    long long roll_index0 = 0;       // pd_set_rollout_stream: global index of the first local particle
+    unsigned int roll_generation = 0;
     std::vector<void *> allocs;
     const double *tape = nullptr;
     int tape_len = 0;
@@ -56,21 +60,25 @@ struct PdEnv {
     float *obs_carry = nullptr;      // [n_envs*O] observation the next action is computed from
     bool obs_valid = false;
     unsigned int collect_step = 0;
-    int n_sm = 148;
+    int n_sm = 0;                    // queried in pd_create
     bool info_full = false;          // pd_set_info_mode
 };
 
-// the __constant__ blocks are per precision TU and per process: re-upload on handle switch
-static PdEnv *g_active[2] = {nullptr, nullptr};
-
-static int activate(PdEnv *e) {
-    int p = e->cfg.precision;
-    if (g_active[p] == e) return 0;
-    CK(cudaDeviceSynchronize());
-    if (e->impl->upload(&e->sd, &e->sf, &e->tb)) return fail("constant upload failed");
-    g_active[p] = e;
-    return 0;
-}
+// Every entry point runs on the handle's own device and leaves the caller's current device as it
+// found it (a process may hold handles on several GPUs).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(e)                                                        \
+    DeviceGuard _guard((e)->cfg.device);                                    \
+    if (!_guard.ok) return fail("cannot select the handle's CUDA device")
 
 template <typename T>
 static int dev_copy(PdEnv *e, const T *host, size_t n, const T **out) {
@@ -281,7 +289,7 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
 extern "C" {
 
 const char *pd_last_error(void) { return g_err.c_str(); }
-int pd_version(void) { return 120; }
+int pd_version(void) { return 200; }
 uint64_t pd_launch_count(void) { return g_launches.load(); }
 
 int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
@@ -298,9 +306,18 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("pd_create: no CUDA device (this library has no CPU fallback)");
-    CK(cudaSetDevice(cfg->device));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("pd_create: no such CUDA device");
     PdEnv *e = new PdEnv();
     e->cfg = *cfg;
+    ON_DEVICE(e);
+    {
+        int n_sm = 0;
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || n_sm <= 0) {
+            delete e;
+            return fail("pd_create: cannot query the SM count");
+        }
+        e->n_sm = n_sm;
+    }
     e->impl = cfg->precision == PD_FP64 ? impl_fp64() : impl_fp32();
     fill_scalars(*cfg, *p, e->sd);
     memset(&e->tb, 0, sizeof(e->tb));
@@ -383,8 +400,7 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
 
 int pd_destroy(PdEnv *e) {
     if (!e) return 0;
-    for (int p = 0; p < 2; ++p)
-        if (g_active[p] == e) g_active[p] = nullptr;
+    DeviceGuard guard(e->cfg.device);
     for (void *a : e->allocs) cudaFree(a);
     if (e->wT) cudaFree(e->wT);
     if (e->cont_d) cudaFree(e->cont_d);
@@ -402,6 +418,7 @@ static WindCtx wind_ctx(const PdEnv *e) {
     wc.tape_len = e->tape_len;
     wc.seed = e->cfg.seed;
     wc.stochastic = e->cfg.stochastic_wind;
+    wc.id_offset = 0;
     return wc;
 }
 
@@ -422,8 +439,8 @@ int pd_set_info_mode(PdEnv *e, int full) {
 
 int pd_reset(PdEnv *e, const uint8_t *mask, void *stream) {
     if (!e) return fail("pd_reset: null handle");
-    if (activate(e)) return 1;
-    e->impl->reset(e->soa, mask, wind_ctx(e), e->sigma_uv, (cudaStream_t)stream);
+    ON_DEVICE(e);
+    e->impl->reset(e->lc(), e->soa, mask, wind_ctx(e), e->sigma_uv, (cudaStream_t)stream);
     e->obs_valid = false;
     g_launches++;
     CK(cudaGetLastError());
@@ -434,7 +451,7 @@ int pd_step(PdEnv *e, const void *actions, int action_dtype, void *obs, void *re
             uint8_t *truncated, int32_t *trunc_id, void *next_obs, double *dbg, void *stream) {
     if (!e || !actions) return fail("pd_step: null argument");
     if (action_dtype != PD_ACT_F64 && action_dtype != PD_ACT_F32) return fail("pd_step: action dtype");
-    if (activate(e)) return 1;
+    ON_DEVICE(e);
     StepIO io;
     io.actions = actions; io.action_dtype = action_dtype; io.obs = obs; io.reward = reward;
     io.raw_actions = e->cfg.raw_actions || e->cfg.rtd == PD_RTD_SUPERVISORY;
@@ -442,7 +459,7 @@ int pd_step(PdEnv *e, const void *actions, int action_dtype, void *obs, void *re
     io.supervisory = e->cfg.rtd == PD_RTD_SUPERVISORY;
     io.next_obs = next_obs; io.done = done; io.truncated = truncated; io.trunc_id = trunc_id;
     io.dbg = dbg;
-    e->impl->step(e->cfg.phase, kernel_rtd(e), e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
+    e->impl->step(e->lc(), e->cfg.phase, kernel_rtd(e), e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
                   e->cfg.auto_reset, (cudaStream_t)stream);
     g_launches++;
     CK(cudaGetLastError());
@@ -452,6 +469,7 @@ int pd_step(PdEnv *e, const void *actions, int action_dtype, void *obs, void *re
 int pd_get_state(PdEnv *e, double *state, double *g_window, int32_t *n_window, double *act_prev,
                  void *stream) {
     if (!e) return fail("pd_get_state: null handle");
+    ON_DEVICE(e);
     e->impl->get_state(e->soa, state, g_window, n_window, act_prev, (cudaStream_t)stream);
     g_launches++;
     CK(cudaGetLastError());
@@ -461,6 +479,7 @@ int pd_get_state(PdEnv *e, double *state, double *g_window, int32_t *n_window, d
 int pd_set_state(PdEnv *e, const double *state, const double *g_window, const int32_t *n_window,
                  const double *act_prev, void *stream) {
     if (!e) return fail("pd_set_state: null handle");
+    ON_DEVICE(e);
     e->impl->set_state(e->soa, state, g_window, n_window, act_prev, (cudaStream_t)stream);
     e->obs_valid = false;
     g_launches++;
@@ -491,13 +510,17 @@ int pd_pso_update(double *x, double *v, double *best, double *best_fit, const do
     return 0;
 }
 
-int pd_activate(PdEnv *e) {
-    if (!e) return fail("pd_activate: null handle");
-    return activate(e);
+int pd_set_rollout_stream(PdEnv *e, int64_t index0, uint32_t generation) {
+    if (!e) return fail("pd_set_rollout_stream: null handle");
+    if (index0 < 0) return fail("pd_set_rollout_stream: index0 must be >= 0");
+    e->roll_index0 = index0;
+    e->roll_generation = generation;
+    return 0;
 }
 
 int pd_check_status(PdEnv *e, int32_t *status) {
     if (!e || !status) return fail("pd_check_status: null argument");
+    ON_DEVICE(e);
     int a = 0, b = 0;
     CK(cudaMemcpy(&a, e->soa.status, sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&b, e->roll_status, sizeof(int), cudaMemcpyDeviceToHost));
@@ -527,22 +550,28 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
     if (n_particles <= 0 || n_seeds <= 0 || max_steps <= 0) return fail("pd_rollout_pso: bad sizes");
     if (e->cfg.rtd != PD_RTD_PSO) return fail("pd_rollout_pso: handle was not created with type='pso'");
     if (e->cfg.phase > PD_PHASE_GIMBALLED) return fail("pd_rollout_pso: landing phases only");
-    if (activate(e)) return 1;
+    ON_DEVICE(e);
     if (ensure_wT(e, (size_t)n_particles * n_params)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    e->impl->transpose(weights, e->wT, n_particles, n_params, st);
+    // landing_burn: the fitness evaluation always runs the fp64 instantiation.  The phase's pitch
+    // channel amplifies a perturbation ~50x per 0.4 s env step, so fp32 rounding decides the length
+    // of 8 % of even the well-conditioned episodes (tests/golden/pso_many_G.npz: 92 % agreement with
+    // the reference in fp32, 99 % in fp64) - a different optimiser landscape, for 20 % of speed.
+    const Impl *impl = e->cfg.phase == PD_PHASE_GIMBALLED ? impl_fp64() : e->impl;
+    impl->transpose(weights, e->wT, n_particles, n_params, st);
     g_launches++;
     RolloutIO io;
     memset(&io, 0, sizeof(io));
     io.n_episodes = n_particles * n_seeds;
     io.n_seeds = n_seeds;
     io.max_steps = max_steps;
+    io.generation = e->roll_generation;
     io.wT = e->wT;
     io.w_stride = (size_t)n_particles;
     io.ret = fitness; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
     io.traj = traj; io.act_out = actions_out; io.rewards = rewards;
     io.queue = e->roll_queue;
-    if (e->handoff_steps > 0 && io.n_episodes > 148 * 448 * 3 / 4 / 8) {
+    if (e->handoff_steps > 0 && (long long)io.n_episodes * 8 > (long long)e->n_sm * 448 * 3 / 4) {
         // continuation records for the straggler hand-off (used when one lane runs one episode)
         if (e->cont_cap < io.n_episodes) {
             if (e->cont_d) { cudaFree(e->cont_d); cudaFree(e->cont_i); e->cont_d = nullptr; e->cont_i = nullptr; }
@@ -557,7 +586,11 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
         io.handoff_steps = e->handoff_steps;
         io.cont_d = e->cont_d; io.cont_i = e->cont_i; io.cont_count = e->cont_count; io.cont_cap = e->cont_cap;
     }
-    if (e->impl->rollout(PD_POLICY_MLP, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
+    WindCtx wc = wind_ctx(e);
+    // gust-noise stream id = GLOBAL episode index (particle * n_seeds + seed), so that a windy
+    // fitness does not depend on how the swarm is sharded over ranks
+    wc.id_offset = (unsigned int)(e->roll_index0 * n_seeds);
+    if (impl->rollout(e->lc(), PD_POLICY_MLP, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wc,
                          e->sigma_uv, e->roll_status, st))
         return fail("pd_rollout_pso: unsupported configuration");
     g_launches++;
@@ -574,18 +607,19 @@ int pd_rollout_policy(PdEnv *e, int policy, const void *actions, int action_dtyp
     if (policy == PD_POLICY_TAPE && e->cfg.rtd == PD_RTD_SUPERVISORY)
         return fail("pd_rollout_policy: type 'supervisory' is served by pd_step only");
     if (n_episodes <= 0 || max_steps <= 0) return fail("pd_rollout_policy: bad sizes");
-    if (activate(e)) return 1;
+    ON_DEVICE(e);
     RolloutIO io;
     memset(&io, 0, sizeof(io));
     io.n_episodes = n_episodes;
     io.n_seeds = 1;
     io.max_steps = max_steps;
+    io.generation = e->roll_generation;
     io.actions = actions;
     io.action_dtype = action_dtype;
     io.ret = ret; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
     io.traj = traj; io.rewards = rewards;
     io.queue = e->roll_queue;
-    if (e->impl->rollout(policy, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
+    if (e->impl->rollout(e->lc(), policy, e->cfg.phase, e->cfg.rtd, e->cfg.enable_wind, io, wind_ctx(e),
                          e->sigma_uv, e->roll_status, (cudaStream_t)stream))
         return fail("pd_rollout_policy: unsupported configuration (classical controller is "
                     "landing_burn_pure_throttle only)");
@@ -608,9 +642,6 @@ static int actor_args(PdEnv *e, const PdSharedActor *a, ActorArgs &p, int &use_t
         if (!e->w2_img) {
             CK(cudaMalloc(&e->w2_img, 256 * 256 * 2));
             e->allocs.push_back(e->w2_img);
-            cudaDeviceProp prop;
-            CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-            e->n_sm = prop.multiProcessorCount;
         }
         // weights change between collection phases (the learner updates them): rebuild the image
         if (actor_prep_w2(a->w2, e->w2_img, st)) return fail("shared actor: W2 image kernel failed");
@@ -624,6 +655,7 @@ static int actor_args(PdEnv *e, const PdSharedActor *a, ActorArgs &p, int &use_t
 int pd_actor_forward(PdEnv *e, const PdSharedActor *actor, const float *obs, int n, float *act,
                      float *mean_out, void *stream) {
     if (!e || !actor || !obs || !act || n <= 0) return fail("pd_actor_forward: bad argument");
+    ON_DEVICE(e);
     const int O = pd::phase_odim(e->cfg.phase), A = pd::phase_adim(e->cfg.phase);
     ActorArgs p;
     int use_tc = 0;
@@ -641,7 +673,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
     if (e->cfg.precision != PD_FP32) return fail("pd_collect_shared_actor: needs the PD_FP32 build (float obs)");
     if (!e->cfg.auto_reset) return fail("pd_collect_shared_actor: handle must be created with auto_reset");
     if (e->cfg.rtd != PD_RTD_RL) return fail("pd_collect_shared_actor: handle must be created with type='rl'");
-    if (activate(e)) return 1;
+    ON_DEVICE(e);
     cudaStream_t st = (cudaStream_t)stream;
     const int O = pd::phase_odim(e->cfg.phase), A = pd::phase_adim(e->cfg.phase);
     const size_t B = (size_t)e->cfg.n_envs;
@@ -650,7 +682,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
         e->allocs.push_back(e->obs_carry);
     }
     if (!e->obs_valid) {
-        e->impl->observe(e->cfg.phase, kernel_rtd(e), e->soa, e->obs_carry, st);
+        e->impl->observe(e->lc(), e->cfg.phase, kernel_rtd(e), e->soa, e->obs_carry, st);
         g_launches++;
         e->obs_valid = true;
     }
@@ -677,7 +709,7 @@ int pd_collect_shared_actor(PdEnv *e, const PdSharedActor *actor, int n_steps, f
         io.dbg = nullptr;
         // post-reset observation feeds the next action
         io.next_obs = (obs_out && t + 1 < n_steps) ? (void *)(obs_out + (size_t)(t + 1) * B * O) : (void *)e->obs_carry;
-        e->impl->step(e->cfg.phase, kernel_rtd(e), e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
+        e->impl->step(e->lc(), e->cfg.phase, kernel_rtd(e), e->cfg.enable_wind, e->soa, io, wind_ctx(e), e->sigma_uv,
                       e->cfg.auto_reset, st);
         g_launches++;
     }

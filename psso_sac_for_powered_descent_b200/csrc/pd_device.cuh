@@ -149,14 +149,18 @@ constexpr unsigned PD_SH_BYTES = sizeof(SharedTables) + PD_SH_ALIGN;      // dyn
 constexpr unsigned PD_SH_IMAGE_BYTES = (PD_LOG_N + 256 + 144) * PD_REP * 16;
 constexpr unsigned PD_LOG_MASK = (PD_LOG_N - 1) << 7;                     // byte-offset field of a table index
 
-// per-TU copies (no relocatable device code): each precision TU uploads its own
-static __constant__ Scalars<double> g_sd;
-static __constant__ Scalars<float> g_sf;
-static __constant__ Tables g_tb;
-
-template <typename R> __device__ __forceinline__ const Scalars<R> &SC();
-template <> __device__ __forceinline__ const Scalars<double> &SC<double>() { return g_sd; }
-template <> __device__ __forceinline__ const Scalars<float> &SC<float>() { return g_sf; }
+// Per-handle constants: the whole block travels as ONE __grid_constant__ kernel parameter (4.4 KB of
+// the 32 KB parameter space), so it sits in constant bank 0 of every launch, two handles can be
+// stepped on two streams at the same time, and a captured CUDA graph carries its own copy - there
+// is no process-global __constant__ state and no "active handle".
+struct KParams {
+    Scalars<double> sd;
+    Scalars<float> sf;
+    Tables tb;
+#ifdef PD_EXP_PARAM_PAD
+    char pad[PD_EXP_PARAM_PAD];      // experiment: does the launch cost depend on the block's size?
+#endif
+};
 
 // ------------------------------------------------------------------ small math shims
 __device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
@@ -165,14 +169,16 @@ __device__ __forceinline__ double m_exp(double x) { return exp(x); }
 __device__ __forceinline__ float m_exp(float x) { return expf(x); }
 __device__ __forceinline__ double m_pow(double x, double y) { return pow(x, y); }
 __device__ __forceinline__ float m_pow(float x, float y) { return powf(x, y); }
-// fp32 production build, sub-steps of every phase but the gimballed landing burn: x^y =
-// exp2(y log2 x) on the MUFU pipe.  Only the ISA pressure ratio uses it (x in (0.7, 1.3), y = 5.26
-// or -34.2 / 12.2): relative error < 4e-6 on p and rho, i.e. < 1e-8 relative on a velocity per
-// sub-step - three decades inside the build's 1e-5 tolerance - for ~10 instructions instead of
-// ~100 with a branchy slow path.  `landing_burn` keeps the accurate libm paths: its 0.4 s env steps
-// amplify a 1e-6 perturbation enough to change the length of some of its 7-27-step episodes.
-__device__ __forceinline__ double m_pow_fast(double x, double y) { return pow(x, y); }
-__device__ __forceinline__ float m_pow_fast(float x, float y) { return __powf(x, y); }
+// fp32 production build: the ISA pressure
+// ratio (1 + z)^y, z = beta/T_b (H - H_b) in (-0.3, 0.3), y = 5.26 or -34.2 / 12.2, as
+// exp(y log1p(z)).  Forming 1 + z in float first would already cost 6e-8 * |y| = 2e-6 relative on
+// p in the stratosphere layers - as much as the MUFU-only __powf this replaces (4e-6), which showed
+// up as a systematic drift of q and 62 flag disagreements with the fp64 build per 65.5 M env-steps,
+// all of them q within 5e-6 of the 65 kPa threshold (tools/fp32_flag_probe.py).  log1pf / expf
+// are 1-2 ulp: ~3e-7 relative on p and rho for ~40 instructions, a third of powf's cost and more
+// accurate than powf(1 + z, y), so every phase and the rtd closures' q use it.
+__device__ __forceinline__ double m_pow1p(double z, double y) { return pow(1.0 + z, y); }
+__device__ __forceinline__ float m_pow1p(float z, float y) { return expf(y * log1pf(z)); }
 __device__ __forceinline__ double m_log(double x) { return log(x); }
 __device__ __forceinline__ float m_log(float x) { return logf(x); }
 __device__ __forceinline__ double m_tanh(double x) { return tanh(x); }
@@ -207,7 +213,8 @@ struct ActPrev {   // landing_burn only: gimbal_angle_deg_prev, delta_command_{l
 struct WindState {
     double xu0, xu1, xv0, xv1;     // gust filter states
     double sigma_u, sigma_v;
-    unsigned int ctr;              // draws consumed (tape position / Philox counter)
+    unsigned int ctr;              // draws consumed this episode (tape position / Philox counter)
+    unsigned int episode;          // episode number of this env / rollout generation (Philox counter word)
 };
 
 // values of the last sub-step (reference `info` dict, rockets_physics.py:649-702).  FULL adds
@@ -234,6 +241,59 @@ struct Info<R, true> {
     R x[PD_INFO_X];
 };
 
+// ------------------------------------------------------------------ plain per-env types
+struct WindCtx {
+    const double *tape;     // N(0,1) tape or nullptr -> Philox
+    int tape_len;
+    unsigned long long seed;
+    int stochastic;
+    unsigned int id_offset; // added to the env / episode index for the Philox stream id only (global
+                            // particle index of a sharded swarm); the tape is indexed by the local id
+};
+
+// The action as the reference sees it: either float64 (pure fp64 step) or float32
+// (NumPy NEP-50: throttle / thrust / mass-flow become float32; SURVEY 8a dtype rule).
+template <int A>
+struct Action {
+    double u[A];
+    bool f32;
+};
+
+template <typename R>
+struct Control {
+    R par, perp, mz, mass_flow_dt;   // mass_flow * dt_phys, rounded as the reference rounds it
+    R mass_flow, throttle;
+    double gimbal_deg, dl_cmd, dr_cmd;
+    bool f32_forces;                 // par / perp are np.float32 upstream (ascent, float32 action):
+                                     // the body->inertial rotation then runs in float32 too
+};
+
+template <typename R>
+struct GWindow {
+    R w[10];
+    int n;
+};
+
+template <typename R>
+struct Rtd {
+    R reward;
+    int done, truncated, trunc_id;
+};
+
+// ------------------------------------------------------------------ device physics
+// All functions that read the per-handle constants are members of Dev, which only holds three
+// references into the kernel's __grid_constant__ parameter block; everything is force-inlined, so
+// the references fold into direct constant-bank operands.
+struct Dev {
+    const Scalars<double> &sd;
+    const Scalars<float> &sf;
+    const Tables &tb;
+    __device__ __forceinline__ explicit Dev(const KParams &k) : sd(k.sd), sf(k.sf), tb(k.tb) {}
+    template <typename R>
+    __device__ __forceinline__ const Scalars<R> &SC() const {
+        if constexpr (sizeof(R) == 8) return sd; else return sf;
+    }
+
 // ------------------------------------------------------------------ ISA
 template <typename R, bool FAST = false>
 __device__ __forceinline__ void isa(R alt, R &rho, R &p, R &a) {
@@ -255,8 +315,7 @@ __device__ __forceinline__ void isa(R alt, R &rho, R &p, R &a) {
     if (beta == R(0))
         p = c.isa_pb[k] * m_exp(c.isa_iso[k] * dH);
     else
-        p = c.isa_pb[k] * (FAST ? m_pow_fast(R(1) + c.isa_boT[k] * dH, c.isa_expo[k])
-                                : m_pow(R(1) + c.isa_boT[k] * dH, c.isa_expo[k]));
+        p = c.isa_pb[k] * m_pow1p(c.isa_boT[k] * dH, c.isa_expo[k]);
     const R Rgas = R(287.05287);
     rho = m_div(p, Rgas * T);
     a = m_sqrt(R(1.4 * 287.05287) * T);
@@ -324,7 +383,7 @@ __device__ __forceinline__ void cog_inertia_full(R fill, R &x_cog, R &inertia) {
 }
 
 // ------------------------------------------------------------------ local TPS RBF
-__device__ __forceinline__ unsigned long long hash_u64(unsigned long long k) {
+static __device__ __forceinline__ unsigned long long hash_u64(unsigned long long k) {
     k ^= k >> 30;
     k *= 0xBF58476D1CE4E5B9ULL;
     k ^= k >> 27;
@@ -341,7 +400,7 @@ __device__ __forceinline__ unsigned long long hash_u64(unsigned long long k) {
 // of (M, a).  Sets are one contiguous [lo,hi) interval per level; the check compares the
 // farthest interval end against the nearest point just outside any interval.
 template <int NL>
-__device__ __noinline__ int rbf_walk(const RbfDev &T, const double *levels_d, double M, double a,
+static __device__ __noinline__ int rbf_walk(const RbfDev &T, const double *levels_d, double M, double a,
                                      unsigned long long hint, int &sid) {
     int lo[NL], hi[NL];
     double dl2[NL];
@@ -472,7 +531,7 @@ __device__ __forceinline__ int rbf_resolve(const RbfDev &T, const RbfGrid &G, co
 // phi(0) = 0 * finite = 0 needs no special case.
 template <int DEG>
 __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab) {
-    const double *K = g_sd.log_c;
+    const double *K = sd.log_c;
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
     const double2 t = tab[((hi >> (20 - PD_LOG_BITS)) & (PD_LOG_N - 1)) * PD_REP];
@@ -543,7 +602,7 @@ __device__ __forceinline__ double2 lds_d2(unsigned addr) {
 // of terms before the first dependent fma)
 template <int DEG>
 __device__ __forceinline__ double fast_log_t(double x, double2 t) {
-    const double *K = g_sd.log_c;
+    const double *K = sd.log_c;
     const int hi = __double2hiint(x);
     // r = m u_j - 1 with m = x 2^-e: the power of two goes into u_j (integer subtract on its high
     // word, exact), so m is never assembled: r = fma(x, u_j 2^-e, -1)
@@ -672,22 +731,27 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     const double aL = neg_line ? -10.0 : fmin(fmax(fabs(aoa), 1e-6), 10.0);
     const bool flip = !neg_line && aoa < 0.0;
     // both grid-cell loads in flight before either is consumed
-    const RbfGrid &GL = neg_line ? g_tb.cl.grid[1] : g_tb.cl.grid[0];
-    const int cellD = __ldg(rbf_cell_ptr(g_tb.cd.grid[0], M, aD));
+    const RbfGrid &GL = neg_line ? tb.cl.grid[1] : tb.cl.grid[0];
+    const int cellD = __ldg(rbf_cell_ptr(tb.cd.grid[0], M, aD));
     const int cellL = __ldg(rbf_cell_ptr(GL, M, aL));
     const int copy = threadIdx.x & (PD_REP - 1);          // this lane's replica of the tables
-    const int sidD = rbf_resolve<5>(g_tb.cd, g_tb.cd.grid[0], g_sd.cd_levels, sh->cd_pts + copy, M, aD, cellD, status);
-    const int sidL = rbf_resolve<5>(g_tb.cl, GL, g_sd.cl_levels, sh->cl_pts + copy, M, aL, cellL, status);
+    const int sidD = rbf_resolve<5>(tb.cd, tb.cd.grid[0], sd.cd_levels, sh->cd_pts + copy, M, aD, cellD, status);
+    const int sidL = rbf_resolve<5>(tb.cl, GL, sd.cl_levels, sh->cl_pts + copy, M, aL, cellL, status);
     double vL, vD;
     constexpr int DEG = (sizeof(R) == 8 ? 5 : 4) - (PD_LOG_BITS >= 9 ? 1 : 0);
     if constexpr (COOP == 1)
-        rbf_eval2<DEG>(g_tb.cl.rows, sidL, sh->cl_pts + copy, aL, g_tb.cd.rows, sidD, sh->cd_pts + copy, aD, M,
+        rbf_eval2<DEG>(tb.cl.rows, sidL, sh->cl_pts + copy, aL, tb.cd.rows, sidD, sh->cd_pts + copy, aD, M,
                        sh->logtab + copy, vL, vD);
     else
-        rbf_eval2_coop<DEG, COOP>(g_tb.cl.rows, sidL, sh->cl_pts + copy, aL, g_tb.cd.rows, sidD,
+        rbf_eval2_coop<DEG, COOP>(tb.cl.rows, sidL, sh->cl_pts + copy, aL, tb.cd.rows, sidD,
                                   sh->cd_pts + copy, aD, M, sh->logtab + copy, vL, vD);
     C_L = zero ? R(0) : (R)(flip ? -vL : vL);
     C_D = (R)vD;
+    // A neighbourhood outside the enumerated set table cannot happen for finite states (the
+    // enumeration covers the whole clamped query box, rbf_sets.py); if it ever did, the lane's
+    // coefficients are poisoned so that the env turns NaN instead of carrying on with the wrong
+    // interpolant, and the sticky status bit makes pd_check_status fail.
+    if (status) { C_L = R(NAN); C_D = R(NAN); }
 }
 
 // ------------------------------------------------------------------ grid fins
@@ -706,23 +770,23 @@ __device__ __forceinline__ int seg_index(const double *x, int n, double v) {
 template <typename R>
 __device__ __forceinline__ R gridfin_ca(R mach) {
     const double M = (double)mach;
-    if (M < __ldg(g_tb.ca_x)) return (R)__ldg(g_tb.ca_y);
-    int lo = seg_index(g_tb.ca_x, g_tb.n_ca, M);
-    return (R)(__ldg(g_tb.ca_s + lo) * (M - __ldg(g_tb.ca_x + lo)) + __ldg(g_tb.ca_y + lo));
+    if (M < __ldg(tb.ca_x)) return (R)__ldg(tb.ca_y);
+    int lo = seg_index(tb.ca_x, tb.n_ca, M);
+    return (R)(__ldg(tb.ca_s + lo) * (M - __ldg(tb.ca_x + lo)) + __ldg(tb.ca_y + lo));
 }
 
 // returns C_n_alpha(M); caller multiplies by degrees(alpha_local)
 template <typename R>
 __device__ __forceinline__ R gridfin_cn_alpha(R mach) {
     const double M = (double)mach;
-    const int n = g_tb.n_cn;
-    if (M < __ldg(g_tb.cn_x)) return (R)__ldg(g_tb.cn_y);
-    double xmax = __ldg(g_tb.cn_x + n - 1);
+    const int n = tb.n_cn;
+    if (M < __ldg(tb.cn_x)) return (R)__ldg(tb.cn_y);
+    double xmax = __ldg(tb.cn_x + n - 1);
     if (M <= xmax) {
-        int lo = seg_index(g_tb.cn_x, n, M);
-        return (R)(__ldg(g_tb.cn_s + lo) * (M - __ldg(g_tb.cn_x + lo)) + __ldg(g_tb.cn_y + lo));
+        int lo = seg_index(tb.cn_x, n, M);
+        return (R)(__ldg(tb.cn_s + lo) * (M - __ldg(tb.cn_x + lo)) + __ldg(tb.cn_y + lo));
     }
-    return (R)(__ldg(g_tb.cn_y + n - 1) + __ldg(g_tb.cn_s + n - 2) * (M - xmax));
+    return (R)(__ldg(tb.cn_y + n - 1) + __ldg(tb.cn_s + n - 2) * (M - xmax));
 }
 
 // ------------------------------------------------------------------ Philox4x32-10
@@ -746,19 +810,13 @@ __device__ __forceinline__ double u01(unsigned int a, unsigned int b) {
     return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-struct WindCtx {
-    const double *tape;     // N(0,1) tape or nullptr -> Philox
-    int tape_len;
-    unsigned long long seed;
-    int stochastic;
-};
 
 // ------------------------------------------------------------------ wind
 template <typename R>
 __device__ __forceinline__ void wind_sample(double y, WindState &w, const WindCtx &wc,
                                             unsigned int env_id, R &ug, R &vg) {
-    const Scalars<double> &c = g_sd;
-    const int n = g_tb.n_wind;
+    const Scalars<double> &c = sd;
+    const int n = tb.n_wind;
     double akm = y / 1000.0;
     double fixed;
     if (akm < c.wind_x[0]) fixed = c.wind_y[0];
@@ -780,7 +838,9 @@ __device__ __forceinline__ void wind_sample(double y, WindState &w, const WindCt
             n1 = p1 < (unsigned)wc.tape_len ? wc.tape[base + p1] : 0.0;
         } else {
             unsigned int r[4];
-            philox4x32(env_id, w.ctr, 0x57494E44u, 0u, (unsigned int)wc.seed,
+            // counter = (stream id, draw, tag, episode): fresh noise every episode, as upstream's
+            // reset() re-seeds and rebuilds the filters (vonkarman.py:86-96)
+            philox4x32(env_id + wc.id_offset, w.ctr, 0x57494E44u, w.episode, (unsigned int)wc.seed,
                        (unsigned int)(wc.seed >> 32), r);
             double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
             double rad = sqrt(-2.0 * log(u1));
@@ -810,12 +870,13 @@ __device__ __forceinline__ void wind_reset(WindState &w, const WindCtx &wc, unsi
                                            unsigned int episode, const double *sigma_uv) {
     w.xu0 = w.xu1 = w.xv0 = w.xv1 = 0.0;
     w.ctr = 0;
+    w.episode = episode;
     if (sigma_uv) {
         w.sigma_u = sigma_uv[2 * (size_t)env_id];
         w.sigma_v = sigma_uv[2 * (size_t)env_id + 1];
     } else {
         unsigned int r[4];
-        philox4x32(env_id, episode, 0x5349474Du, 1u, (unsigned int)wc.seed,
+        philox4x32(env_id + wc.id_offset, episode, 0x5349474Du, 1u, (unsigned int)wc.seed,
                    (unsigned int)(wc.seed >> 32), r);
         w.sigma_u = 0.5 + (2.25 - 0.5) * u01(r[0], r[1]);
         w.sigma_v = 1.25 + (2.0 - 1.25) * u01(r[2], r[3]);
@@ -823,22 +884,7 @@ __device__ __forceinline__ void wind_reset(WindState &w, const WindCtx &wc, unsi
 }
 
 // ------------------------------------------------------------------ actions
-// The action as the reference sees it: either float64 (pure fp64 step) or float32
-// (NumPy NEP-50: throttle / thrust / mass-flow become float32; SURVEY 8a dtype rule).
-template <int A>
-struct Action {
-    double u[A];
-    bool f32;
-};
 
-template <typename R>
-struct Control {
-    R par, perp, mz, mass_flow_dt;   // mass_flow * dt_phys, rounded as the reference rounds it
-    R mass_flow, throttle;
-    double gimbal_deg, dl_cmd, dr_cmd;
-    bool f32_forces;                 // par / perp are np.float32 upstream (ascent, float32 action):
-                                     // the body->inertial rotation then runs in float32 too
-};
 
 // ACS (grid fins), acs_model.py:13-86.  d_cmd_* = delta_command_*_rad =
 // radians(deflection_command_deg * 60), formed by the caller (its dtype depends on the action).
@@ -846,7 +892,7 @@ template <typename R>
 __device__ __forceinline__ void acs(R alpha_eff, R q, R mach, R x_cog, double d_cmd_l, double d_cmd_r,
                                     double prev_l, double prev_r, R &f_perp, R &f_par, R &m_z) {
     const Scalars<R> &c = SC<R>();
-    const double dt = g_sd.dt_act;
+    const double dt = sd.dt_act;
     R d_l = (R)(prev_l + dt * ((-prev_l + d_cmd_l) / 0.5));
     R d_r = (R)(prev_r + dt * ((-prev_r + d_cmd_r) / 0.5));
     R a_l = alpha_eff - d_l;
@@ -870,7 +916,7 @@ __device__ __forceinline__ void acs(R alpha_eff, R q, R mach, R x_cog, double d_
 //   mass_flow = f32(T_e/v_ex) * n_tot, mass_flow*dt in f32.
 __device__ __forceinline__ float f32_throttle(float u) {
     float nn = __fdiv_rn(__fadd_rn(u, 1.0f), 2.0f);
-    return __fadd_rn(__fmul_rn(nn, g_sf.one_minus_nominal), g_sf.nominal);
+    return __fadd_rn(__fmul_rn(nn, sf.one_minus_nominal), sf.nominal);
 }
 
 // landing_burn_pure_throttle: rockets_physics.py:340-400
@@ -888,10 +934,10 @@ __device__ __forceinline__ void control_P(const Action<1> &act, R p_atm, R alpha
         float thr = f32_throttle((float)act.u[0]);
         float thrust = __fmul_rn((float)((double)t_full * (double)c.n_eng), thr);
         float n_tot = __fdiv_rn(thrust, (float)t_full);
-        float mf = __fmul_rn(g_sf.te_over_vex, n_tot);
+        float mf = __fmul_rn(sf.te_over_vex, n_tot);
         o.par = (R)thrust + f_par;
         o.mass_flow = (R)mf;
-        o.mass_flow_dt = (R)__fmul_rn(mf, g_sf.dt_phys);
+        o.mass_flow_dt = (R)__fmul_rn(mf, sf.dt_phys);
         o.throttle = (R)thr;
     } else {
         R u0 = (R)act.u[0];
@@ -918,11 +964,11 @@ __device__ __forceinline__ void control_G(const Action<4> &act, const ActPrev &p
     R t_full = c.T_e + (c.p_e - p_atm) * c.A_e;
     // gimbal: first-order low-pass (tau 1.0, dt_act) on degrees, clipped
     double gimbal_cmd_deg;
-    if (f32) gimbal_cmd_deg = (double)__fmul_rn((float)act.u[0], g_sf.max_gimbal_rad) * (180.0 / PD_PI);
-    else gimbal_cmd_deg = (act.u[0] * g_sd.max_gimbal_rad) * (180.0 / PD_PI);
+    if (f32) gimbal_cmd_deg = (double)__fmul_rn((float)act.u[0], sf.max_gimbal_rad) * (180.0 / PD_PI);
+    else gimbal_cmd_deg = (act.u[0] * sd.max_gimbal_rad) * (180.0 / PD_PI);
     double x = prev.gimbal_deg;
-    double gdeg = x + g_sd.dt_act * ((-x + gimbal_cmd_deg) / 1.0);
-    const double gmax = g_sd.max_gimbal_deg;
+    double gdeg = x + sd.dt_act * ((-x + gimbal_cmd_deg) / 1.0);
+    const double gmax = sd.max_gimbal_deg;
     gdeg = gdeg < -gmax ? -gmax : (gdeg > gmax ? gmax : gdeg);
     double grad = gdeg * (PD_PI / 180.0);
     R sg, cg;
@@ -936,11 +982,11 @@ __device__ __forceinline__ void control_G(const Action<4> &act, const ActPrev &p
         m_z = (R)((double)__fmul_rn(-thrust, (float)sg) * (double)d_thrust_cg);
         float total = __fsqrt_rn(__fadd_rn(__fmul_rn(fpar, fpar), __fmul_rn(fperp, fperp)));
         float n_tot = __fdiv_rn(total, (float)t_full);
-        float mf = __fmul_rn(g_sf.te_over_vex, n_tot);
+        float mf = __fmul_rn(sf.te_over_vex, n_tot);
         t_par = (R)fpar;
         t_perp = (R)fperp;
         o.mass_flow = (R)mf;
-        o.mass_flow_dt = (R)__fmul_rn(mf, g_sf.dt_phys);
+        o.mass_flow_dt = (R)__fmul_rn(mf, sf.dt_phys);
         o.throttle = (R)thr;
     } else {
         R u1 = (R)act.u[1];
@@ -959,13 +1005,13 @@ __device__ __forceinline__ void control_G(const Action<4> &act, const ActPrev &p
     o.gimbal_deg = grad * (180.0 / PD_PI);
     // fin commands: u * radians(20) is called "deg" upstream and multiplied by 60 in ACS
     if (f32) {
-        float cl60 = __fmul_rn(__fmul_rn((float)act.u[2], g_sf.max_defl_rad), 60.0f);
-        float cr60 = __fmul_rn(__fmul_rn((float)act.u[3], g_sf.max_defl_rad), 60.0f);
+        float cl60 = __fmul_rn(__fmul_rn((float)act.u[2], sf.max_defl_rad), 60.0f);
+        float cr60 = __fmul_rn(__fmul_rn((float)act.u[3], sf.max_defl_rad), 60.0f);
         o.dl_cmd = (double)cl60 * (PD_PI / 180.0);
         o.dr_cmd = (double)cr60 * (PD_PI / 180.0);
     } else {
-        o.dl_cmd = ((act.u[2] * g_sd.max_defl_rad) * 60.0) * (PD_PI / 180.0);
-        o.dr_cmd = ((act.u[3] * g_sd.max_defl_rad) * 60.0) * (PD_PI / 180.0);
+        o.dl_cmd = ((act.u[2] * sd.max_defl_rad) * 60.0) * (PD_PI / 180.0);
+        o.dr_cmd = ((act.u[3] * sd.max_defl_rad) * 60.0) * (PD_PI / 180.0);
     }
     R f_perp, f_par, a_mz;
     acs<R>(alpha_eff, q, mach, x_cog, o.dl_cmd, o.dr_cmd, prev.dl, prev.dr, f_perp, f_par, a_mz);
@@ -984,7 +1030,7 @@ __device__ __forceinline__ void control_ascent(const Action<2> &act, R p_atm, R 
     const Scalars<R> &c = SC<R>();
     R t_full = c.T_e + (c.p_e - p_atm) * c.A_e;
     if (sizeof(R) == 8 && act.f32) {
-        float grad = __fmul_rn((float)act.u[0], g_sf.max_gimbal_rad);
+        float grad = __fmul_rn((float)act.u[0], sf.max_gimbal_rad);
         double sgd, cgd;
         sincos((double)grad, &sgd, &cgd);
         float sg = (float)sgd, cg = (float)cgd;
@@ -996,11 +1042,11 @@ __device__ __forceinline__ void control_ascent(const Action<2> &act, R p_atm, R 
         o.mz = (R)((double)__fmul_rn(-thrust_g, sg) * (double)d_thrust_cg);
         float total = __fsqrt_rn(__fadd_rn(__fmul_rn(fpar, fpar), __fmul_rn(fperp, fperp)));
         float n_tot = __fdiv_rn(total, (float)t_full);
-        float mf = __fmul_rn(g_sf.te_over_vex, n_tot);
+        float mf = __fmul_rn(sf.te_over_vex, n_tot);
         o.par = (R)fpar;
         o.perp = (R)fperp;
         o.mass_flow = (R)mf;
-        o.mass_flow_dt = (R)__fmul_rn(mf, g_sf.dt_phys);
+        o.mass_flow_dt = (R)__fmul_rn(mf, sf.dt_phys);
         o.throttle = (R)thr;
         o.f32_forces = true;         // no np.float64 ACS term is added here, unlike the landing burns
     } else {
@@ -1031,7 +1077,7 @@ template <typename R>
 __device__ __forceinline__ void control_rcs(const Action<1> &act, R x_cog, Control<R> &o) {
     const Scalars<R> &c = SC<R>();
     R F;
-    if (sizeof(R) == 8 && act.f32) F = (R)__fmul_rn(g_sf.rcs_force, (float)act.u[0]);
+    if (sizeof(R) == 8 && act.f32) F = (R)__fmul_rn(sf.rcs_force, (float)act.u[0]);
     else F = c.rcs_force * (R)act.u[0];
     o.mz = -F * (x_cog - c.d_rcs_bottom) + F * (c.d_rcs_top - x_cog);
     o.par = R(0); o.perp = R(0);
@@ -1139,9 +1185,9 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
         // to float32, and so is the aerodynamic force - a Python float (weak) here, since the
         // RBF coefficients come back as Python floats - before the float32 sum; the wind force
         // (np.float64) then promotes the total
-        const float pf = (float)c_par, qf = (float)c_perp, cf = (float)ct, sf = (float)st;
-        const float cxf = __fadd_rn(__fmul_rn(pf, cf), __fmul_rn(qf, sf));
-        const float cyf = __fsub_rn(__fmul_rn(pf, sf), __fmul_rn(qf, cf));
+        const float pf = (float)c_par, qf = (float)c_perp, cf = (float)ct, stf = (float)st;
+        const float cxf = __fadd_rn(__fmul_rn(pf, cf), __fmul_rn(qf, stf));
+        const float cyf = __fsub_rn(__fmul_rn(pf, stf), __fmul_rn(qf, cf));
         fx = (R)__fadd_rn((float)aero_x, cxf) + f_wind_x;
         fy = (R)__fadd_rn((float)aero_y, cyf);
     }
@@ -1151,7 +1197,7 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
     R mass = (R)s.mass;
     R vx_dot = m_div(fx, mass);
     R vy_dot = m_div(fy, mass) - g;
-    const double dt = g_sd.dt_phys;
+    const double dt = sd.dt_phys;
     s.vx += (double)(vx_dot * c.dt_phys);
     s.vy += (double)(vy_dot * c.dt_phys);
     s.x += s.vx * dt;
@@ -1179,7 +1225,7 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
         x[5] = c_par; x[6] = c_perp; x[7] = c_x; x[8] = c_y; x[9] = aero_x; x[10] = aero_y;
         x[11] = g; x[12] = c_mz; x[13] = aero_mz; x[14] = mz; x[15] = tdd; x[16] = vx_dot;
         x[17] = vy_dot; x[18] = f_wind_x;
-        x[19] = PHASE == 1 ? (R)ctl.gimbal_deg : (phase_ascent(PHASE) ? (R)(act.u[0] * g_sd.max_gimbal_rad * (180.0 / PD_PI)) : R(0));
+        x[19] = PHASE == 1 ? (R)ctl.gimbal_deg : (phase_ascent(PHASE) ? (R)(act.u[0] * sd.max_gimbal_rad * (180.0 / PD_PI)) : R(0));
         x[20] = PHASE == 1 ? (R)ctl.dl_cmd : R(0);
         x[21] = PHASE == 1 ? (R)ctl.dr_cmd : R(0);
         const R qmax = PHASE <= 1 || PHASE == 5 ? R(65000) : R(30000);
@@ -1187,19 +1233,14 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
         x[23] = (R)theta_pre;
         x[24] = gridfin_ca<R>(mach);
         x[25] = gridfin_cn_alpha<R>(mach);
-        x[26] = PHASE == 1 ? (R)(prev.dl + g_sd.dt_act * ((-prev.dl + ctl.dl_cmd) / 0.5)) : R(0);
-        x[27] = PHASE == 1 ? (R)(prev.dr + g_sd.dt_act * ((-prev.dr + ctl.dr_cmd) / 0.5)) : R(0);
+        x[26] = PHASE == 1 ? (R)(prev.dl + sd.dt_act * ((-prev.dl + ctl.dl_cmd) / 0.5)) : R(0);
+        x[27] = PHASE == 1 ? (R)(prev.dr + sd.dt_act * ((-prev.dr + ctl.dr_cmd) / 0.5)) : R(0);
 #pragma unroll
         for (int k = 28; k < PD_INFO_X; ++k) x[k] = R(0);
     }
 }
 
 // ------------------------------------------------------------------ g-load window
-template <typename R>
-struct GWindow {
-    R w[10];
-    int n;
-};
 
 template <typename R>
 __device__ __forceinline__ R gwindow_push(GWindow<R> &g, R g_load) {
@@ -1221,11 +1262,6 @@ __device__ __forceinline__ R gwindow_push(GWindow<R> &g, R g_load) {
 }
 
 // ------------------------------------------------------------------ reward / truncation / done
-template <typename R>
-struct Rtd {
-    R reward;
-    int done, truncated, trunc_id;
-};
 
 template <typename R>
 __device__ __forceinline__ R overshoot(double x, double y) {
@@ -1265,9 +1301,9 @@ __device__ __forceinline__ void rtd_ascent(const State &s, Rtd<R> &o) {
     R vx = (R)s.vx, vy = (R)s.vy;
     R speed = m_sqrt(vx * vx + vy * vy);
     R mach = (speed != R(0) && a_snd != R(0)) ? speed / a_snd : R(0);
-    const R xr = (R)interp_global(g_tb.ref_y, g_tb.ref_v[0], g_tb.ref_s[0], g_tb.n_ref, s.y);
-    const R vxr = (R)interp_global(g_tb.ref_y, g_tb.ref_v[1], g_tb.ref_s[1], g_tb.n_ref, s.y);
-    const R vyr = (R)interp_global(g_tb.ref_y, g_tb.ref_v[2], g_tb.ref_s[2], g_tb.n_ref, s.y);
+    const R xr = (R)interp_global(tb.ref_y, tb.ref_v[0], tb.ref_s[0], tb.n_ref, s.y);
+    const R vxr = (R)interp_global(tb.ref_y, tb.ref_v[1], tb.ref_s[1], tb.n_ref, s.y);
+    const R vyr = (R)interp_global(tb.ref_y, tb.ref_v[2], tb.ref_s[2], tb.n_ref, s.y);
     const R max_x = hyper<R>(0, mach), max_vy = hyper<R>(1, mach), max_vx = hyper<R>(2, mach),
             max_al = hyper<R>(3, mach);
     R ex = (R)s.x - xr, evx = vx - vxr, evy = vy - vyr;
@@ -1336,7 +1372,7 @@ __device__ __forceinline__ void rtd_pcontrol(const State &s, R g1, double v_ref,
         R e = (g1 - R(5.5)) / R(0.5);
         r -= m_min(e * e, R(1));
     }
-    R prog = (R)((g_sd.y0 - s.y) / g_sd.y0);
+    R prog = (R)((sd.y0 - s.y) / sd.y0);
     R track;
     if (sizeof(R) == 8 && vref_f32) {
         // np.float32 arithmetic: abs(speed - v_ref) / 10.0, 1.0 - ..., then max(0.0, .)
@@ -1355,10 +1391,10 @@ __device__ __forceinline__ void rtd_pcontrol(const State &s, R g1, double v_ref,
     r += c.alive_bonus;
     if (dn && !tr) {
         r += R(5);
-        R used = (R)(g_sd.y0 * 0.0 + (g_sd.mass0 - s.mass));
+        R used = (R)(sd.y0 * 0.0 + (sd.mass0 - s.mass));
         r -= m_min(R(0.1) * used, R(1));
     } else if (tr) {
-        r -= m_min(R(4) * (R)(s.y / g_sd.y0) * (m_abs(vy) / R(100)), R(5));
+        r -= m_min(R(4) * (R)(s.y / sd.y0) * (m_abs(vy) / R(100)), R(5));
     }
     r = r < R(-10) ? R(-10) : (r > R(10) ? R(10) : r);
     o.reward = r; o.done = dn; o.truncated = tr; o.trunc_id = id;
@@ -1381,7 +1417,7 @@ __device__ __forceinline__ void rtd_supervisory(const State &s, R g1, Rtd<R> &o)
         dn = speed / a_snd > R(1.1);
         if (s.m_prop <= 0.0) { tr = 1; id = 1; }
     } else if constexpr (PHASE == 3) {
-        dn = s.y > (double)g_sd.sup_terminal_alt;
+        dn = s.y > (double)sd.sup_terminal_alt;
         if (s.m_prop <= 0.0) { tr = 1; id = 1; }
     } else if constexpr (PHASE == 4) {
         dn = q > R(65000) && ae < 3.0 * (PD_PI / 180.0);
@@ -1457,7 +1493,7 @@ __device__ __forceinline__ void rtd_eval(const State &s, R g1, R u0, Rtd<R> &o) 
                 R e = (g1 - R(5.5)) / R(0.5);
                 r -= m_min(e * e, R(1));
             }
-            R prog = (R)((g_sd.y0 - s.y) / g_sd.y0);
+            R prog = (R)((sd.y0 - s.y) / sd.y0);
             R wp = (qq <= R(60000) && g1 <= R(5.5)) ? R(0.5) : R(0.5 * 0.1);
             r += wp * prog;
             if (s.y < 100.0) r += R(5.5) * (R(1) - m_abs(vy) / R(50));
@@ -1471,7 +1507,7 @@ __device__ __forceinline__ void rtd_eval(const State &s, R g1, R u0, Rtd<R> &o) 
             R ae = (R)fabs(s.gamma - s.theta - PD_PI);
             R tau = (u0 + R(1)) / R(2);
             const R lmax = R(0.29941239026616734);    // math.log(1 + math.radians(20))
-            R r = (R(1.5) - m_log(R(1) + ae) / lmax - tau * R(0.5)) * (R)(1.0 - s.y / g_sd.y0) * R(2) / R(3);
+            R r = (R(1.5) - m_log(R(1) + ae) / lmax - tau * R(0.5)) * (R)(1.0 - s.y / sd.y0) * R(2) / R(3);
             if (s.y < 100.0) r += R(1) - m_tanh((speed - R(15)) / R(15));
             if (tr && s.y < 5.0) r += R(1) - m_tanh((speed - R(5)) / R(5));
             if (dn) r += R(5);
@@ -1479,6 +1515,25 @@ __device__ __forceinline__ void rtd_eval(const State &s, R g1, R u0, Rtd<R> &o) 
         }
     }
     o.reward = reward; o.done = dn; o.truncated = tr; o.trunc_id = id;
+}
+
+// An episode cut off by the caller's step cap.  The reference has no cap (env_wrapped_ea.py:209:
+// `while not done_or_truncated`), so such a particle would fly on to a truncation; scoring the
+// partial sum (0 for the pso closures, which only pay at a terminal state) would rank a stalling
+// policy above every crashed one.  The final state is therefore scored with the closures' own
+// *truncated* branch (rtd_pso.py:222-229 / 300-316), and the rollout reports truncation id -1.
+template <typename R, int PHASE>
+__device__ __forceinline__ R cap_reward(const State &s) {
+    R vx = (R)s.vx, vy = (R)s.vy;
+    R speed = m_sqrt(vx * vx + vy * vy);
+    if (PHASE == 0) {
+        if (s.y > 0.0) return -(R)fabs(s.y);
+        if (s.y < 0.0) return R(200) - speed;
+        return R(0);
+    }
+    R over = overshoot<R>(s.x, s.y);
+    R dist = m_sqrt((R)s.x * (R)s.x + (R)s.y * (R)s.y);
+    return over < R(0.5) ? -dist : R(200) - speed;
 }
 
 // ------------------------------------------------------------------ observations
@@ -1494,13 +1549,13 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
         if constexpr (phase_ascent(PHASE)) {
             const double v[8] = {s.x, s.y, s.vx, s.vy, s.theta, s.theta_dot, s.alpha, s.mass};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = (R)(float)((double)(float)v[k] / g_sd.norm8[k]);
+            for (int k = 0; k < 8; ++k) o[k] = (R)(float)((double)(float)v[k] / sd.norm8[k]);
         } else if constexpr (PHASE == 4) {
             const double v[4] = {s.theta, s.theta_dot, s.gamma, s.alpha};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = (R)(float)((double)(float)v[k] / g_sd.norm8[k]);
+            for (int k = 0; k < 4; ++k) o[k] = (R)(float)((double)(float)v[k] / sd.norm8[k]);
         } else {
-            o[0] = (R)((1.0 - (double)(float)s.y / g_sd.norm_y) * 2 - 1);
+            o[0] = (R)((1.0 - (double)(float)s.y / sd.norm_y) * 2 - 1);
         }
         return;
     }
@@ -1519,16 +1574,16 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
         float yf = (float)s.y, vyf = (float)s.vy;
         // np.float32 scalar / np.float64 norm -> float64 arithmetic on fp32-rounded inputs
         if (PHASE == 0) {
-            o[0] = (R)((1.0 - (double)yf / g_sd.norm_y) * 2 - 1);
-            o[1] = (R)((1.0 - (double)vyf / g_sd.norm_vy) * 2 - 1);
+            o[0] = (R)((1.0 - (double)yf / sd.norm_y) * 2 - 1);
+            o[1] = (R)((1.0 - (double)vyf / sd.norm_vy) * 2 - 1);
         } else {
             float th = (float)s.theta, thd = (float)s.theta_dot, gm = (float)s.gamma;
-            o[0] = (R)((double)yf / g_sd.norm_y);
-            o[1] = (R)((double)vyf / g_sd.norm_vy);
+            o[0] = (R)((double)yf / sd.norm_y);
+            o[1] = (R)((double)vyf / sd.norm_vy);
             // np.float32 scalar (-, *) Python float stays float32 (NEP 50); math.tanh promotes
-            o[2] = (R)tanh((double)__fmul_rn(g_sf.k_theta_rl, __fsub_rn(th, (float)(PD_PI / 2))));
-            o[3] = (R)tanh((double)__fmul_rn(g_sf.k_thetadot_rl, thd));
-            o[4] = (R)tanh((double)__fmul_rn(g_sf.k_theta_rl, __fsub_rn(gm, (float)(1.5 * PD_PI))));
+            o[2] = (R)tanh((double)__fmul_rn(sf.k_theta_rl, __fsub_rn(th, (float)(PD_PI / 2))));
+            o[3] = (R)tanh((double)__fmul_rn(sf.k_thetadot_rl, thd));
+            o[4] = (R)tanh((double)__fmul_rn(sf.k_theta_rl, __fsub_rn(gm, (float)(1.5 * PD_PI))));
         }
     }
 }
@@ -1571,9 +1626,11 @@ __device__ __forceinline__ void env_step(State &s, const Action<phase_adim(PHASE
 }
 
 __device__ __forceinline__ void state_reset(State &s) {
-    const double *i = g_tb.init;
+    const double *i = tb.init;
     s.x = i[0]; s.y = i[1]; s.vx = i[2]; s.vy = i[3]; s.theta = i[4]; s.theta_dot = i[5];
     s.gamma = i[6]; s.alpha = i[7]; s.mass = i[8]; s.m_prop = i[9]; s.time = i[10];
 }
+
+};  // struct Dev
 
 }  // namespace pd

@@ -9,6 +9,15 @@ namespace pd {
 template <typename R> struct Scalars;
 struct Tables;
 struct WindCtx;
+struct KParams;
+
+// what a launch needs besides its data: the handle's constant block (passed to every kernel as a
+// __grid_constant__ parameter), the SM count of the handle's device and the device ordinal
+struct LaunchCtx {
+    const KParams *kp;
+    int n_sm;
+    int device;
+};
 
 // Per-env persistent data, field-major (SoA) so that a warp touches 32 consecutive words.
 struct EnvSoA {
@@ -39,6 +48,7 @@ struct StepIO {
 
 struct RolloutIO {
     int n_episodes, n_seeds, max_steps;
+    unsigned int generation;   // Philox episode word of the gust noise (fresh draws every generation)
     const float *wT;       // [n_params][w_stride]
     size_t w_stride;
     const void *actions;   // tape [max_steps][n_episodes][A]
@@ -62,17 +72,16 @@ struct RolloutIO {
 #define PD_CONT_I 4
 
 struct Impl {
-    int (*upload)(const Scalars<double> *, const Scalars<float> *, const Tables *);
-    void (*reset)(const EnvSoA &, const uint8_t *, const WindCtx &, const double *, cudaStream_t);
-    void (*step)(int phase, int rtd, int wind, const EnvSoA &, const StepIO &, const WindCtx &,
+    void (*reset)(const LaunchCtx &, const EnvSoA &, const uint8_t *, const WindCtx &, const double *, cudaStream_t);
+    void (*step)(const LaunchCtx &, int phase, int rtd, int wind, const EnvSoA &, const StepIO &, const WindCtx &,
                  const double *, int auto_reset, cudaStream_t);
-    int (*rollout)(int policy, int phase, int rtd, int wind, const RolloutIO &, const WindCtx &,
+    int (*rollout)(const LaunchCtx &, int policy, int phase, int rtd, int wind, const RolloutIO &, const WindCtx &,
                    const double *, int *status, cudaStream_t);
     void (*get_state)(const EnvSoA &, double *, double *, int *, double *, cudaStream_t);
     void (*set_state)(const EnvSoA &, const double *, const double *, const int *, const double *,
                       cudaStream_t);
     void (*transpose)(const float *, float *, int, int, cudaStream_t);
-    void (*observe)(int phase, int rtd, const EnvSoA &, void *obs, cudaStream_t);
+    void (*observe)(const LaunchCtx &, int phase, int rtd, const EnvSoA &, void *obs, cudaStream_t);
 };
 
 const Impl *impl_fp64();

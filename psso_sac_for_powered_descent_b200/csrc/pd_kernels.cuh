@@ -2,6 +2,10 @@
 // Included by pd_fp64.cu (R = double) and pd_fp32.cu (R = float); each TU owns its copy of
 // the __constant__ parameter blocks and exports an Impl table to pd_api.cu.
 #pragma once
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "pd_device.cuh"
 #include "pd_impl.h"
 
@@ -39,6 +43,7 @@ __device__ __forceinline__ void load_wind(const EnvSoA &e, int i, WindState &w) 
     w.xu0 = e.wst[i]; w.xu1 = e.wst[B + i]; w.xv0 = e.wst[2 * B + i]; w.xv1 = e.wst[3 * B + i];
     w.sigma_u = e.wst[4 * B + i]; w.sigma_v = e.wst[5 * B + i];
     w.ctr = e.wctr[i];
+    w.episode = e.episode[i];
 }
 __device__ __forceinline__ void store_wind(const EnvSoA &e, int i, const WindState &w) {
     const size_t B = e.n;
@@ -65,12 +70,12 @@ __device__ __forceinline__ void read_action(const void *actions, int dtype, size
 }
 
 template <int PHASE, int RTD>
-__device__ __forceinline__ void shape_action(Action<phase_adim(PHASE)> &a) {
+__device__ __forceinline__ void shape_action(const Dev &D, Action<phase_adim(PHASE)> &a) {
     if constexpr (PHASE == 5 && RTD == 1) {
         // rl_wrapped_env_pytorch.augment_action (env_wrapped_rl_pytorch.py:158-164):
         // v_ref = (u0 + 1)/2 * speed0, float32 arithmetic for a float32 action
-        if (a.f32) a.u[0] = (double)__fmul_rn(__fdiv_rn(__fadd_rn((float)a.u[0], 1.0f), 2.0f), g_sf.speed0);
-        else a.u[0] = (a.u[0] + 1.0) / 2.0 * g_sd.speed0;
+        if (a.f32) a.u[0] = (double)__fmul_rn(__fdiv_rn(__fadd_rn((float)a.u[0], 1.0f), 2.0f), D.sf.speed0);
+        else a.u[0] = (a.u[0] + 1.0) / 2.0 * D.sd.speed0;
     }
     if constexpr (PHASE == 1 && RTD == 1) {
         // np.array([...python floats...]) -> float64 action
@@ -90,7 +95,7 @@ __device__ __forceinline__ SharedTables *aligned_tables(unsigned char *raw) {
     const unsigned a = smem_addr(raw);
     return reinterpret_cast<SharedTables *>(raw + (((a + PD_SH_ALIGN - 1) & ~(PD_SH_ALIGN - 1)) - a));
 }
-__device__ __forceinline__ void stage_tables(SharedTables *sh) {
+__device__ __forceinline__ void stage_tables(SharedTables *sh, const void *image) {
     const unsigned bar = smem_addr(&sh->bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
@@ -100,7 +105,7 @@ __device__ __forceinline__ void stage_tables(SharedTables *sh) {
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PD_SH_IMAGE_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_addr(sh)), "l"(g_tb.sh_image), "r"(PD_SH_IMAGE_BYTES), "r"(bar) : "memory");
+                     ::"r"(smem_addr(sh)), "l"(image), "r"(PD_SH_IMAGE_BYTES), "r"(bar) : "memory");
     }
 }
 __device__ __forceinline__ void wait_tables(SharedTables *sh) {
@@ -135,12 +140,14 @@ static inline void big_block_config(long long lanes, int n_sm, int &threads, int
 
 // ------------------------------------------------------------------ reset kernel
 template <typename R>
-__global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const double *sigma_uv) {
+__global__ void reset_kernel(const __grid_constant__ KParams kp, EnvSoA e, const uint8_t *mask, WindCtx wc,
+                             const double *sigma_uv) {
+    Dev D(kp);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n) return;
     if (mask && !mask[i]) return;
     State s;
-    state_reset(s);
+    D.state_reset(s);
     store_state(e, i, s);
     e.gwin_n[i] = 0;
 #pragma unroll
@@ -149,7 +156,7 @@ __global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const do
     unsigned int ep = e.episode[i] + 1;
     e.episode[i] = ep;
     WindState w;
-    wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
+    D.wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
     store_wind(e, i, w);
     e.trunc_id[i] = 0;
     e.ep_steps[i] = 0;
@@ -157,14 +164,15 @@ __global__ void reset_kernel(EnvSoA e, const uint8_t *mask, WindCtx wc, const do
 
 // observation of the current state (first step of a collection run)
 template <typename R, int PHASE, int RTD>
-__global__ void observe_kernel(EnvSoA e, R *obs) {
+__global__ void observe_kernel(const __grid_constant__ KParams kp, EnvSoA e, R *obs) {
     constexpr int O = phase_odim(PHASE);
+    Dev D(kp);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n) return;
     State s;
     load_state(e, i, s);
     R o[O];
-    observe<R, PHASE, RTD>(s, o);
+    D.observe<R, PHASE, RTD>(s, o);
 #pragma unroll
     for (int k = 0; k < O; ++k) obs[(size_t)i * O + k] = o[k];
 }
@@ -176,12 +184,14 @@ __global__ void observe_kernel(EnvSoA e, R *obs) {
 #endif
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, bool FULL = false>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
-step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_reset) {
+step_kernel(const __grid_constant__ KParams kp, EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv,
+            int auto_reset) {
     constexpr int A = phase_adim(PHASE);
     constexpr int O = phase_odim(PHASE);
+    Dev D(kp);
     extern __shared__ __align__(16) unsigned char pd_smem[];
     SharedTables &sh = *aligned_tables(pd_smem);
-    stage_tables(&sh);
+    stage_tables(&sh, kp.tb.sh_image);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n) return;
     State s;
@@ -197,20 +207,20 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     if (WIND) load_wind(e, i, w);
     Action<A> act;
     read_action<A>(io.actions, io.action_dtype, (size_t)i, act);
-    if (!io.raw_actions) shape_action<PHASE, RTD>(act);
+    if (!io.raw_actions) shape_action<PHASE, RTD>(D, act);
     Info<R, FULL> info;
     info.rbf_status = 0;
     Rtd<R> out;
     R g1;
     const int ep_steps_in = e.ep_steps[i];      // issued with the other state loads, consumed at the end
     wait_tables(&sh);
-    env_step<R, RT, PHASE, RTD, WIND, 1, FULL>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
+    D.env_step<R, RT, PHASE, RTD, WIND, 1, FULL>(s, act, prev, w, wc, (unsigned)i, gw, info, out, g1, &sh);
     if constexpr (RTD == 1) {
-        if (io.supervisory) rtd_supervisory<R, PHASE>(s, g1, out);
+        if (io.supervisory) D.rtd_supervisory<R, PHASE>(s, g1, out);
     }
     if (info.rbf_status) atomicOr(e.status, info.rbf_status);
     R obs[O];
-    observe<R, PHASE, RTD>(s, obs);
+    D.observe<R, PHASE, RTD>(s, obs);
     if (io.obs) {
 #pragma unroll
         for (int k = 0; k < O; ++k) ((R *)io.obs)[(size_t)i * O + k] = obs[k];
@@ -233,16 +243,16 @@ step_kernel(EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv, int auto_re
     e.trunc_id[i] = out.trunc_id;
     int ep_steps = ep_steps_in + 1;
     if (auto_reset && (out.done || out.truncated)) {
-        state_reset(s);
+        D.state_reset(s);
         gw.n = 0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
         prev.gimbal_deg = prev.dl = prev.dr = 0.0;
         unsigned int ep = e.episode[i] + 1;
         e.episode[i] = ep;
-        if (WIND) wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
+        if (WIND) D.wind_reset(w, wc, (unsigned)i, ep, sigma_uv);
         ep_steps = 0;
-        observe<R, PHASE, RTD>(s, obs);
+        D.observe<R, PHASE, RTD>(s, obs);
     }
     if (io.next_obs) {
 #pragma unroll
@@ -333,12 +343,13 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
 // MODE 2: second pass, episodes = continuation records.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE = 0>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
-rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
+rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = phase_adim(PHASE);
     constexpr int O = phase_odim(PHASE);
+    Dev D(kp);
     extern __shared__ __align__(16) unsigned char pd_smem[];
     SharedTables &sh = *aligned_tables(pd_smem);
-    stage_tables(&sh);
+    stage_tables(&sh, kp.tb.sh_image);
     wait_tables(&sh);
     // Persistent lanes with a work queue: episode lengths are ragged (P: 101..460 steps,
     // G: 7..27), so a lane that finishes pulls the next episode index instead of idling until
@@ -372,16 +383,17 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
             prev.gimbal_deg = d[21 * cap]; prev.dl = d[22 * cap]; prev.dr = d[23 * cap];
             w.xu0 = d[24 * cap]; w.xu1 = d[25 * cap]; w.xv0 = d[26 * cap]; w.xv1 = d[27 * cap];
             w.sigma_u = d[28 * cap]; w.sigma_v = d[29 * cap];
+            w.episode = io.generation + 1u;
             total = d[30 * cap];
             info.q = R(0);
         } else {
             eid = e;
-            state_reset(s);
+            D.state_reset(s);
             gw.n = 0;
 #pragma unroll
             for (int k = 0; k < 10; ++k) gw.w[k] = R(0);
             prev.gimbal_deg = prev.dl = prev.dr = 0.0;
-            if (WIND) wind_reset(w, wc, (unsigned)eid, 1u, sigma_uv);
+            if (WIND) D.wind_reset(w, wc, (unsigned)eid, io.generation + 1u, sigma_uv);
             info.q = R(0);
             total = 0.0;
             t = 0;
@@ -395,7 +407,7 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
         bool stop = false;
         if constexpr (POLICY == 0) {
             R obs[O];
-            observe<R, PHASE, 0>(s, obs);
+            D.observe<R, PHASE, 0>(s, obs);
             float of[O], af[A];
 #pragma unroll
             for (int k = 0; k < O; ++k) of[k] = (float)obs[k];
@@ -409,14 +421,14 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
             }
         } else if constexpr (POLICY == 1) {
             read_action<A>(io.actions, io.action_dtype, (size_t)t * io.n_episodes + eid, act);
-            shape_action<PHASE, RTD>(act);
+            shape_action<PHASE, RTD>(D, act);
         } else {
             // classical P controller on v_ref(y) (landing_burn_pure_throttle.py:261-339)
             double alpha_eff = s.gamma - s.theta - PD_PI;
             stop = !(s.m_prop > 0.0 && s.y > 1.0 && (double)info.q < 65e3 && s.vy < 0.0 &&
                      alpha_eff < 5.0 * (180.0 / PD_PI));
             double speed = sqrt(s.vx * s.vx + s.vy * s.vy);
-            double v_ref = g_sd.v_opt_a * (s.y * s.y) + g_sd.v_opt_b * s.y;
+            double v_ref = D.sd.v_opt_a * (s.y * s.y) + D.sd.v_opt_b * s.y;
             double nn = -0.10 * (v_ref - speed) + 0.0;
             nn = nn < 0.0 ? 0.0 : (nn > 1.0 ? 1.0 : nn);
             act.u[0] = 2.0 * (nn - 0.5);
@@ -430,10 +442,10 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
                 Control<R> ctl;
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k)
-                    substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, (unsigned)eid, info, ctl, &sh);
+                    D.substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, (unsigned)eid, info, ctl, &sh);
             } else {
                 R g1;
-                env_step<R, RT, PHASE, RTD, WIND, COOP>(s, act, prev, w, wc, (unsigned)eid, gw, info, out, g1, &sh);
+                D.env_step<R, RT, PHASE, RTD, WIND, COOP>(s, act, prev, w, wc, (unsigned)eid, gw, info, out, g1, &sh);
             }
             total -= (double)out.reward;
             if (io.traj && writer) {
@@ -444,7 +456,15 @@ rollout_kernel(RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
             if (io.rewards && writer) io.rewards[(size_t)t * io.n_episodes + eid] = (double)out.reward;
             ++t;
             if (out.done || out.truncated) { tid = out.trunc_id; stop = true; }
-            else if (t >= io.max_steps) stop = true;
+            else if (t >= io.max_steps) {
+                stop = true;         // step cap: truncation id stays -1
+                if constexpr (POLICY == 0) {
+                    // per-particle MLP = PSO fitness: score the cut-off episode as a truncation
+                    const R rc = D.cap_reward<R, PHASE>(s);
+                    total -= (double)rc;
+                    if (io.rewards && writer) io.rewards[(size_t)(t - 1) * io.n_episodes + eid] += (double)rc;
+                }
+            }
         }
         bool handoff = false;
         if constexpr (MODE == 1) {
@@ -520,66 +540,67 @@ static __global__ void set_state_kernel(EnvSoA e, const double *state, const dou
 }
 
 // ------------------------------------------------------------------ launch tables
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of every kernel
+// instantiation: remember (kernel, device) pairs instead of one flag per process.
+static void ensure_smem(const void *kernel, int device) {
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert({kernel, device}).second)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
+}
+#define PD_SMEM_OPT_IN(kernel, lc) ensure_smem(reinterpret_cast<const void *>(&kernel), (lc).device)
+
 template <typename R, typename RT>
 struct Launch {
     template <int PHASE, int RTD, bool WIND>
-    static void step_t(const EnvSoA &e, const StepIO &io, const WindCtx &wc, const double *sig,
+    static void step_t(const LaunchCtx &lc, const EnvSoA &e, const StepIO &io, const WindCtx &wc, const double *sig,
                        int auto_reset, cudaStream_t st) {
         int threads, blocks;
-        big_block_config(e.n, 148, threads, blocks);
+        big_block_config(e.n, lc.n_sm, threads, blocks);
         if constexpr (sizeof(R) == 8 && !WIND) {
             // full-info diagnostic variant (fp64, no wind): the scalar drop-in env and the
             // trajectory export use it; never on the throughput path
             if (io.dbg_full) {
-                static bool attr_f = false;
-                if (!attr_f) {
-                    cudaFuncSetAttribute(step_kernel<R, RT, PHASE, RTD, WIND, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
-                    attr_f = true;
-                }
-                step_kernel<R, RT, PHASE, RTD, WIND, true><<<blocks, threads, PD_SH_BYTES, st>>>(e, io, wc, sig, auto_reset);
+                PD_SMEM_OPT_IN((step_kernel<R, RT, PHASE, RTD, WIND, true>), lc);
+                step_kernel<R, RT, PHASE, RTD, WIND, true><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, e, io, wc, sig, auto_reset);
                 return;
             }
         }
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(step_kernel<R, RT, PHASE, RTD, WIND>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
-            attr = true;
-        }
-        step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, PD_SH_BYTES, st>>>(e, io, wc, sig, auto_reset);
+        PD_SMEM_OPT_IN((step_kernel<R, RT, PHASE, RTD, WIND>), lc);
+        step_kernel<R, RT, PHASE, RTD, WIND><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, e, io, wc, sig, auto_reset);
     }
-    static void step(int phase, int rtd, int wind, const EnvSoA &e, const StepIO &io,
+    static void step(const LaunchCtx &lc, int phase, int rtd, int wind, const EnvSoA &e, const StepIO &io,
                      const WindCtx &wc, const double *sig, int auto_reset, cudaStream_t st) {
         int key = phase * 4 + rtd * 2 + (wind ? 1 : 0);
         switch (key) {
-            case 0: step_t<0, 0, false>(e, io, wc, sig, auto_reset, st); break;
-            case 1: step_t<0, 0, true>(e, io, wc, sig, auto_reset, st); break;
-            case 2: step_t<0, 1, false>(e, io, wc, sig, auto_reset, st); break;
-            case 3: step_t<0, 1, true>(e, io, wc, sig, auto_reset, st); break;
-            case 4: step_t<1, 0, false>(e, io, wc, sig, auto_reset, st); break;
-            case 5: step_t<1, 0, true>(e, io, wc, sig, auto_reset, st); break;
-            case 6: step_t<1, 1, false>(e, io, wc, sig, auto_reset, st); break;
-            case 7: step_t<1, 1, true>(e, io, wc, sig, auto_reset, st); break;
-            // phases 2..5 exist with the rl closures only (pd_create rejects type 'pso')
-            case 10: step_t<2, 1, false>(e, io, wc, sig, auto_reset, st); break;
-            case 11: step_t<2, 1, true>(e, io, wc, sig, auto_reset, st); break;
-            case 14: step_t<3, 1, false>(e, io, wc, sig, auto_reset, st); break;
-            case 15: step_t<3, 1, true>(e, io, wc, sig, auto_reset, st); break;
-            case 18: step_t<4, 1, false>(e, io, wc, sig, auto_reset, st); break;
-            case 19: step_t<4, 1, true>(e, io, wc, sig, auto_reset, st); break;
-            case 22: step_t<5, 1, false>(e, io, wc, sig, auto_reset, st); break;
-            default: step_t<5, 1, true>(e, io, wc, sig, auto_reset, st); break;
+            case 0: step_t<0, 0, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 1: step_t<0, 0, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 2: step_t<0, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 3: step_t<0, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 4: step_t<1, 0, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 5: step_t<1, 0, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 6: step_t<1, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 7: step_t<1, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            // phases 2..6 exist with the rl closures only (pd_create rejects type 'pso')
+            case 10: step_t<2, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 11: step_t<2, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 14: step_t<3, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 15: step_t<3, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 18: step_t<4, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 19: step_t<4, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 22: step_t<5, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            default: step_t<5, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
         }
     }
     template <int PHASE, int RTD, bool WIND, int POLICY>
-    static void roll_t(const RolloutIO &io, const WindCtx &wc, const double *sig, int *status,
+    static void roll_t(const LaunchCtx &lc, const RolloutIO &io, const WindCtx &wc, const double *sig, int *status,
                        cudaStream_t st) {
-        // A persistent grid (at most 8 blocks of 64 lanes per SM at 128 registers) fed by the
-        // work queue.  Fewer episodes than ~1/4 of the GPU's lanes: 8 lanes co-operate on each
-        // episode (splits the 100 RBF terms per sub-step), which both fills the SMs and cuts the
-        // per-step latency that bounds a generation by its longest episode.
-        const int n_sm = 148;
+        // A persistent grid (one block per SM) fed by the work queue.  Fewer episodes than ~3/4 of
+        // the GPU's lanes / 8: 8 lanes co-operate on each episode (splits the 100 RBF terms per
+        // sub-step), which both fills the SMs and cuts the per-step latency that bounds a
+        // generation by its longest episode.
+        const int n_sm = lc.n_sm;
         const bool coop = (long long)io.n_episodes * 8 <= (long long)n_sm * PD_MAX_BLOCK * 3 / 4;
         const int lanes_per = coop ? 8 : 1;
         long long lanes = (long long)io.n_episodes * lanes_per;
@@ -587,71 +608,59 @@ struct Launch {
         big_block_config(lanes, n_sm, threads, blocks);
         if (blocks > n_sm) blocks = n_sm;              // persistent: the queue feeds the rest
         init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads / lanes_per);
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
-            cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
-            attr = true;
-        }
         if (coop) {
-            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
+            PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8>), lc);
+            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
             return;
         }
         if constexpr (POLICY == 0) {
             if (io.handoff_steps > 0 && io.handoff_steps < io.max_steps && io.cont_d && io.cont_i && io.cont_count) {
                 // two passes: one lane per episode up to handoff_steps, then the stragglers (about
                 // 1 % of a random swarm) 8 lanes each
-                static bool attr2 = false;
-                if (!attr2) {
-                    cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
-                    cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SH_BYTES);
-                    attr2 = true;
-                }
+                PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1>), lc);
+                PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2>), lc);
                 cudaMemsetAsync(io.cont_count, 0, sizeof(int), st);
-                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
+                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
                 const int b2 = n_sm, t2 = PD_MAX_BLOCK;
                 init_queue_kernel<<<1, 1, 0, st>>>(io.queue, b2 * t2 / 8);
-                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2><<<b2, t2, PD_SH_BYTES, st>>>(io, wc, sig, status);
+                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2><<<b2, t2, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
                 return;
             }
         }
-        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, PD_SH_BYTES, st>>>(io, wc, sig, status);
+        PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1>), lc);
+        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
     }
-    static int rollout(int policy, int phase, int rtd, int wind, const RolloutIO &io,
+    static int rollout(const LaunchCtx &lc, int policy, int phase, int rtd, int wind, const RolloutIO &io,
                        const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {
         if (phase > 1) return 1;    // whole-episode rollouts: the two landing phases
         if (policy == 0) {          // per-particle MLP: pso rtd only
             int key = phase * 2 + (wind ? 1 : 0);
             switch (key) {
-                case 0: roll_t<0, 0, false, 0>(io, wc, sig, status, st); break;
-                case 1: roll_t<0, 0, true, 0>(io, wc, sig, status, st); break;
-                case 2: roll_t<1, 0, false, 0>(io, wc, sig, status, st); break;
-                default: roll_t<1, 0, true, 0>(io, wc, sig, status, st); break;
+                case 0: roll_t<0, 0, false, 0>(lc, io, wc, sig, status, st); break;
+                case 1: roll_t<0, 0, true, 0>(lc, io, wc, sig, status, st); break;
+                case 2: roll_t<1, 0, false, 0>(lc, io, wc, sig, status, st); break;
+                default: roll_t<1, 0, true, 0>(lc, io, wc, sig, status, st); break;
             }
             return 0;
         }
         if (policy == 1) {
             int key = phase * 4 + rtd * 2 + (wind ? 1 : 0);
             switch (key) {
-                case 0: roll_t<0, 0, false, 1>(io, wc, sig, status, st); break;
-                case 1: roll_t<0, 0, true, 1>(io, wc, sig, status, st); break;
-                case 2: roll_t<0, 1, false, 1>(io, wc, sig, status, st); break;
-                case 3: roll_t<0, 1, true, 1>(io, wc, sig, status, st); break;
-                case 4: roll_t<1, 0, false, 1>(io, wc, sig, status, st); break;
-                case 5: roll_t<1, 0, true, 1>(io, wc, sig, status, st); break;
-                case 6: roll_t<1, 1, false, 1>(io, wc, sig, status, st); break;
-                default: roll_t<1, 1, true, 1>(io, wc, sig, status, st); break;
+                case 0: roll_t<0, 0, false, 1>(lc, io, wc, sig, status, st); break;
+                case 1: roll_t<0, 0, true, 1>(lc, io, wc, sig, status, st); break;
+                case 2: roll_t<0, 1, false, 1>(lc, io, wc, sig, status, st); break;
+                case 3: roll_t<0, 1, true, 1>(lc, io, wc, sig, status, st); break;
+                case 4: roll_t<1, 0, false, 1>(lc, io, wc, sig, status, st); break;
+                case 5: roll_t<1, 0, true, 1>(lc, io, wc, sig, status, st); break;
+                case 6: roll_t<1, 1, false, 1>(lc, io, wc, sig, status, st); break;
+                default: roll_t<1, 1, true, 1>(lc, io, wc, sig, status, st); break;
             }
             return 0;
         }
         if (policy == 2) {
             if (phase != 0) return 1;
-            if (wind) roll_t<0, 0, true, 2>(io, wc, sig, status, st);
-            else roll_t<0, 0, false, 2>(io, wc, sig, status, st);
+            if (wind) roll_t<0, 0, true, 2>(lc, io, wc, sig, status, st);
+            else roll_t<0, 0, false, 2>(lc, io, wc, sig, status, st);
             return 0;
         }
         return 1;
@@ -659,26 +668,27 @@ struct Launch {
 };
 
 template <typename R>
-static void impl_observe(int phase, int rtd, const EnvSoA &e, void *obs, cudaStream_t st) {
+static void impl_observe(const LaunchCtx &lc, int phase, int rtd, const EnvSoA &e, void *obs, cudaStream_t st) {
     int threads = 128, blocks = (e.n + threads - 1) / threads;
+    const KParams &kp = *lc.kp;
     int key = phase * 2 + rtd;
     switch (key) {
-        case 0: observe_kernel<R, 0, 0><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        case 1: observe_kernel<R, 0, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        case 2: observe_kernel<R, 1, 0><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        case 3: observe_kernel<R, 1, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        case 5: observe_kernel<R, 2, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        case 7: observe_kernel<R, 3, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        case 9: observe_kernel<R, 4, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
-        default: observe_kernel<R, 5, 1><<<blocks, threads, 0, st>>>(e, (R *)obs); break;
+        case 0: observe_kernel<R, 0, 0><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        case 1: observe_kernel<R, 0, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        case 2: observe_kernel<R, 1, 0><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        case 3: observe_kernel<R, 1, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        case 5: observe_kernel<R, 2, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        case 7: observe_kernel<R, 3, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        case 9: observe_kernel<R, 4, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        default: observe_kernel<R, 5, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
     }
 }
 
 template <typename R, typename RT>
-static void impl_reset(const EnvSoA &e, const uint8_t *mask, const WindCtx &wc, const double *sig,
+static void impl_reset(const LaunchCtx &lc, const EnvSoA &e, const uint8_t *mask, const WindCtx &wc, const double *sig,
                        cudaStream_t st) {
     int threads = 128, blocks = (e.n + threads - 1) / threads;
-    reset_kernel<R><<<blocks, threads, 0, st>>>(e, mask, wc, sig);
+    reset_kernel<R><<<blocks, threads, 0, st>>>(*lc.kp, e, mask, wc, sig);
 }
 
 static void impl_get_state(const EnvSoA &e, double *state, double *gwin, int *nwin, double *aprev,
@@ -695,11 +705,4 @@ static void impl_transpose(const float *w, float *wT, int n_particles, int n_par
     dim3 grid((n_particles + 31) / 32, (n_params + 31) / 32), block(32, 8);
     transpose_weights_kernel<<<grid, block, 0, st>>>(w, wT, n_particles, n_params);
 }
-static int impl_upload(const Scalars<double> *sd, const Scalars<float> *sf, const Tables *tb) {
-    if (cudaMemcpyToSymbol(g_sd, sd, sizeof(*sd)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(g_sf, sf, sizeof(*sf)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(g_tb, tb, sizeof(*tb)) != cudaSuccess) return 1;
-    return 0;
-}
-
 }  // namespace pd

@@ -127,6 +127,7 @@ class BatchedRocketEnv:
         self.next_obs = torch.empty(B, self.obs_dim, dtype=self.dtype, device=dev)
         self._tape = self._sigma = None
         self._host = None
+        self._dirty = True      # device-side calls since the last step_host (stream ordering)
 
     def __del__(self):
         try:
@@ -143,6 +144,7 @@ class BatchedRocketEnv:
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         N.check(self.lib.pd_reset(self._h, _ptr(mask), _stream()))
+        self._dirty = True
         return self.get_state()
 
     def step(self, actions: torch.Tensor, dbg: torch.Tensor | None = None, _out=None):
@@ -155,6 +157,7 @@ class BatchedRocketEnv:
         if a.device != self.device and not a.is_pinned():
             raise ValueError("actions must live on the env's device")
         obs, reward, done, truncated = _out or (self.obs, self.reward, self.done, self.truncated)
+        self._dirty = True
         N.check(self.lib.pd_step(self._h, _ptr(a), 1 if a.dtype == torch.float32 else 0,
                                  _ptr(obs), _ptr(reward), _ptr(done),
                                  _ptr(truncated), _ptr(self.trunc_id), _ptr(self.next_obs),
@@ -202,7 +205,6 @@ class BatchedRocketEnv:
                                                               h["stream"].cuda_stream)
             with torch.cuda.stream(h["stream"]) if mode != "zc_all" else contextlib.nullcontext():
                 if mode == "zc_all":
-                    N.check(self.lib.pd_activate(self._h))
                     self._host = h
                     return self.step_host(actions)
 
@@ -213,7 +215,6 @@ class BatchedRocketEnv:
                     else:       # the kernel stores its results straight into mapped pinned memory
                         self.step(h["act_dev"], _out=pinned_out)
                 h["act_dev"].zero_()
-                N.check(self.lib.pd_activate(self._h))      # not allowed inside a capture
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=h["stream"]):
@@ -221,6 +222,10 @@ class BatchedRocketEnv:
                 h["graph"] = g
             self._host = h
         h = self._host
+        if self._dirty:
+            # reset() / step() / set_state() / collect() run on torch's current stream and return
+            # without synchronising; the host step runs on the handle's own stream: order it after them
+            h["stream"].wait_stream(torch.cuda.current_stream())
         if h["mode"] == "zc_all":
             # lean path: one ctypes call with cached pointers on the handle's own stream
             if not (a.is_pinned() and a.is_contiguous()):
@@ -232,17 +237,18 @@ class BatchedRocketEnv:
             else:
                 N.check(self.lib.pd_step(self._h, a.data_ptr(), h["act_code"], *h["ptrs"]))
             h["stream"].synchronize()
+            self._dirty = False
             return h["views"]
         if a.is_pinned() and a.is_contiguous():
             src = a
         else:
             h["act_pin"].copy_(a)
             src = h["act_pin"]
-        N.check(self.lib.pd_activate(self._h))
         with torch.cuda.stream(h["stream"]):
             h["act_dev"].copy_(src, non_blocking=True)
             h["graph"].replay()
         h["stream"].synchronize()
+        self._dirty = False
         return h["views"]
 
     # ------------------------------------------------------------------ state access
@@ -269,6 +275,7 @@ class BatchedRocketEnv:
         nw = prep(n_window, torch.int32, (B,))
         ap = prep(act_prev, torch.float64, (B, 3))
         N.check(self.lib.pd_set_state(self._h, _ptr(st), _ptr(gw), _ptr(nw), _ptr(ap), _stream()))
+        self._dirty = True
         torch.cuda.current_stream().synchronize()
 
     def set_wind_tape(self, tape, sigma_uv):
@@ -287,11 +294,15 @@ class BatchedRocketEnv:
 
     # ------------------------------------------------------------------ rollouts
     def rollout_pso(self, weights: torch.Tensor, n_seeds=1, max_steps=4096, terminal=False,
-                    trace=False):
+                    trace=False, index0=0, generation=0):
         """weights: cuda float32 [n_particles, n_params].  Returns fitness (float64
         [n_particles*n_seeds]), steps, trunc_id (, terminal_state).  trace=True returns a dict
-        with the per-step states / actions / rewards as well."""
+        with the per-step states / actions / rewards as well.  index0 / generation select the
+        gust-noise stream (pd_set_rollout_stream): global index of the first particle of this
+        call and the PSO generation.  An episode that reaches max_steps has trunc_id -1 and is
+        scored as a truncation at its final state."""
         w = weights.to(device=self.device, dtype=torch.float32).contiguous()
+        N.check(self.lib.pd_set_rollout_stream(self._h, int(index0), int(generation) & 0xFFFFFFFF))
         n, p = w.shape
         E = n * n_seeds
         fit = torch.empty(E, dtype=torch.float64, device=self.device)
@@ -396,6 +407,7 @@ class BatchedRocketEnv:
                        truncated=torch.empty(T, B, dtype=torch.uint8, device=dev))
             if next_obs:
                 out["next_obs"] = torch.empty(T, B, self.obs_dim, dtype=torch.float32, device=dev)
+        self._dirty = True
         N.check(self.lib.pd_collect_shared_actor(self._h, C.byref(a), T, _ptr(out["obs"]), _ptr(out["actions"]),
                                                  _ptr(out["rewards"]), _ptr(out["done"]), _ptr(out["truncated"]),
                                                  _ptr(out.get("next_obs")), _stream()))
@@ -582,6 +594,7 @@ class pso_wrapped_env:
             self.actor = simple_actor_spec(5, 4, 4, 8)
         self.mock_dictionary_of_opt_params, self.bounds = self.actor.return_setup_vals()
         self.max_steps = max_steps
+        self.capped, self.warn_on_cap = 0, True
         self.experience_buffer = []
         self.episode_idx = 0
         self._individual = None
@@ -597,11 +610,23 @@ class pso_wrapped_env:
     def reset(self):
         self.experience_buffer = []
 
-    def evaluate(self, positions, n_seeds=1, terminal=False):
-        w = np.asarray(positions, dtype=np.float64).reshape(-1, self.actor.number_of_network_parameters)
-        wt = torch.as_tensor(w.astype(np.float32)).to(self._b.device)
-        out = self._b.rollout_pso(wt, n_seeds=n_seeds, max_steps=self.max_steps, terminal=terminal)
+    def evaluate(self, positions, n_seeds=1, terminal=False, index0=0, generation=0):
+        """Batched objective_function: positions [n, P] (numpy / list, or a cuda float32 tensor that is
+        used where it is) -> (fitness[n*n_seeds], steps, trunc_id [, terminal_state]) device tensors.
+        `self.capped` = number of episodes of this call that hit max_steps (trunc_id -1)."""
+        if isinstance(positions, torch.Tensor) and positions.is_cuda:
+            wt = positions.reshape(-1, self.actor.number_of_network_parameters)
+        else:
+            w = np.asarray(positions, dtype=np.float64).reshape(-1, self.actor.number_of_network_parameters)
+            wt = torch.as_tensor(w.astype(np.float32)).to(self._b.device)
+        out = self._b.rollout_pso(wt, n_seeds=n_seeds, max_steps=self.max_steps, terminal=terminal,
+                                  index0=index0, generation=generation)
         self._b.check_status()
+        self.capped = int((out[2] < 0).sum())
+        if self.capped and self.warn_on_cap:
+            import warnings
+            warnings.warn(f"{self.capped} episode(s) reached max_steps={self.max_steps} and were scored as "
+                          "truncated at their final state (the reference has no step cap)", RuntimeWarning)
         return out
 
     def objective_function(self, individual):

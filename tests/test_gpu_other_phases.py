@@ -86,7 +86,26 @@ def test_single_step_fp32(envs_mod, golden, tag):
     assert err.max() < 1e-5, (int(err.argmax()), err.max())
     same = (done.cpu().numpy() == ref[:, 12]) & (trunc.cpu().numpy() == ref[:, 13]) & \
         (tid.cpu().numpy() == ref[:, 14])
-    assert same.mean() > 0.97
+    # flags: exact.  A row may differ only if the REFERENCE's own verdict on it is unstable under a
+    # perturbation of the input state of the size of the fp32 build's tolerance (1e-5 relative with
+    # the per-component floors): the reference-exact fp64 build is run on 48 such perturbations of
+    # every mismatching row and must itself return both verdicts.
+    bad = np.nonzero(~same)[0]
+    print(f"fp32 single step {tag}: {len(bad)} of {len(same)} fixture rows differ in a flag")
+    if len(bad):
+        K = 48
+        rng = np.random.default_rng(0)
+        st0 = np.repeat(g["state"][bad], K, axis=0)
+        pert = st0 + 1e-5 * np.maximum(np.abs(st0), FLOOR[phase]) * rng.uniform(-1, 1, st0.shape)
+        e64 = envs_mod.BatchedRocketEnv(len(pert), "rl", phase, precision="fp64", trajectory_length=1000,
+                                        discount_factor=0.99, raw_actions=True)
+        e64.set_state(pert, np.repeat(g["win"][bad], K, axis=0), np.repeat(g["nwin"][bad], K).astype(np.int32),
+                      np.zeros((len(pert), 3)))
+        _, _, d2, t2, i2 = e64.step(torch.as_tensor(np.repeat(g["act32"][bad], K, axis=0)).cuda())
+        v = np.stack([d2.cpu().numpy(), t2.cpu().numpy(), i2.cpu().numpy()], 1).reshape(len(bad), K, 3)
+        for n, k in enumerate(bad):
+            assert len({tuple(x) for x in v[n].tolist()}) > 1, \
+                f"row {k}: fp32 flags differ from the reference's and the row is not near any threshold"
     r = rew.cpu().numpy().astype(float)
     assert np.max(np.abs(r - ref[:, 11])[same] / np.maximum(np.abs(ref[:, 11][same]), 1.0)) < 1e-5
 

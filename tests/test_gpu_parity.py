@@ -91,10 +91,20 @@ def test_single_step_vs_reference_fp32(envs_mod, golden, tag, phase):
     ref = g["o32"]
     err = state_err(st, ref[:, :11], phase)
     assert err.max() < 1e-5, (err.argmax(), err.max())
-    # flags: exact wherever the fp64 quantity is not within fp32 resolution of a threshold
-    same = (done.cpu().numpy() == ref[:, 12]) & (trunc.cpu().numpy() == ref[:, 13]) & \
-        (tid.cpu().numpy() == ref[:, 14])
-    assert same.mean() > 0.98
+    # flags: exact.  A row may only differ if one of the closures' thresholded quantities of the
+    # REFERENCE's next state (y, q - 65 kPa, speed - 5.5, g - 6, vy, theta - theta_lim, m_prop ...)
+    # lies within the fp32 build's own 1e-5 state tolerance of its threshold; any other mismatch fails.
+    d, t, i = done.cpu().numpy(), trunc.cpu().numpy(), tid.cpu().numpy()
+    same = (d == ref[:, 12]) & (t == ref[:, 13]) & (i == ref[:, 14])
+    from oracle import pd_oracle as O
+    from psso_sac_for_powered_descent_b200.parity import threshold_margins
+    jg = list(g["out_cols"]).index("g1")
+    for k in np.nonzero(~same)[0]:
+        m = threshold_margins(phase, "pso", ref[k, :11], ref[k, jg], O.isa(ref[k, 1])[0])
+        key = min(m, key=m.get)
+        assert m[key] < 1e-5, (f"row {k}: flags {(d[k], t[k], i[k])} vs reference {tuple(ref[k, 12:15])} with no "
+                               f"threshold nearby (nearest: {key}, margin {m[key]:.2e})")
+    print(f"fp32 single step {tag}: {int((~same).sum())} of {len(same)} fixture rows differ in a flag")
     ok = same
     r = rew.cpu().numpy().astype(float)
     assert np.max(np.abs(r - ref[:, 11])[ok] / np.maximum(np.abs(ref[:, 11][ok]), 1.0)) < 1e-5
@@ -145,6 +155,122 @@ def test_pso_fitness_vs_reference(envs_mod, golden, tag, phase, precision):
         assert np.mean(steps[wc] == g["steps"][wc]) >= 0.8
         ok = wc & (steps == g["steps"])
         assert np.max(np.abs(fit - g["fitness"])[ok] / np.abs(g["fitness"][ok])) < 1e-3
+
+
+@pytest.mark.parametrize("tag,phase", [("P", P), ("G", G)])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_pso_many_particles_vs_reference(envs_mod, golden, tag, phase, precision):
+    """256 random particles per phase through the unmodified reference's objective_function
+    (tools/make_golden.py pso_fitness_many): episode length, truncation id and fitness.
+    Particles whose episode changes length when every action is nudged by one float32 ulp IN THE
+    REFERENCE are ill-conditioned for any implementation whose fp32 MLP rounds differently from
+    torch-CPU; the stated agreement numbers are asserted on the well-conditioned ones and printed
+    for all."""
+    g = golden(f"pso_many_{tag}.npz")
+    model = envs_mod.pso_wrapped_env(flight_phase=phase, precision=precision)
+    fit, steps, tid, term = model.evaluate(g["positions"], terminal=True)
+    fit, steps, tid = fit.cpu().numpy(), steps.cpu().numpy(), tid.cpu().numpy()
+    wc = g["well_conditioned"].astype(bool)
+    assert wc.sum() >= 200
+    same_len = steps == g["steps"]
+    same_id = tid == g["trunc_id"]
+    rel = np.abs(fit - g["fitness"]) / np.maximum(np.abs(g["fitness"]), 1.0)
+    print(f"pso_many {tag} {precision}: same length {same_len.mean():.4f} (well-conditioned "
+          f"{same_len[wc].mean():.4f}), same id {same_id[wc].mean():.4f}, max fitness rel err on "
+          f"same-length well-conditioned {rel[wc & same_len].max():.2e}")
+    assert np.isfinite(fit).all() and (tid >= 0).all()
+    if precision == "fp64":
+        # the fp64 build differs from the reference only by the fp32 MLP summation order
+        assert same_len[wc].mean() >= 0.99 and same_id[wc].mean() >= 0.99
+        assert rel[wc & same_len].max() < 1e-4
+    else:
+        # production build: stated agreement on >= 200 well-conditioned particles per phase
+        # (landing_burn fitness evaluations run the fp64 instantiation in every handle: a phase
+        # whose pitch channel amplifies ~50x per step turns fp32 rounding into episode lengths)
+        assert same_len[wc].mean() >= 0.99, same_len[wc].mean()
+        assert same_id[wc & same_len].all()
+        assert rel[wc & same_len].max() < 1e-3
+
+
+@pytest.mark.parametrize("tag,phase", [("P", P), ("G", G)])
+@pytest.mark.parametrize("key,dtype", [("f64", torch.float64), ("f32", torch.float32)])
+def test_batch_tape_vs_reference(envs_mod, golden, tag, phase, key, dtype):
+    """SURVEY 8(d) config-2 parity subset: 1 024 envs x 64 steps of random actions from reset through
+    the UNMODIFIED reference env (committed fixture, float64 tape and the same values as float32),
+    against the fp64 build: every step's flags and reward, states at steps 1, 2, 4, ..., 64."""
+    g = golden(f"batch_tape_{tag}.npz")
+    acts = torch.as_tensor(g["actions"]).to(dtype).cuda()          # [E, T, A]
+    E, T, A = acts.shape
+    env = envs_mod.BatchedRocketEnv(E, "pso", phase, precision="fp64")
+    out = env.rollout_tape(acts.permute(1, 0, 2).contiguous(), record=True)
+    env.check_status()
+    steps_ref, flags_ref = g[f"steps_{key}"], g[f"flags_{key}"]
+    steps = out["steps"].cpu().numpy()
+    tid = out["trunc_id"].cpu().numpy()
+    traj = out["traj"].cpu().numpy()                                # [T, E, 11]
+    rew = out["rewards"].cpu().numpy()                              # [T, E]
+    ended_ref = steps_ref < T
+    same_len = steps == steps_ref
+    # G under random actions is chaotic: its pitch channel amplifies a perturbation ~50x per 0.4 s
+    # env step, so a 1e-13 rounding difference (another libm) decides some episode lengths after
+    # 8+ steps - the reference's own float32 and float64 tapes end 21 % of these episodes at
+    # different steps.  The bulk must agree; flags are compared wherever the final state still does.
+    need = 0.999 if phase == P else 0.90
+    assert same_len.mean() >= need, same_len.mean()
+    last_id = flags_ref[np.arange(E), steps_ref - 1, 2]
+    term_ok = same_len & (state_err(out["terminal"].cpu().numpy(), g[f"last_{key}"], phase) < 1e-6)
+    assert term_ok.mean() >= (0.999 if phase == P else 0.80), term_ok.mean()
+    assert np.array_equal(np.where(ended_ref, last_id, -1)[term_ok], tid[term_ok])
+    # the first 4 steps are pinned for every env (before the chaos has had time to act)
+    for j, k in enumerate(g["keep_steps"][:3]):
+        live = steps_ref > k
+        e4 = state_err(traj[k][live], g[f"states_{key}"][:, j][live], phase)
+        assert e4.max() < (1e-10 if phase == P else 1e-8), (k, e4.max())
+        fl = flags_ref[:, k]
+        assert np.array_equal(fl[live & (steps > k), 0] + fl[live & (steps > k), 1] > 0,
+                              (steps == k + 1)[live & (steps > k)])
+    worst = np.zeros(E)
+    for j, k in enumerate(g["keep_steps"]):
+        ref = g[f"states_{key}"][:, j]
+        live = same_len & (steps_ref > k)
+        if live.any():
+            worst[live] = np.maximum(worst[live], state_err(traj[k][live], ref[live], phase))
+    live = same_len
+    ridx = np.minimum(steps_ref, T) - 1
+    rr = g[f"rewards_{key}"][np.arange(E), ridx]
+    rerr = np.abs(rew[ridx, np.arange(E)] - rr) / np.maximum(np.abs(rr), 1.0)
+    w = np.sort(worst[same_len])
+    print(f"batch tape {tag} {key}: same length {same_len.mean():.4f}; state err median {w[len(w) // 2]:.2e} "
+          f"p99 {w[int(0.99 * len(w))]:.2e} max {w[-1]:.2e}; terminal reward err max {rerr[live].max():.2e}")
+    # 64 steps = 256 sub-steps of growth on the 1e-12 single-step bar; the aero interpolant is
+    # discontinuous (a neighbour-set boundary crossed one sub-step earlier separates two
+    # trajectories by ~1e-5) and the pitch channel is unstable: the bulk stays tight, none blows up
+    assert w[len(w) // 2] < (1e-9 if phase == P else 1e-4), w[len(w) // 2]
+    assert w[int(0.99 * len(w))] < (1e-5 if phase == P else 1.0)
+
+
+@pytest.mark.parametrize("phase,n_steps", [(P, 1000), (G, 200)])
+def test_fp32_vs_fp64_config2_tape(phase, n_steps):
+    """BASELINE config 2 at full size (65 536 envs, random float32 actions, auto-reset) through the
+    fp32 production build and the oracle-pinned fp64 build in lock step: termination-flag and
+    episode-length agreement, with the conditioning baseline (fp64 vs fp64 under a 1-ulp action
+    nudge) measured beside it.  Every recorded P disagreement must sit on a threshold."""
+    from psso_sac_for_powered_descent_b200 import parity
+    r = parity.fp32_vs_fp64_tape(65536, n_steps, phase=phase)
+    b = parity.fp32_vs_fp64_tape(65536, n_steps, phase=phase, test="ulp")
+    print({k: r[k] for k in ("flag_match_frac", "episode_same_length_frac", "episodes", "flag_mismatches",
+                             "max_translational_err")},
+          "baseline", {k: b[k] for k in ("flag_match_frac", "episode_same_length_frac", "flag_mismatches")})
+    if phase == P:
+        assert r["flag_match_frac"] >= 0.99999 and r["episode_same_length_frac"] >= 0.9995
+        for rec in r["first_mismatches"]:
+            if "margin" in rec:
+                assert rec["margin"] < 1e-5, rec
+    else:
+        # chaotic phase: a 1-ulp action change alone alters > 10 % of the episode lengths; the fp32
+        # build must stay within a factor 3 of that intrinsic disagreement
+        assert (1 - r["episode_same_length_frac"]) <= 3.0 * (1 - b["episode_same_length_frac"]) + 0.01
+        assert r["flag_match_frac"] >= 0.95
 
 
 def test_pso_best_actor_known_answer(envs_mod, golden):

@@ -210,6 +210,134 @@ def pso_fitness(phase, tag, n=12, seed=0):
     print("pso_fitness", tag, "fitness", np.round(fit, 3), "steps", steps, "tid", tid, "well-conditioned", cond)
 
 
+def _pso_many_worker(args):
+    """One particle through the reference's own objective_function (fresh model state per call),
+    plus the +-1-ulp action conditioning probe of pso_fitness()."""
+    phase, p_, probe = args
+    from src.envs.pso.env_wrapped_ea import pso_wrapped_env
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    g = globals()
+    key = ("_many_model", phase)
+    if key not in g:
+        g[key] = (quiet(pso_wrapped_env, flight_phase=phase, enable_wind=False),
+                  quiet(rocket_environment_pre_wrap, type="pso", flight_phase=phase, enable_wind=False))
+    model, env = g[key]
+    model.reset()
+    model.individual_update_model(p_)
+    obs = model.env.reset()
+    acts, tot = [], 0.0
+    while True:
+        a = model.actor.forward(obs)
+        acts.append(a.detach().numpy().copy())
+        obs, r, dn, tr, info = quiet(model.env.step, a)
+        tot -= r
+        if dn or tr:
+            break
+    f, n = float(tot), len(acts)
+    tid = model.env.truncation_id()
+    term = [float(v) for v in model.env.env.state]
+    ok = True
+    if probe:
+        for direction in (2.0, -2.0):
+            env.reset()
+            t2, k = 0.0, 0
+            for a in acts:
+                a2 = np.nextafter(a.astype(np.float32), np.float32(direction)).astype(np.float32)
+                s_, r, dn, tr, info = quiet(env.step, a2)
+                t2 -= r; k += 1
+                if dn or tr:
+                    break
+            if k != n or not (dn or tr) or abs(t2 - f) > 1e-6 * abs(f):
+                ok = False
+    return f, n, tid, term, ok
+
+
+def pso_fitness_many(phase, tag, n=256, seed=100, procs=None):
+    """>= 256 randomly initialised particles per phase through the unmodified reference
+    (objective_function semantics, Pool over particles as parallel_evaluate does): fitness, episode
+    length, truncation id, terminal state and the +-1-ulp conditioning flag.  Pins the step-count
+    agreement of the fp32 production build with a stated number."""
+    import multiprocessing as mp
+    import torch
+    torch.set_num_threads(1)        # forked workers: no OpenMP pool to inherit
+    from src.envs.pso.env_wrapped_ea import pso_wrapped_env
+    model = quiet(pso_wrapped_env, flight_phase=phase, enable_wind=False)
+    random.seed(seed)
+    pos = [np.array([random.uniform(b[0], b[1]) for b in model.bounds]) for _ in range(n)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs or os.cpu_count()) as pool:
+        res = pool.map(_pso_many_worker, [(phase, p_, True) for p_ in pos], chunksize=4)
+    np.savez_compressed(os.path.join(OUT, f"pso_many_{tag}.npz"), positions=np.array(pos),
+                        fitness=np.array([r[0] for r in res]), steps=np.array([r[1] for r in res]),
+                        trunc_id=np.array([r[2] for r in res]), terminal_state=np.array([r[3] for r in res]),
+                        well_conditioned=np.array([r[4] for r in res]), seed=seed)
+    st = np.array([r[1] for r in res])
+    print("pso_many", tag, n, "particles; steps min/median/max", st.min(), int(np.median(st)), st.max(),
+          "well-conditioned", int(sum(r[4] for r in res)), "ids",
+          np.unique([r[2] for r in res], return_counts=True))
+
+
+BATCH_KEEP = (0, 1, 3, 7, 15, 31, 63)
+
+
+def _batch_tape_worker(args):
+    phase, acts32, use32 = args
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    g = globals()
+    key = ("_batch_env", phase)
+    if key not in g:
+        g[key] = quiet(rocket_environment_pre_wrap, type="pso", flight_phase=phase, enable_wind=False)
+    env = g[key]
+    env.reset()
+    T = len(acts32)
+    flags = np.zeros((T, 3), np.int8)
+    rew = np.zeros(T)
+    kept = np.full((len(BATCH_KEEP), 11), np.nan)
+    n = 0
+    last = None
+    for k in range(T):
+        a = acts32[k] if use32 else acts32[k].astype(np.float64)
+        s, r, d, t, info = quiet(env.step, a)
+        flags[k] = (int(d), int(t), int(env.truncation_id))
+        rew[k] = float(r)
+        last = [float(v) for v in s]
+        if k in BATCH_KEEP:
+            kept[BATCH_KEEP.index(k)] = last
+        n = k + 1
+        if d or t:
+            break
+    return flags, rew, kept, n, last
+
+
+def batch_tape(phase, tag, n_envs=1024, n_steps=64, seed=200, procs=None):
+    """SURVEY 8(d) config-2 parity subset: n_envs x n_steps random U(-1,1) actions from reset through
+    the unmodified reference env (pso closures), once with the float64 tape and once with the same
+    values as float32 (NEP-50 path).  Episodes stop at done / truncated.  Kept: every step's flags
+    and reward, the state at steps BATCH_KEEP and the last state."""
+    import multiprocessing as mp
+    rng = np.random.default_rng(seed)
+    adim = 1 if phase == P else 4
+    acts = rng.uniform(-1, 1, (n_envs, n_steps, adim)).astype(np.float32)
+    # a quarter of the envs get a biased policy so that episodes live longer / end differently
+    bias = rng.uniform(-0.8, 0.8, (n_envs, 1, adim)).astype(np.float32)
+    acts[::4] = np.clip(bias[::4] + 0.3 * acts[::4], -1, 1)
+    ctx = mp.get_context("fork")
+    out = {"actions": acts, "keep_steps": np.array(BATCH_KEEP)}
+    with ctx.Pool(procs or os.cpu_count()) as pool:
+        for key, use32 in (("f64", False), ("f32", True)):
+            res = pool.map(_batch_tape_worker, [(phase, acts[i], use32) for i in range(n_envs)], chunksize=8)
+            out[f"flags_{key}"] = np.array([r[0] for r in res])
+            out[f"rewards_{key}"] = np.array([r[1] for r in res])
+            out[f"states_{key}"] = np.array([r[2] for r in res])
+            out[f"steps_{key}"] = np.array([r[3] for r in res])
+            out[f"last_{key}"] = np.array([r[4] for r in res])
+    np.savez_compressed(os.path.join(OUT, f"batch_tape_{tag}.npz"), **out)
+    print("batch_tape", tag, n_envs, "envs; steps f64 min/median/max", out["steps_f64"].min(),
+          int(np.median(out["steps_f64"])), out["steps_f64"].max(), "ended",
+          int((out["steps_f64"] < n_steps).sum()), "f32 length differs in",
+          int((out["steps_f64"] != out["steps_f32"]).sum()))
+
+
 def pso_best_actor():
     """The reference's own saved best P actor: weights -> fitness / trajectory."""
     import pandas as pd
@@ -643,6 +771,12 @@ if __name__ == "__main__":
     if "pso" in which:
         pso_fitness(P, "P", n=10)
         pso_fitness(G, "G", n=16)
+    if "many" in which:         # not in the default list: ~10 min of Pool(all cores)
+        pso_fitness_many(P, "P")
+        pso_fitness_many(G, "G")
+    if "batch" in which:        # not in the default list: ~5 min of Pool(all cores)
+        batch_tape(P, "P")
+        batch_tape(G, "G")
     if "best" in which:
         pso_best_actor()
     if "rl" in which:
