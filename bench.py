@@ -14,8 +14,12 @@ The JSON line carries: value (device-timed, actions resident in HBM, launches re
 CUDA graph), e2e (same metric through the public step() call with pinned-host actions copied
 in and obs/reward/flags copied out every step), roofline (HBM, algorithmic 160 B/env-step as
 SURVEY.md 8d counts it), fp_roofline (the bound that actually applies: FP32/FP64 pipes),
-cpu_baseline (the oracle port timed on this box's host cores), pso (fitness evals/s of the
-persistent rollout kernel at the 4 096-particle swarm of config 3).
+with the measured FFMA / DFMA peaks of this device as denominators), parity (fp32 production
+build vs the oracle-pinned fp64 build on this very workload: flag / episode-length agreement),
+cpu_baseline (the oracle port timed on this box's host cores), pso (fitness evals/s: config 3 =
+4 096 particles in phases P and G; 65 536 particles; config 5 = 65 536 particles x 8 wind seeds in
+G and P through the device-resident optimiser with its NCCL fitness all-gather + best sync),
+sac_collect (config 4 shape), other_phases.
 """
 import argparse
 import json
@@ -29,6 +33,8 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 P = "landing_burn_pure_throttle"
+G = "landing_burn"
+OTHER_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol")
 N_ENVS = 65536
 ALGO_BYTES_PER_STEP = 160.0        # 40 words x 4 B, phase P, fp32
 ALGO_FLOP_PER_STEP = 4800.0        # canonical flop per env-step (P, no wind)
@@ -88,18 +94,20 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
-    seed, n_steps, fast = args
+    """One process = one core: `warm` untimed + `n_steps` timed env.step calls of the oracle port."""
+    seed, n_steps, fast, warm = args
     import numpy as np
     from oracle import pd_oracle as O
     env = O.OracleEnv(P, "pso", tables=O.Tables(fast_rbf=fast))
     rng = np.random.default_rng(seed)
     env.reset()
-    t0 = time.perf_counter()
-    done_steps = 0
-    for _ in range(n_steps):
+    done_steps, t0 = 0, time.perf_counter()
+    for k in range(warm + n_steps):
+        if k == warm:
+            t0 = time.perf_counter()
         a = rng.uniform(-1, 1, 1).astype(np.float32)
         s, r, d, tr, info = env.step(a)
-        done_steps += 1
+        done_steps += k >= warm
         if d or tr:
             env.reset()
     return done_steps, time.perf_counter() - t0
@@ -126,57 +134,48 @@ def cpu_pso_rate(phase, per_core=4, cores=None):
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(i, 2, False) for i in range(cores)])
+        pool.map(_cpu_worker, [(i, 2, False, 0) for i in range(cores)])
         t0 = time.perf_counter()
         res = pool.map(_cpu_pso_worker, [(500 + i, phase) for i in range(cores * per_core)])
         dt = time.perf_counter() - t0
     return len(res) / dt, sum(r[0] for r in res) / dt, cores, len(res)
 
 
-def cpu_rate(n_steps_per_core, cores=None, repeats=1):
+def cpu_rate(n_steps_per_core, cores=None, warm=20):
     """The oracle port (same scipy RBFInterpolator-per-call cost structure as the reference's
-    env.step) on `cores` processes; returns env-steps/s aggregate."""
+    env.step) on `cores` processes, ONE task per core (no per-step dispatch in the timed region);
+    returns (env-steps/s aggregate = all steps / slowest worker, cores)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(i, 2, False) for i in range(cores)])     # import + table warm-up
-        best = 0.0
-        for rep in range(repeats):
-            t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(1000 * rep + i, n_steps_per_core, False) for i in range(cores)])
-            dt = time.perf_counter() - t0
-            best = max(best, sum(r[0] for r in res) / dt)
-    return best, cores
+        res = pool.map(_cpu_worker, [(i, n_steps_per_core, False, warm) for i in range(cores)], chunksize=1)
+    return sum(r[0] for r in res) / max(r[1] for r in res), cores
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port) on all host
+    cores.  One long task per core; a bench 'step' is per_core env.step calls on each core, sized
+    so that every worker runs >= 6 000 steps in total (stable to a few per cent) whatever K is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_core = 20
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(i, 2, False) for i in range(cores)])
-        for w in range(args.warmup):
-            pool.map(_cpu_worker, [(10_000 + 100 * w + i, per_core, False) for i in range(cores)])
-        t0 = time.perf_counter()
-        total = 0
-        for k in range(args.steps):
-            res = pool.map(_cpu_worker, [(100 * k + i, per_core, False) for i in range(cores)])
-            total += sum(r[0] for r in res)
-        dt = time.perf_counter() - t0
-    val = total / dt
-    sample = (f"{cores} processes x {per_core} env.step calls per bench step, oracle/pd_oracle.py "
-              f"(scalar Python port; scipy RBFInterpolator per call as upstream), random U(-1,1) actions")
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    per_core = max(2, min(300, -(-6000 // K)))
+    t0 = time.perf_counter()
+    val, cores = cpu_rate(K * per_core, cores, warm=max(20, W * per_core))
+    wall = time.perf_counter() - t0
+    total = K * per_core * cores
+    sample = (f"{cores} processes x {K} bench steps x {per_core} env.step calls each (one task per core, "
+              f"{W * per_core} untimed warm-up calls), oracle/pd_oracle.py (scalar Python port; scipy "
+              f"RBFInterpolator per call as upstream), random U(-1,1) float32 actions, auto-reset")
     line = {"impl": "reference", "metric": "env_steps_per_sec", "value": val, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+            "ms_per_step": 1e3 * (total / val) / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config2: landing_burn_pure_throttle env.step, random actions, "
-                                   "ISA, no wind (bounded CPU sample)"},
+                                   "ISA, no wind (bounded CPU sample)", "wall_s": wall},
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
@@ -187,6 +186,7 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
+    import ctypes as C
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -215,6 +215,18 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allmax(*vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def allsum(*vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
     # ---- device-timed region: K fused step launches replayed from one CUDA graph
     with torch.cuda.stream(stream):
         env.reset()
@@ -230,7 +242,6 @@ def run_cuda(args):
         barrier()
         if rank == 0:
             sampler.start()
-        l0 = lib.pd_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
@@ -241,13 +252,10 @@ def run_cuda(args):
         clocks = sampler.stop() if rank == 0 else None
         env.check_status()
     launches = K          # K step-kernel launches inside the replayed graph
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max, = allmax(ms)
     value = world * B * K / (ms_max * 1e-3)
 
-    # ---- per-launch duration of the dominant kernel, L2 flushed between launches
+    # ---- per-launch duration of the dominant kernel with a cold L2 (flushed between launches)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     durs = []
     with torch.cuda.stream(stream):
@@ -260,8 +268,16 @@ def run_cuda(args):
             stream.synchronize()
             durs.append(a0.elapsed_time(a1))
     durs.sort()
-    kern_ms = durs[len(durs) // 2]
+    kern_ms_cold = durs[len(durs) // 2]
     del flush
+
+    # ---- measured FFMA / DFMA pipe peaks of this device, same run
+    peaks = {}
+    for name, f64 in (("fp32_fma_tflops", 0), ("fp64_fma_tflops", 1)):
+        tf, kms = C.c_double(0), C.c_double(0)
+        _native.check(lib.pd_measure_fma_peak(local, f64, C.byref(tf), C.byref(kms)))
+        peaks[name] = tf.value
+    barrier()
 
     # ---- end-to-end through the public host-facing call: numpy actions in, numpy results out,
     # every step (BatchedRocketEnv.step_host: the step kernel reads the actions from and stores its
@@ -279,98 +295,115 @@ def run_cuda(args):
         obs, rew, done, trunc, tid = env.step_host(host_tape[W + k])
         chk += float(rew[0])                      # the caller reads the result before the next action
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * Ke / float(t.item())
+    e2e_s, = allmax(time.perf_counter() - t0)
+    e2e_val = world * B * Ke / e2e_s
     h2d = B * 4
     d2h = int(env._host["n_copy"])
+    del env
 
-    # ---- PSO fitness evaluation (config 3 / 5): the swarm is block-sharded over the ranks, each
+    # ---- fp32 production build vs fp64 parity build on this very workload (rank 0's GPU)
+    par = None
+    if not args.no_parity and rank == 0:
+        from psso_sac_for_powered_descent_b200 import parity
+        par = {}
+        for ph, T in ((P, args.parity_steps), (G, min(args.parity_steps, 200))):
+            r = parity.fp32_vs_fp64_tape(args.parity_envs, T, phase=ph, device=local)
+            b = parity.fp32_vs_fp64_tape(args.parity_envs, T, phase=ph, device=local, test="ulp", max_records=0)
+            recs = r.pop("first_mismatches")
+            b.pop("first_mismatches")
+            margins = [m["margin"] for m in recs if "margin" in m]
+            keep = ("n_envs", "n_steps", "env_steps", "flag_match_frac", "flag_mismatches", "episodes",
+                    "episode_same_length_frac", "max_state_err", "max_translational_err", "what")
+            par[ph] = {k: r[k] for k in keep}
+            par[ph]["largest_threshold_margin_of_recorded_mismatches"] = max(margins) if margins else None
+            par[ph]["nearest_thresholds"] = sorted({m["nearest_threshold"] for m in recs if "margin" in m})
+            par[ph]["conditioning_baseline"] = {k: b[k] for k in keep}
+    barrier()
+
+    # ---- PSO fitness evaluation (configs 3 and 5): the swarm is block-sharded over the ranks, each
     # rank rolls out its particles (x wind seeds) in one persistent kernel, then one fp64
-    # all-gather of the fitness vector and one broadcast of the best position (NCCL).
+    # all-gather of the fitness and the sync of the best position (NCCL).
     pso = None
     if not args.no_pso:
         from psso_sac_for_powered_descent_b200 import pso as pso_mod
-        phase = args.pso_phase
-        n_par = 249 if phase == P else 372
-        model = envs.pso_wrapped_env(flight_phase=phase, enable_wind=args.pso_wind,
-                                     stochastic_wind=args.pso_wind, precision=args.precision,
-                                     max_steps=4096, seed=99)
-        rngp = np.random.default_rng(7)
-        pos = rngp.uniform(-1.5, 1.5, (args.particles, n_par))        # identical on every rank
-        stats = {}
+        pso = {"collectives": "per generation: 1 all_gather(fp64 fitness) + 1 broadcast of the best position "
+                              "(ShardedEvaluator.broadcast_best; DeviceSwarm: all-reduce of the masked rows)"}
 
-        def local_eval(p):
-            fit, steps, tid = model.evaluate(p, n_seeds=args.seeds)
-            stats["steps"] = float(steps.sum())
-            stats["capped"] = int((tid < 0).sum())
-            return fit.reshape(len(p), args.seeds).mean(dim=1).cpu().numpy()
-        ev = pso_mod.ShardedEvaluator(local_eval)
-        lo, hi = pso_mod.shard_bounds(args.particles, world, rank)
-        fw = ev(pos)                                                # warm-up (weights upload, caches,
-        ev.broadcast_best(fw, pos[lo:hi], args.particles)           # NCCL channels of both collectives)
-        barrier()
-        t0 = time.perf_counter()
-        fitness = ev(pos)
-        idx, best, best_pos = ev.broadcast_best(fitness, pos[lo:hi], args.particles)
-        barrier()
-        dt = time.perf_counter() - t0
-        # north_star's swarm size: 65 536 particles through the same sharded evaluation
-        big = None
-        if args.particles < 65536 and not args.no_pso_scale:
-            pos_big = rngp.uniform(-1.5, 1.5, (65536, n_par))
-            ev(pos_big)
-            barrier()
-            b0 = time.perf_counter()
-            fb = ev(pos_big)
-            barrier()
-            bdt = time.perf_counter() - b0
-            tb = torch.tensor([bdt, stats["steps"]], device=dev, dtype=torch.float64)
-            if world > 1:
-                mb = tb.clone(); dist.all_reduce(mb, op=dist.ReduceOp.MAX)
-                sb = tb.clone(); dist.all_reduce(sb, op=dist.ReduceOp.SUM)
-                bdt, bsteps = float(mb[0]), float(sb[1])
-            else:
-                bsteps = stats["steps"]
-            big = {"particles": 65536, "wind_seeds": args.seeds, "fitness_evals_per_s": 65536 / bdt, "ms": bdt * 1e3,
-                   "env_steps_per_s": bsteps / bdt, "mean_episode_steps": bsteps / (65536 * args.seeds),
-                   "what": "host list of positions in, fitness list out (ShardedEvaluator): weights upload, "
-                           "rollout with straggler hand-off, fitness all-gather"}
-            del pos_big, fb
-        # device-resident optimiser (swarm never leaves HBM): whole generations
-        params = dict(pso_mod.PSO_PARAMS[phase], pop_size=args.particles)
-        sw = pso_mod.DeviceSwarm(model, args.particles, params, n_seeds=args.seeds, seed=5, max_steps=4096)
-        sw.step()
-        barrier()
-        g0 = time.perf_counter()
-        n_gen = 5
-        gsteps = 0.0
-        for _ in range(n_gen):
+        def host_list_eval(phase, n, wind, seeds, reps=1):
+            """parallel_evaluate semantics: host array of positions in, fitness out, sharded."""
+            n_par = 249 if phase == P else 372
+            model = envs.pso_wrapped_env(flight_phase=phase, enable_wind=wind, stochastic_wind=wind,
+                                         precision=args.precision, max_steps=4096, seed=99)
+            model.warn_on_cap = False
+            pos = np.random.default_rng(7).uniform(-1.5, 1.5, (n, n_par))      # identical on every rank
+            st = {}
+
+            def local_eval(p, index0=0, generation=0):
+                fit, steps, tid = model.evaluate(p, n_seeds=seeds, index0=index0, generation=generation)
+                st["steps"], st["capped"] = float(steps.sum()), int((tid < 0).sum())
+                return fit.reshape(len(p), seeds).mean(dim=1).cpu().numpy()
+            ev = pso_mod.ShardedEvaluator(local_eval)
+            lo, hi = pso_mod.shard_bounds(n, world, rank)
+            fw = ev(pos)                                       # warm-up (weights upload, caches, NCCL channels)
+            ev.broadcast_best(fw, pos[lo:hi], n)
+            best_dt = float("inf")
+            for _ in range(reps):
+                barrier()
+                t0 = time.perf_counter()
+                fitness = ev(pos)
+                idx, best, best_pos = ev.broadcast_best(fitness, pos[lo:hi], n)
+                barrier()
+                best_dt = min(best_dt, time.perf_counter() - t0)
+            dt, = allmax(best_dt)
+            tot_steps, capped = allsum(st["steps"], st["capped"])
+            del model
+            return {"phase": phase, "particles": n, "wind_seeds": seeds, "wind": bool(wind),
+                    "fitness_evals_per_s": n / dt, "episodes_per_s": n * seeds / dt, "ms": dt * 1e3,
+                    "env_steps_per_s": tot_steps / dt, "mean_episode_steps": tot_steps / (n * seeds),
+                    "episodes_hitting_step_cap": int(capped), "best_fitness": best, "best_index": idx,
+                    "timing": "wall clock between device-synchronised barriers, max over ranks",
+                    "what": "host array of positions in, fitness out (ShardedEvaluator): float32 conversion + "
+                            "upload of this rank's shard, rollout kernel(s), fitness all-gather, best broadcast"}
+
+        def device_swarm(phase, n, wind, seeds, n_gen=5):
+            """Whole generations of the device-resident optimiser, timed on the device."""
+            model = envs.pso_wrapped_env(flight_phase=phase, enable_wind=wind, stochastic_wind=wind,
+                                         precision=args.precision, max_steps=4096, seed=99)
+            params = dict(pso_mod.PSO_PARAMS[phase], pop_size=n, re_initialise_generation=10 ** 9)
+            sw = pso_mod.DeviceSwarm(model, n, params, n_seeds=seeds, seed=5, max_steps=4096)
             sw.step()
-            gsteps += float(sw.last_steps.sum())
-        barrier()
-        gdt = (time.perf_counter() - g0) / n_gen
-        tt = torch.tensor([dt, stats["steps"], stats["capped"], gdt, gsteps / n_gen], device=dev, dtype=torch.float64)
-        if world > 1:
-            mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            dt, tot_steps, capped, gdt, gsteps = float(mx[0]), float(sm[1]), int(sm[2]), float(mx[3]), float(sm[4])
-        else:
-            tot_steps, capped, gsteps = stats["steps"], stats["capped"], gsteps / n_gen
-        episodes = args.particles * args.seeds
-        pso = {"phase": phase, "particles": args.particles, "wind_seeds": args.seeds, "wind": bool(args.pso_wind),
-               "fitness_evals_per_s": args.particles / dt, "episodes_per_s": episodes / dt,
-               "env_steps_per_s": tot_steps / dt, "ms": dt * 1e3, "mean_episode_steps": tot_steps / episodes,
-               "episodes_hitting_step_cap": capped, "best_fitness": best, "best_index": idx,
-               "collectives": "1 all_gather(fp64 fitness) + 1 broadcast(best position) per generation",
-               "timing": "wall clock between device-synchronised barriers, max over ranks",
-               "at_65536_particles": big,
-               "device_swarm": {"ms_per_generation": gdt * 1e3, "fitness_evals_per_s": args.particles / gdt,
-                                "env_steps_per_s": gsteps / gdt,
-                                "what": "evaluate (rollout kernel) + fitness all-gather + sub-swarm best "
-                                        "broadcast + pd_pso_update, swarm resident in HBM"}}
+            sw.step()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gsteps = torch.zeros((), dtype=torch.float64, device=dev)
+            barrier()
+            g0.record()
+            for _ in range(n_gen):
+                sw.step()
+                gsteps += sw.last_steps.sum()
+            g1.record()
+            barrier()
+            gms, = allmax(g0.elapsed_time(g1) / n_gen)
+            tot, capped = allsum(float(gsteps) / n_gen, float(sw.capped_episodes))
+            out = {"phase": phase, "particles": sw.N_total, "wind_seeds": seeds, "wind": bool(wind),
+                   "ms_per_generation": gms, "fitness_evals_per_s": sw.N_total / (gms * 1e-3),
+                   "episodes_per_s": sw.N_total * seeds / (gms * 1e-3), "env_steps_per_s": tot / (gms * 1e-3),
+                   "mean_episode_steps": tot / (sw.N_total * seeds),
+                   "episodes_hitting_step_cap_total": int(capped), "generations_timed": n_gen,
+                   "global_best_fitness": sw.global_best_fitness,
+                   "timing": "CUDA events around the generations, max over ranks",
+                   "what": "rollout kernel + seed mean + fitness all-gather + per-sub-swarm arg-min / metrics + "
+                           "best-row all-reduce + pd_pso_update; swarm resident in HBM, no host sync inside a "
+                           "generation; sharing / migration on their generations"}
+            del sw, model
+            return out
+
+        pso["config3_P"] = host_list_eval(P, 4096, False, 1, reps=3)
+        pso["config3_G"] = host_list_eval(G, 4096, False, 1, reps=3)
+        if not args.no_pso_scale:
+            pso["swarm_65536_P"] = host_list_eval(P, 65536, False, 1, reps=2)
+            pso["config5_G"] = device_swarm(G, 65536, True, 8)
+            pso["config5_P"] = device_swarm(P, 65536, True, 8)
+            pso["device_swarm_65536_P_nowind"] = device_swarm(P, 65536, False, 1)
 
     # ---- SAC data collection (config 4 shape): shared 2-256-256-(1,1) actor on the tensor cores
     # + fused env step with stochastic wind, 131 072 envs per GPU, auto-reset
@@ -396,20 +429,18 @@ def run_cuda(args):
             barrier()
             best_ms = min(best_ms, s0.elapsed_time(s1))
         senv.check_status()
-        sms = torch.tensor([best_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
-        sac = {"envs_per_gpu": Bs, "steps": Ts, "env_steps_per_s": world * Bs * Ts / (sms.item() * 1e-3),
-               "ms_per_step": sms.item() / Ts, "actor": "2-256-256-(1,1), bf16 tcgen05 UMMA + fp32 heads",
+        sms, = allmax(best_ms)
+        sac = {"envs_per_gpu": Bs, "steps": Ts, "env_steps_per_s": world * Bs * Ts / (sms * 1e-3),
+               "ms_per_step": sms / Ts, "actor": "2-256-256-(1,1), bf16 tcgen05 UMMA + fp32 heads",
                "wind": "stochastic, percentile 50, Philox gusts", "rtd": "rl",
                "mean_reward": float(out["rewards"].mean()), "resets": int(out["truncated"].sum() + out["done"].sum())}
         del senv, out
 
-    # ---- the four further flight phases, RL closures, same fused step kernel
+    # ---- the further flight phases, RL closures, same fused step kernel
     phases = None
     if not args.no_phases:
         phases = {}
-        for ph in ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol"):
+        for ph in OTHER_PHASES:
             penv = envs.BatchedRocketEnv(B, "rl", ph, precision=args.precision, auto_reset=True, device=local,
                                          trajectory_length=1000, discount_factor=0.99, seed=5 + rank)
             ptape = torch.rand(40, B, penv.act_dim, device=dev, generator=gen, dtype=torch.float32) * 2 - 1
@@ -425,10 +456,8 @@ def run_cuda(args):
                 p1.record(stream)
                 barrier()
                 penv.check_status()
-            pms = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(pms, op=dist.ReduceOp.MAX)
-            phases[ph] = {"env_steps_per_s": world * B * 30 / (pms.item() * 1e-3), "us_per_step": pms.item() / 30 * 1e3}
+            pms, = allmax(p0.elapsed_time(p1))
+            phases[ph] = {"env_steps_per_s": world * B * 30 / (pms * 1e-3), "us_per_step": pms / 30 * 1e3}
             del penv, ptape
 
     if rank != 0:
@@ -436,26 +465,35 @@ def run_cuda(args):
             dist.destroy_process_group()
         return
     hbm_peak, sm_max, peak_src = load_peaks()
-    achieved = ALGO_BYTES_PER_STEP * B / (kern_ms * 1e-3) / 1e9
+    kern_ms = ms_max / K                      # average launch duration inside the timed region (graph replay)
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
-    fp_ach = ALGO_FLOP_PER_STEP * B / (kern_ms * 1e-3) / 1e12
+    nominal_fp32 = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+
+    def hbm(kms):
+        a = ALGO_BYTES_PER_STEP * B / (kms * 1e-3) / 1e9
+        return {"kernel_ms": kms, "achieved": a, "frac": a / hbm_peak}
+
+    def fp(kms):
+        a = ALGO_FLOP_PER_STEP * B / (kms * 1e-3) / 1e12
+        return {"kernel_ms": kms, "achieved": a, "frac": a / peaks["fp32_fma_tflops"]}
     cpu = None
     if not args.no_cpu:
         v, cores = cpu_rate(args.cpu_steps_per_core)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": f"{cores} processes x {args.cpu_steps_per_core} env.step calls of oracle/pd_oracle.py "
-                         "(scalar Python port of the reference env, scipy RBFInterpolator per call), "
-                         "same phase / rtd / random-action workload"}
+                         "(scalar Python port of the reference env, scipy RBFInterpolator per call), one task "
+                         "per core, same phase / rtd / random-action workload"}
         if pso is not None:
-            ev_s, st_s, c2, n_ep = cpu_pso_rate(args.pso_phase)
-            cpu["pso_fitness_evals_per_s"] = ev_s
-            cpu["pso_env_steps_per_s"] = st_s
-            cpu["pso_sample"] = (f"{n_ep} random particles, Pool({c2}) over the oracle's objective_function with a "
-                                 "fresh model per particle (the reference's evaluate_worker_function structure)")
-            pso["vs_cpu_port"] = pso["fitness_evals_per_s"] / ev_s
-            if pso.get("at_65536_particles"):
-                pso["at_65536_particles"]["vs_cpu_port"] = pso["at_65536_particles"]["fitness_evals_per_s"] / ev_s
+            for ph, tag in ((P, "P"), (G, "G")):
+                ev_s, st_s, c2, n_ep = cpu_pso_rate(ph)
+                cpu[f"pso_{tag}_fitness_evals_per_s"] = ev_s
+                cpu[f"pso_{tag}_env_steps_per_s"] = st_s
+                cpu[f"pso_{tag}_sample"] = (f"{n_ep} random particles, Pool({c2}) over the oracle's objective_function "
+                                            "with a fresh model per particle (the reference's "
+                                            "evaluate_worker_function structure), no wind")
+                for key, blk in pso.items():
+                    if isinstance(blk, dict) and blk.get("phase") == ph:
+                        blk["vs_cpu_port"] = blk["fitness_evals_per_s"] / ev_s
     line = {
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
@@ -465,25 +503,29 @@ def run_cuda(args):
                                "random U(-1,1) float32 actions, ISA, no wind, auto-reset",
                    "envs_per_gpu": B, "precision_build": args.precision,
                    "l2": "state (~19 MB/step at 65 536 envs) stays L2-resident between launches as in the "
-                         "real rollout; the kernel is FP-pipe bound; roofline launch durations are "
-                         "measured with a 256 MB L2 flush between launches",
+                         "real rollout; the kernel is FP-pipe bound.  roofline / fp_roofline are quoted on the "
+                         "SAME time base as `value` (average launch duration inside the timed region); their "
+                         "`cold_l2` sub-objects repeat them on single launches separated by a 256 MB L2 flush",
                    "launch": "K step launches captured in one CUDA graph"},
         "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": Ke,
-                "transport": {"zc_all": "step kernel reads the pinned host actions and stores its results to "
-                                        "pinned host memory directly (mapped, same bytes over PCIe)",
-                              "zc_out": "H2D copy of the actions, results stored to mapped pinned memory",
-                              "copy": "H2D copy, kernel, one D2H copy (CUDA graph)"}[env._host["mode"]]},
+                "transport": "step kernel reads the pinned host actions and stores its results to pinned host "
+                             "memory directly (mapped, same bytes over PCIe); PD_HOST_STEP=copy|zc_out select "
+                             "explicit copies"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": f"step_kernel<{args.precision}>", "kernel_ms": kern_ms,
-                     "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP,
-                     "note": "HBM is not the limiter of this path (SURVEY 8d); see fp_roofline"},
-        "fp_roofline": {"bound": "fp32_pipe", "achieved": fp_ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                        "frac": fp_ach / fp32_peak, "flop_per_env_step": ALGO_FLOP_PER_STEP,
-                        "peak_def": f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz", "sm_mhz_under_load": sm_mhz},
+        "roofline": dict(hbm(kern_ms), bound="hbm", peak=hbm_peak, unit="GB/s", traffic=None,
+                         peak_source=peak_src, kernel=f"step_kernel<{args.precision}>",
+                         time_base="timed region / K (CUDA events around the graph replay)",
+                         algorithmic_bytes_per_env_step=ALGO_BYTES_PER_STEP, cold_l2=hbm(kern_ms_cold),
+                         note="HBM is not the limiter of this path (SURVEY 8d); see fp_roofline"),
+        "fp_roofline": dict(fp(kern_ms), bound="fp32_pipe", peak=peaks["fp32_fma_tflops"], unit="TFLOP/s",
+                            peak_source="measured in this run (pd_measure_fma_peak: 8 FMA chains/thread, 64 warps/SM)",
+                            peak_fp64_fma_tflops=peaks["fp64_fma_tflops"], nominal_fp32_tflops=nominal_fp32,
+                            flop_per_env_step=ALGO_FLOP_PER_STEP,
+                            time_base="timed region / K (CUDA events around the graph replay)",
+                            cold_l2=fp(kern_ms_cold), sm_mhz_under_load=sm_mhz),
+        "parity": par,
         "cpu_baseline": cpu,
         "pso": pso,
         "sac_collect": sac,
@@ -511,11 +553,10 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
-    ap.add_argument("--particles", type=int, default=4096)
-    ap.add_argument("--seeds", type=int, default=1)
-    ap.add_argument("--pso-phase", default=P, choices=[P, "landing_burn"])
-    ap.add_argument("--pso-wind", action="store_true")
-    ap.add_argument("--cpu-steps-per-core", type=int, default=1500)
+    ap.add_argument("--cpu-steps-per-core", type=int, default=3000)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-envs", type=int, default=65536)
+    ap.add_argument("--parity-steps", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pso", action="store_true")
     ap.add_argument("--no-sac", action="store_true")

@@ -298,11 +298,36 @@ int pd_actor_forward(PdEnv *env, const PdSharedActor *actor, const float *obs, i
  *   x, v, best [n*P] fp64 (updated in place), best_fit [n], fitness [n] (of x), swarm_of int32[n],
  *   swarm_best [S*P] (sub-swarm bests, already including this generation),
  *   weights_out float[n*P] or NULL (fp32 copy of the new x for the next pd_rollout_pso).
- *   r1, r2 = Philox(seed, generation, index0 + i): independent of the sharding. */
+ *   r1, r2 = Philox(seed, generation, index0 + i): independent of the sharding.  Rows with
+ *   swarm_of < 0 are skipped.  The update is evaluated in NumPy's order without fused
+ *   multiply-adds, so the host drop-in (rng='philox') follows the identical trajectory. */
 int pd_pso_update(double *x, double *v, double *best, double *best_fit, const double *fitness,
                   const int32_t *swarm_of, const double *swarm_best, float *weights_out, int n, int P,
                   int64_t index0, double w, double c1, double c2, double lo, double hi, uint64_t seed,
                   int generation, void *stream);
+
+/* The rest of one PSO generation on the device, no host synchronisation anywhere
+ * (ParticleSubswarmOptimisation.run, particle_swarm_optimisation.py:425-477).  All pointers dev.
+ *   pd_pso_seed_mean  fitness[n*n_seeds] -> out[n], mean over a particle's wind seeds (sequential sum)
+ *   pd_pso_select     allfit[N] = this generation's fitness of EVERY particle (the all-gathered
+ *                     slices), swarm_of_all int32[N] (sub-swarm id, < 0 = slot not in use).  Per
+ *                     sub-swarm k: sel_idx[k] = global index of its best particle (first occurrence),
+ *                     improved[k] = it beat swarm_best_fit[k] (which is updated in place), and the
+ *                     reference's per-generation metrics stats[(S+1)*6] = best so far, avg, min, max,
+ *                     std (population), count per sub-swarm (:455-470); row S = the whole swarm.
+ *   pd_pso_gather     cand[S*P]: row k = x[sel_idx[k] - lo] if this rank owns that particle and
+ *                     improved[k], else zeros - so that ONE all-reduce(sum) of cand over the ranks
+ *                     is the broadcast of every improved sub-swarm best from its (unknown) owner.
+ *   pd_pso_apply      swarm_best[k] <- cand[k] where improved[k]; global best = sequential scan of
+ *                     the sub-swarm bests (:474-477); hist_row[0] = global best fitness (or NULL). */
+int pd_pso_seed_mean(const double *fitness, int n, int n_seeds, double *out, void *stream);
+int pd_pso_select(const double *allfit, const int32_t *swarm_of_all, int N, int S, double *swarm_best_fit,
+                  int32_t *sel_idx, int32_t *improved, double *stats, void *stream);
+int pd_pso_gather(const double *x, int64_t lo, int n_local, int P, const int32_t *sel_idx,
+                  const int32_t *improved, int S, double *cand, void *stream);
+int pd_pso_apply(const double *cand, const int32_t *improved, int S, int P, double *swarm_best,
+                 const double *swarm_best_fit, double *gbest_pos, double *gbest_fit, double *hist_row,
+                 void *stream);
 
 /* Gust-noise stream of the next pd_rollout_pso / pd_rollout_policy calls.  The Philox counter of
  * an episode's noise is (index0 * n_seeds + local episode, draw, episode word = generation + 1):
@@ -319,6 +344,11 @@ int pd_set_rollout_stream(PdEnv *env, int64_t index0, uint32_t generation);
  * finite states (the enumeration covers the whole clamped query box); a lane that hits it has its
  * C_L / C_D set to NaN, so the env turns NaN instead of continuing on a wrong interpolant. */
 int pd_check_status(PdEnv *env, int32_t *status);
+
+/* Measured peak of the FP32 (fp64 = 0) or FP64 (fp64 = 1) FMA pipe of `device`, TFLOP/s at 2 FLOP
+ * per FMA: 8 independent FMA chains per thread, 64 warps per SM, best of 3 timed launches (CUDA
+ * events).  Synchronous.  The denominator of bench.py's fp_roofline. */
+int pd_measure_fma_peak(int device, int fp64, double *tflops, double *kernel_ms);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t pd_launch_count(void);

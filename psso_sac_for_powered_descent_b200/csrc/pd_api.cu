@@ -13,6 +13,7 @@
 #include "pd_impl.h"
 #include "pd_actor.h"
 #include "pd_pso.h"
+#include "pd_peak.h"
 
 using namespace pd;
 
@@ -506,6 +507,60 @@ int pd_pso_update(double *x, double *v, double *best, double *best_fit, const do
     a.swarm_best = swarm_best; a.weights_out = weights_out; a.n = n; a.P = P; a.index0 = index0;
     a.w = w; a.c1 = c1; a.c2 = c2; a.lo = lo; a.hi = hi; a.seed = seed; a.generation = generation;
     if (pso_update_launch(a, (cudaStream_t)stream)) return fail("pd_pso_update: launch failed");
+    g_launches++;
+    return 0;
+}
+
+int pd_measure_fma_peak(int device, int fp64, double *tflops, double *kernel_ms) {
+    if (!tflops) return fail("pd_measure_fma_peak: null argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail("pd_measure_fma_peak: cannot select the device");
+    int n_sm = 0;
+    CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    double ms = 0.0;
+    if (measure_fma_peak(fp64, n_sm, tflops, &ms)) return fail("pd_measure_fma_peak: kernel failed");
+    if (kernel_ms) *kernel_ms = ms;
+    g_launches += 4;
+    return 0;
+}
+
+int pd_pso_seed_mean(const double *fitness, int n, int n_seeds, double *out, void *stream) {
+    if (!fitness || !out || n <= 0 || n_seeds <= 0) return fail("pd_pso_seed_mean: bad argument");
+    if (pso_seed_mean_launch(fitness, n, n_seeds, out, (cudaStream_t)stream)) return fail("pd_pso_seed_mean: launch failed");
+    g_launches++;
+    return 0;
+}
+
+int pd_pso_select(const double *allfit, const int32_t *swarm_of_all, int N, int S, double *swarm_best_fit,
+                  int32_t *sel_idx, int32_t *improved, double *stats, void *stream) {
+    if (!allfit || !swarm_of_all || !swarm_best_fit || !sel_idx || !improved || !stats || N <= 0 || S <= 0)
+        return fail("pd_pso_select: bad argument");
+    PsoSelectArgs a;
+    a.allfit = allfit; a.swarm_of_all = swarm_of_all; a.N = N; a.S = S; a.swarm_best_fit = swarm_best_fit;
+    a.sel_idx = sel_idx; a.improved = improved; a.stats = stats;
+    if (pso_select_launch(a, (cudaStream_t)stream)) return fail("pd_pso_select: launch failed");
+    g_launches++;
+    return 0;
+}
+
+int pd_pso_gather(const double *x, int64_t lo, int n_local, int P, const int32_t *sel_idx,
+                  const int32_t *improved, int S, double *cand, void *stream) {
+    if (!x || !sel_idx || !improved || !cand || n_local < 0 || P <= 0 || S <= 0)
+        return fail("pd_pso_gather: bad argument");
+    if (pso_gather_launch(x, lo, n_local, P, sel_idx, improved, S, cand, (cudaStream_t)stream))
+        return fail("pd_pso_gather: launch failed");
+    g_launches++;
+    return 0;
+}
+
+int pd_pso_apply(const double *cand, const int32_t *improved, int S, int P, double *swarm_best,
+                 const double *swarm_best_fit, double *gbest_pos, double *gbest_fit, double *hist_row,
+                 void *stream) {
+    if (!cand || !improved || !swarm_best || !swarm_best_fit || !gbest_pos || !gbest_fit || S <= 0 || P <= 0)
+        return fail("pd_pso_apply: bad argument");
+    if (pso_apply_launch(cand, improved, S, P, swarm_best, swarm_best_fit, gbest_pos, gbest_fit, hist_row,
+                         (cudaStream_t)stream))
+        return fail("pd_pso_apply: launch failed");
     g_launches++;
     return 0;
 }

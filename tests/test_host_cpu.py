@@ -379,3 +379,91 @@ def test_single_edge_cells_resolve_exactly(tables):
                 lo, hi = tbl.find_set(m, a)
                 assert got == tbl.lookup(lo, hi), (flat, m, a)
             assert n_edge > 300
+
+
+# --------------------------------------------------------------------------- PSO streams / formats
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors) for the numpy implementation the
+    host optimiser shares with csrc/pd_pso.cu."""
+    from psso_sac_for_powered_descent_b200.pso import philox4x32
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:
+        out = philox4x32(np.array([ctr[0]]), ctr[1], ctr[2], ctr[3], key[0], key[1])
+        assert tuple(int(v[0]) for v in out) == exp
+
+
+def test_pso_reference_rng_draw_order(tmp_path):
+    """rng='reference': initial positions from random.Random(seed) in the reference's order, the
+    velocity update consumes RandomState(seed).rand() twice per particle in swarm order."""
+    opt = _mk(tmp_path)
+    x0 = opt.position.copy()
+    opt.step_generation(0)
+    fit = ((x0 - 0.3) ** 2).sum(1)
+    draws = np.random.RandomState(4).rand(2 * 40)
+    lb = np.stack([x0[:20][np.argmin(fit[:20])]] * 20 + [x0[20:][np.argmin(fit[20:])]] * 20)
+    v = 0.9 * 0 + (1 * draws[0::2])[:, None] * (x0 - x0) + (1 * draws[1::2])[:, None] * (lb - x0)
+    assert np.array_equal(opt.velocity, v)
+    assert np.array_equal(opt.position, np.clip(x0 + v, -1.5, 1.5))
+
+
+def test_pso_migration_and_reinit_keep_list_order(tmp_path):
+    opt = _mk(tmp_path, rng="philox")
+    for g in range(13):
+        opt.step_generation(g)
+    # two migrations (generations 5, 10): the migrant sits at the END of its target list until the
+    # re-initialisation at generation 12 sorts each list by personal best
+    assert sorted(opt.members[0] + opt.members[1]) == list(range(len(opt.position)))
+    for m in opt.members:
+        bf = opt.best_fitness[m]
+        assert np.all(np.diff(bf) >= 0) and len(m) <= 10
+    sw = opt.swarms
+    assert [len(s) for s in sw] == [len(m) for m in opt.members]
+
+
+def test_pso_metrics_files_have_reference_layout(tmp_path):
+    import csv
+    opt = _mk(tmp_path)
+    opt.run(generations=12)
+    opt.save_results()
+    rows = list(csv.reader(open(tmp_path / "metrics" / "subswarm_1_metrics.csv")))
+    assert rows[0] == ["swarm_idx", "best_fitness", "avg_fitness", "min_fitness", "max_fitness", "std_fitness",
+                       "num_particles", "generation", "global_best_fitness", "global_avg_fitness"]
+    assert len(rows) == 13 and rows[5][0] == "1" and rows[5][7] == "4" and rows[5][6] == "20"
+    g = list(csv.reader(open(tmp_path / "metrics" / "global_metrics.csv")))
+    assert g[0] == ["generation", "global_best_fitness", "global_avg_fitness"] and len(g) == 13
+    assert float(g[-1][1]) == opt.global_best_fitness_array[-1]
+    h = list(csv.reader(open(tmp_path / "metrics" / "fitness_history.csv")))
+    assert h[0] == ["Generation", "Global_Best_Fitness", "Average_Fitness", "Subswarm_1_Best",
+                    "Subswarm_1_Average", "Subswarm_2_Best", "Subswarm_2_Average"]
+    assert len(h) == 13 and float(h[3][1]) == opt.global_best_fitness_array[2]
+    import json
+    cfg = json.load(open(tmp_path / "pso_config.json"))
+    assert cfg["flight_phase"] == "landing_burn_pure_throttle" and cfg["pop_size"] == 40
+
+
+def _gloo_seedless_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, REPO)
+    from psso_sac_for_powered_descent_b200 import pso
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    params = dict(pso.landing_burn_pure_throttle_pso_params, pop_size=20, generations=12,
+                  re_initialise_generation=100, communication_freq=3, migration_freq=2)
+    opt = pso.ParticleSubswarmOptimisation("landing_burn_pure_throttle", save_interval=0, model=_Sphere(),
+                                           pso_params=params, seed=None, base_save_dir=out_dir)
+    opt.run()
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), x=opt.position, g=opt.global_best_fitness, seed=opt.seed)
+    dist.destroy_process_group()
+
+
+def test_seedless_optimiser_agrees_across_ranks(tmp_path):
+    """seed=None under torch.distributed: rank 0 draws a seed and broadcasts it, so every rank builds
+    the same swarm and issues the same collectives (sharing re-evaluations included)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_gloo_seedless_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "s0.npz"), np.load(tmp_path / "s1.npz")
+    assert int(r0["seed"]) == int(r1["seed"])
+    assert np.array_equal(r0["x"], r1["x"]) and float(r0["g"]) == float(r1["g"])
