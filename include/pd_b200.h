@@ -246,6 +246,7 @@ int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_para
  * 65 536 particles 116 -> 61 ms, 16 384 particles 84 -> 47 ms on one B200.  Results are identical to the one-pass
  * rollout up to the summation order of the cooperative RBF sums (as for small swarms).  0 = off. */
 int pd_set_rollout_handoff(PdEnv *env, int steps);
+int pd_set_rollout_handoff2(PdEnv *env, int steps, int steps2);
 
 /* Whole-episode rollouts with a scripted policy, one launch:
  *   PD_POLICY_TAPE       actions dev [max_steps * n_episodes * A] (step-major), dtype per

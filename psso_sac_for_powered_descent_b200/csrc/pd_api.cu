@@ -50,11 +50,12 @@ struct PdEnv {
     size_t wT_cap = 0;
     int *roll_status = nullptr;
     int *roll_queue = nullptr;
-    double *cont_d = nullptr;        // straggler hand-off records (pd_rollout_pso)
-    int *cont_i = nullptr;
-    int *cont_count = nullptr;
+    double *cont_d[2] = {nullptr, nullptr};   // straggler hand-off records A / B (pd_rollout_pso)
+    int *cont_i[2] = {nullptr, nullptr};
+    int *cont_count = nullptr;       // [2]
     int cont_cap = 0;
-    int handoff_steps = 256;         // pd_set_rollout_handoff
+    int handoff_steps = 128;         // pd_set_rollout_handoff
+    int handoff2_steps = 512;
     // shared-actor collection
     void *w2_img = nullptr;          // bf16 smem image of W2
     const float *w2_src = nullptr;   // which W2 the image was built from
@@ -404,8 +405,10 @@ int pd_destroy(PdEnv *e) {
     DeviceGuard guard(e->cfg.device);
     for (void *a : e->allocs) cudaFree(a);
     if (e->wT) cudaFree(e->wT);
-    if (e->cont_d) cudaFree(e->cont_d);
-    if (e->cont_i) cudaFree(e->cont_i);
+    for (int k = 0; k < 2; ++k) {
+        if (e->cont_d[k]) cudaFree(e->cont_d[k]);
+        if (e->cont_i[k]) cudaFree(e->cont_i[k]);
+    }
     delete e;
     return 0;
 }
@@ -427,6 +430,15 @@ int pd_set_rollout_handoff(PdEnv *e, int steps) {
     if (!e) return fail("pd_set_rollout_handoff: null handle");
     if (steps < 0) return fail("pd_set_rollout_handoff: steps must be >= 0 (0 = off)");
     e->handoff_steps = steps;
+    e->handoff2_steps = 4 * steps;
+    return 0;
+}
+
+int pd_set_rollout_handoff2(PdEnv *e, int steps, int steps2) {
+    if (!e) return fail("pd_set_rollout_handoff2: null handle");
+    if (steps < 0 || steps2 < 0) return fail("pd_set_rollout_handoff2: steps must be >= 0 (0 = off)");
+    e->handoff_steps = steps;
+    e->handoff2_steps = steps2 > steps ? steps2 : 4 * steps;
     return 0;
 }
 
@@ -626,20 +638,24 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
     io.ret = fitness; io.steps = steps; io.trunc_id = trunc_id; io.terminal = terminal_state;
     io.traj = traj; io.act_out = actions_out; io.rewards = rewards;
     io.queue = e->roll_queue;
-    if (e->handoff_steps > 0 && (long long)io.n_episodes * 8 > (long long)e->n_sm * 448 * 3 / 4) {
-        // continuation records for the straggler hand-off (used when one lane runs one episode)
+    if (e->handoff_steps > 0) {
+        // continuation records of the staged hand-off (two buffers, the stages ping-pong)
         if (e->cont_cap < io.n_episodes) {
-            if (e->cont_d) { cudaFree(e->cont_d); cudaFree(e->cont_i); e->cont_d = nullptr; e->cont_i = nullptr; }
-            CK(cudaMalloc(&e->cont_d, (size_t)PD_CONT_D * io.n_episodes * sizeof(double)));
-            CK(cudaMalloc(&e->cont_i, (size_t)PD_CONT_I * io.n_episodes * sizeof(int)));
+            for (int k = 0; k < 2; ++k) {
+                if (e->cont_d[k]) { cudaFree(e->cont_d[k]); cudaFree(e->cont_i[k]); e->cont_d[k] = nullptr; e->cont_i[k] = nullptr; }
+                CK(cudaMalloc(&e->cont_d[k], (size_t)PD_CONT_D * io.n_episodes * sizeof(double)));
+                CK(cudaMalloc(&e->cont_i[k], (size_t)PD_CONT_I * io.n_episodes * sizeof(int)));
+            }
             e->cont_cap = io.n_episodes;
         }
         if (!e->cont_count) {
-            CK(cudaMalloc(&e->cont_count, sizeof(int)));
+            CK(cudaMalloc(&e->cont_count, 2 * sizeof(int)));
             e->allocs.push_back(e->cont_count);
         }
         io.handoff_steps = e->handoff_steps;
-        io.cont_d = e->cont_d; io.cont_i = e->cont_i; io.cont_count = e->cont_count; io.cont_cap = e->cont_cap;
+        io.handoff2_steps = e->handoff2_steps;
+        io.cont_d = e->cont_d[0]; io.cont_i = e->cont_i[0]; io.cont_count = e->cont_count; io.cont_cap = e->cont_cap;
+        io.out_d = e->cont_d[1]; io.out_i = e->cont_i[1]; io.out_count = e->cont_count + 1; io.out_cap = e->cont_cap;
     }
     WindCtx wc = wind_ctx(e);
     // gust-noise stream id = GLOBAL episode index (particle * n_seeds + seed), so that a windy

@@ -7,6 +7,6 @@
 namespace pd {
 static const Impl k_impl = {
     impl_reset<float, PD_FP32_RBF_T>, Launch<float, PD_FP32_RBF_T>::step,
-    Launch<float, PD_FP32_RBF_T>::rollout, impl_get_state, impl_set_state, impl_transpose, impl_observe<float>};
+    rollout_fp32, impl_get_state, impl_set_state, impl_transpose, impl_observe<float>};
 const Impl *impl_fp32() { return &k_impl; }
 }  // namespace pd

@@ -58,15 +58,21 @@ struct RolloutIO {
     double *terminal, *traj, *rewards;
     float *act_out;        // [max_steps][n_episodes][A] actions applied (MLP policy)
     int *queue;            // work-queue head (next episode index to hand out)
-    // Straggler hand-off (per-particle MLP policy, large swarms): the first pass gives up
-    // episodes that are still running after handoff_steps and appends their complete state to
-    // the continuation records; a second, 8-lane cooperative pass finishes them at ~2.5x lower
-    // per-step latency (a generation is otherwise bounded by its longest episode).
+    // Straggler hand-off (per-particle MLP policy): an episode still running after handoff_steps
+    // (then handoff2_steps) is appended with its complete state to continuation records and
+    // finished by a later stage with more lanes per episode (1 -> 8 -> 32): a generation is
+    // otherwise bounded by the sequential latency of its longest episode.
     int handoff_steps;     // 0 = off
-    double *cont_d;        // [PD_CONT_D][cont_cap]
+    int handoff2_steps;    // second threshold (<= handoff_steps: 4 x handoff_steps)
+    int run_if_gt, run_if_le;   // record-fed stages run only if the input record count is in (gt, le]
+    double *cont_d;        // input records [PD_CONT_D][cont_cap]
     int *cont_i;           // [PD_CONT_I][cont_cap]: episode, t, g-window count, wind draw counter
     int *cont_count;       // [1]
     int cont_cap;
+    double *out_d;         // output records of a hand-off stage
+    int *out_i;
+    int *out_count;
+    int out_cap;
 };
 #define PD_CONT_D 32
 #define PD_CONT_I 4
@@ -86,5 +92,11 @@ struct Impl {
 
 const Impl *impl_fp64();
 const Impl *impl_fp32();
+
+// the rollout kernels of each precision are compiled in their own translation unit (build time)
+int rollout_fp64(const LaunchCtx &, int policy, int phase, int rtd, int wind, const RolloutIO &, const WindCtx &,
+                 const double *, int *status, cudaStream_t);
+int rollout_fp32(const LaunchCtx &, int policy, int phase, int rtd, int wind, const RolloutIO &, const WindCtx &,
+                 const double *, int *status, cudaStream_t);
 
 }  // namespace pd

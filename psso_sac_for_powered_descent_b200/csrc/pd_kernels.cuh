@@ -334,30 +334,109 @@ static __global__ void transpose_weights_kernel(const float *__restrict__ w, flo
     }
 }
 
+// ------------------------------------------------------------------ cooperative per-particle MLP
+// The lanes of a cooperative group (COOP = 8 or 32) all hold the same episode.  The hidden width of
+// simple_actor is 8, so lane j (mod 8) owns hidden unit j of every layer: its weight rows - IN + 1,
+// NH x 9 and 9 floats - are fetched ONCE per episode into a thread-private column of shared memory,
+// a layer is 8 FMAs + 8 shuffles, and the per-step reload of all 249 / 372 weights through L2 by
+// every lane (37 % of a lone episode's step latency, profiles/r2_rollout_mode2_before.txt) is gone.
+// The FMA order per unit is that of actor_mlp, so both paths return bit-identical actions.
+template <int IN, int NH>
+__host__ __device__ constexpr int mlp_words() { return (IN + 1) + NH * 9 + 9; }
+
+template <int IN, int OUT, int NH>
+__device__ __forceinline__ void coop_mlp_load(const float *__restrict__ wT, size_t stride, size_t col, float *wcol) {
+    constexpr int H = 8;
+    const int j = threadIdx.x & 7;
+    const float *p = wT + col;
+    int n = 0;
+    const int nt = blockDim.x;
+#pragma unroll
+    for (int k = 0; k < IN; ++k) wcol[(n++) * nt] = __ldg(p + (size_t)(j * IN + k) * stride);
+    wcol[(n++) * nt] = __ldg(p + (size_t)(H * IN + j) * stride);
+    size_t off = (size_t)(H * IN + H);
+#pragma unroll
+    for (int l = 0; l < NH; ++l) {
+#pragma unroll
+        for (int k = 0; k < H; ++k) wcol[(n++) * nt] = __ldg(p + (off + j * H + k) * stride);
+        wcol[(n++) * nt] = __ldg(p + (off + H * H + j) * stride);
+        off += H * H + H;
+    }
+    const int o = j < OUT ? j : 0;            // output layer: unit j < OUT (the others repeat unit 0)
+#pragma unroll
+    for (int k = 0; k < H; ++k) wcol[(n++) * nt] = __ldg(p + (off + o * H + k) * stride);
+    wcol[(n++) * nt] = __ldg(p + (off + OUT * H + o) * stride);
+}
+
+template <int IN, int OUT, int NH, int COOP>
+__device__ __forceinline__ void coop_mlp_forward(const float *wcol, const float *obs, float *act) {
+    constexpr int H = 8;
+    const int nt = blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int base = lane & ~7;                // the 8 lanes that hold units 0..7 for this lane
+    const unsigned gmask = (COOP == 32 ? 0xffffffffu : ((1u << COOP) - 1u)) << (lane & ~(COOP - 1));
+    float h[H];
+    int n = 0;
+    {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < IN; ++k) acc = fmaf(wcol[(n++) * nt], obs[k], acc);
+        const float u = fmaxf(acc + wcol[(n++) * nt], 0.f);
+#pragma unroll
+        for (int k = 0; k < H; ++k) h[k] = __shfl_sync(gmask, u, base + k);
+    }
+#pragma unroll
+    for (int l = 0; l < NH; ++l) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < H; ++k) acc = fmaf(wcol[(n++) * nt], h[k], acc);
+        const float u = fmaxf(acc + wcol[(n++) * nt], 0.f);
+#pragma unroll
+        for (int k = 0; k < H; ++k) h[k] = __shfl_sync(gmask, u, base + k);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) acc = fmaf(wcol[(n++) * nt], h[k], acc);
+    const float u = tanhf(acc + wcol[(n++) * nt]);
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) act[o] = __shfl_sync(gmask, u, base + o);
+}
+
 // ------------------------------------------------------------------ persistent rollout kernel
-// One episode per thread from reset to done/truncated: objective_function
-// (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for POLICY_TAPE,
-// LandingBurn.run_closed_loop for POLICY_CLASSICAL.
-// MODE 0: whole episodes.  MODE 1: first pass of the straggler hand-off (episodes still running
-// after io.handoff_steps are written to the continuation records instead of being finished).
-// MODE 2: second pass, episodes = continuation records.
+// One episode per thread (or per cooperative group of COOP lanes) from reset to done/truncated:
+// objective_function (env_wrapped_ea.py:200-222) for POLICY_MLP, an env.step loop over a tape for
+// POLICY_TAPE, LandingBurn.run_closed_loop for POLICY_CLASSICAL.
+// MODE bit 0: hand-off - an episode still running after io.handoff_steps is written to the output
+//             continuation records instead of being finished.
+// MODE bit 1: the episodes are the input continuation records of an earlier stage; the launch is
+//             a no-op unless their number is in (io.run_if_gt, io.run_if_le].
+// Ragged episode lengths (P: 101 .. 4000+ steps) are served in stages of growing cooperation:
+// one lane per episode while there are more episodes than lanes, 8 lanes, then 32 lanes for the
+// handful of long ones whose sequential latency bounds the generation.
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE = 0>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = phase_adim(PHASE);
     constexpr int O = phase_odim(PHASE);
+    constexpr bool FROM_RECORDS = (MODE & 2) != 0, HANDOFF = (MODE & 1) != 0;
+    constexpr bool COOP_MLP = POLICY == 0 && COOP >= 8;
+    constexpr int NH = PHASE == 0 ? 3 : 4;
+    int n_work = io.n_episodes;
+    if constexpr (FROM_RECORDS) {
+        const int cnt = min(*io.cont_count, io.cont_cap);
+        if (cnt <= io.run_if_gt || cnt > io.run_if_le) return;       // another stage variant's job
+        n_work = cnt;
+    }
     Dev D(kp);
     extern __shared__ __align__(16) unsigned char pd_smem[];
     SharedTables &sh = *aligned_tables(pd_smem);
+    float *wcol = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(&sh) + sizeof(SharedTables)) + threadIdx.x;
     stage_tables(&sh, kp.tb.sh_image);
     wait_tables(&sh);
-    // Persistent lanes with a work queue: episode lengths are ragged (P: 101..460 steps,
-    // G: 7..27), so a lane that finishes pulls the next episode index instead of idling until
-    // the slowest lane of its warp is done.
-    // COOP lanes share one episode (identical state in each; only the RBF sums are split)
-    int e = (blockIdx.x * blockDim.x + threadIdx.x) / COOP;      // MODE 2: record index
+    // Persistent lanes with a work queue: a lane (group) that finishes pulls the next episode
+    // index instead of idling until the slowest lane of its warp is done.
+    int e = (blockIdx.x * blockDim.x + threadIdx.x) / COOP;      // FROM_RECORDS: record index
     const bool writer = (threadIdx.x & (COOP - 1)) == 0;
-    const int n_work = MODE == 2 ? min(*io.cont_count, io.cont_cap) : io.n_episodes;
     bool active = e < n_work;
     int eid = e;                                                  // episode the lane works on
     State s;
@@ -370,7 +449,7 @@ rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, con
     int t = 0;
     size_t col = 0;
     auto begin_episode = [&]() {
-        if constexpr (MODE == 2) {
+        if constexpr (FROM_RECORDS) {
             const size_t cap = (size_t)io.cont_cap;
             const double *d = io.cont_d + e;
             const int *ci = io.cont_i + e;
@@ -399,6 +478,7 @@ rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, con
             t = 0;
         }
         col = (size_t)(eid / io.n_seeds);
+        if constexpr (COOP_MLP) coop_mlp_load<O, A, NH>(io.wT, io.w_stride, col, wcol);
     };
     if (active) begin_episode();
     while (__any_sync(0xffffffffu, active)) {
@@ -411,7 +491,8 @@ rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, con
             float of[O], af[A];
 #pragma unroll
             for (int k = 0; k < O; ++k) of[k] = (float)obs[k];
-            actor_mlp<O, A, (PHASE == 0 ? 3 : 4)>(io.wT, io.w_stride, col, of, af);
+            if constexpr (COOP_MLP) coop_mlp_forward<O, A, NH, COOP>(wcol, of, af);
+            else actor_mlp<O, A, NH>(io.wT, io.w_stride, col, of, af);
             act.f32 = true;
 #pragma unroll
             for (int k = 0; k < A; ++k) act.u[k] = (double)af[k];
@@ -467,39 +548,47 @@ rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, con
             }
         }
         bool handoff = false;
-        if constexpr (MODE == 1) {
+        if constexpr (HANDOFF) {
             if (!stop && t >= io.handoff_steps) {
-                // still running: append the complete episode state to the continuation records
-                const int r = atomicAdd(io.cont_count, 1);
-                if (r < io.cont_cap) {
-                    const size_t cap = (size_t)io.cont_cap;
-                    double *d = io.cont_d + r;
-                    int *ci = io.cont_i + r;
-                    ci[0] = eid; ci[cap] = t; ci[2 * cap] = gw.n; ci[3 * cap] = (int)w.ctr;
-                    d[0] = s.x; d[cap] = s.y; d[2 * cap] = s.vx; d[3 * cap] = s.vy; d[4 * cap] = s.theta;
-                    d[5 * cap] = s.theta_dot; d[6 * cap] = s.gamma; d[7 * cap] = s.alpha; d[8 * cap] = s.mass;
-                    d[9 * cap] = s.m_prop; d[10 * cap] = s.time;
+                // still running: append the complete episode state to the output continuation records
+                int r = 0;
+                if (writer) r = atomicAdd(io.out_count, 1);
+                if (COOP > 1) {
+                    const int leader = (threadIdx.x & 31) & ~(COOP - 1);
+                    const unsigned gmask = (COOP == 32 ? 0xffffffffu : ((1u << COOP) - 1u)) << leader;
+                    r = __shfl_sync(gmask, r, leader);
+                }
+                if (r < io.out_cap) {
+                    if (writer) {
+                        const size_t cap = (size_t)io.out_cap;
+                        double *d = io.out_d + r;
+                        int *ci = io.out_i + r;
+                        ci[0] = eid; ci[cap] = t; ci[2 * cap] = gw.n; ci[3 * cap] = (int)w.ctr;
+                        d[0] = s.x; d[cap] = s.y; d[2 * cap] = s.vx; d[3 * cap] = s.vy; d[4 * cap] = s.theta;
+                        d[5 * cap] = s.theta_dot; d[6 * cap] = s.gamma; d[7 * cap] = s.alpha; d[8 * cap] = s.mass;
+                        d[9 * cap] = s.m_prop; d[10 * cap] = s.time;
 #pragma unroll
-                    for (int k = 0; k < 10; ++k) d[(11 + k) * cap] = (double)gw.w[k];
-                    d[21 * cap] = prev.gimbal_deg; d[22 * cap] = prev.dl; d[23 * cap] = prev.dr;
-                    d[24 * cap] = w.xu0; d[25 * cap] = w.xu1; d[26 * cap] = w.xv0; d[27 * cap] = w.xv1;
-                    d[28 * cap] = w.sigma_u; d[29 * cap] = w.sigma_v;
-                    d[30 * cap] = total;
+                        for (int k = 0; k < 10; ++k) d[(11 + k) * cap] = (double)gw.w[k];
+                        d[21 * cap] = prev.gimbal_deg; d[22 * cap] = prev.dl; d[23 * cap] = prev.dr;
+                        d[24 * cap] = w.xu0; d[25 * cap] = w.xu1; d[26 * cap] = w.xv0; d[27 * cap] = w.xv1;
+                        d[28 * cap] = w.sigma_u; d[29 * cap] = w.sigma_v;
+                        d[30 * cap] = total;
+                    }
                     handoff = true;
                     stop = true;
                 }
             }
         }
         if (stop) {
-            if (!handoff) {
-            if (io.ret && writer) io.ret[eid] = total;
-            if (io.steps && writer) io.steps[eid] = t;
-            if (io.trunc_id && writer) io.trunc_id[eid] = tid;
-            }
-            if (io.terminal && writer && !handoff) {
-                double *p = io.terminal + (size_t)eid * 11;
-                p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
-                p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
+            if (!handoff && writer) {
+                if (io.ret) io.ret[eid] = total;
+                if (io.steps) io.steps[eid] = t;
+                if (io.trunc_id) io.trunc_id[eid] = tid;
+                if (io.terminal) {
+                    double *p = io.terminal + (size_t)eid * 11;
+                    p[0] = s.x; p[1] = s.y; p[2] = s.vx; p[3] = s.vy; p[4] = s.theta; p[5] = s.theta_dot;
+                    p[6] = s.gamma; p[7] = s.alpha; p[8] = s.mass; p[9] = s.m_prop; p[10] = s.time;
+                }
             }
             if (writer) e = atomicAdd(io.queue, 1);
             if (COOP > 1) {
@@ -593,42 +682,91 @@ struct Launch {
             default: step_t<5, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
         }
     }
-    template <int PHASE, int RTD, bool WIND, int POLICY>
-    static void roll_t(const LaunchCtx &lc, const RolloutIO &io, const WindCtx &wc, const double *sig, int *status,
-                       cudaStream_t st) {
-        // A persistent grid (one block per SM) fed by the work queue.  Fewer episodes than ~3/4 of
-        // the GPU's lanes / 8: 8 lanes co-operate on each episode (splits the 100 RBF terms per
-        // sub-step), which both fills the SMs and cuts the per-step latency that bounds a
-        // generation by its longest episode.
-        const int n_sm = lc.n_sm;
-        const bool coop = (long long)io.n_episodes * 8 <= (long long)n_sm * PD_MAX_BLOCK * 3 / 4;
-        const int lanes_per = coop ? 8 : 1;
-        long long lanes = (long long)io.n_episodes * lanes_per;
-        int threads, blocks;
-        big_block_config(lanes, n_sm, threads, blocks);
-        if (blocks > n_sm) blocks = n_sm;              // persistent: the queue feeds the rest
-        init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads / lanes_per);
-        if (coop) {
-            PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8>), lc);
-            rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
-            return;
+    template <int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE>
+    static void roll_launch(const LaunchCtx &lc, int blocks, int threads, const RolloutIO &io, const WindCtx &wc,
+                            const double *sig, int *status, cudaStream_t st) {
+        constexpr int O = phase_odim(PHASE);
+        constexpr int NH = PHASE == 0 ? 3 : 4;
+        // cooperative per-particle MLP: a thread-private column of weight rows behind the tables
+        const unsigned smem = PD_SH_BYTES + ((POLICY == 0 && COOP >= 8) ? mlp_words<O, NH>() * threads * 4 + 16 : 0);
+        static std::mutex mu;
+        static std::set<int> done;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (done.insert(lc.device).second)
+                cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, COOP, MODE>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(PD_SH_BYTES + 52 * PD_MAX_BLOCK * 4 + 16));
         }
+        init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads / COOP);
+        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, COOP, MODE><<<blocks, threads, smem, st>>>(*lc.kp, io, wc, sig, status);
+    }
+    template <int PHASE, int RTD, bool WIND, int POLICY>
+    static void roll_t(const LaunchCtx &lc, const RolloutIO &io_in, const WindCtx &wc, const double *sig, int *status,
+                       cudaStream_t st) {
+        // Persistent grids (one block per SM) fed by a work queue.  Fewer episodes than ~3/4 of the
+        // GPU's lanes / 8: 8 lanes co-operate on each episode from the start (they split the 100 RBF
+        // terms per sub-step and the 8 hidden units of the actor), which both fills the SMs and cuts
+        // the per-step latency that bounds a generation by its longest episode.
+        RolloutIO io = io_in;
+        const int n_sm = lc.n_sm;
+        const long long L = (long long)n_sm * PD_MAX_BLOCK;
+        const bool coop = (long long)io.n_episodes * 8 <= L * 3 / 4;
+        const int lanes_per = coop ? 8 : 1;
+        int threads, blocks;
+        big_block_config((long long)io.n_episodes * lanes_per, n_sm, threads, blocks);
+        if (blocks > n_sm) blocks = n_sm;              // persistent: the queue feeds the rest
         if constexpr (POLICY == 0) {
-            if (io.handoff_steps > 0 && io.handoff_steps < io.max_steps && io.cont_d && io.cont_i && io.cont_count) {
-                // two passes: one lane per episode up to handoff_steps, then the stragglers (about
-                // 1 % of a random swarm) 8 lanes each
-                PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1>), lc);
-                PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2>), lc);
-                cudaMemsetAsync(io.cont_count, 0, sizeof(int), st);
-                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1, 1><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
-                const int b2 = n_sm, t2 = PD_MAX_BLOCK;
-                init_queue_kernel<<<1, 1, 0, st>>>(io.queue, b2 * t2 / 8);
-                rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 8, 2><<<b2, t2, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
+            const bool staged = io.handoff_steps > 0 && io.cont_d && io.out_d;
+            const int h1 = io.handoff_steps, h2 = io.handoff2_steps > h1 ? io.handoff2_steps : 4 * h1;
+            if (staged && h1 < io.max_steps) {
+                // Stage records ping-pong between two buffers: A = (cont_*), B = (out_*) of io_in.
+                RolloutIO A2B = io;                    // reads A, writes B
+                RolloutIO fromB = io;                  // reads B
+                fromB.cont_d = io.out_d; fromB.cont_i = io.out_i; fromB.cont_count = io.out_count; fromB.cont_cap = io.out_cap;
+                // more survivors than lanes: one lane each (the queue keeps the SMs full); fewer than
+                // 4 waves of 32-lane groups: 32 lanes each; 8 lanes in between
+                const int T8 = (int)L, T32 = (int)(L / 8);
+                cudaMemsetAsync(io.out_count, 0, sizeof(int), st);
+                if (coop) {
+                    // small swarm: 8 lanes from reset up to h2, then 32 lanes for what is left
+                    RolloutIO first = io;
+                    first.handoff_steps = h2;
+                    if (h2 < io.max_steps) {
+                        roll_launch<PHASE, RTD, WIND, POLICY, 8, 1>(lc, blocks, threads, first, wc, sig, status, st);
+                    } else {
+                        roll_launch<PHASE, RTD, WIND, POLICY, 8, 0>(lc, blocks, threads, io, wc, sig, status, st);
+                        return;
+                    }
+                } else {
+                    // large swarm: one lane per episode up to h1 -> records A; A -> B up to h2 with one
+                    // lane (more stragglers than 8-lane groups fit twice) or 8 lanes
+                    RolloutIO first = io;              // writes A
+                    first.out_d = io.cont_d; first.out_i = io.cont_i; first.out_count = io.cont_count; first.out_cap = io.cont_cap;
+                    cudaMemsetAsync(io.cont_count, 0, sizeof(int), st);
+                    roll_launch<PHASE, RTD, WIND, POLICY, 1, 1>(lc, blocks, threads, first, wc, sig, status, st);
+                    if (h2 < io.max_steps) {
+                        A2B.handoff_steps = h2;
+                        A2B.run_if_gt = T8; A2B.run_if_le = 0x7fffffff;
+                        roll_launch<PHASE, RTD, WIND, POLICY, 1, 3>(lc, n_sm, PD_MAX_BLOCK, A2B, wc, sig, status, st);
+                        A2B.run_if_gt = -1; A2B.run_if_le = T8;
+                        roll_launch<PHASE, RTD, WIND, POLICY, 8, 3>(lc, n_sm, PD_MAX_BLOCK, A2B, wc, sig, status, st);
+                    } else {
+                        fromB = io;                    // no second stage: finish from A
+                    }
+                }
+                // final stage: as much cooperation as the number of survivors allows
+                fromB.run_if_gt = T8; fromB.run_if_le = 0x7fffffff;
+                roll_launch<PHASE, RTD, WIND, POLICY, 1, 2>(lc, n_sm, PD_MAX_BLOCK, fromB, wc, sig, status, st);
+                fromB.run_if_gt = T32; fromB.run_if_le = T8;
+                roll_launch<PHASE, RTD, WIND, POLICY, 8, 2>(lc, n_sm, PD_MAX_BLOCK, fromB, wc, sig, status, st);
+                fromB.run_if_gt = -1; fromB.run_if_le = T32;
+                roll_launch<PHASE, RTD, WIND, POLICY, 32, 2>(lc, n_sm, PD_MAX_BLOCK, fromB, wc, sig, status, st);
                 return;
             }
         }
-        PD_SMEM_OPT_IN((rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1>), lc);
-        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, 1><<<blocks, threads, PD_SH_BYTES, st>>>(*lc.kp, io, wc, sig, status);
+        if (coop) roll_launch<PHASE, RTD, WIND, POLICY, 8, 0>(lc, blocks, threads, io, wc, sig, status, st);
+        else roll_launch<PHASE, RTD, WIND, POLICY, 1, 0>(lc, blocks, threads, io, wc, sig, status, st);
     }
     static int rollout(const LaunchCtx &lc, int policy, int phase, int rtd, int wind, const RolloutIO &io,
                        const WindCtx &wc, const double *sig, int *status, cudaStream_t st) {

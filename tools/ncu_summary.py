@@ -74,7 +74,7 @@ def main():
                         pass
     T, S = sum(tot.values()) or 1, sum(samp.values()) or 1
     lines.append(f"top source lines of the first profiled launch (instructions {T}, samples {S})")
-    for k, v in tot.most_common(25):
+    for k, v in tot.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 25):
         lines.append(f"  {k[0]:18s}:{k[1]:>5s}  inst {100*v/T:5.1f}%  samples {100*samp[k]/S:5.1f}%  {text[k]}")
     lines.append("")
     lines.append("warp stall reasons (all samples): " + ", ".join(f"{k[6:]} {100*v/max(sum(stall.values()),1):.1f}%" for k, v in stall.most_common(8)))
