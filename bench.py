@@ -34,7 +34,8 @@ sys.path.insert(0, REPO)
 
 P = "landing_burn_pure_throttle"
 G = "landing_burn"
-OTHER_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol")
+OTHER_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol",
+                "flip_over_boostbackburn")
 N_ENVS = 65536
 ALGO_BYTES_PER_STEP = 160.0        # 40 words x 4 B, phase P, fp32
 ALGO_FLOP_PER_STEP = 4800.0        # canonical flop per env-step (P, no wind)
@@ -441,7 +442,8 @@ def run_cuda(args):
     if not args.no_phases:
         phases = {}
         for ph in OTHER_PHASES:
-            penv = envs.BatchedRocketEnv(B, "rl", ph, precision=args.precision, auto_reset=True, device=local,
+            penv = envs.BatchedRocketEnv(B, "supervisory" if ph == "flip_over_boostbackburn" else "rl", ph,
+                                         precision=args.precision, auto_reset=True, device=local,
                                          trajectory_length=1000, discount_factor=0.99, seed=5 + rank)
             ptape = torch.rand(40, B, penv.act_dim, device=dev, generator=gen, dtype=torch.float32) * 2 - 1
             with torch.cuda.stream(stream):

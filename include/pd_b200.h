@@ -44,7 +44,8 @@ extern "C" {
  * and are not offered. */
 enum { PD_PHASE_PURE_THROTTLE = 0, PD_PHASE_GIMBALLED = 1, PD_PHASE_SUBSONIC = 2,
        PD_PHASE_SUPERSONIC = 3, PD_PHASE_BALLISTIC_ARC = 4, PD_PHASE_PCONTROL = 5,
-       PD_N_PHASES = 6 };
+       PD_PHASE_FLIP_OVER = 6,   /* flip_over_boostbackburn: type 'supervisory' only, as upstream */
+       PD_N_PHASES = 7 };
 /* type = 'pso' | 'rl' | 'supervisory' (src/envs/supervisory/rtd_supervisory_mock.py: done /
  * truncation per phase, reward 0; pd_step only, actions as the base env takes them) */
 enum { PD_RTD_PSO = 0, PD_RTD_RL = 1, PD_RTD_SUPERVISORY = 2 };
@@ -102,8 +103,8 @@ typedef struct {
      * m_1_ox, m_1_f, h_lower_1 */
     double inertia_full[13];
     double engine_height_full, cop_full;
-    double initial_state[3][PD_STATE_DIM]; /* subsonic, supersonic, ballistic_arc_descent */
-    double norm_vals[3][8];               /* same order; ballistic uses the first 4 */
+    double initial_state[4][PD_STATE_DIM]; /* subsonic, supersonic, ballistic_arc_descent, flip_over_boostbackburn */
+    double norm_vals[4][8];               /* same order; ballistic uses the first 4, flip-over the first 2 */
     const double *ref_y, *ref_x, *ref_vx, *ref_vy;   /* host [n_ref], raw csv order */
     double ref_terminal[5];               /* last row: x, y, vx, vy, mass */
 } PdOtherPhases;
@@ -134,7 +135,7 @@ typedef struct {
     const double *wind_alt_km, *wind_speed;   /* host */
     double vk_Adu[4], vk_Bdu[2], vk_Adv[4], vk_Bdv[2];
     PdRbfTable cd, cl;
-    const PdOtherPhases *other;           /* host; required for PD_PHASE_SUBSONIC .. PD_PHASE_PCONTROL */
+    const PdOtherPhases *other;           /* host; required for PD_PHASE_SUBSONIC .. PD_PHASE_BALLISTIC_ARC and PD_PHASE_FLIP_OVER */
 } PdParams;
 
 /* rocket_environment_pre_wrap.__init__ kwargs (src/envs/base_environment.py:12-20) + batch */
@@ -246,7 +247,10 @@ int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_para
  * 65 536 particles 116 -> 61 ms, 16 384 particles 84 -> 47 ms on one B200.  Results are identical to the one-pass
  * rollout up to the summation order of the cooperative RBF sums (as for small swarms).  0 = off. */
 int pd_set_rollout_handoff(PdEnv *env, int steps);
-int pd_set_rollout_handoff2(PdEnv *env, int steps, int steps2);
+/* Both thresholds of the staged hand-off: 1 lane per episode up to `steps`, 8 lanes up to `steps2`
+ * (default 128 / 512; steps2 <= steps: 4 x steps), 32 lanes from there; each later stage picks its
+ * cooperation from the number of surviving episodes.  0 = off. */
+int pd_set_rollout_stages(PdEnv *env, int steps, int steps2);
 
 /* Whole-episode rollouts with a scripted policy, one launch:
  *   PD_POLICY_TAPE       actions dev [max_steps * n_episodes * A] (step-major), dtype per

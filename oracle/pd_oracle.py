@@ -33,6 +33,7 @@ following, function by function (paths relative to /root/reference):
     cog_inertia()         src/RocketSizing/functions/rocket_dimensions.py:167-196
     control_P()/control_G()  src/envs/rockets_physics.py:340-400 / 168-269
     control_ascent()/control_rcs()/control_C()  rockets_physics.py:17-56 / 149-166 / 402-451
+    control_flip()        src/envs/rockets_physics.py:63-92 (+ :542-560: no aerodynamic forces)
     cog_inertia_full()    src/RocketSizing/functions/rocket_dimensions.py:199-241
     ascent / ballistic / P-control rtd   src/envs/rl/rtd_rl.py:11-114, 147-188, 353-534
     substep()             src/envs/rockets_physics.py:455-646
@@ -76,6 +77,7 @@ PHASE_S = "subsonic"
 PHASE_U = "supersonic"
 PHASE_B = "ballistic_arc_descent"
 PHASE_C = "landing_burn_pure_throttle_Pcontrol"
+PHASE_F = "flip_over_boostbackburn"
 RL_ONLY_PHASES = (PHASE_S, PHASE_U, PHASE_B, PHASE_C)
 
 # Mach-scheduled truncation thresholds / reward weights of the ascent phases
@@ -443,8 +445,11 @@ class OracleEnv:
     def __init__(self, flight_phase=PHASE_P, type="pso", enable_wind=False,
                  stochastic_wind=False, horiontal_wind_percentile=50, tables=None,
                  wind_noise=None, fast_rbf=False, trajectory_length=1, discount_factor=0.99):
-        assert flight_phase in (PHASE_P, PHASE_G) + RL_ONLY_PHASES
+        assert flight_phase in (PHASE_P, PHASE_G, PHASE_F) + RL_ONLY_PHASES
         assert type in ("pso", "rl", "supervisory")
+        if flight_phase == PHASE_F and type != "supervisory":
+            raise TypeError("flip_over_boostbackburn: only type='supervisory' works upstream (its rl and pso "
+                            "truncated_func take one argument, rtd_rl.py:132 / rtd_pso.py:107)")
         if flight_phase in RL_ONLY_PHASES and type == "pso":
             raise TypeError(f"{flight_phase}: the reference's pso closures have the wrong arity "
                             "(rtd_pso.py:38-157); only type='rl' works upstream")
@@ -481,7 +486,7 @@ class OracleEnv:
                                    horiontal_wind_percentile, noise=wind_noise)
         else:
             self.wind = None
-        if flight_phase in (PHASE_S, PHASE_U, PHASE_B):
+        if flight_phase in (PHASE_S, PHASE_U, PHASE_B, PHASE_F):
             self.state_initial = list(self.T.initial_states[flight_phase])
         else:
             self.state_initial = list(self.T.initial_state)
@@ -585,6 +590,25 @@ class OracleEnv:
         mass_flow = (p["thrust_per_engine"] / p["v_exhaust"]) * n_tot
         return t_par, t_perp, m_z, mass_flow, throttle, None
 
+    def _control_flip(self, action, p_atm, d_thrust_cg):
+        """force_moment_decomposer_flipoverboostbackburn, rockets_physics.py:63-92 (max gimbal 10 deg,
+        first-order low-pass tau 1.0 on the env dt, throttle 1, the gimballed engines only)."""
+        p = self.T.p
+        cmd_deg = action * 10
+        x = self.gimbal_prev
+        gimbal_deg = x + self.dt_act * ((-x + cmd_deg) / 1.0)
+        gimbal_rad = math.radians(gimbal_deg)
+        throttle = 1
+        t_full = p["thrust_per_engine"] + (p["nozzle_exit_pressure"] - p_atm) * p["nozzle_exit_area"]
+        thrust = t_full * int(p["n_engines_gimballed"]) * throttle
+        t_par = thrust * math.cos(gimbal_rad)
+        t_perp = -thrust * math.sin(gimbal_rad)
+        m_z = -thrust * math.sin(gimbal_rad) * d_thrust_cg
+        total = np.sqrt(t_par ** 2 + t_perp ** 2)
+        n_tot = total / t_full
+        mass_flow = (p["thrust_per_engine"] / p["v_exhaust"]) * n_tot
+        return t_par, t_perp, m_z, mass_flow, None, (gimbal_deg, 0.0, 0.0)
+
     def _control_rcs(self, action, x_cog):
         """RCS, rockets_physics.py:149-166."""
         o = self.T.other
@@ -665,6 +689,12 @@ class OracleEnv:
                 actions, p_atm, d_thrust_cg)
         elif self.flight_phase == PHASE_B:
             c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_rcs(actions, x_cog)
+        elif self.flight_phase == PHASE_F:
+            c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_flip(actions, p_atm, d_thrust_cg)
+            # "No aerodynamic forces in upper atmosphere, this is a redundancy." (:556-560)
+            aero_x = 0.0
+            aero_y = 0.0
+            aero_mz = 0.0
         else:
             c_par, c_perp, c_mz, mass_flow, throttle, act = self._control_C(
                 actions, p_atm, theta, alpha_eff, q, x_cog, mach, speed)
@@ -710,7 +740,7 @@ class OracleEnv:
         for _ in range(self.n_sub):
             state, info = self.substep(state, actions)
         self.state = state
-        if self.flight_phase == PHASE_G:
+        if self.flight_phase in (PHASE_G, PHASE_F):
             # only the 4th sub-step's actuator outputs are fed back, and the deltas
             # fed back are the *commands*
             self.gimbal_prev, self.delta_l_prev, self.delta_r_prev = info["act"]
@@ -750,6 +780,8 @@ class OracleEnv:
             return bool(y > self.T.other["ref_traj_ascent_terminal"][1])
         if self.flight_phase == PHASE_B:
             return bool(0.5 * rho * speed ** 2 > 65000 and abs(gamma - theta - math.pi) < math.radians(3))
+        if self.flight_phase == PHASE_F:
+            return bool(vx < -60)
         return bool(y < 1)
 
     def _sup_truncated(self, s, info):
@@ -757,7 +789,7 @@ class OracleEnv:
         rho, _, _ = isa(y)
         speed = math.sqrt(vx ** 2 + vy ** 2)
         q = 0.5 * rho * speed ** 2
-        if self.ascent:
+        if self.ascent or self.flight_phase == PHASE_F:
             return (True, 1) if m_prop <= 0 else (False, 0)
         if self.flight_phase == PHASE_B:
             return (True, 1) if (q > 35000 and abs(gamma - theta - math.pi) > math.radians(3)) else (False, 0)
@@ -1168,6 +1200,8 @@ class SupervisoryEnv:
             return np.array([x, y, vx, vy, theta, theta_dot, alpha, mass]) / self.nv
         if self.flight_phase == PHASE_B:
             return np.array([theta, theta_dot, gamma, alpha]) / self.nv
+        if self.flight_phase == PHASE_F:
+            return np.array([theta, theta_dot]) / self.nv
         if self.flight_phase == PHASE_P:
             return np.array([(1 - y / self.nv[0]) * 2 - 1, (1 - vy / self.nv[1]) * 2 - 1])
         return np.array([(1 - y / self.nv[0]) * 2 - 1])

@@ -16,12 +16,13 @@ LIB_PATH = os.environ.get("PD_LIB_PATH") or os.path.join(HERE, "libpd_b200.so")
 CACHE_DIR = os.path.join(HERE, "_cache")
 
 PHASES = {"landing_burn_pure_throttle": 0, "landing_burn": 1, "subsonic": 2, "supersonic": 3,
-          "ballistic_arc_descent": 4, "landing_burn_pure_throttle_Pcontrol": 5}
+          "ballistic_arc_descent": 4, "landing_burn_pure_throttle_Pcontrol": 5, "flip_over_boostbackburn": 6}
 RL_ONLY_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn_pure_throttle_Pcontrol")
+SUPERVISORY_ONLY_PHASES = ("flip_over_boostbackburn",)
 RTD = {"pso": 0, "rl": 1, "supervisory": 2}
 PRECISION = {"fp64": 0, "fp32": 1}
-OBS_DIM = {0: 2, 1: 5, 2: 8, 3: 8, 4: 4, 5: 1}
-ACT_DIM = {0: 1, 1: 4, 2: 2, 3: 2, 4: 1, 5: 1}
+OBS_DIM = {0: 2, 1: 5, 2: 8, 3: 8, 4: 4, 5: 1, 6: 2}
+ACT_DIM = {0: 1, 1: 4, 2: 2, 3: 2, 4: 1, 5: 1, 6: 1}
 N_PARAMS = {0: 249, 1: 372}
 INERTIA_FULL_ORDER = ("m_s_1", "x_dry_1", "I_dry_1", "m_2", "m_pay", "x_wet_2_initial", "I_wet_2_initial",
                       "h_1", "h_1_ox", "h_1_f", "m_1_ox", "m_1_f", "h_lower_1")
@@ -46,7 +47,7 @@ class PdOtherPhases(C.Structure):
                 ("max_rcs_force_per_thruster", C.c_double), ("d_base_rcs_bottom", C.c_double),
                 ("d_base_rcs_top", C.c_double), ("inertia_full", C.c_double * 13),
                 ("engine_height_full", C.c_double), ("cop_full", C.c_double),
-                ("initial_state", (C.c_double * 11) * 3), ("norm_vals", (C.c_double * 8) * 3),
+                ("initial_state", (C.c_double * 11) * 4), ("norm_vals", (C.c_double * 8) * 4),
                 ("ref_y", C.c_void_p), ("ref_x", C.c_void_p), ("ref_vx", C.c_void_p), ("ref_vy", C.c_void_p),
                 ("ref_terminal", C.c_double * 5)]
 
@@ -91,7 +92,7 @@ EXPORTS = ["pd_last_error", "pd_version", "pd_create", "pd_destroy", "pd_reset",
            "pd_get_state", "pd_set_state", "pd_set_wind_tape", "pd_rollout_pso", "pd_rollout_policy",
            "pd_collect_shared_actor", "pd_actor_forward", "pd_pso_update", "pd_pso_seed_mean", "pd_pso_select", "pd_pso_gather", "pd_pso_apply",
            "pd_set_rollout_stream", "pd_measure_fma_peak", "pd_check_status", "pd_launch_count",
-           "pd_set_info_mode", "pd_set_rollout_handoff", "pd_set_rollout_handoff2"]
+           "pd_set_info_mode", "pd_set_rollout_handoff", "pd_set_rollout_stages"]
 
 _lib = None
 
@@ -125,7 +126,7 @@ def load_library():
     lib.pd_set_rollout_stream.argtypes = [vp, C.c_int64, C.c_uint32]
     lib.pd_set_info_mode.argtypes = [vp, i32]
     lib.pd_set_rollout_handoff.argtypes = [vp, i32]
-    lib.pd_set_rollout_handoff2.argtypes = [vp, i32, i32]
+    lib.pd_set_rollout_stages.argtypes = [vp, i32, i32]
     lib.pd_measure_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pd_pso_seed_mean.argtypes = [vp, i32, i32, vp, vp]
     lib.pd_pso_select.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
@@ -306,7 +307,7 @@ def make_params(p: RocketParams, percentile=50):
             t.inertia_full[i] = o["inertia_full"][k]
         t.engine_height_full = o["engine_height_full"]
         t.cop_full = o["cop_d0_full"] * o["cop_length_full"]
-        for r, ph in enumerate(("subsonic", "supersonic", "ballistic_arc_descent")):
+        for r, ph in enumerate(("subsonic", "supersonic", "ballistic_arc_descent", "flip_over_boostbackburn")):
             for i in range(11):
                 t.initial_state[r][i] = o["initial_states"][ph][i]
             for i, v in enumerate(o["norm_vals"][ph]):

@@ -195,7 +195,9 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
         s.nominal = (cfg.phase == PD_PHASE_SUBSONIC || cfg.phase == PD_PHASE_SUPERSONIC) ? 0.5 : (0 * 0.4) / n_gim;
         s.dt_phys = 0.1;
     }
-    s.dt_act = 0.025;
+    // actuator low-pass: the landing burns filter on dt_temp = 0.025 (:805, 911), the flip-over on the env dt
+    s.dt_act = cfg.phase == PD_PHASE_FLIP_OVER ? 0.1 : 0.025;
+    s.flip_max_gimbal_deg = 10;
     s.one_minus_nominal = 1 - s.nominal;
     s.S_gf = p.grid_fin_area;
     s.d_gf = p.d_base_grid_fin;
@@ -224,7 +226,8 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
             s.engine_height = o.engine_height_full;
             s.cop = o.cop_full;
         }
-        const int row = cfg.phase == PD_PHASE_SUBSONIC ? 0 : cfg.phase == PD_PHASE_SUPERSONIC ? 1 : 2;
+        const int row = cfg.phase == PD_PHASE_SUBSONIC ? 0 : cfg.phase == PD_PHASE_SUPERSONIC ? 1
+                        : cfg.phase == PD_PHASE_FLIP_OVER ? 3 : 2;
         for (int i = 0; i < 8; ++i) s.norm8[i] = o.norm_vals[row][i] != 0.0 ? o.norm_vals[row][i] : 1.0;
         // Mach schedules of rtd_rl.py:544-575: max_x, max_vy, max_vx, max_alpha_deg
         static const double SUB[12][5] = {
@@ -298,6 +301,9 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     if (!cfg || !p || !out) return fail("pd_create: null argument");
     if (cfg->n_envs <= 0) return fail("pd_create: n_envs must be positive");
     if (cfg->phase < 0 || cfg->phase >= PD_N_PHASES) return fail("pd_create: unknown flight phase");
+    if (cfg->phase == PD_PHASE_FLIP_OVER && cfg->rtd != PD_RTD_SUPERVISORY)
+        return fail("pd_create: flip_over_boostbackburn only works with type='supervisory' upstream (its rl "
+                    "and pso truncated_func take one argument, rtd_rl.py:132 / rtd_pso.py:107)");
     if (cfg->phase > PD_PHASE_GIMBALLED && cfg->rtd == PD_RTD_PSO)
         return fail("pd_create: this flight phase only works with type='rl' upstream (its pso "
                     "closures have the wrong arity, rtd_pso.py:38-157)");
@@ -363,6 +369,8 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     for (int k = 0; k < 11; ++k) e->tb.init[k] = p->initial_state[k];
     if (cfg->phase >= PD_PHASE_SUBSONIC && cfg->phase <= PD_PHASE_BALLISTIC_ARC)
         for (int k = 0; k < 11; ++k) e->tb.init[k] = p->other->initial_state[cfg->phase - PD_PHASE_SUBSONIC][k];
+    if (cfg->phase == PD_PHASE_FLIP_OVER)
+        for (int k = 0; k < 11; ++k) e->tb.init[k] = p->other->initial_state[3][k];
     if (p->other && p->other->n_ref >= 2 && (cfg->phase == PD_PHASE_SUBSONIC || cfg->phase == PD_PHASE_SUPERSONIC)) {
         // scipy interp1d sorts by x with a stable sort (reference_trajectory_interpolation.py:14-16)
         const PdOtherPhases &o = *p->other;
@@ -434,9 +442,9 @@ int pd_set_rollout_handoff(PdEnv *e, int steps) {
     return 0;
 }
 
-int pd_set_rollout_handoff2(PdEnv *e, int steps, int steps2) {
-    if (!e) return fail("pd_set_rollout_handoff2: null handle");
-    if (steps < 0 || steps2 < 0) return fail("pd_set_rollout_handoff2: steps must be >= 0 (0 = off)");
+int pd_set_rollout_stages(PdEnv *e, int steps, int steps2) {
+    if (!e) return fail("pd_set_rollout_stages: null handle");
+    if (steps < 0 || steps2 < 0) return fail("pd_set_rollout_stages: steps must be >= 0 (0 = off)");
     e->handoff_steps = steps;
     e->handoff2_steps = steps2 > steps ? steps2 : 4 * steps;
     return 0;

@@ -33,11 +33,13 @@ namespace pd {
 
 // ------------------------------------------------------------------ flight phases
 // 0 landing_burn_pure_throttle, 1 landing_burn, 2 subsonic, 3 supersonic,
-// 4 ballistic_arc_descent, 5 landing_burn_pure_throttle_Pcontrol
+// 4 ballistic_arc_descent, 5 landing_burn_pure_throttle_Pcontrol, 6 flip_over_boostbackburn
 __host__ __device__ constexpr int phase_adim(int ph) { return ph == 1 ? 4 : ((ph == 2 || ph == 3) ? 2 : 1); }
 __host__ __device__ constexpr int phase_odim(int ph) {
-    return ph == 0 ? 2 : ph == 1 ? 5 : (ph == 2 || ph == 3) ? 8 : ph == 4 ? 4 : 1;
+    return ph == 0 ? 2 : ph == 1 ? 5 : (ph == 2 || ph == 3) ? 8 : ph == 4 ? 4 : ph == 6 ? 2 : 1;
 }
+// phases that carry the gimbal (and, landing_burn, the fin commands) from one env step to the next
+__host__ __device__ constexpr bool phase_has_actuator_memory(int ph) { return ph == 1 || ph == 6; }
 __host__ __device__ constexpr int phase_nsub(int ph) { return ph <= 1 ? 4 : 1; }
 __host__ __device__ constexpr bool phase_ascent(int ph) { return ph == 2 || ph == 3; }
 
@@ -73,6 +75,7 @@ struct Scalars {
     R norm8[8];                     // obs normalisation of phases 2..4
     R speed0, terminal_mach, alive_bonus;
     R sup_terminal_alt;             // supervisory closures: last altitude of the supersonic recording
+    R flip_max_gimbal_deg;          // flip_over_boostbackburn: 10 (rockets_physics.py:759)
     // Mach-scheduled ascent thresholds (rtd_rl.py:544-575): grid, 4 value rows (max_x, max_vy,
     // max_vx, max_alpha_deg) and their segment slopes; the reward weights are 100 everywhere
     R hyp_m[12], hyp_v[4][12], hyp_s[4][12];
@@ -1084,6 +1087,44 @@ __device__ __forceinline__ void control_rcs(const Action<1> &act, R x_cog, Contr
     o.mass_flow = R(0); o.mass_flow_dt = R(0); o.throttle = R(0);
 }
 
+// flip_over_boostbackburn: force_moment_decomposer_flipoverboostbackburn, rockets_physics.py:63-92
+// (max gimbal 10 deg, :759).  Gimbal command through a first-order low-pass (tau 1.0) on the ENV dt,
+// throttle 1, gimballed engines only.  float32 action (NEP 50): the command and the filter run in
+// float32 (0.1 and 1.0 are weak Python floats) and the filtered angle stays a float32 array in the
+// env's memory; math.radians() then promotes, so thrust, moment and mass flow are float64.
+template <typename R>
+__device__ __forceinline__ void control_flip(const Action<1> &act, const ActPrev &prev, R p_atm, R d_thrust_cg,
+                                             Control<R> &o) {
+    const Scalars<R> &c = SC<R>();
+    double gdeg;
+    if (sizeof(R) == 8 && act.f32) {
+        const float u = __fmul_rn((float)act.u[0], sf.flip_max_gimbal_deg);
+        const float x = (float)prev.gimbal_deg;
+        gdeg = (double)__fadd_rn(x, __fmul_rn(sf.dt_act, __fdiv_rn(__fadd_rn(-x, u), 1.0f)));
+    } else {
+        const double u = act.u[0] * sd.flip_max_gimbal_deg;
+        const double x = prev.gimbal_deg;
+        gdeg = x + sd.dt_act * ((-x + u) / 1.0);
+    }
+    const double grad = gdeg * (PD_PI / 180.0);
+    R sg, cg;
+    m_sincos((R)grad, &sg, &cg);
+    R t_full = c.T_e + (c.p_e - p_atm) * c.A_e;
+    R thrust = t_full * c.n_eng * R(1);
+    o.par = thrust * cg;
+    o.perp = -thrust * sg;
+    o.mz = -thrust * sg * d_thrust_cg;
+    R total = m_sqrt(o.par * o.par + o.perp * o.perp);
+    R n_tot = total / t_full;
+    R mf = c.te_over_vex * n_tot;
+    o.mass_flow = mf;
+    o.mass_flow_dt = mf * c.dt_phys;
+    o.throttle = R(1);
+    o.gimbal_deg = gdeg;
+    o.dl_cmd = 0.0;
+    o.dr_cmd = 0.0;
+}
+
 // landing_burn_pure_throttle_Pcontrol: force_moment_decomposer_landing_burn_throttle_PID,
 // rockets_physics.py:402-451.  action = reference speed; Kp = -0.08; the inner throttle
 // command is handed on as a *list*, which upstream unpacks with float(): whatever the dtype of
@@ -1169,7 +1210,12 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
         control_ascent<R>(act, p_atm, d_thrust_cg, ctl);
     else if constexpr (PHASE == 4)
         control_rcs<R>(act, x_cog, ctl);
-    else
+    else if constexpr (PHASE == 6) {
+        control_flip<R>(act, prev, p_atm, d_thrust_cg, ctl);
+        // "No aerodynamic forces in upper atmosphere, this is a redundancy." (rockets_physics.py:556-560;
+        // C_L and C_D are still evaluated and reported)
+        aero_x = R(0); aero_y = R(0); aero_mz = R(0);
+    } else
         control_C<R>(act, speed, p_atm, alpha_eff, q, x_cog, mach, ctl);
     R c_par = ctl.par, c_perp = ctl.perp, c_mz = ctl.mz;
     // NaN guards are an if/elif chain upstream: only the first NaN is cleared
@@ -1225,7 +1271,7 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
         x[5] = c_par; x[6] = c_perp; x[7] = c_x; x[8] = c_y; x[9] = aero_x; x[10] = aero_y;
         x[11] = g; x[12] = c_mz; x[13] = aero_mz; x[14] = mz; x[15] = tdd; x[16] = vx_dot;
         x[17] = vy_dot; x[18] = f_wind_x;
-        x[19] = PHASE == 1 ? (R)ctl.gimbal_deg : (phase_ascent(PHASE) ? (R)(act.u[0] * sd.max_gimbal_rad * (180.0 / PD_PI)) : R(0));
+        x[19] = (PHASE == 1 || PHASE == 6) ? (R)ctl.gimbal_deg : (phase_ascent(PHASE) ? (R)(act.u[0] * sd.max_gimbal_rad * (180.0 / PD_PI)) : R(0));
         x[20] = PHASE == 1 ? (R)ctl.dl_cmd : R(0);
         x[21] = PHASE == 1 ? (R)ctl.dr_cmd : R(0);
         const R qmax = PHASE <= 1 || PHASE == 5 ? R(65000) : R(30000);
@@ -1422,6 +1468,9 @@ __device__ __forceinline__ void rtd_supervisory(const State &s, R g1, Rtd<R> &o)
     } else if constexpr (PHASE == 4) {
         dn = q > R(65000) && ae < 3.0 * (PD_PI / 180.0);
         if (q > R(35000) && ae > 3.0 * (PD_PI / 180.0)) { tr = 1; id = 1; }
+    } else if constexpr (PHASE == 6) {
+        dn = s.vx < -60.0;          // flip_over_boostbackburn_terminal_vx, rtd_supervisory_mock.py:14, 34-38
+        if (s.m_prop <= 0.0) { tr = 1; id = 1; }
     } else {
         dn = s.y < 1.0;
         if (s.y < -10.0) { tr = 1; id = 1; }
@@ -1554,6 +1603,10 @@ __device__ __forceinline__ void observe(const State &s, R *o) {
             const double v[4] = {s.theta, s.theta_dot, s.gamma, s.alpha};
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = (R)(float)((double)(float)v[k] / sd.norm8[k]);
+        } else if constexpr (PHASE == 6) {
+            const double v[2] = {s.theta, s.theta_dot};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) o[k] = (R)(float)((double)(float)v[k] / sd.norm8[k]);
         } else {
             o[0] = (R)((1.0 - (double)(float)s.y / sd.norm_y) * 2 - 1);
         }
@@ -1602,7 +1655,7 @@ __device__ __forceinline__ void env_step(State &s, const Action<phase_adim(PHASE
 #pragma unroll 1
     for (int k = 0; k < phase_nsub(PHASE); ++k)
         substep<R, RT, PHASE, WIND, COOP, FULL>(s, act, prev, w, wc, env_id, info, ctl, sh);
-    if (PHASE == 1) {
+    if (phase_has_actuator_memory(PHASE)) {
         prev.gimbal_deg = ctl.gimbal_deg;
         prev.dl = ctl.dl_cmd;
         prev.dr = ctl.dr_cmd;
@@ -1618,6 +1671,8 @@ __device__ __forceinline__ void env_step(State &s, const Action<phase_adim(PHASE
         rtd_ballistic<R>(s, out);
     } else if constexpr (PHASE == 5) {
         rtd_pcontrol<R>(s, g1, act.u[0], act.f32, out);
+    } else if constexpr (PHASE == 6) {
+        rtd_supervisory<R, 6>(s, g1, out);     // the one closure set that runs this phase upstream
     } else {
         R u0 = (R)act.u[0];
         if (sizeof(R) == 8 && act.f32) u0 = (R)(float)act.u[0];

@@ -199,7 +199,7 @@ step_kernel(const __grid_constant__ KParams kp, EnvSoA e, StepIO io, WindCtx wc,
     GWindow<R> gw;
     load_window<R>(e, i, gw);
     ActPrev prev = {0.0, 0.0, 0.0};
-    if (PHASE == 1) {
+    if (phase_has_actuator_memory(PHASE)) {
         prev.gimbal_deg = e.aprev[i]; prev.dl = e.aprev[(size_t)e.n + i];
         prev.dr = e.aprev[2 * (size_t)e.n + i];
     }
@@ -261,7 +261,7 @@ step_kernel(const __grid_constant__ KParams kp, EnvSoA e, StepIO io, WindCtx wc,
     e.ep_steps[i] = ep_steps;
     store_state(e, i, s);
     store_window<R>(e, i, gw);
-    if (PHASE == 1) {
+    if (phase_has_actuator_memory(PHASE)) {
         e.aprev[i] = prev.gimbal_deg; e.aprev[(size_t)e.n + i] = prev.dl;
         e.aprev[2 * (size_t)e.n + i] = prev.dr;
     }
@@ -679,7 +679,9 @@ struct Launch {
             case 18: step_t<4, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
             case 19: step_t<4, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
             case 22: step_t<5, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
-            default: step_t<5, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 23: step_t<5, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
+            case 26: step_t<6, 1, false>(lc, e, io, wc, sig, auto_reset, st); break;
+            default: step_t<6, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
         }
     }
     template <int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE>
@@ -818,7 +820,8 @@ static void impl_observe(const LaunchCtx &lc, int phase, int rtd, const EnvSoA &
         case 5: observe_kernel<R, 2, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
         case 7: observe_kernel<R, 3, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
         case 9: observe_kernel<R, 4, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
-        default: observe_kernel<R, 5, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        case 11: observe_kernel<R, 5, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
+        default: observe_kernel<R, 6, 1><<<blocks, threads, 0, st>>>(kp, e, (R *)obs); break;
     }
 }
 

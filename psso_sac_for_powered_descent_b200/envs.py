@@ -29,8 +29,11 @@ from .params import RocketParams
 # landing_burn_pure_throttle / landing_burn: type 'pso' and 'rl'.  subsonic, supersonic,
 # ballistic_arc_descent, landing_burn_pure_throttle_Pcontrol: type 'rl' only - upstream their pso
 # closures have the wrong arity (rtd_pso.py:38-157 vs base_environment.py:150-152 -> TypeError).
-# flip_over_boostbackburn (TypeError in rl mode too, rtd_rl.py:132) and landing_burn_ACS (broken in
-# compile_physics, rockets_physics.py:867-889) do not run upstream and are not offered.
+# flip_over_boostbackburn: type 'supervisory' only - its rl and pso truncated_func take one argument
+# (rtd_rl.py:132, rtd_pso.py:107 -> TypeError in step), the supervisory closures
+# (rtd_supervisory_mock.py:34-38, 57-61) and the classical controller run it.
+# landing_burn_ACS (broken in compile_physics, rockets_physics.py:867-889) does not run upstream and is
+# not offered.
 WORKING_PHASES = tuple(N.PHASES)
 ALL_PHASES = ["subsonic", "supersonic", "flip_over_boostbackburn", "ballistic_arc_descent",
               "landing_burn", "landing_burn_ACS", "landing_burn_pure_throttle",
@@ -65,9 +68,11 @@ class BatchedRocketEnv:
         if flight_phase not in WORKING_PHASES:
             raise NotImplementedError(
                 f"flight phase {flight_phase!r} does not run in the reference either "
-                "(flip_over_boostbackburn: rtd_rl.py:132 TypeError; landing_burn_ACS: "
-                "rockets_physics.py:867-889); see DESIGN.md")
+                "(landing_burn_ACS: rockets_physics.py:867-889); see DESIGN.md")
         assert type in ("rl", "pso", "supervisory")
+        if flight_phase in N.SUPERVISORY_ONLY_PHASES and type != "supervisory":
+            raise TypeError(f"{flight_phase}: only type='supervisory' works upstream (the rl and pso "
+                            "truncated_func of this phase take one argument, rtd_rl.py:132 / rtd_pso.py:107)")
         if flight_phase in N.RL_ONLY_PHASES and type == "pso":
             raise TypeError(f"{flight_phase}: only type='rl' works upstream (the pso closures of this "
                             "phase have the wrong arity, rtd_pso.py:38-157)")
@@ -714,7 +719,8 @@ class supervisory_wrapper:
     then takes the action as it is).  As upstream, the wind arguments are accepted and ignored."""
 
     _SLICES = {"subsonic": [0, 1, 2, 3, 4, 5, 7, 8], "supersonic": [0, 1, 2, 3, 4, 5, 7, 8],
-               "landing_burn": [0, 1, 2, 3, 4, 5, 7, 8], "ballistic_arc_descent": [4, 5, 6, 7]}
+               "landing_burn": [0, 1, 2, 3, 4, 5, 7, 8], "ballistic_arc_descent": [4, 5, 6, 7],
+               "flip_over_boostbackburn": [4, 5]}
 
     def __init__(self, input_normalisation_values, flight_phase="subsonic", enable_wind=False,
                  stochastic_wind=False, horiontal_wind_percentile=95, precision="fp64", seed=0):

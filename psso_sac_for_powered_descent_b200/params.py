@@ -228,6 +228,13 @@ def _other_phases(root, sizing, cc, ballistic_traj):
     bs = ballistic_traj[["theta[rad]", "theta_dot[rad/s]", "alpha[rad]", "gamma[rad]"]].values
     bm = np.max(np.abs(bs), axis=0)
     states = ref[["x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "mass[kg]"]].values
+    # load_flip_over_initial_state (load_initial_states.py:33-45): last supersonic row, mass rebuilt
+    # from the propellant left and the stage-1 structural mass
+    last = sup.iloc[-1]
+    init_flip = [float(last[c]) for c in _STATE_COLS]
+    init_flip[8] = float(last["mass_propellant[kg]"]) + float(sizing["Actual structural mass stage 1"]) * 1000
+    fs = flip[["theta[rad]", "theta_dot[rad/s]"]].values
+    fm = np.max(np.abs(fs), axis=0)
     return dict(
         n_engines_stage1=int(sizing["Number of engines stage 1"]),
         max_rcs_force_per_thruster=float(sizing["max_RCS_force_per_thruster"]),
@@ -237,11 +244,13 @@ def _other_phases(root, sizing, cc, ballistic_traj):
         engine_height_full=float(cc["engine_height_full"]),
         cop_length_full=float(cc["cop_length_full"]), cop_d0_full=float(cc["cop_d0_full"]),
         initial_states=dict(subsonic=fl(init_sub), supersonic=fl(sub.iloc[-1][list(_STATE_COLS)]),
-                            ballistic_arc_descent=fl(flip.iloc[-1][list(_STATE_COLS)])),
+                            ballistic_arc_descent=fl(flip.iloc[-1][list(_STATE_COLS)]),
+                            flip_over_boostbackburn=fl(init_flip)),
         norm_vals=dict(subsonic=fl(ascent_norm(sub, (100, 500, 5, 50, 2))),
                        supersonic=fl(ascent_norm(sup, (2500, 5000, 100, 150, 5))),
                        ballistic_arc_descent=fl([bm[0] + math.radians(5), bm[1] * 2.5,
-                                                 bm[3] + math.radians(5), bm[2] + math.radians(5)])),
+                                                 bm[3] + math.radians(5), bm[2] + math.radians(5)]),
+                       flip_over_boostbackburn=fl([fm[0] + math.radians(5), fm[1] * 2.5])),
         ref_traj_ascent=dict(y=fl(ref["y[m]"].values), x=fl(ref["x[m]"].values),
                              vx=fl(ref["vx[m/s]"].values), vy=fl(ref["vy[m/s]"].values)),
         ref_traj_ascent_terminal=fl(states[-1]))

@@ -200,8 +200,10 @@ def test_ascent_reference_csv(envs_mod, golden, tag, phase, n):
 def test_rl_only_phases_reject_pso(envs_mod):
     with pytest.raises(TypeError):
         envs_mod.BatchedRocketEnv(4, "pso", S)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):      # rtd_rl.py:132: the rl truncated_func of this phase takes one argument
         envs_mod.BatchedRocketEnv(4, "rl", "flip_over_boostbackburn")
+    with pytest.raises(NotImplementedError):
+        envs_mod.BatchedRocketEnv(4, "rl", "landing_burn_ACS")
 
 
 @pytest.mark.parametrize("phase", [S, U, B, C])
@@ -475,3 +477,73 @@ def test_supervisory_closures_fp32_build(envs_mod, golden, tag, phase):
     assert float(rew.abs().max()) == 0.0
     same = (trunc.cpu().numpy().astype(float) == ref[:, 13]) & (tid.cpu().numpy().astype(float) == ref[:, 14])
     assert same.mean() >= 0.97
+
+
+# --------------------------------------------------------------------------- flip_over_boostbackburn
+F = "flip_over_boostbackburn"
+FLOOR[F] = np.array([1e4, 1e4, 1e2, 1e2, 1.0, 1.0, 1.0, 1.0, 1e6, 1e6, 1e2])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-12), ("fp32", 1e-5)])
+@pytest.mark.parametrize("key,akey", [("o64", "act64"), ("o32", "act32")])
+def test_flip_over_single_step(envs_mod, golden, precision, tol, key, akey):
+    """force_moment_decomposer_flipoverboostbackburn + the phase's physics branch (no aerodynamic
+    forces) + the supervisory closures, one step from 96 fixture rows of the unmodified reference:
+    float64 and float32 actions (the float32 gimbal filter of NEP 50), non-zero gimbal memory."""
+    g = golden("flip_over.npz")
+    n = len(g["ss_state"])
+    env = envs_mod.BatchedRocketEnv(n, "supervisory", F, precision=precision)
+    env.set_state(g["ss_state"], g["ss_win"], g["ss_nwin"].astype(np.int32), g["ss_aprev"])
+    dbg = torch.zeros(n, 16, dtype=torch.float64, device="cuda")
+    obs, rew, done, trunc, tid = env.step(torch.as_tensor(g[f"ss_{akey}"]).cuda(), dbg=dbg)
+    env.check_status()
+    st, gw, nw, ap = env.get_state(full=True)
+    ref = g[f"ss_{key}"]
+    err = state_err(st.cpu().numpy(), ref[:, :11], F)
+    assert err.max() < tol, (int(err.argmax()), err.max())
+    assert float(rew.abs().max()) == 0.0
+    assert np.array_equal(done.cpu().numpy().astype(float), ref[:, 12])
+    assert np.array_equal(trunc.cpu().numpy().astype(float), ref[:, 13])
+    assert np.array_equal(tid.cpu().numpy().astype(float), ref[:, 14])
+    gd = ap.cpu().numpy()[:, 0]
+    assert np.max(np.abs(gd - ref[:, 15])) < (1e-13 if precision == "fp64" else 1e-5)
+    d = dbg.cpu().numpy()
+    for name, j_dbg, t64 in (("mach", 0, 1e-12), ("q", 1, 1e-12), ("x_cog", 7, 1e-13), ("inertia", 8, 1e-13),
+                             ("mass_flow", 9, 1e-12), ("CL", 2, 2e-9), ("CD", 3, 2e-9)):
+        refv = ref[:, list(g["ss_cols"]).index(name)]
+        e = np.max(np.abs(d[:, j_dbg] - refv) / np.maximum(np.abs(refv), 1e-3))
+        assert e < (t64 if precision == "fp64" else 2e-5), (name, e)
+
+
+def test_flip_over_committed_csv_replay(envs_mod, golden):
+    """The reference's own committed flip-over / boostback controller recording (173 steps of 0.1 s):
+    its u0 column replayed from reset through pd_step, against the CSV (1e-8, written on the author's
+    machine) and against the unmodified reference replayed here (1e-9 free-running)."""
+    g = golden("flip_over.npz")
+    env = envs_mod.BatchedRocketEnv(1, "supervisory", F, precision="fp64")
+    assert np.array_equal(env.reset().cpu().numpy()[0], g["initial_state"])
+    n = len(g["replay_states"])
+    worst_csv = worst_ref = 0.0
+    for k in range(n):
+        obs, rew, done, trunc, tid = env.step(torch.tensor([[g["csv_u0"][k]]], dtype=torch.float64, device="cuda"))
+        st, gw, nw, ap = env.get_state(full=True)
+        st = st.cpu().numpy()[0]
+        worst_ref = max(worst_ref, float(state_err(st, g["replay_states"][k], F)))
+        worst_csv = max(worst_csv, float(state_err(st, g["csv_states"][k], F)))
+        assert (float(rew[0]), float(done[0]), float(trunc[0]), float(tid[0])) == tuple(g["replay_flags"][k]), k
+        assert abs(float(ap[0, 0]) - g["replay_gimbal_deg"][k]) < 1e-10
+        if k < 4:
+            assert float(state_err(st, g["replay_states"][k], F)) < 1e-12
+    env.check_status()
+    assert worst_ref < 1e-9 and worst_csv < 1e-8, (worst_ref, worst_csv)
+
+
+def test_flip_over_supervisory_wrapper(envs_mod, golden):
+    g = golden("flip_over.npz")
+    env = envs_mod.supervisory_wrapper(g["w_nv"], flight_phase=F)
+    assert np.allclose(env.reset(), g["w_obs"][0], rtol=1e-15, atol=0)
+    for k, a in enumerate(g["w_act"]):
+        o, r, d, t, _ = env.step(a)
+        err = np.abs(np.reshape(o, -1) - g["w_obs"][k + 1]) / np.maximum(np.abs(g["w_obs"][k + 1]), 1e-3)
+        assert err.max() < 1e-9, (k, err)
+        assert [float(r), float(d), float(t), float(env.truncation_id())] == list(g["w_flags"][k])

@@ -611,6 +611,8 @@ def test_scalar_drop_in_api(envs_mod):
         envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase="subsonic", enable_wind=False)
     with pytest.raises(NotImplementedError):    # does not run upstream either
         envs_mod.rocket_environment_pre_wrap(type="rl", flight_phase="landing_burn_ACS", enable_wind=False)
+    with pytest.raises(TypeError):              # upstream: rl closures of the flip-over take one argument
+        envs_mod.rocket_environment_pre_wrap(type="rl", flight_phase="flip_over_boostbackburn", enable_wind=False)
     with pytest.raises(AssertionError):
         envs_mod.rocket_environment_pre_wrap(type="pso", flight_phase="nonsense", enable_wind=False)
     m = envs_mod.pso_wrapped_env(flight_phase=G)

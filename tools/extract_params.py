@@ -36,7 +36,8 @@ def other_phases(cc):
     import csv
     load_reference()
     from src.envs.load_initial_states import (load_subsonic_initial_state, load_supersonic_initial_state,
-                                              load_high_altitude_ballistic_arc_initial_state)
+                                              load_high_altitude_ballistic_arc_initial_state,
+                                              load_flip_over_initial_state)
     from src.envs.utils.input_normalisation import find_input_normalisation_vals
     from src.envs.utils.reference_trajectory_interpolation import reference_trajectory_lambda_func_y
     import pandas as pd
@@ -56,9 +57,10 @@ def other_phases(cc):
         cop_length_full=cc["cop_length_full"], cop_d0_full=cc["cop_d0_full"],
         initial_states=dict(subsonic=fl(load_subsonic_initial_state()),
                             supersonic=fl(load_supersonic_initial_state()),
-                            ballistic_arc_descent=fl(load_high_altitude_ballistic_arc_initial_state())),
+                            ballistic_arc_descent=fl(load_high_altitude_ballistic_arc_initial_state()),
+                            flip_over_boostbackburn=fl(load_flip_over_initial_state())),
         norm_vals={ph: fl(find_input_normalisation_vals(ph))
-                   for ph in ("subsonic", "supersonic", "ballistic_arc_descent")},
+                   for ph in ("subsonic", "supersonic", "ballistic_arc_descent", "flip_over_boostbackburn")},
         ref_traj_ascent=dict(y=fl(data["y[m]"].values), x=fl(data["x[m]"].values),
                              vx=fl(data["vx[m/s]"].values), vy=fl(data["vy[m/s]"].values)),
         ref_traj_ascent_terminal=fl(term))

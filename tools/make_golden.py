@@ -611,6 +611,96 @@ def supervisory_wrapper_sequences(n_steps=8, seed=43):
     print("supervisory_wrapper", {k: v.shape for k, v in out.items() if k.startswith("obs")})
 
 
+F_ = "flip_over_boostbackburn"
+
+
+def flip_over(n=96, seed=51):
+    """flip_over_boostbackburn (rockets_physics.py:63-92, 542-560, 755-780) under type='supervisory'
+    - the one closure set that runs this phase upstream (rtd_supervisory_mock.py:34-38, 57-61):
+    (1) the reference's committed controller recording (u0 + states per 0.1 s step) and its replay
+    through env.step from reset; (2) single steps from perturbed states of that recording with
+    float64 and float32 actions and a non-zero gimbal memory; (3) the supervisory_wrapper
+    observation / step sequence."""
+    import pandas as pd
+    from src.envs.base_environment import rocket_environment_pre_wrap
+    from src.envs.supervisory.env_wrapped_supervisory import supervisory_wrapper
+    from src.envs.utils.input_normalisation import find_input_normalisation_vals
+    rng = np.random.default_rng(seed)
+    g = pd.read_csv("data/reference_trajectory/flip_over_and_boostbackburn_controls/"
+                    "state_action_flip_over_and_boostbackburn_control.csv")
+    cols = ["x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "theta[rad]", "theta_dot[rad/s]", "gamma[rad]",
+            "alpha[rad]", "mass[kg]", "mass_propellant[kg]", "time[s]"]
+    out = {"csv_states": g[cols].values, "csv_u0": g["u0"].values,
+           "csv_gimbal_cmd_deg": g["gimbalanglecommanded[deg]"].values}
+    env = quiet(rocket_environment_pre_wrap, type="supervisory", flight_phase=F_, enable_wind=False)
+    out["initial_state"] = np.array([float(v) for v in quiet(env.reset)])
+    S, FL, GD = [], [], []
+    for u in g["u0"].values:
+        s, r, d, t, info = quiet(env.step, np.array([u]))
+        S.append([float(v) for v in s]); FL.append([float(r), float(d), float(t), float(env.truncation_id)])
+        GD.append(float(np.asarray(env.gimbal_angle_deg).reshape(-1)[0]))
+        if d or t:
+            break
+    out["replay_states"], out["replay_flags"], out["replay_gimbal_deg"] = np.array(S), np.array(FL), np.array(GD)
+    pool = np.array(S)
+    rows = dict(state=[], win=[], nwin=[], aprev=[], act32=[], act64=[], o64=[], o32=[])
+    for i in range(n):
+        k = rng.integers(len(pool))
+        s = pool[k].copy()
+        if i % 3 == 1:
+            s = s * (1 + 0.01 * rng.standard_normal(11))
+            s[6] = math.atan2(s[3], s[2]) % (2 * math.pi)
+            s[7] = s[4] - s[6]
+        elif i % 3 == 2:          # around the done threshold vx < -60 and propellant exhaustion
+            s[2] = rng.uniform(-75.0, -45.0)
+            s[6] = math.atan2(s[3], s[2]) % (2 * math.pi)
+            s[7] = s[4] - s[6]
+            if i % 2:
+                s[9] = rng.uniform(-500.0, 15000.0)
+        gprev = float(np.float32(rng.uniform(-10, 10))) if i % 4 else 0.0      # float32-representable
+        nwin = int(rng.integers(0, 11))
+        win = list(rng.uniform(0.0, 3.0, nwin))
+        a32 = rng.uniform(-1, 1, 1).astype(np.float32)
+        outs = {}
+        for key, a in (("o64", a32.astype(np.float64)), ("o32", a32)):
+            quiet(env.reset)
+            env.state = [np.float64(v) for v in s]
+            env.previous_state = env.state
+            env.g_loads_window = list(win)
+            # the memory is what the previous step of the same dtype left behind
+            env.gimbal_angle_deg = gprev if key == "o64" else np.array([gprev], dtype=np.float32)
+            ns, r, d, t, info = quiet(env.step, a)
+            outs[key] = [float(v) for v in ns] + [float(r), float(d), float(t), float(env.truncation_id),
+                                                  float(np.asarray(env.gimbal_angle_deg).reshape(-1)[0]),
+                                                  info["mach_number"], info["dynamic_pressure"], info["CL"],
+                                                  info["CD"], info["x_cog"], info["inertia"],
+                                                  float(info["mass_flow"]), info["g_load_1_sec_window"]]
+        w = np.zeros(10); w[:nwin] = win
+        rows["state"].append(s); rows["win"].append(w); rows["nwin"].append(nwin)
+        rows["aprev"].append([float(np.float32(gprev)), 0.0, 0.0])
+        rows["act32"].append(a32); rows["act64"].append(a32.astype(np.float64))
+        rows["o64"].append(outs["o64"]); rows["o32"].append(outs["o32"])
+    out.update({f"ss_{k}": np.array(v) for k, v in rows.items()})
+    out["ss_cols"] = ["x", "y", "vx", "vy", "theta", "theta_dot", "gamma", "alpha", "mass", "m_prop", "time",
+                      "reward", "done", "truncated", "trunc_id", "gimbal_deg", "mach", "q", "CL", "CD",
+                      "x_cog", "inertia", "mass_flow", "g1"]
+    nv = quiet(find_input_normalisation_vals, F_)
+    wenv = quiet(supervisory_wrapper, nv, flight_phase=F_)
+    obs = [np.asarray(quiet(wenv.reset), dtype=np.float64).reshape(-1)]
+    acts = rng.uniform(-1, 1, size=(12, 1))
+    flags = []
+    for a in acts:
+        o, r, d, t, _ = quiet(wenv.step, a)
+        obs.append(np.asarray(o, dtype=np.float64).reshape(-1))
+        flags.append([float(r), float(d), float(t), float(wenv.truncation_id())])
+    out["w_nv"], out["w_act"], out["w_obs"], out["w_flags"] = np.asarray(nv, float), acts, np.array(obs), np.array(flags)
+    np.savez_compressed(os.path.join(OUT, "flip_over.npz"), **out)
+    o = np.array(rows["o64"])
+    print("flip_over: replay", len(S), "steps, max |replay - csv|",
+          float(np.max(np.abs(np.array(S) - g[cols].values[:len(S)]))), "; single steps", n, "done",
+          int(o[:, 12].sum()), "trunc", int(o[:, 13].sum()))
+
+
 def ascent_csv():
     """The reference's own committed ascent controller recordings (actions + states per 0.1 s
     step) - golden vectors written on the author's machine, copied verbatim."""
@@ -761,6 +851,8 @@ if __name__ == "__main__":
         pool = rl_sequence_other(C_, "C", 400, mode="random")
         pool2 = rl_sequence_other(C_, "C2", 2500, mode="track")
         single_step_other(C_, "C", np.concatenate([pool, pool2]))
+    if "flip" in which:
+        flip_over()
     if "aero" in which:
         aero_probe()
     if "tape" in which:

@@ -8,7 +8,7 @@ allpos = torch.as_tensor(np.random.default_rng(7).uniform(-1.5, 1.5, (65536, 249
 for n in (4096, 16384, 65536):
     pos = allpos[:n].contiguous()
     for h1, h2 in ((0, 0), (128, 512), (128, 256), (192, 768), (256, 1024), (256, 512), (384, 1536), (128, 4096), (256, 4096)):
-        N.check(m._b.lib.pd_set_rollout_handoff2(m._b._h, h1, h2))
+        N.check(m._b.lib.pd_set_rollout_stages(m._b._h, h1, h2))
         best = 1e9
         for rep in range(4):
             torch.cuda.synchronize(); t0 = time.perf_counter()
