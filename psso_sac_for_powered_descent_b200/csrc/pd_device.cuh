@@ -727,12 +727,22 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     const double M = (double)mach;
     const double deg = (double)alpha_eff * (180.0 / PD_PI);
     const double lim = 10.0 * (PD_PI / 180.0);
-    const double aD = fmin(fmax(deg, -lim), lim);
+    double aD = fmin(fmax(deg, -lim), lim);
     const double aoa = deg * (180.0 / PD_PI);
     const bool zero = fabs(aoa) < 1e-6;
     const bool neg_line = aoa < -10.0;
-    const double aL = neg_line ? -10.0 : fmin(fmax(fabs(aoa), 1e-6), 10.0);
+    double aL = neg_line ? -10.0 : fmin(fmax(fabs(aoa), 1e-6), 10.0);
     const bool flip = !neg_line && aoa < 0.0;
+    {   // Pin the two clamped angles in registers.  Under the 128-register cap ptxas otherwise re-derives
+        // them from alpha_eff (float -> double, two multiplies, two fmin / fmax chains: 42 of the 274
+        // instructions of EVERY trip of the summation loop, 11 % of the kernel,
+        // profiles/r2_step_kernel_grid_constant.txt).  An empty asm does not survive to ptxas; an identity
+        // shuffle is the one copy it cannot see through: 4 SHFL per sub-step instead of ~500 instructions.
+        const unsigned m = __activemask();
+        const int me = threadIdx.x & 31;
+        aL = __shfl_sync(m, aL, me);
+        aD = __shfl_sync(m, aD, me);
+    }
     // both grid-cell loads in flight before either is consumed
     const RbfGrid &GL = neg_line ? tb.cl.grid[1] : tb.cl.grid[0];
     const int cellD = __ldg(rbf_cell_ptr(tb.cd.grid[0], M, aD));

@@ -120,10 +120,10 @@ __device__ __forceinline__ void wait_tables(SharedTables *sh) {
     }
 }
 
-// One block per SM, at most PD_MAX_BLOCK = 448 threads: 65 536 registers / 448 = 146, so ptxas may
-// use 144 registers per thread and keeps the loop invariants of the RBF sums (clamped angles,
-// table bases) in registers instead of rematerialising ~50 instructions per trip (128-register
-// build, gpurun_out/prof_step_r1f).
+// One block per SM, at most PD_MAX_BLOCK = 448 threads = the 443 lanes per SM that BASELINE config 2
+// (65 536 envs over 148 SMs) provides.  The register file is allocated for warp counts rounded up to
+// a multiple of 4, so these blocks are capped at 65 536 / 512 = 128 registers per thread (ptxas
+// reports 128; a 144-register build is refused at launch).
 #ifndef PD_MAX_BLOCK
 #define PD_MAX_BLOCK 448
 #endif
@@ -182,6 +182,9 @@ __global__ void observe_kernel(const __grid_constant__ KParams kp, EnvSoA e, R *
 #ifndef PD_STEP_MIN_BLOCKS
 #define PD_STEP_MIN_BLOCKS 8
 #endif
+// (448 threads: the register file is allocated for warp counts rounded up to a multiple of 4, so the
+// cap is 65 536 / 512 = 128 registers per thread - a launch with __maxnreg__(144) is refused with
+// "too many resources requested")
 template <typename R, typename RT, int PHASE, int RTD, bool WIND, bool FULL = false>
 __global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
 step_kernel(const __grid_constant__ KParams kp, EnvSoA e, StepIO io, WindCtx wc, const double *sigma_uv,
