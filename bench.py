@@ -432,7 +432,7 @@ def run_cuda(args):
         senv.check_status()
         sms, = allmax(best_ms)
         sac = {"envs_per_gpu": Bs, "steps": Ts, "env_steps_per_s": world * Bs * Ts / (sms * 1e-3),
-               "ms_per_step": sms / Ts, "actor": "2-256-256-(1,1), bf16 tcgen05 UMMA + fp32 heads",
+               "ms_per_step": sms / Ts, "actor": "2-256-256-(1,1), fp16-operand tcgen05 UMMA (fp32 accumulate) + fp32 heads",
                "wind": "stochastic, percentile 50, Philox gusts", "rtd": "rl",
                "mean_reward": float(out["rewards"].mean()), "resets": int(out["truncated"].sum() + out["done"].sum())}
         del senv, out

@@ -271,7 +271,8 @@ int pd_rollout_policy(PdEnv *env, int policy, const void *actions, int action_dt
  * action = tanh(mean + std * eps) * max_action).  Runs n_steps x [actor inference -> fused env
  * step with auto-reset] on the handle's batch (type 'rl', PD_FP32 build) and writes the
  * transitions step-major.  hidden == 256 and fp32_path == 0: the 256x256 layer runs on the
- * tcgen05 tensor cores in bf16 with fp32 accumulation; otherwise an fp32 CUDA-core kernel.
+ * tcgen05 tensor cores with IEEE-half operands and fp32 accumulation (~3e-4 of the activation
+ * scale against torch fp32); otherwise an exact fp32 CUDA-core kernel.
  *   w1 [H*O], b1 [H], w2 [H*H], b2 [H], wm [A*H], bm [A], ws [A*H], bs [A]  dev float
  *   (torch nn.Linear layouts: weight[out][in])
  *   obs_out      dev float[n_steps*n_envs*O]  observation the action was computed from

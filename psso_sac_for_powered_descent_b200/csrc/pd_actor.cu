@@ -8,11 +8,11 @@
 // Only the 256x256 layer is a real GEMM (2*65536 flop/env of 133 120).  It runs on the
 // 5th-generation tensor cores:
 //   * a persistent CTA per SM owns a 128-env row tile at a time (UMMA M = 128, N = 256);
-//   * W2 is converted once to bf16 and stored in global memory as the exact shared-memory
+//   * W2 is converted once to fp16 and stored in global memory as the exact shared-memory
 //     image (K-major, 128-byte swizzle, four 64-wide K blocks); each CTA pulls the 128 KB image
 //     with 1-D TMA bulk copies (cp.async.bulk, completes on an mbarrier) once per launch;
 //   * layer 1 (K = 2 or 5: plain FMAs) is computed by the 128 threads straight into the
-//     swizzled A tile in shared memory as bf16;
+//     swizzled A tile in shared memory as fp16;
 //   * one elected thread issues 16 tcgen05.mma (K = 16 each) accumulating fp32 into 256 TMEM
 //     columns, commits to an mbarrier;
 //   * the epilogue reads each env's row back with tcgen05.ld (one TMEM lane per thread), applies
@@ -20,7 +20,7 @@
 //     leaves TMEM/registers.
 // An fp32 CUDA-core variant (actor_fp32_kernel) serves other hidden sizes and is the numerics
 // reference for the tensor-core path in the GPU tests.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -104,17 +104,23 @@ __global__ void __launch_bounds__(128) actor_fp32_kernel(ActorArgs p, const floa
     head_and_sample<A>(p, mean, lstd, (unsigned)env, act, mean_out);
 }
 
-// ------------------------------------------------------------------ W2 -> bf16 smem image
+// Operand precision.  The 256 x 256 layer's operands are IEEE half (11-bit significand), not bfloat16
+// (8 bits): h1 = relu(.) of normalised observations and the weights of a tanh-headed policy are
+// O(1), far inside half's range, so the 8x finer rounding is free - measured max error of the
+// pre-tanh mean against torch fp32: ~3e-4 of the activation scale (bfloat16: 2e-3).  fp32 accuracy
+// (1e-6) needs a 3-term operand split whose operands (W2 alone: 2 x 128 KB) do not fit the 227 KB of
+// shared memory next to the A tile; `fp32_path` selects the exact CUDA-core kernel instead.
+// ------------------------------------------------------------------ W2 -> fp16 smem image
 // image[kb][n][swizzled 128 B row]: K block kb (64 k's), row n of W2 (N = 256 rows, K-major),
 // 16-byte chunk c stored at chunk position c ^ (n & 7)  (UMMA SWIZZLE_128B canonical layout).
-__global__ void actor_prep_w2_kernel(const float *__restrict__ w2, __nv_bfloat16 *__restrict__ img) {
+__global__ void actor_prep_w2_kernel(const float *__restrict__ w2, __half *__restrict__ img) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 elements) each
     if (idx >= 4 * 256 * 8) return;
     int c = idx & 7, n = (idx >> 3) & 255, kb = idx >> 11;
     const float *src = w2 + (size_t)n * 256 + kb * 64 + c * 8;
-    __nv_bfloat16 *dst = img + (size_t)kb * 256 * 64 + (size_t)n * 64 + ((c ^ (n & 7)) * 8);
+    __half *dst = img + (size_t)kb * 256 * 64 + (size_t)n * 64 + ((c ^ (n & 7)) * 8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    for (int j = 0; j < 8; ++j) dst[j] = __float2half_rn(src[j]);
 }
 
 // ------------------------------------------------------------------ PTX helpers
@@ -152,11 +158,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 256
-__device__ __forceinline__ uint32_t umma_idesc_bf16_m128_n256() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (format fields at bits 7-9 and
+// 10-12 = 0; 1 would be F16), both K-major, N >> 3 at bit 17, M >> 4 at bit 24: M = 128, N = 256
+__device__ __forceinline__ uint32_t umma_idesc_f16_m128_n256() {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_fp16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -203,8 +210,8 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
                 int B, int n_tiles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;                                  // [4][128][64] bf16, swizzled
-    uint8_t *sB = smem + A_BYTES;                        // [4][256][64] bf16, swizzled (W2 image)
+    uint8_t *sA = smem;                                  // [4][128][64] fp16, swizzled
+    uint8_t *sB = smem + A_BYTES;                        // [4][256][64] fp16, swizzled (W2 image)
     float *s_w1 = (float *)(smem + A_BYTES + B_BYTES);   // [256][O]
     float *s_b1 = s_w1 + ACT_H * O;
     float *s_b2 = s_b1 + ACT_H;
@@ -241,7 +248,7 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) tma_bulk_g2s(smem_u32(sB) + i * 16384, src + (size_t)i * 16384, 16384, bar_w2);
     }
-    const uint32_t idesc = umma_idesc_bf16_m128_n256();
+    const uint32_t idesc = umma_idesc_f16_m128_n256();
     uint32_t mma_phase = 0;
     bool w2_ready = false;
 
@@ -297,7 +304,7 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
         float o[O];
 #pragma unroll
         for (int k = 0; k < O; ++k) o[k] = o_next[k];
-        // layer 1 -> bf16 -> swizzled A tile (row = tid & 127), this half's two K blocks
+        // layer 1 -> fp16 -> swizzled A tile (row = tid & 127), this half's two K blocks
         const uint32_t row_off = (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128;
 #pragma unroll 1
         for (int kq = 0; kq < 2; ++kq) {
@@ -316,7 +323,7 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
                         for (int q = 0; q < O; ++q) acc = fmaf(s_w1[k * O + q], o[q], acc);
                         h[e] = fmaxf(acc, 0.f);
                     }
-                    __nv_bfloat162 b2v = __floats2bfloat162_rn(h[0], h[1]);
+                    __half2 b2v = __floats2half2_rn(h[0], h[1]);
                     packed[j] = *reinterpret_cast<uint32_t *>(&b2v);
                 }
                 uint8_t *dst = sA + kb * 16384 + row_off + ((c ^ (row & 7)) * 16);
@@ -333,10 +340,10 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {      // UMMA_K = 16 bf16 = 32 bytes inside the 128 B atom
+                for (int k = 0; k < 4; ++k) {      // UMMA_K = 16 fp16 = 32 bytes inside the 128 B atom
                     uint64_t ad = umma_desc_sw128(smem_u32(sA) + kb * 16384 + k * 32);
                     uint64_t bd = umma_desc_sw128(smem_u32(sB) + kb * 32768 + k * 32);
-                    umma_bf16(tmem_base + buf * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    umma_fp16(tmem_base + buf * 256, ad, bd, idesc, (kb | k) ? 1u : 0u);
                 }
             }
             umma_commit(bar_mma);
@@ -369,7 +376,7 @@ size_t actor_tc_smem_bytes(int O, int A) {
 }
 
 int actor_prep_w2(const float *w2, void *img, cudaStream_t st) {
-    actor_prep_w2_kernel<<<(4 * 256 * 8 + 255) / 256, 256, 0, st>>>(w2, (__nv_bfloat16 *)img);
+    actor_prep_w2_kernel<<<(4 * 256 * 8 + 255) / 256, 256, 0, st>>>(w2, (__half *)img);
     return cudaGetLastError() != cudaSuccess;
 }
 

@@ -474,10 +474,13 @@ def test_shared_actor_tensor_core_vs_torch_fp32(envs_mod, phase, O, A):
     assert torch.allclose(mean32.cpu(), mean_ref, rtol=1e-5, atol=2e-6)
     assert torch.allclose(act32.cpu(), act_ref, rtol=1e-5, atol=2e-6)
     act_tc, mean_tc = env.actor_forward(actor, obs.cuda(), deterministic=True, want_mean=True)
-    # bf16 operands (8-bit mantissa), fp32 accumulation over K = 256: ~2e-3 of the activation scale
+    # IEEE-half operands (11-bit significand), fp32 accumulation over K = 256: ~3e-4 of the activation
+    # scale (bfloat16 operands gave 2e-3 and a 1e-2 bound here)
     scale = float(mean_ref.abs().max())
-    assert float((mean_tc.cpu() - mean_ref).abs().max()) < 1e-2 * max(scale, 1.0)
-    assert float((act_tc.cpu() - act_ref).abs().max()) < 1e-2
+    err_m, err_a = float((mean_tc.cpu() - mean_ref).abs().max()), float((act_tc.cpu() - act_ref).abs().max())
+    print(f"tensor-core actor {phase}: max |mean - torch fp32| = {err_m:.2e} (scale {scale:.2f}), action {err_a:.2e}")
+    assert err_m < 1.5e-3 * max(scale, 1.0)
+    assert err_a < 1.5e-3
     # and it must not be a trivially-zero output
     assert float(mean_tc.abs().max()) > 0.05
 
