@@ -733,11 +733,14 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
     const bool neg_line = aoa < -10.0;
     double aL = neg_line ? -10.0 : fmin(fmax(fabs(aoa), 1e-6), 10.0);
     const bool flip = !neg_line && aoa < 0.0;
-    {   // Pin the two clamped angles in registers.  Under the 128-register cap ptxas otherwise re-derives
-        // them from alpha_eff (float -> double, two multiplies, two fmin / fmax chains: 42 of the 274
-        // instructions of EVERY trip of the summation loop, 11 % of the kernel,
-        // profiles/r2_step_kernel_grid_constant.txt).  An empty asm does not survive to ptxas; an identity
-        // shuffle is the one copy it cannot see through: 4 SHFL per sub-step instead of ~500 instructions.
+    if constexpr (sizeof(R) == 8) {
+        // fp64 build: pin the two clamped angles in registers.  Under the 128-register cap ptxas
+        // otherwise re-derives them from alpha_eff (two multiplies, two fmin / fmax chains: 42 of the
+        // 274 instructions of EVERY trip of the summation loop).  An empty asm does not survive to
+        // ptxas; an identity shuffle is the one copy it cannot see through.  Measured: fp64 build
+        // 81.2 -> 78.5 us per 65 536-env step; the fp32 build loses 2 % (66.1 -> 67.8 us: it is
+        // latency-bound, the re-derived instructions ride in its stall slots and the two extra live
+        // registers cost more), so it keeps ptxas' choice.
         const unsigned m = __activemask();
         const int me = threadIdx.x & 31;
         aL = __shfl_sync(m, aL, me);
