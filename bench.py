@@ -437,12 +437,14 @@ def run_cuda(args):
                "mean_reward": float(out["rewards"].mean()), "resets": int(out["truncated"].sum() + out["done"].sum())}
         del senv, out
 
-    # ---- the further flight phases, RL closures, same fused step kernel
+    # ---- config 2 in phase G (pso closures) and the further flight phases (RL / supervisory
+    # closures), same fused step kernel
     phases = None
     if not args.no_phases:
         phases = {}
-        for ph in OTHER_PHASES:
-            penv = envs.BatchedRocketEnv(B, "supervisory" if ph == "flip_over_boostbackburn" else "rl", ph,
+        for ph in (G,) + OTHER_PHASES:
+            penv = envs.BatchedRocketEnv(B, "supervisory" if ph == "flip_over_boostbackburn" else
+                                         ("pso" if ph == G else "rl"), ph,
                                          precision=args.precision, auto_reset=True, device=local,
                                          trajectory_length=1000, discount_factor=0.99, seed=5 + rank)
             ptape = torch.rand(40, B, penv.act_dim, device=dev, generator=gen, dtype=torch.float32) * 2 - 1

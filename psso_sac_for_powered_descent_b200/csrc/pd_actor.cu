@@ -212,12 +212,14 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                  // [4][128][64] fp16, swizzled
     uint8_t *sB = smem + A_BYTES;                        // [4][256][64] fp16, swizzled (W2 image)
-    float *s_w1 = (float *)(smem + A_BYTES + B_BYTES);   // [256][O]
-    float *s_b1 = s_w1 + ACT_H * O;
-    float *s_b2 = s_b1 + ACT_H;
-    float *s_wm = s_b2 + ACT_H;                          // [A][256]
-    float *s_ws = s_wm + A * ACT_H;
-    float *s_part = s_ws + A * ACT_H;                    // [128][2A] head partial sums of half 1
+    // Per-hidden-unit records, padded to float4 so that a (warp-uniform, broadcast) LDS.128 brings a
+    // whole record: layer 1 {b1[k], w1[k][0..O)} and epilogue {b2[n], wm[0..A)[n], ws[0..A)[n]}.  With
+    // scalar loads these were 3 LDS per accumulator column and per hidden unit - 46 % + 27 % of the
+    // kernel's instructions sat in those two loops (profiles/r2_actor_tc_kernel.txt).
+    constexpr int L1W = (O + 1 + 3) / 4 * 4, EPW = (1 + 2 * A + 3) / 4 * 4;
+    float *s_l1 = (float *)(smem + A_BYTES + B_BYTES);   // [256][L1W]
+    float *s_ep = s_l1 + ACT_H * L1W;                    // [256][EPW]
+    float *s_part = s_ep + ACT_H * EPW;                  // [128][2A] head partial sums of half 1
     uint64_t *bars = (uint64_t *)(s_part + TILE_M * 2 * A);   // [0] W2 landed, [1] MMA done
     uint32_t *s_tmem = (uint32_t *)(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -234,9 +236,18 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
                      ::"r"(smem_u32(s_tmem)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < ACT_H * O; i += ACT_THREADS) s_w1[i] = p.w1[i];
-    for (int i = tid; i < ACT_H; i += ACT_THREADS) { s_b1[i] = p.b1[i]; s_b2[i] = p.b2[i]; }
-    for (int i = tid; i < A * ACT_H; i += ACT_THREADS) { s_wm[i] = p.wm[i]; s_ws[i] = p.ws[i]; }
+    for (int k = tid; k < ACT_H; k += ACT_THREADS) {
+        s_l1[k * L1W] = p.b1[k];
+#pragma unroll
+        for (int q = 0; q < O; ++q) s_l1[k * L1W + 1 + q] = p.w1[k * O + q];
+#pragma unroll
+        for (int q = O + 1; q < L1W; ++q) s_l1[k * L1W + q] = 0.f;
+        s_ep[k * EPW] = p.b2[k];
+#pragma unroll
+        for (int a = 0; a < A; ++a) { s_ep[k * EPW + 1 + a] = p.wm[a * ACT_H + k]; s_ep[k * EPW + 1 + A + a] = p.ws[a * ACT_H + k]; }
+#pragma unroll
+        for (int q = 1 + 2 * A; q < EPW; ++q) s_ep[k * EPW + q] = 0.f;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -266,11 +277,15 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int n = half * 128 + cb * 32 + j;
-                const float h2 = fmaxf(__uint_as_float(v[j]) + s_b2[n], 0.f);
+                float rec[EPW];
+#pragma unroll
+                for (int q = 0; q < EPW; q += 4)
+                    *reinterpret_cast<float4 *>(rec + q) = *reinterpret_cast<const float4 *>(s_ep + n * EPW + q);
+                const float h2 = fmaxf(__uint_as_float(v[j]) + rec[0], 0.f);
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
-                    mean[a] = fmaf(s_wm[a * ACT_H + n], h2, mean[a]);
-                    lstd[a] = fmaf(s_ws[a * ACT_H + n], h2, lstd[a]);
+                    mean[a] = fmaf(rec[1 + a], h2, mean[a]);
+                    lstd[a] = fmaf(rec[1 + A + a], h2, lstd[a]);
                 }
             }
         }
@@ -318,9 +333,13 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int k = kb * 64 + c * 8 + j * 2 + e;
-                        float acc = s_b1[k];
+                        float rec[L1W];
 #pragma unroll
-                        for (int q = 0; q < O; ++q) acc = fmaf(s_w1[k * O + q], o[q], acc);
+                        for (int q = 0; q < L1W; q += 4)
+                            *reinterpret_cast<float4 *>(rec + q) = *reinterpret_cast<const float4 *>(s_l1 + k * L1W + q);
+                        float acc = rec[0];
+#pragma unroll
+                        for (int q = 0; q < O; ++q) acc = fmaf(rec[1 + q], o[q], acc);
                         h[e] = fmaxf(acc, 0.f);
                     }
                     __half2 b2v = __floats2half2_rn(h[0], h[1]);
@@ -372,7 +391,8 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
 }
 
 size_t actor_tc_smem_bytes(int O, int A) {
-    return 1024 + A_BYTES + B_BYTES + sizeof(float) * (ACT_H * O + 3 * ACT_H + 2 * A * ACT_H + TILE_M * 2 * A) + 64;
+    const int l1w = (O + 1 + 3) / 4 * 4, epw = (1 + 2 * A + 3) / 4 * 4;
+    return 1024 + A_BYTES + B_BYTES + sizeof(float) * (ACT_H * l1w + ACT_H * epw + TILE_M * 2 * A) + 64;
 }
 
 int actor_prep_w2(const float *w2, void *img, cudaStream_t st) {

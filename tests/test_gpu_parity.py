@@ -784,3 +784,90 @@ def test_rollout_straggler_handoff(envs_mod):
     same = s0[late] == s1[late]
     assert same.mean() > 0.9
     assert np.max(np.abs(f0[late][same] - f1[late][same]) / np.maximum(np.abs(f0[late][same]), 1.0)) < 1e-6
+
+
+# --------------------------------------------------------------------------- round-2 robustness
+def test_captured_graph_survives_other_handles(envs_mod):
+    """A handle's constants travel with every launch (a __grid_constant__ kernel parameter): a CUDA
+    graph captured on one handle replays correctly after other handles - another phase, another
+    precision - have been created and stepped in between (round 1 needed pd_activate for that)."""
+    B = 2048
+    rng = np.random.default_rng(3)
+    acts = torch.as_tensor(rng.uniform(-1, 1, (6, B, 1)).astype(np.float32)).cuda()
+    ref = envs_mod.BatchedRocketEnv(B, "pso", P, precision="fp32", auto_reset=True)
+    for k in range(6):
+        ref.step(acts[k])
+    want = ref.get_state().clone()
+    env = envs_mod.BatchedRocketEnv(B, "pso", P, precision="fp32", auto_reset=True)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        env.step(acts[0])                    # warm-up launch (module load, shared-memory opt-in)
+        env.reset()
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for k in range(6):
+                env.step(acts[k])
+    other = envs_mod.BatchedRocketEnv(512, "rl", G, precision="fp32", auto_reset=True)
+    other64 = envs_mod.BatchedRocketEnv(512, "pso", P, precision="fp64", enable_wind=True, stochastic_wind=True)
+    other.step(torch.zeros(512, 4, device="cuda"))
+    other64.step(torch.zeros(512, 1, dtype=torch.float64, device="cuda"))
+    with torch.cuda.stream(stream):
+        graph.replay()
+        other.step(torch.zeros(512, 4, device="cuda"))       # interleaved with the replay's stream
+    torch.cuda.synchronize()
+    assert torch.equal(env.get_state(), want)
+    env.check_status(); other.check_status(); other64.check_status()
+
+
+def test_gust_noise_is_fresh_every_episode_and_generation(envs_mod):
+    """Upstream's reset() re-seeds and rebuilds the gust filters (vonkarman.py:86-96): consecutive
+    episodes of one env, and consecutive PSO generations, must see different noise; the stream of
+    a particle must not depend on how the swarm is sharded (index0)."""
+    B = 64
+    env = envs_mod.BatchedRocketEnv(B, "pso", P, enable_wind=True, stochastic_wind=True, precision="fp64", seed=3)
+    dbg = torch.zeros(B, 16, dtype=torch.float64, device="cuda")
+    a = torch.full((B, 1), 0.8, dtype=torch.float32, device="cuda")    # brakes: below 15 km after ~17 s, where gusts act
+    runs = []
+    for episode in range(2):
+        env.reset()
+        vg = []
+        for t in range(300):
+            obs, rew, done, trunc, tid = env.step(a, dbg=dbg)
+            assert not bool((done | trunc).any())
+            vg.append(dbg[:, 14].clone())                # v-gust: pure filter output, no altitude profile
+        runs.append(torch.stack(vg))
+    first, second = runs[0][:, 0], runs[1][:, 0]
+    active = (first != 0) & (second != 0)
+    assert int(active.sum()) > 50
+    assert not torch.equal(first, second)                               # not a replay of episode 1 ...
+    ratio = second[active] / first[active]
+    assert float(ratio.std()) > 1e-2 * float(ratio.abs().mean())        # ... and not a rescaled replay either
+    assert not torch.equal(runs[0][:, 0], runs[0][:, 1])                # envs differ among themselves
+    # rollouts: generation-dependent noise, sharding-independent streams
+    rng = np.random.default_rng(4)
+    pos = torch.as_tensor(rng.uniform(-1.5, 1.5, (16, 249)).astype(np.float32)).cuda()
+    m = envs_mod.pso_wrapped_env(flight_phase=P, enable_wind=True, stochastic_wind=True, precision="fp32", seed=11)
+    f0, _, _ = m._b.rollout_pso(pos, n_seeds=4, generation=0)
+    f0b, _, _ = m._b.rollout_pso(pos, n_seeds=4, generation=0)
+    f1, _, _ = m._b.rollout_pso(pos, n_seeds=4, generation=1)
+    assert torch.equal(f0, f0b) and not torch.equal(f0, f1)
+    fs, _, _ = m._b.rollout_pso(pos[8:], n_seeds=4, generation=0, index0=8)
+    assert torch.equal(fs, f0[8 * 4:])
+
+
+def test_step_cap_is_scored_as_truncation(envs_mod):
+    """The reference's episode loop has no step cap; an episode cut by max_steps keeps truncation id -1
+    and is scored with the closures' truncated branch at its final state (P: +|y| while airborne), so a
+    stalling policy cannot outrank a crash."""
+    rng = np.random.default_rng(5)
+    pos = rng.uniform(-1.5, 1.5, (256, 249))
+    m = envs_mod.pso_wrapped_env(flight_phase=P, precision="fp64", max_steps=40)
+    with pytest.warns(RuntimeWarning, match="max_steps"):
+        fit, steps, tid, term = m.evaluate(pos, terminal=True)
+    assert m.capped == 256 and (tid == -1).all() and (steps == 40).all()
+    y = term[:, 1]
+    assert (y > 0).all() and torch.allclose(fit, y.abs(), rtol=1e-12)
+    m2 = envs_mod.pso_wrapped_env(flight_phase=P, precision="fp64", max_steps=4096)
+    fit2, steps2, tid2 = m2.evaluate(pos[:32])
+    assert (tid2 >= 0).all() and m2.capped == 0
