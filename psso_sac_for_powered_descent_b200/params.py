@@ -149,6 +149,12 @@ class RocketParams:
         p.stage1_mass_ton = float(sizing["Stage 1 Mass"])
 
         if closure_cells is None:
+            closure_cells = read_pickled_closures(root)
+        if closure_cells is None:
+            import warnings
+            warnings.warn("rocket_functions.pkl could not be read here (needs `dill` and the reference's own "
+                          "`src` package under the given root); taking the inertia / engine-height / CoP / "
+                          "velocity-profile constants from the committed snapshot", RuntimeWarning)
             snap = cls.default()
             so = snap.other_phases
             closure_cells = dict(inertia=snap.inertia, engine_height=snap.engine_height,
@@ -197,6 +203,73 @@ class RocketParams:
         p.wind_table = _parse_wind_table(os.path.join(root, "data/Wind/horizontal_wind.csv"))
         p.other_phases = _other_phases(root, sizing, closure_cells, traj)
         return p
+
+
+def read_pickled_closures(root):
+    """The constants the reference keeps inside its two dill pickles
+    (`data/rocket_parameters/rocket_functions.pkl`, loaded at rockets_physics.py:721-722, and
+    `landing_initial_velocity_profile_guess.pkl`, landing_burn_pure_throttle.py:175-176), read from the
+    pickles themselves: the closures were dilled under Python <= 3.10 and cannot be *executed* on a
+    newer interpreter, but their closure cells (the numbers stage_inertia / full_rocket_inertia /
+    d_cg_thrusters / cop_func close over) unpickle fine.  Needs `dill` and the reference's `src` package
+    under `root` (the pickles reference its classes); plotting imports are stubbed for the duration.
+    Returns None when that is not available."""
+    import sys
+    from unittest.mock import MagicMock
+    try:
+        import dill._dill as _d
+    except Exception:
+        return None
+    stubs = ["matplotlib", "matplotlib.pyplot", "matplotlib.gridspec", "matplotlib.patches", "matplotlib.lines",
+             "matplotlib.cm", "matplotlib.colors", "matplotlib.ticker", "matplotlib.animation",
+             "matplotlib.collections", "mpl_toolkits", "mpl_toolkits.mplot3d", "pyswarm", "ambiance",
+             "gymnasium", "lmdb"]
+
+    def missing(m):
+        import importlib.util
+        try:
+            return m not in sys.modules and importlib.util.find_spec(m.split(".")[0]) is None
+        except (ImportError, ValueError):
+            return True
+    added = [m for m in stubs if missing(m)]            # only what this interpreter does not have
+    cwd, had_path = os.getcwd(), root in sys.path
+    before = set(sys.modules)
+    try:
+        for m in added:
+            sys.modules[m] = MagicMock()
+        if not had_path:
+            sys.path.insert(0, root)
+        os.chdir(root)                                  # the reference's data paths are relative
+        import importlib
+        importlib.import_module("src.RocketSizing.main_sizing")     # classes the pickle refers to
+
+        def cells(fn):
+            return {n: c.cell_contents for n, c in zip(fn.__code__.co_freevars, fn.__closure__ or ())}
+        with open(os.path.join(root, "data/rocket_parameters/rocket_functions.pkl"), "rb") as f:
+            raw = _d.load(f)
+        with open(os.path.join(root, "data/reference_trajectory/landing_burn_controls/"
+                                     "landing_initial_velocity_profile_guess.pkl"), "rb") as f:
+            vc = cells(_d.load(f))
+        lengths = cells(raw["cop_subrocket_2_lambda"])["self"].lengths
+        return dict(
+            inertia={k: float(v) for k, v in cells(raw["x_cog_inertia_subrocket_2_lambda"]).items()},
+            engine_height=float(cells(raw["d_cg_thrusters_subrocket_2_lambda"])["self"].engine_height),
+            cop_length=float(lengths[2]), cop_d0=0.75,         # main_sizing.py:215-217
+            v_opt_a=float(vc["a_opt"]), v_opt_b=float(vc["b_opt"]),
+            inertia_full={k: float(v) for k, v in cells(raw["x_cog_inertia_subrocket_0_lambda"]).items()},
+            engine_height_full=float(cells(raw["d_cg_thrusters_subrocket_0_lambda"])["self"].engine_height),
+            cop_length_full=float(lengths[0]), cop_d0_full=0.25)
+    except Exception:
+        return None
+    finally:
+        os.chdir(cwd)
+        if not had_path and root in sys.path:
+            sys.path.remove(root)
+        for m in added:
+            sys.modules.pop(m, None)
+        for m in set(sys.modules) - before:             # the reference's `src.*` modules imported for unpickling
+            if m == "src" or m.startswith("src."):
+                sys.modules.pop(m, None)
 
 
 _STATE_COLS = ("x[m]", "y[m]", "vx[m/s]", "vy[m/s]", "theta[rad]", "theta_dot[rad/s]", "gamma[rad]",

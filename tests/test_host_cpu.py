@@ -88,9 +88,19 @@ def test_params_snapshot_values():
 def test_params_from_reference_data_equals_snapshot():
     from dataclasses import asdict
     from psso_sac_for_powered_descent_b200 import RocketParams
+    import warnings
+    from psso_sac_for_powered_descent_b200.params import read_pickled_closures
     a = asdict(RocketParams.default())
-    b = asdict(RocketParams.from_reference_data("/root/reference"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)          # no silent fall-back to the snapshot
+        b = asdict(RocketParams.from_reference_data("/root/reference"))
     assert a == b
+    # the constants inside rocket_functions.pkl are read from the pickle itself (closure cells; the
+    # Python <= 3.10 bytecode is never executed), and the import of the reference's modules is undone
+    cc = read_pickled_closures("/root/reference")
+    assert cc["inertia"]["m_dry"] == 921070.0851247016 and cc["engine_height"] == 3.1
+    assert cc["v_opt_a"] == -7.445479767703873e-07
+    assert not any(m == "src" or m.startswith("src.") for m in sys.modules)
 
 
 def test_wind_profile_and_gust_filter_constants():
