@@ -628,11 +628,14 @@ class pso_wrapped_env:
             # multi-threaded cast (numpy's astype is single-threaded: 30 ms for 65 536 x 249), through a
             # pinned staging buffer so that the upload is one DMA
             n = w.shape[0] * w.shape[1]
-            if getattr(self, "_stage", None) is None or self._stage.numel() < n:
-                self._stage = torch.empty(n, dtype=torch.float32).pin_memory()
-            st = self._stage[:n].view(w.shape)
-            st.copy_(torch.from_numpy(w))
-            wt = st.to(self._b.device, non_blocking=True)
+            if n < (1 << 21):       # small swarms: waking torch's thread pool costs more than the cast
+                wt = torch.as_tensor(w.astype(np.float32)).to(self._b.device)
+            else:
+                if getattr(self, "_stage", None) is None or self._stage.numel() < n:
+                    self._stage = torch.empty(n, dtype=torch.float32).pin_memory()
+                st = self._stage[:n].view(w.shape)
+                st.copy_(torch.from_numpy(w))
+                wt = st.to(self._b.device, non_blocking=True)
         out = self._b.rollout_pso(wt, n_seeds=n_seeds, max_steps=self.max_steps, terminal=terminal,
                                   index0=index0, generation=generation)
         self._b.check_status()
