@@ -39,6 +39,10 @@ OTHER_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn
 N_ENVS = 65536
 ALGO_BYTES_PER_STEP = 160.0        # 40 words x 4 B, phase P, fp32
 ALGO_FLOP_PER_STEP = 4800.0        # canonical flop per env-step (P, no wind)
+# Per-step latency of ONE episode at the highest cooperation (32 lanes; profiles/r2_rollout_coop32_stage.txt,
+# G: fp64 instantiation, 8 lanes): longest episode x this = the time below which no number of GPUs can
+# bring a generation - reported next to every PSO timing as `sequential_floor_ms`
+LONE_EPISODE_US_PER_STEP = {"landing_burn_pure_throttle": 7.6, "landing_burn": 27.0}
 
 
 def load_peaks():
@@ -341,7 +345,7 @@ def run_cuda(args):
 
             def local_eval(p, index0=0, generation=0):
                 fit, steps, tid = model.evaluate(p, n_seeds=seeds, index0=index0, generation=generation)
-                st["steps"], st["capped"] = float(steps.sum()), int((tid < 0).sum())
+                st["steps"], st["capped"], st["longest"] = float(steps.sum()), int((tid < 0).sum()), int(steps.max())
                 return fit.reshape(len(p), seeds).mean(dim=1).cpu().numpy()
             ev = pso_mod.ShardedEvaluator(local_eval)
             lo, hi = pso_mod.shard_bounds(n, world, rank)
@@ -357,11 +361,14 @@ def run_cuda(args):
                 best_dt = min(best_dt, time.perf_counter() - t0)
             dt, = allmax(best_dt)
             tot_steps, capped = allsum(st["steps"], st["capped"])
+            longest, = allmax(st["longest"])
             del model
             return {"phase": phase, "particles": n, "wind_seeds": seeds, "wind": bool(wind),
                     "fitness_evals_per_s": n / dt, "episodes_per_s": n * seeds / dt, "ms": dt * 1e3,
                     "env_steps_per_s": tot_steps / dt, "mean_episode_steps": tot_steps / (n * seeds),
-                    "episodes_hitting_step_cap": int(capped), "best_fitness": best, "best_index": idx,
+                    "episodes_hitting_step_cap": int(capped), "longest_episode_steps": int(longest),
+                    "sequential_floor_ms": longest * LONE_EPISODE_US_PER_STEP[phase] * 1e-3,
+                    "best_fitness": best, "best_index": idx,
                     "timing": "wall clock between device-synchronised barriers, max over ranks",
                     "what": "host array of positions in, fitness out (ShardedEvaluator): float32 conversion + "
                             "upload of this rank's shard, rollout kernel(s), fitness all-gather, best broadcast"}
@@ -376,20 +383,25 @@ def run_cuda(args):
             sw.step()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             gsteps = torch.zeros((), dtype=torch.float64, device=dev)
+            glong = torch.zeros((), dtype=torch.int32, device=dev)
             barrier()
             g0.record()
             for _ in range(n_gen):
                 sw.step()
                 gsteps += sw.last_steps.sum()
+                glong = torch.maximum(glong, sw.last_steps.max())
             g1.record()
             barrier()
             gms, = allmax(g0.elapsed_time(g1) / n_gen)
             tot, capped = allsum(float(gsteps) / n_gen, float(sw.capped_episodes))
+            longest, = allmax(float(glong))
             out = {"phase": phase, "particles": sw.N_total, "wind_seeds": seeds, "wind": bool(wind),
                    "ms_per_generation": gms, "fitness_evals_per_s": sw.N_total / (gms * 1e-3),
                    "episodes_per_s": sw.N_total * seeds / (gms * 1e-3), "env_steps_per_s": tot / (gms * 1e-3),
                    "mean_episode_steps": tot / (sw.N_total * seeds),
                    "episodes_hitting_step_cap_total": int(capped), "generations_timed": n_gen,
+                   "longest_episode_steps": int(longest),
+                   "sequential_floor_ms": longest * LONE_EPISODE_US_PER_STEP[phase] * 1e-3,
                    "global_best_fitness": sw.global_best_fitness,
                    "timing": "CUDA events around the generations, max over ranks",
                    "what": "rollout kernel + seed mean + fitness all-gather + per-sub-swarm arg-min / metrics + "
@@ -471,7 +483,8 @@ def run_cuda(args):
     hbm_peak, sm_max, peak_src = load_peaks()
     kern_ms = ms_max / K                      # average launch duration inside the timed region (graph replay)
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-    nominal_fp32 = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    nominal_fp32 = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
 
     def hbm(kms):
         a = ALGO_BYTES_PER_STEP * B / (kms * 1e-3) / 1e9

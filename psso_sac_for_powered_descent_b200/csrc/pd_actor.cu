@@ -194,15 +194,22 @@ constexpr int TILE_M = 128;
 constexpr uint32_t A_BYTES = TILE_M * ACT_H * 2;        // 64 KB: 4 K-blocks x 16 KB
 constexpr uint32_t B_BYTES = ACT_H * ACT_H * 2;         // 128 KB: 4 K-blocks x 32 KB
 
-// 256 threads = two halves of 4 warps.  Row (env) of a thread = tid & 127; half h = tid >> 7
-// takes K blocks {2h, 2h+1} of layer 1 and accumulator columns [128h, 128h + 128) of the epilogue
-// (a warp may only touch TMEM lanes 32 (warp % 4) .. +31, so the two halves share lanes and split
-// columns).  The fp32 accumulator is double-buffered in TMEM (2 x 256 of the 512 columns): the
+// 128 x ACT_GROUPS threads = groups of 4 warps.  Row (env) of a thread = tid & 127; group h = tid >> 7
+// takes 4 / ACT_GROUPS K blocks of layer 1 and 256 / ACT_GROUPS accumulator columns of the epilogue
+// (a warp may only touch TMEM lanes 32 (warp % 4) .. +31, so the groups share lanes and split
+// columns).  The tile loop is bound by this CUDA-core work at few warps per SM, not by the MMA
+// (profiles/r2_actor_tc_kernel.txt: 2 groups = 8 warps: issue 34 %, tensor pipe 20 %).  The fp32 accumulator is double-buffered in TMEM (2 x 256 of the 512 columns): the
 // 16 UMMAs of tile i are issued asynchronously and run on the tensor core while all 8 warps do the
 // epilogue of tile i-1; only then does the CTA wait for tile i's commit (its A tile may not be
 // overwritten earlier).  Per tile the CTA therefore pays layer 1 + epilogue, each at half the
 // former per-thread work, and no longer the MMA latency.
-constexpr int ACT_THREADS = 256;
+#ifndef PD_ACT_GROUPS
+#define PD_ACT_GROUPS 4
+#endif
+constexpr int ACT_GROUPS = PD_ACT_GROUPS;            // column groups of 4 warps: 2 (256 threads) or 4 (512 threads)
+constexpr int ACT_THREADS = 128 * ACT_GROUPS;
+constexpr int ACT_COLS = ACT_H / ACT_GROUPS;         // accumulator columns per group
+constexpr int ACT_KB = 4 / ACT_GROUPS;               // layer-1 K blocks per group
 
 template <int O, int A>
 __global__ void __launch_bounds__(ACT_THREADS, 1)
@@ -219,8 +226,8 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
     constexpr int L1W = (O + 1 + 3) / 4 * 4, EPW = (1 + 2 * A + 3) / 4 * 4;
     float *s_l1 = (float *)(smem + A_BYTES + B_BYTES);   // [256][L1W]
     float *s_ep = s_l1 + ACT_H * L1W;                    // [256][EPW]
-    float *s_part = s_ep + ACT_H * EPW;                  // [128][2A] head partial sums of half 1
-    uint64_t *bars = (uint64_t *)(s_part + TILE_M * 2 * A);   // [0] W2 landed, [1] MMA done
+    float *s_part = s_ep + ACT_H * EPW;                  // [ACT_GROUPS - 1][128][2A] head partial sums of groups 1..
+    uint64_t *bars = (uint64_t *)(s_part + (ACT_GROUPS - 1) * TILE_M * 2 * A);   // [0] W2 landed, [1] MMA done
     uint32_t *s_tmem = (uint32_t *)(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & (TILE_M - 1), half = tid >> 7;
@@ -269,14 +276,14 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
         float mean[A], lstd[A];
 #pragma unroll
         for (int a = 0; a < A; ++a) { mean[a] = 0.f; lstd[a] = 0.f; }
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256 + half * 128;
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256 + half * ACT_COLS;
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < ACT_COLS / 32; ++cb) {
             uint32_t v[32];
             tmem_ld32(lane_base + cb * 32, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int n = half * 128 + cb * 32 + j;
+                const int n = half * ACT_COLS + cb * 32 + j;
                 float rec[EPW];
 #pragma unroll
                 for (int q = 0; q < EPW; q += 4)
@@ -289,9 +296,10 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
                 }
             }
         }
-        if (half == 1) {
+        if (half > 0) {
+            float *dst = s_part + ((half - 1) * TILE_M + row) * 2 * A;
 #pragma unroll
-            for (int a = 0; a < A; ++a) { s_part[row * 2 * A + a] = mean[a]; s_part[row * 2 * A + A + a] = lstd[a]; }
+            for (int a = 0; a < A; ++a) { dst[a] = mean[a]; dst[A + a] = lstd[a]; }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();      // partial sums visible; all TMEM reads of this buffer are done
@@ -299,8 +307,13 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
             const int env = tile * TILE_M + row;
 #pragma unroll
             for (int a = 0; a < A; ++a) {
-                mean[a] += s_part[row * 2 * A + a] + p.bm[a];
-                lstd[a] += s_part[row * 2 * A + A + a] + p.bs[a];
+#pragma unroll
+                for (int g = 0; g < ACT_GROUPS - 1; ++g) {
+                    mean[a] += s_part[(g * TILE_M + row) * 2 * A + a];
+                    lstd[a] += s_part[(g * TILE_M + row) * 2 * A + A + a];
+                }
+                mean[a] += p.bm[a];
+                lstd[a] += p.bs[a];
             }
             if (env < B) head_and_sample<A>(p, mean, lstd, (unsigned)env, act, mean_out);
         }
@@ -322,8 +335,8 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
         // layer 1 -> fp16 -> swizzled A tile (row = tid & 127), this half's two K blocks
         const uint32_t row_off = (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128;
 #pragma unroll 1
-        for (int kq = 0; kq < 2; ++kq) {
-            const int kb = half * 2 + kq;
+        for (int kq = 0; kq < ACT_KB; ++kq) {
+            const int kb = half * ACT_KB + kq;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 uint32_t packed[4];
@@ -392,7 +405,7 @@ actor_tc_kernel(ActorArgs p, const float *__restrict__ obs, float *__restrict__ 
 
 size_t actor_tc_smem_bytes(int O, int A) {
     const int l1w = (O + 1 + 3) / 4 * 4, epw = (1 + 2 * A + 3) / 4 * 4;
-    return 1024 + A_BYTES + B_BYTES + sizeof(float) * (ACT_H * l1w + ACT_H * epw + TILE_M * 2 * A) + 64;
+    return 1024 + A_BYTES + B_BYTES + sizeof(float) * (ACT_H * l1w + ACT_H * epw + (ACT_GROUPS - 1) * TILE_M * 2 * A) + 64;
 }
 
 int actor_prep_w2(const float *w2, void *img, cudaStream_t st) {
