@@ -372,9 +372,16 @@ class ParticleSubswarmOptimisation:
 
     # ------------------------------------------------------------------ swarm state
     def initialize_swarms(self):
-        """Same draw order as the reference (:389-411): sub-swarm, particle, bound."""
+        """Same draws as the reference: its base class first builds a plain `pop_size` swarm that the
+        sub-swarm optimiser never uses (`ParticleSwarmOptimisation.__init__` -> `initialize_swarm`,
+        :57, 76-90) - pop_size x P `random.uniform` draws are consumed - and only then come the
+        sub-swarms (:389-411): sub-swarm, particle, bound.  With the same seed the swarm is therefore
+        the one `random.seed(seed)` gives upstream (tests/golden/pso_run_reference.npz)."""
         n_sub = self.pop_size // self.num_sub_swarms
         N, P = n_sub * self.num_sub_swarms, len(self.bounds)
+        for _ in range(self.pop_size):
+            for b in self.bounds:
+                self.rng_py.uniform(b[0], b[1])
         self.position = np.empty((N, P), dtype=np.float64)
         for i in range(N):
             for j, b in enumerate(self.bounds):

@@ -722,6 +722,32 @@ def test_device_swarm_follows_host_dropin_exactly(envs_mod, tmp_path):
     assert hdr[0] == "Algorithm" and hdr[1] == "0_weight_0" and len(hdr) == 374
 
 
+def test_optimisers_follow_the_reference_optimiser(envs_mod, golden, tmp_path):
+    """The recorded run of the UNMODIFIED reference optimiser (tests/golden/pso_run_reference.npz: 7
+    generations with sharing, migration, re-initialisation) followed (1) by the host drop-in with the
+    CUDA fitness evaluation - same positions in every generation, bit for bit - and (2) by checking
+    that the device-resident swarm started from the same positions evaluates the same first
+    generation."""
+    import json
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).parent))
+    from test_host_cpu import _follow_reference_run
+    from psso_sac_for_powered_descent_b200 import pso
+    g = golden("pso_run_reference.npz")
+    phase = str(g["phase"])
+    params = dict(pso.PSO_PARAMS[phase], **json.loads(str(g["knobs"])))
+    model = envs_mod.pso_wrapped_env(flight_phase=phase, precision="fp64", max_steps=8192)
+    opt = pso.ParticleSubswarmOptimisation(phase, save_interval=0, model=model, pso_params=params,
+                                           seed=int(g["seed"]), rng="reference", base_save_dir=str(tmp_path))
+    x0 = opt.position.copy()
+    _follow_reference_run(g, opt, fit_tol=1e-4)
+    dev = pso.DeviceSwarm(model, len(x0), params, seed=int(g["seed"]), max_steps=8192, positions=x0)
+    fit = dev.step()[:len(x0)].cpu().numpy()
+    ref_min = [g["g0_metrics"][k][2] for k in range(2)]
+    assert np.allclose([fit[:4].min(), fit[4:].min()], ref_min, rtol=1e-4)
+    assert abs(dev.global_best_fitness - g["g0_global"][0]) <= 1e-4 * abs(g["g0_global"][0])
+
+
 @pytest.mark.parametrize("n", [1, 33, 449, 1000])
 def test_ragged_batch_sizes_bitwise(envs_mod, golden, n):
     """Batch sizes that do not fill a warp / a block / a wave: every env's result is bit-identical

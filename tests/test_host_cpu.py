@@ -231,6 +231,7 @@ def test_pso_init_order_and_bounds(tmp_path):
     import random
     opt = _mk(tmp_path)
     r = random.Random(4)
+    [r.uniform(-1.5, 1.5) for _ in range(40 * 6)]       # the base class's unused swarm (:57, 76-90)
     exp = np.array([[r.uniform(-1.5, 1.5) for _ in range(6)] for _ in range(40)])
     assert np.array_equal(opt.position, exp)            # initialize_swarms draw order (:401)
     assert [len(s) for s in opt.swarms] == [20, 20]
@@ -477,3 +478,67 @@ def test_seedless_optimiser_agrees_across_ranks(tmp_path):
     r0, r1 = np.load(tmp_path / "s0.npz"), np.load(tmp_path / "s1.npz")
     assert int(r0["seed"]) == int(r1["seed"])
     assert np.array_equal(r0["x"], r1["x"]) and float(r0["g"]) == float(r1["g"])
+
+
+# --------------------------------------------------------------------------- the reference optimiser itself
+class _OracleModel:
+    """pso_wrapped_env stand-in on the CPU oracle (objective_function per particle)."""
+
+    def __init__(self, phase, tables):
+        from oracle import pd_oracle as O
+        self._m = O.PsoModel(phase, tables=tables)
+        n = self._m.n_params
+        self.bounds = [(-1.5, 1.5)] * n
+        self.mock_dictionary_of_opt_params = {f"p_{j}": 0.0 for j in range(n)}
+
+    def objective_function(self, individual):
+        return self._m.objective_function(np.asarray(individual, dtype=np.float64))
+
+
+def _follow_reference_run(g, opt, pos_tol=0.0, fit_tol=1e-6):
+    """Drive `opt` generation by generation next to the recorded run of the unmodified reference
+    optimiser (tools/make_golden.py pso_run): evaluated positions per sub-swarm in list order (exact),
+    per-sub-swarm metrics and global best (fit_tol: the fitness itself carries the evaluator's
+    tolerance - 1e-6 for the oracle, 1e-4 for the CUDA path whose fp32 MLP sums in another order than
+    torch-CPU - the swarm dynamics only see it through comparisons)."""
+    for gen in range(int(g["n_generations"])):
+        for k, m in enumerate(opt.members):
+            ref = g[f"g{gen}_pos_{k}"]
+            assert ref.shape == (len(m), opt.position.shape[1]), (gen, k, ref.shape, len(m))
+            assert np.max(np.abs(opt.position[m] - ref)) <= pos_tol, (gen, k)
+        opt.step_generation(gen)
+        gb, gavg = g[f"g{gen}_global"]
+        assert abs(opt.global_best_fitness - gb) <= fit_tol * abs(gb), gen
+        assert abs(opt.average_particle_fitness_array[-1] - gavg) <= fit_tol * abs(gavg), gen
+    assert np.allclose(opt.global_best_fitness_array, g["global_best_fitness_array"], rtol=fit_tol, atol=0)
+    final = np.concatenate([opt.position[m] for m in opt.members])
+    assert [len(m) for m in opt.members] == list(g["final_sizes"])
+    assert np.max(np.abs(final - g["final_positions"])) <= pos_tol
+    fv = np.concatenate([opt.velocity[m] for m in opt.members])
+    assert np.max(np.abs(fv - g["final_velocities"])) <= pos_tol
+    assert np.max(np.abs(opt.global_best_position - g["global_best_position"])) <= pos_tol
+
+
+def test_host_dropin_follows_the_reference_optimiser(golden, oracle_tables, tmp_path):
+    """ParticleSubswarmOptimisation (rng='reference', same seed) against a recorded run of the
+    UNMODIFIED reference optimiser: 7 generations of landing_burn_pure_throttle through sharing,
+    migration and re-initialisation - the same particles at the same positions in every generation,
+    bit for bit, and the same metrics files."""
+    import csv
+    import json
+    from psso_sac_for_powered_descent_b200 import pso
+    g = golden("pso_run_reference.npz")
+    phase = str(g["phase"])
+    params = dict(pso.PSO_PARAMS[phase], **json.loads(str(g["knobs"])))
+    opt = pso.ParticleSubswarmOptimisation(phase, save_interval=0, model=_OracleModel(phase, oracle_tables),
+                                           pso_params=params, seed=int(g["seed"]), rng="reference",
+                                           base_save_dir=str(tmp_path))
+    _follow_reference_run(g, opt)
+    ours = list(csv.reader(open(tmp_path / "metrics" / "subswarm_0_metrics.csv")))
+    ref = list(csv.reader(str(g["metrics_csv_subswarm_0"]).strip().splitlines()))
+    assert ours[0] == ref[0] and len(ours) == len(ref)
+    for a, b in zip(ours[1:], ref[1:]):
+        assert a[0] == b[0] and a[6] == b[6] and a[7] == b[7]          # swarm_idx, num_particles, generation
+        assert np.allclose([float(v) for v in a[1:6] + a[8:]], [float(v) for v in b[1:6] + b[8:]], rtol=1e-6)
+    gl = list(csv.reader(open(tmp_path / "metrics" / "global_metrics.csv")))
+    assert gl[0] == list(csv.reader(str(g["metrics_csv_global"]).strip().splitlines()))[0]

@@ -10,6 +10,7 @@ identical data on a box where /root/reference does not exist.
 """
 import io
 import contextlib
+import json
 import math
 import os
 import random
@@ -701,6 +702,73 @@ def flip_over(n=96, seed=51):
           int(o[:, 12].sum()), "trunc", int(o[:, 13].sum()))
 
 
+def pso_run(seed=12, phase=P):
+    """A short seeded run of the UNMODIFIED reference optimiser (ParticleSubswarmOptimisation.run,
+    serial evaluation): 8 particles in 2 sub-swarms, 7 generations with sharing (every 2), migration
+    (every 3) and the re-initialisation (generation 4).  Recorded per generation: the positions that
+    were evaluated (per sub-swarm, in list order), the per-sub-swarm metrics and the global best;
+    at the end the swarm dicts.  The reference writes its metrics under cwd, so it runs in a
+    scratch directory whose `data/*`, `src`, `configs` are links into the read-only checkout."""
+    import tempfile
+    import configs.evolutionary_algorithms_config as cfg
+    import src.particle_swarm_optimisation.particle_swarm_optimisation as ref_pso
+    params = cfg.landing_burn_pure_throttle_pso_params if phase == P else cfg.landing_burn_pso_params
+    saved = dict(params)
+    knobs = dict(pop_size=8, generations=7, communication_freq=2, migration_freq=3, re_initialise_generation=4,
+                 re_initialise_number_of_particles=6)
+    params.update(knobs)
+    root = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="pd_pso_run_")
+    os.makedirs(os.path.join(tmp, "data"))
+    for name in os.listdir(os.path.join(root, "data")):
+        if name != "pso_saves":
+            os.symlink(os.path.join(root, "data", name), os.path.join(tmp, "data", name))
+    os.makedirs(os.path.join(tmp, "data", "pso_saves"))
+    for name in ("src", "configs"):
+        os.symlink(os.path.join(root, name), os.path.join(tmp, name))
+    os.chdir(tmp)
+    try:
+        random.seed(seed)
+        np.random.seed(seed)
+        opt = quiet(ref_pso.ParticleSubswarmOptimisation, flight_phase=phase, save_interval=10 ** 6,
+                    enable_wind=False, use_multiprocessing=False)
+        gens = []
+        orig = opt.save_generation_metrics
+
+        def record(metrics, generation):
+            gens.append(dict(
+                positions=[np.array([p["position"] for p in sw]) for sw in opt.swarms],
+                best_fitness=[np.array([p["best_fitness"] for p in sw]) for sw in opt.swarms],
+                swarm_metrics=[[m["best_fitness"], m["avg_fitness"], m["min_fitness"], m["max_fitness"],
+                                m["std_fitness"], m["num_particles"]] for m in metrics["swarm_metrics"]],
+                global_best=metrics["global_best_fitness"], global_avg=metrics["global_avg_fitness"]))
+            orig(metrics, generation)
+        opt.save_generation_metrics = record
+        best_pos, best_fit = quiet(opt.run)
+        files = {}
+        for f in ("subswarm_0_metrics.csv", "global_metrics.csv"):
+            files[f] = open(os.path.join(opt.metrics_dir, f)).read()
+    finally:
+        os.chdir(root)
+        params.clear(); params.update(saved)
+    out = dict(seed=seed, phase=phase, knobs=json.dumps(knobs), n_generations=len(gens),
+               global_best_fitness_array=np.array(opt.global_best_fitness_array),
+               global_best_position=np.array(best_pos), global_best_fitness=best_fit,
+               final_positions=np.array([p["position"] for sw in opt.swarms for p in sw]),
+               final_velocities=np.array([p["velocity"] for sw in opt.swarms for p in sw]),
+               final_sizes=np.array([len(sw) for sw in opt.swarms]),
+               metrics_csv_subswarm_0=files["subswarm_0_metrics.csv"], metrics_csv_global=files["global_metrics.csv"])
+    for g, rec in enumerate(gens):
+        for k in range(len(rec["positions"])):
+            out[f"g{g}_pos_{k}"] = rec["positions"][k]
+            out[f"g{g}_pbest_{k}"] = rec["best_fitness"][k]
+        out[f"g{g}_metrics"] = np.array(rec["swarm_metrics"], dtype=float)
+        out[f"g{g}_global"] = np.array([rec["global_best"], rec["global_avg"]])
+    np.savez_compressed(os.path.join(OUT, "pso_run_reference.npz"), **out)
+    print("pso_run:", len(gens), "generations; global best history", opt.global_best_fitness_array,
+          "final sizes", [len(sw) for sw in opt.swarms])
+
+
 def ascent_csv():
     """The reference's own committed ascent controller recordings (actions + states per 0.1 s
     step) - golden vectors written on the author's machine, copied verbatim."""
@@ -853,6 +921,8 @@ if __name__ == "__main__":
         single_step_other(C_, "C", np.concatenate([pool, pool2]))
     if "flip" in which:
         flip_over()
+    if "psorun" in which:
+        pso_run()
     if "aero" in which:
         aero_probe()
     if "tape" in which:
