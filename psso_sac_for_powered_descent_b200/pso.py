@@ -948,6 +948,49 @@ class DeviceSwarm:
                   'best_position': b[i].copy() if np.isfinite(bf[i]) else None, 'best_fitness': float(bf[i])}
                  for i in m] for m in self.members]
 
+    def load_swarms(self, file_path):
+        """Resume from a `swarm.pkl` in the reference's layout (load_swarms, :651-688): positions,
+        velocities and personal bests are re-sharded over the ranks; sub-swarm and global bests are
+        rebuilt from the personal bests, as upstream does."""
+        torch = self.torch
+        with open(file_path, "rb") as f:
+            swarms = pickle.load(f)
+        parts = [p for sw in swarms for p in sw]
+        P = self.P
+        x = np.array([p["position"] for p in parts], dtype=np.float64).reshape(-1, P)
+        v = np.array([p["velocity"] for p in parts], dtype=np.float64).reshape(-1, P)
+        bf = np.array([p["best_fitness"] for p in parts], dtype=np.float64)
+        b = np.array([p["best_position"] if p["best_position"] is not None else p["position"] for p in parts],
+                     dtype=np.float64).reshape(-1, P)
+        self.members, i = [], 0
+        for sw in swarms:
+            self.members.append(list(range(i, i + len(sw))))
+            i += len(sw)
+        self.S = len(swarms)
+        self._layout(len(parts))
+        sl = slice(self.lo, self.hi)
+        self.x = torch.as_tensor(x[sl]).to(self.dev).contiguous()
+        self.v = torch.as_tensor(v[sl]).to(self.dev).contiguous()
+        self.best = torch.as_tensor(b[sl]).to(self.dev).contiguous()
+        self.best_fit = torch.as_tensor(bf[sl]).to(self.dev).contiguous()
+        self.weights = self.x.to(torch.float32).contiguous()
+        sb, sbf = np.zeros((self.S, P)), np.full(self.S, np.inf)
+        for k, m in enumerate(self.members):
+            if len(m):
+                j = m[int(np.argmin(bf[m]))]            # first occurrence, as the sequential scan
+                if np.isfinite(bf[j]):
+                    sb[k], sbf[k] = b[j], bf[j]
+        self.swarm_best = torch.as_tensor(sb).to(self.dev).contiguous()
+        self.swarm_best_fit = torch.as_tensor(sbf).to(self.dev).contiguous()
+        k = int(np.argmin(sbf))
+        self.gbest_fit = torch.as_tensor(sbf[k:k + 1].copy()).to(self.dev)
+        self.gbest_pos = torch.as_tensor(sb[k].copy()).to(self.dev)
+        S, dev = self.S, self.dev
+        self.sel_idx = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.improved = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.cand = torch.zeros(S, P, dtype=torch.float64, device=dev)
+        self.hist_stats = torch.zeros(self._cap, S + 1, 6, dtype=torch.float64, device=dev)
+
     def save(self, base_save_dir=None):
         d = f"{base_save_dir or self.base_save_dir}/saves"
         sw = self.swarms()

@@ -714,6 +714,17 @@ def test_device_swarm_follows_host_dropin_exactly(envs_mod, tmp_path):
         sw = pickle.load(f)
     assert [len(x) for x in sw] == [len(m) for m in host.members]
     assert np.array_equal(sw[1][0]["position"], host.swarms[1][0]["position"])
+    # resume on the device from that file (load_swarms renumbers the particles in list order, as a reload
+    # of the reference's lists does): same particles, same bests, same fitness of the next generation
+    dev2 = pso.DeviceSwarm(model, 96, params, seed=9, max_steps=256)
+    dev2.load_swarms(str(tmp_path / "dev" / "saves" / "swarm.pkl"))
+    dev2.generation = dev.generation
+    order = torch.as_tensor([i for m in dev.members for i in m], device="cuda")
+    assert [len(m) for m in dev2.members] == [len(m) for m in dev.members]
+    assert torch.equal(dev2.x, dev.x[order]) and torch.equal(dev2.best_fit, dev.best_fit[order])
+    assert torch.equal(dev2.swarm_best_fit, dev.swarm_best_fit) and dev2.global_best_fitness == dev.global_best_fitness
+    fa, fb = dev.step().clone(), dev2.step().clone()
+    assert torch.equal(fa[:60][order], fb[:60])
     host2 = pso.ParticleSubswarmOptimisation(G, save_interval=0, model=model, pso_params=params, seed=1,
                                              base_save_dir=str(tmp_path / "h2"), write_metrics=False)
     host2.load_swarms(str(tmp_path / "dev" / "saves" / "swarm.pkl"))       # the reference's resume path
