@@ -653,9 +653,10 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
     if (e->handoff_default && e->cfg.phase == PD_PHASE_GIMBALLED) {
         // landing_burn episodes last 7-38 steps: one hand-off after 16 steps straight to the final
         // stage while the swarm is small enough for its tail to matter (8 192 particles x 8 seeds:
-        // 2.55 -> 2.16 ms), none in the throughput regime (the extra launches cost 5 % there)
+        // 2.55 -> 2.16 ms), none in the throughput regime (131 072 episodes and more: the extra
+        // launches and the record round trip cost 5-9 %, tools/device_swarm_G_probe.py)
         const long long L = (long long)e->n_sm * 448;
-        h1 = (long long)io.n_episodes < 4 * L ? 16 : 0;
+        h1 = 2 * (long long)io.n_episodes <= 3 * L ? 16 : 0;
         h2 = max_steps;
     }
     if (h1 > 0) {
