@@ -239,18 +239,23 @@ int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_para
                    double *terminal_state, double *traj, float *actions_out, double *rewards,
                    void *stream);
 
-/* Straggler hand-off of pd_rollout_pso for swarms large enough that one lane runs one episode:
- * episodes still running after `steps` env steps (default 256; a random
- * landing_burn_pure_throttle swarm has a median of 130 steps, 10 % above 400 and a few episodes at
- * the cap) are finished by a second, 8-lane cooperative pass at ~2.5x lower per-step latency, fed
- * from a work queue, instead of holding a single lane each while the rest of the GPU idles:
- * 65 536 particles 116 -> 61 ms, 16 384 particles 84 -> 47 ms on one B200.  Results are identical to the one-pass
- * rollout up to the summation order of the cooperative RBF sums (as for small swarms).  0 = off. */
+/* Straggler hand-off of pd_rollout_pso.  Episode lengths are ragged (a random
+ * landing_burn_pure_throttle swarm has a median of 130 steps, 2 % above 512 and a few episodes at
+ * the cap; after 30 generations of the optimiser 20-30 % are above 512), and a generation cannot
+ * end before its longest episode has, so the rollout runs as a chain of stages
+ *     reset -> steps -> steps2 -> 2 steps2 -> 4 steps2 -> ... -> end:
+ * an episode still running at a boundary is appended, with its complete state, to continuation
+ * records, and the next stage serves the records with 1, 8 or 32 lanes per episode depending on how
+ * many there are (per-step latency of a lone episode 50 / 11 / 7.6 us, instructions per
+ * episode-step 625 / 2 000 / 3 000).  Defaults: 128 / 256 for landing_burn_pure_throttle; one
+ * hand-off after 16 steps for landing_burn while a call has at most 1.5 x the GPU's lane count of
+ * episodes.  Results are identical to the one-pass rollout up to the summation order of the
+ * cooperative RBF sums.  steps = 0: off.  steps2 <= steps: 2 x steps. */
 int pd_set_rollout_handoff(PdEnv *env, int steps);
-/* Both thresholds of the staged hand-off: 1 lane per episode up to `steps`, 8 lanes up to `steps2`
- * (default 128 / 512; steps2 <= steps: 4 x steps), 32 lanes from there; each later stage picks its
- * cooperation from the number of surviving episodes.  0 = off. */
 int pd_set_rollout_stages(PdEnv *env, int steps, int steps2);
+/* Survivor counts at or below which a record-fed stage uses 8 / 32 lanes per episode
+ * (0 = default: lanes / 4 and lanes / 24 with lanes = SMs x 448, the measured cross-over points). */
+int pd_set_rollout_lanes(PdEnv *env, int lanes8_below, int lanes32_below);
 
 /* Whole-episode rollouts with a scripted policy, one launch:
  *   PD_POLICY_TAPE       actions dev [max_steps * n_episodes * A] (step-major), dtype per

@@ -55,7 +55,8 @@ struct PdEnv {
     int *cont_count = nullptr;       // [2]
     int cont_cap = 0;
     int handoff_steps = 128;         // pd_set_rollout_handoff / pd_set_rollout_stages
-    int handoff2_steps = 512;
+    int handoff2_steps = 256;
+    int lanes8_below = 0, lanes32_below = 0;   // pd_set_rollout_lanes (0 = default)
     bool handoff_default = true;     // thresholds never set by the caller: per-phase defaults apply
     // shared-actor collection
     void *w2_img = nullptr;          // bf16 smem image of W2
@@ -439,7 +440,7 @@ int pd_set_rollout_handoff(PdEnv *e, int steps) {
     if (!e) return fail("pd_set_rollout_handoff: null handle");
     if (steps < 0) return fail("pd_set_rollout_handoff: steps must be >= 0 (0 = off)");
     e->handoff_steps = steps;
-    e->handoff2_steps = 4 * steps;
+    e->handoff2_steps = 2 * steps;
     e->handoff_default = false;
     return 0;
 }
@@ -448,8 +449,17 @@ int pd_set_rollout_stages(PdEnv *e, int steps, int steps2) {
     if (!e) return fail("pd_set_rollout_stages: null handle");
     if (steps < 0 || steps2 < 0) return fail("pd_set_rollout_stages: steps must be >= 0 (0 = off)");
     e->handoff_steps = steps;
-    e->handoff2_steps = steps2 > steps ? steps2 : 4 * steps;
+    e->handoff2_steps = steps2 > steps ? steps2 : 2 * steps;
     e->handoff_default = false;
+    return 0;
+}
+
+int pd_set_rollout_lanes(PdEnv *e, int lanes8_below, int lanes32_below) {
+    if (!e) return fail("pd_set_rollout_lanes: null handle");
+    if (lanes8_below < 0 || lanes32_below < 0 || (lanes8_below > 0 && lanes32_below > lanes8_below))
+        return fail("pd_set_rollout_lanes: need 0 <= lanes32_below <= lanes8_below (0 = default)");
+    e->lanes8_below = lanes8_below;
+    e->lanes32_below = lanes32_below;
     return 0;
 }
 
@@ -675,6 +685,8 @@ int pd_rollout_pso(PdEnv *e, const float *weights, int n_particles, int n_params
         }
         io.handoff_steps = h1;
         io.handoff2_steps = h2;
+        io.lanes8_below = e->lanes8_below;
+        io.lanes32_below = e->lanes32_below;
         io.cont_d = e->cont_d[0]; io.cont_i = e->cont_i[0]; io.cont_count = e->cont_count; io.cont_cap = e->cont_cap;
         io.out_d = e->cont_d[1]; io.out_i = e->cont_i[1]; io.out_count = e->cont_count + 1; io.out_cap = e->cont_cap;
     }

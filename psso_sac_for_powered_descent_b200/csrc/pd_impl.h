@@ -63,7 +63,8 @@ struct RolloutIO {
     // finished by a later stage with more lanes per episode (1 -> 8 -> 32): a generation is
     // otherwise bounded by the sequential latency of its longest episode.
     int handoff_steps;     // 0 = off
-    int handoff2_steps;    // second threshold (<= handoff_steps: 4 x handoff_steps)
+    int handoff2_steps;    // second boundary (<= handoff_steps: 2 x handoff_steps); later ones double
+    int lanes8_below, lanes32_below;   // survivor counts at or below which a stage uses 8 / 32 lanes (0 = default)
     int run_if_gt, run_if_le;   // record-fed stages run only if the input record count is in (gt, le]
     double *cont_d;        // input records [PD_CONT_D][cont_cap]
     int *cont_i;           // [PD_CONT_I][cont_cap]: episode, t, g-window count, wind draw counter

@@ -4,6 +4,9 @@
 #pragma once
 #include <mutex>
 #include <set>
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
 #include <utility>
 
 #include "pd_device.cuh"
@@ -438,7 +441,9 @@ rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, con
     wait_tables(&sh);
     // Persistent lanes with a work queue: a lane (group) that finishes pulls the next episode
     // index instead of idling until the slowest lane of its warp is done.
-    int e = (blockIdx.x * blockDim.x + threadIdx.x) / COOP;      // FROM_RECORDS: record index
+    // First assignment strided over the blocks warp by warp: c < lanes / COOP pieces of work occupy
+    // c * COOP / 32 warps spread over all SMs instead of filling the first few blocks to 14 warps.
+    int e = (((int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) * 32 + (int)(threadIdx.x & 31)) / COOP;   // FROM_RECORDS: record index
     const bool writer = (threadIdx.x & (COOP - 1)) == 0;
     bool active = e < n_work;
     int eid = e;                                                  // episode the lane works on
@@ -723,50 +728,95 @@ struct Launch {
         if (blocks > n_sm) blocks = n_sm;              // persistent: the queue feeds the rest
         if constexpr (POLICY == 0) {
             const bool staged = io.handoff_steps > 0 && io.cont_d && io.out_d;
-            const int h1 = io.handoff_steps, h2 = io.handoff2_steps > h1 ? io.handoff2_steps : 4 * h1;
+            const int h1 = io.handoff_steps;
             if (staged && h1 < io.max_steps) {
-                // Stage records ping-pong between two buffers: A = (cont_*), B = (out_*) of io_in.
-                RolloutIO A2B = io;                    // reads A, writes B
-                RolloutIO fromB = io;                  // reads B
-                fromB.cont_d = io.out_d; fromB.cont_i = io.out_i; fromB.cont_count = io.out_count; fromB.cont_cap = io.out_cap;
-                // more survivors than lanes: one lane each (the queue keeps the SMs full); fewer than
-                // 4 waves of 32-lane groups: 32 lanes each; 8 lanes in between
-                const int T8 = (int)L, T32 = (int)(L / 8);
-                cudaMemsetAsync(io.out_count, 0, sizeof(int), st);
-                if (coop) {
-                    // small swarm: 8 lanes from reset up to h2, then 32 lanes for what is left
-                    RolloutIO first = io;
-                    first.handoff_steps = h2;
-                    if (h2 < io.max_steps) {
-                        roll_launch<PHASE, RTD, WIND, POLICY, 8, 1>(lc, blocks, threads, first, wc, sig, status, st);
-                    } else {
-                        roll_launch<PHASE, RTD, WIND, POLICY, 8, 0>(lc, blocks, threads, io, wc, sig, status, st);
-                        return;
-                    }
-                } else {
-                    // large swarm: one lane per episode up to h1 -> records A; A -> B up to h2 with one
-                    // lane (more stragglers than 8-lane groups fit twice) or 8 lanes
-                    RolloutIO first = io;              // writes A
-                    first.out_d = io.cont_d; first.out_i = io.cont_i; first.out_count = io.cont_count; first.out_cap = io.cont_cap;
-                    cudaMemsetAsync(io.cont_count, 0, sizeof(int), st);
-                    roll_launch<PHASE, RTD, WIND, POLICY, 1, 1>(lc, blocks, threads, first, wc, sig, status, st);
-                    if (h2 < io.max_steps) {
-                        A2B.handoff_steps = h2;
-                        A2B.run_if_gt = T8; A2B.run_if_le = 0x7fffffff;
-                        roll_launch<PHASE, RTD, WIND, POLICY, 1, 3>(lc, n_sm, PD_MAX_BLOCK, A2B, wc, sig, status, st);
-                        A2B.run_if_gt = -1; A2B.run_if_le = T8;
-                        roll_launch<PHASE, RTD, WIND, POLICY, 8, 3>(lc, n_sm, PD_MAX_BLOCK, A2B, wc, sig, status, st);
-                    } else {
-                        fromB = io;                    // no second stage: finish from A
-                    }
+                // Stage chain: reset -> h1 -> h2 -> 2 h2 -> 4 h2 ... -> end.  The survivors of a stage are
+                // appended to continuation records (two buffers, the stages ping-pong) and the next
+                // stage picks its cooperation from their number c, which only exists on the device: it
+                // is launched in its 1-, 8- and 32-lane variants and the two whose window (run_if_gt,
+                // run_if_le] does not hold c exit at once.  Per env step a stage costs about
+                //   1 lane : max(50 us, 0.9 ns x c)     8 lanes: max(11 us, 2.9 ns x c)
+                //   32 lanes: max(7.6 us, 4.3 ns x c)   (instructions per episode-step 625 / 2 000 / 3 000)
+                // which cross at c = 17 500 and c = 2 560 on 148 SMs.
+                const int T8 = io.lanes8_below > 0 ? io.lanes8_below : (int)(L / 4);
+                const int T32 = io.lanes32_below > 0 ? io.lanes32_below : (int)(L / 24);
+                struct Buf { double *d; int *i; int *count; int cap; };
+                const Buf buf[2] = {{io.cont_d, io.cont_i, io.cont_count, io.cont_cap},
+                                    {io.out_d, io.out_i, io.out_count, io.out_cap}};
+                auto reads = [&](RolloutIO &r, int k) {
+                    r.cont_d = buf[k].d; r.cont_i = buf[k].i; r.cont_count = buf[k].count; r.cont_cap = buf[k].cap;
+                };
+                auto writes = [&](RolloutIO &r, int k) {
+                    r.out_d = buf[k].d; r.out_i = buf[k].i; r.out_count = buf[k].count; r.out_cap = buf[k].cap;
+                    cudaMemsetAsync(buf[k].count, 0, sizeof(int), st);
+                };
+                // PD_ROLLOUT_TRACE=1 (diagnostic): time every stage with events and print the survivor
+                // counts to stderr; synchronises the stream, never set in production
+                const bool trace = getenv("PD_ROLLOUT_TRACE") != nullptr;
+                std::vector<cudaEvent_t> ev;
+                std::vector<int> bounds, srcs;
+                auto mark = [&](int boundary, int k) {
+                    if (!trace) return;
+                    cudaEvent_t x;
+                    cudaEventCreate(&x);
+                    cudaEventRecord(x, st);
+                    ev.push_back(x); bounds.push_back(boundary); srcs.push_back(k);
+                };
+                mark(0, -1);
+                RolloutIO first = io;
+                writes(first, 0);
+                if (coop) roll_launch<PHASE, RTD, WIND, POLICY, 8, 1>(lc, blocks, threads, first, wc, sig, status, st);
+                else roll_launch<PHASE, RTD, WIND, POLICY, 1, 1>(lc, blocks, threads, first, wc, sig, status, st);
+                int src = 0;
+                long long h = io.handoff2_steps > h1 ? io.handoff2_steps : 2LL * h1;
+                std::vector<int> counts;
+                auto snapshot = [&](int k) {          // survivor count of the stage just enqueued
+                    if (!trace) return;
+                    int c = 0;
+                    cudaStreamSynchronize(st);
+                    cudaMemcpy(&c, buf[k].count, sizeof(int), cudaMemcpyDeviceToHost);
+                    counts.push_back(c);
+                };
+                mark(h1, 0);
+                snapshot(0);
+                for (; h < io.max_steps; h *= 2) {
+                    RolloutIO r = io;
+                    reads(r, src);
+                    writes(r, src ^ 1);
+                    r.handoff_steps = (int)h;
+                    r.run_if_gt = T8; r.run_if_le = 0x7fffffff;
+                    roll_launch<PHASE, RTD, WIND, POLICY, 1, 3>(lc, n_sm, PD_MAX_BLOCK, r, wc, sig, status, st);
+                    r.run_if_gt = T32; r.run_if_le = T8;
+                    roll_launch<PHASE, RTD, WIND, POLICY, 8, 3>(lc, n_sm, PD_MAX_BLOCK, r, wc, sig, status, st);
+                    r.run_if_gt = -1; r.run_if_le = T32;
+                    roll_launch<PHASE, RTD, WIND, POLICY, 32, 3>(lc, n_sm, PD_MAX_BLOCK, r, wc, sig, status, st);
+                    src ^= 1;
+                    mark((int)h, src);
+                    snapshot(src);
                 }
-                // final stage: as much cooperation as the number of survivors allows
-                fromB.run_if_gt = T8; fromB.run_if_le = 0x7fffffff;
-                roll_launch<PHASE, RTD, WIND, POLICY, 1, 2>(lc, n_sm, PD_MAX_BLOCK, fromB, wc, sig, status, st);
-                fromB.run_if_gt = T32; fromB.run_if_le = T8;
-                roll_launch<PHASE, RTD, WIND, POLICY, 8, 2>(lc, n_sm, PD_MAX_BLOCK, fromB, wc, sig, status, st);
-                fromB.run_if_gt = -1; fromB.run_if_le = T32;
-                roll_launch<PHASE, RTD, WIND, POLICY, 32, 2>(lc, n_sm, PD_MAX_BLOCK, fromB, wc, sig, status, st);
+                RolloutIO last = io;
+                reads(last, src);
+                last.run_if_gt = T8; last.run_if_le = 0x7fffffff;
+                roll_launch<PHASE, RTD, WIND, POLICY, 1, 2>(lc, n_sm, PD_MAX_BLOCK, last, wc, sig, status, st);
+                last.run_if_gt = T32; last.run_if_le = T8;
+                roll_launch<PHASE, RTD, WIND, POLICY, 8, 2>(lc, n_sm, PD_MAX_BLOCK, last, wc, sig, status, st);
+                last.run_if_gt = -1; last.run_if_le = T32;
+                roll_launch<PHASE, RTD, WIND, POLICY, 32, 2>(lc, n_sm, PD_MAX_BLOCK, last, wc, sig, status, st);
+                if (trace) {
+                    mark(io.max_steps, -1);
+                    cudaStreamSynchronize(st);
+                    fprintf(stderr, "[pd rollout trace] %d episodes (T8 %d, T32 %d):", io.n_episodes, T8, T32);
+                    for (size_t k = 1; k < ev.size(); ++k) {
+                        float ms = 0.f;
+                        cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+                        if (k - 1 < counts.size())
+                            fprintf(stderr, "  ->%d %.2f ms, %d left;", bounds[k], ms, counts[k - 1]);
+                        else
+                            fprintf(stderr, "  ->end %.2f ms", ms);
+                    }
+                    fprintf(stderr, "\n");
+                    for (cudaEvent_t x : ev) cudaEventDestroy(x);
+                }
                 return;
             }
         }

@@ -4,7 +4,7 @@ import torch
 from psso_sac_for_powered_descent_b200 import envs, pso as pso_mod
 G = "landing_burn"
 for phase, n, seeds in ((G, 8192, 8), ("landing_burn_pure_throttle", 8192, 1)):
-    model = envs.pso_wrapped_env(flight_phase=phase, enable_wind=True, stochastic_wind=True, max_steps=4096, seed=99)
+    model = envs.pso_wrapped_env(flight_phase=phase, enable_wind=True, stochastic_wind=True, max_steps=4096, seed=99, precision=os.environ.get("PD_PRECISION", "fp32"))
     params = dict(pso_mod.PSO_PARAMS[phase], pop_size=n)
     sw = pso_mod.DeviceSwarm(model, n, params, n_seeds=seeds, seed=5, max_steps=4096)
     ts = []
