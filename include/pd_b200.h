@@ -254,7 +254,7 @@ int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_para
 int pd_set_rollout_handoff(PdEnv *env, int steps);
 int pd_set_rollout_stages(PdEnv *env, int steps, int steps2);
 /* Survivor counts at or below which a record-fed stage uses 8 / 32 lanes per episode
- * (0 = default: lanes / 4 and lanes / 24 with lanes = SMs x 448, the measured cross-over points). */
+ * (0 = default: lanes / 4 and lanes / 32 with lanes = SMs x 448, the measured cross-over points). */
 int pd_set_rollout_lanes(PdEnv *env, int lanes8_below, int lanes32_below);
 
 /* Whole-episode rollouts with a scripted policy, one launch:

@@ -218,6 +218,10 @@ struct WindState {
     double sigma_u, sigma_v;
     unsigned int ctr;              // draws consumed this episode (tape position / Philox counter)
     unsigned int episode;          // episode number of this env / rollout generation (Philox counter word)
+    // cooperative rollouts: Gaussian pair of draw actr + 2 * (lane mod COOP), made by the first
+    // lanes of the group for all sub-steps of an env step at once (gust_ahead)
+    double an0, an1;
+    unsigned int actr;
 };
 
 // values of the last sub-step (reference `info` dict, rockets_physics.py:649-702).  FULL adds
@@ -828,7 +832,37 @@ __device__ __forceinline__ double u01(unsigned int a, unsigned int b) {
 
 
 // ------------------------------------------------------------------ wind
-template <typename R>
+// One Box-Muller pair of the gust-noise stream.  counter = (stream id, draw, tag, episode): fresh
+// noise every episode, as upstream's reset() re-seeds and rebuilds the filters (vonkarman.py:86-96)
+__device__ __forceinline__ void gauss_pair(unsigned int env_id, const WindCtx &wc, unsigned int ctr,
+                                           unsigned int episode, double &n0, double &n1) {
+    unsigned int r[4];
+    philox4x32(env_id + wc.id_offset, ctr, 0x57494E44u, episode, (unsigned int)wc.seed,
+               (unsigned int)(wc.seed >> 32), r);
+    double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+    double rad = sqrt(-2.0 * log(u1));
+    double s, co;
+    sincospi(2.0 * u2, &s, &co);
+    n0 = rad * co;
+    n1 = rad * s;
+}
+
+// Cooperative groups: the noise of a sub-step does not depend on the state, so lanes 0..3 of the
+// group draw the pairs of the 4 sub-steps of this env step side by side (Philox + log + sqrt +
+// sincospi are a quarter of the dependent chain of a windy sub-step) and wind_sample fetches the
+// pair of the draw it has reached with a shuffle.  Same counters, same values as the serial path.
+template <int NSUB, int COOP>
+__device__ __forceinline__ void gust_ahead(WindState &w, const WindCtx &wc, unsigned int env_id) {
+    if constexpr (COOP > 1) {
+        if (wc.stochastic && !wc.tape) {
+            const unsigned int j = threadIdx.x & (COOP - 1);
+            w.actr = w.ctr;
+            if (j < (unsigned int)NSUB) gauss_pair(env_id, wc, w.ctr + 2u * j, w.episode, w.an0, w.an1);
+        }
+    }
+}
+
+template <typename R, int COOP = 1>
 __device__ __forceinline__ void wind_sample(double y, WindState &w, const WindCtx &wc,
                                             unsigned int env_id, R &ug, R &vg) {
     const Scalars<double> &c = sd;
@@ -852,18 +886,14 @@ __device__ __forceinline__ void wind_sample(double y, WindState &w, const WindCt
             unsigned int p0 = w.ctr, p1 = w.ctr + 1;
             n0 = p0 < (unsigned)wc.tape_len ? wc.tape[base + p0] : 0.0;
             n1 = p1 < (unsigned)wc.tape_len ? wc.tape[base + p1] : 0.0;
+        } else if constexpr (COOP > 1) {
+            const int leader = (threadIdx.x & 31) & ~(COOP - 1);
+            const unsigned gmask = (COOP == 32 ? 0xffffffffu : ((1u << COOP) - 1u)) << leader;
+            const int src = leader + (int)((w.ctr - w.actr) >> 1);
+            n0 = __shfl_sync(gmask, w.an0, src);
+            n1 = __shfl_sync(gmask, w.an1, src);
         } else {
-            unsigned int r[4];
-            // counter = (stream id, draw, tag, episode): fresh noise every episode, as upstream's
-            // reset() re-seeds and rebuilds the filters (vonkarman.py:86-96)
-            philox4x32(env_id + wc.id_offset, w.ctr, 0x57494E44u, w.episode, (unsigned int)wc.seed,
-                       (unsigned int)(wc.seed >> 32), r);
-            double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
-            double rad = sqrt(-2.0 * log(u1));
-            double s, co;
-            sincospi(2.0 * u2, &s, &co);
-            n0 = rad * co;
-            n1 = rad * s;
+            gauss_pair(env_id, wc, w.ctr, w.episode, n0, n1);
         }
         w.ctr += 2;
         double bu0 = c.Bdu[0] * w.sigma_u, bu1 = c.Bdu[1] * w.sigma_u;
@@ -1187,7 +1217,7 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
     R ug = R(0), vg = R(0);
     R f_wind_x = R(0);
     if (WIND) {
-        wind_sample<R>(s.y, w, wc, env_id, ug, vg);
+        wind_sample<R, COOP>(s.y, w, wc, env_id, ug, vg);
         f_wind_x = R(0.5) * rho * (ug * ug) * c.S_ref * c.c_gust_x;
     }
     R C_L = R(0), C_D = R(0);
@@ -1257,6 +1287,7 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
     R vx_dot = m_div(fx, mass);
     R vy_dot = m_div(fy, mass) - g;
     const double dt = sd.dt_phys;
+    const double vx_before = s.vx, vy_before = s.vy;
     s.vx += (double)(vx_dot * c.dt_phys);
     s.vy += (double)(vy_dot * c.dt_phys);
     s.x += s.vx * dt;
@@ -1265,7 +1296,30 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
     R tdd = m_div(mz, inertia);
     s.theta_dot += (double)(tdd * c.dt_phys);
     s.theta += s.theta_dot * dt;
-    double gam = atan2(s.vy, s.vx);
+    double gam;
+    bool turned = false;
+    if constexpr (sizeof(R) == 4 && COOP > 1) {
+        // Straggler stages of the fp32 build: atan2 is 12 % of the dependent instruction chain
+        // that bounds a lone episode.  The velocity turns by a few mrad per 25 ms sub-step, so
+        // gamma advances by atan(cross / dot) of the old and new velocity, |t| < 2^-5: a
+        // float-seeded Newton reciprocal and five series terms, 1e-16 rad from atan2 per
+        // sub-step against the 1e-7 relative rounding of the fp32 forces.
+        const double cross = vx_before * s.vy - vy_before * s.vx;
+        const double dot = vx_before * s.vx + vy_before * s.vy;
+        if (dot > 1e-30 && dot < 1e30 && fabs(cross) < 0.03125 * dot) {
+            double r = (double)__frcp_rn((float)dot);
+            r = r * (2.0 - dot * r);
+            r = r * (2.0 - dot * r);
+            const double t = cross * r, t2 = t * t;
+            double poly = fma(t2, 1.0 / 9.0, -1.0 / 7.0);
+            poly = fma(poly, t2, 1.0 / 5.0);
+            poly = fma(poly, t2, -1.0 / 3.0);
+            gam = s.gamma + fma(t * t2, poly, t);
+            if (gam >= PD_TWO_PI) gam -= PD_TWO_PI;
+            turned = true;
+        }
+    }
+    if (!turned) gam = atan2(s.vy, s.vx);
     if (s.theta > PD_TWO_PI) s.theta -= PD_TWO_PI;
     if (gam < 0.0) gam = PD_TWO_PI + gam;
     s.gamma = gam;
@@ -1665,6 +1719,7 @@ __device__ __forceinline__ void env_step(State &s, const Action<phase_adim(PHASE
     R vxp = (R)s.vx, vyp = (R)s.vy;
     R v_p = m_sqrt(vxp * vxp + vyp * vyp);
     Control<R> ctl;
+    if constexpr (WIND) gust_ahead<phase_nsub(PHASE), COOP>(w, wc, env_id);
 #pragma unroll 1
     for (int k = 0; k < phase_nsub(PHASE); ++k)
         substep<R, RT, PHASE, WIND, COOP, FULL>(s, act, prev, w, wc, env_id, info, ctl, sh);

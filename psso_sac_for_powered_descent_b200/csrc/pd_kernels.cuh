@@ -529,6 +529,7 @@ rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, con
         if (!stop) {
             if constexpr (POLICY == 2) {
                 Control<R> ctl;
+                if constexpr (WIND) D.gust_ahead<4, COOP>(w, wc, (unsigned)eid);
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k)
                     D.substep<R, RT, PHASE, WIND, COOP>(s, act, prev, w, wc, (unsigned)eid, info, ctl, &sh);
@@ -735,11 +736,13 @@ struct Launch {
                 // stage picks its cooperation from their number c, which only exists on the device: it
                 // is launched in its 1-, 8- and 32-lane variants and the two whose window (run_if_gt,
                 // run_if_le] does not hold c exit at once.  Per env step a stage costs about
-                //   1 lane : max(50 us, 0.9 ns x c)     8 lanes: max(11 us, 2.9 ns x c)
-                //   32 lanes: max(7.6 us, 4.3 ns x c)   (instructions per episode-step 625 / 2 000 / 3 000)
-                // which cross at c = 17 500 and c = 2 560 on 148 SMs.
+                //   1 lane : 31 us (c = 2) ... 34 us (c = 8 288), 60 us with every lane busy
+                //   8 lanes: 10 us (c <= 2 072), 14.4 us at c = 8 288 = one wave of 8-lane groups
+                //   32 lanes: 7.4-8.0 us (c <= 592), 10.8 us at c = 2 072 = one wave of warps
+                // (fp32 build, no wind, tools/lone_episode_latency.py), which cross at c = 2 waves of
+                // 8-lane groups and at c = 1 wave of warps.
                 const int T8 = io.lanes8_below > 0 ? io.lanes8_below : (int)(L / 4);
-                const int T32 = io.lanes32_below > 0 ? io.lanes32_below : (int)(L / 24);
+                const int T32 = io.lanes32_below > 0 ? io.lanes32_below : (int)(L / 32);
                 struct Buf { double *d; int *i; int *count; int cap; };
                 const Buf buf[2] = {{io.cont_d, io.cont_i, io.cont_count, io.cont_cap},
                                     {io.out_d, io.out_i, io.out_count, io.out_cap}};
