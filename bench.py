@@ -39,10 +39,11 @@ OTHER_PHASES = ("subsonic", "supersonic", "ballistic_arc_descent", "landing_burn
 N_ENVS = 65536
 ALGO_BYTES_PER_STEP = 160.0        # 40 words x 4 B, phase P, fp32
 ALGO_FLOP_PER_STEP = 4800.0        # canonical flop per env-step (P, no wind)
-# Per-step latency of ONE episode at the highest cooperation (32 lanes; profiles/r2_rollout_coop32_stage.txt,
-# G: fp64 instantiation, 8 lanes): longest episode x this = the time below which no number of GPUs can
+# Per-step latency of ONE episode at the highest cooperation (32 lanes; profiles/r2_rollout_stage_trace.log,
+# G: fp64 instantiation, steps 16-38 of a 38-step episode): longest episode x this = the time below which no number of GPUs can
 # bring a generation - reported next to every PSO timing as `sequential_floor_ms`
-LONE_EPISODE_US_PER_STEP = {"landing_burn_pure_throttle": 7.6, "landing_burn": 27.0}
+LONE_EPISODE_US_PER_STEP = {"landing_burn_pure_throttle": 7.1, "landing_burn": 15.0}
+LONE_EPISODE_US_PER_STEP_WINDY = {"landing_burn_pure_throttle": 9.9, "landing_burn": 15.0}
 
 
 def load_peaks():
@@ -367,7 +368,7 @@ def run_cuda(args):
                     "fitness_evals_per_s": n / dt, "episodes_per_s": n * seeds / dt, "ms": dt * 1e3,
                     "env_steps_per_s": tot_steps / dt, "mean_episode_steps": tot_steps / (n * seeds),
                     "episodes_hitting_step_cap": int(capped), "longest_episode_steps": int(longest),
-                    "sequential_floor_ms": longest * LONE_EPISODE_US_PER_STEP[phase] * 1e-3,
+                    "sequential_floor_ms": longest * (LONE_EPISODE_US_PER_STEP_WINDY if wind else LONE_EPISODE_US_PER_STEP)[phase] * 1e-3,
                     "best_fitness": best, "best_index": idx,
                     "timing": "wall clock between device-synchronised barriers, max over ranks",
                     "what": "host array of positions in, fitness out (ShardedEvaluator): float32 conversion + "
@@ -401,7 +402,7 @@ def run_cuda(args):
                    "mean_episode_steps": tot / (sw.N_total * seeds),
                    "episodes_hitting_step_cap_total": int(capped), "generations_timed": n_gen,
                    "longest_episode_steps": int(longest),
-                   "sequential_floor_ms": longest * LONE_EPISODE_US_PER_STEP[phase] * 1e-3,
+                   "sequential_floor_ms": longest * (LONE_EPISODE_US_PER_STEP_WINDY if wind else LONE_EPISODE_US_PER_STEP)[phase] * 1e-3,
                    "global_best_fitness": sw.global_best_fitness,
                    "timing": "CUDA events around the generations, max over ranks",
                    "what": "rollout kernel + seed mean + fitness all-gather + per-sub-swarm arg-min / metrics + "

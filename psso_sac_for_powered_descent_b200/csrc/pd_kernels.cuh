@@ -419,8 +419,12 @@ __device__ __forceinline__ void coop_mlp_forward(const float *wcol, const float 
 // Ragged episode lengths (P: 101 .. 4000+ steps) are served in stages of growing cooperation:
 // one lane per episode while there are more episodes than lanes, 8 lanes, then 32 lanes for the
 // handful of long ones whose sequential latency bounds the generation.
-template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE = 0>
-__global__ void __launch_bounds__(PD_MAX_BLOCK, 1)
+// MAXB: block-size bound.  The last few stragglers run one warp per episode and at most MAXB / 32
+// of them per SM, so the (32, *, 128) instantiations are compiled for 4 warps per SM and may use
+// 255 registers instead of the 128 the 448-thread blocks are held to.
+template <typename R, typename RT, int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE = 0,
+          int MAXB = PD_MAX_BLOCK>
+__global__ void __launch_bounds__(MAXB, 1)
 rollout_kernel(const __grid_constant__ KParams kp, RolloutIO io, WindCtx wc, const double *sigma_uv, int *status) {
     constexpr int A = phase_adim(PHASE);
     constexpr int O = phase_odim(PHASE);
@@ -693,7 +697,7 @@ struct Launch {
             default: step_t<6, 1, true>(lc, e, io, wc, sig, auto_reset, st); break;
         }
     }
-    template <int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE>
+    template <int PHASE, int RTD, bool WIND, int POLICY, int COOP, int MODE, int MAXB = PD_MAX_BLOCK>
     static void roll_launch(const LaunchCtx &lc, int blocks, int threads, const RolloutIO &io, const WindCtx &wc,
                             const double *sig, int *status, cudaStream_t st) {
         constexpr int O = phase_odim(PHASE);
@@ -705,12 +709,12 @@ struct Launch {
         {
             std::lock_guard<std::mutex> lock(mu);
             if (done.insert(lc.device).second)
-                cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, COOP, MODE>,
+                cudaFuncSetAttribute(rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, COOP, MODE, MAXB>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(PD_SH_BYTES + 52 * PD_MAX_BLOCK * 4 + 16));
         }
         init_queue_kernel<<<1, 1, 0, st>>>(io.queue, blocks * threads / COOP);
-        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, COOP, MODE><<<blocks, threads, smem, st>>>(*lc.kp, io, wc, sig, status);
+        rollout_kernel<R, RT, PHASE, RTD, WIND, POLICY, COOP, MODE, MAXB><<<blocks, threads, smem, st>>>(*lc.kp, io, wc, sig, status);
     }
     template <int PHASE, int RTD, bool WIND, int POLICY>
     static void roll_t(const LaunchCtx &lc, const RolloutIO &io_in, const WindCtx &wc, const double *sig, int *status,
@@ -743,6 +747,7 @@ struct Launch {
                 // 8-lane groups and at c = 1 wave of warps.
                 const int T8 = io.lanes8_below > 0 ? io.lanes8_below : (int)(L / 4);
                 const int T32 = io.lanes32_below > 0 ? io.lanes32_below : (int)(L / 32);
+                const int T32s = T32 < 4 * n_sm ? T32 : 4 * n_sm;   // one wave of 4 warps per SM
                 struct Buf { double *d; int *i; int *count; int cap; };
                 const Buf buf[2] = {{io.cont_d, io.cont_i, io.cont_count, io.cont_cap},
                                     {io.out_d, io.out_i, io.out_count, io.out_cap}};
@@ -791,8 +796,10 @@ struct Launch {
                     roll_launch<PHASE, RTD, WIND, POLICY, 1, 3>(lc, n_sm, PD_MAX_BLOCK, r, wc, sig, status, st);
                     r.run_if_gt = T32; r.run_if_le = T8;
                     roll_launch<PHASE, RTD, WIND, POLICY, 8, 3>(lc, n_sm, PD_MAX_BLOCK, r, wc, sig, status, st);
-                    r.run_if_gt = -1; r.run_if_le = T32;
+                    r.run_if_gt = T32s; r.run_if_le = T32;
                     roll_launch<PHASE, RTD, WIND, POLICY, 32, 3>(lc, n_sm, PD_MAX_BLOCK, r, wc, sig, status, st);
+                    r.run_if_gt = -1; r.run_if_le = T32s;
+                    roll_launch<PHASE, RTD, WIND, POLICY, 32, 3, 128>(lc, n_sm, 128, r, wc, sig, status, st);
                     src ^= 1;
                     mark((int)h, src);
                     snapshot(src);
@@ -803,8 +810,10 @@ struct Launch {
                 roll_launch<PHASE, RTD, WIND, POLICY, 1, 2>(lc, n_sm, PD_MAX_BLOCK, last, wc, sig, status, st);
                 last.run_if_gt = T32; last.run_if_le = T8;
                 roll_launch<PHASE, RTD, WIND, POLICY, 8, 2>(lc, n_sm, PD_MAX_BLOCK, last, wc, sig, status, st);
-                last.run_if_gt = -1; last.run_if_le = T32;
+                last.run_if_gt = T32s; last.run_if_le = T32;
                 roll_launch<PHASE, RTD, WIND, POLICY, 32, 2>(lc, n_sm, PD_MAX_BLOCK, last, wc, sig, status, st);
+                last.run_if_gt = -1; last.run_if_le = T32s;
+                roll_launch<PHASE, RTD, WIND, POLICY, 32, 2, 128>(lc, n_sm, 128, last, wc, sig, status, st);
                 if (trace) {
                     mark(io.max_steps, -1);
                     cudaStreamSynchronize(st);
