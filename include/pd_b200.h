@@ -249,8 +249,13 @@ int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_para
  * many there are (per-step latency of a lone episode 50 / 11 / 7.6 us, instructions per
  * episode-step 625 / 2 000 / 3 000).  Defaults: 128 / 256 for landing_burn_pure_throttle; one
  * hand-off after 16 steps for landing_burn while a call has at most 1.5 x the GPU's lane count of
- * episodes.  Results are identical to the one-pass rollout up to the summation order of the
- * cooperative RBF sums.  steps = 0: off.  steps2 <= steps: 2 x steps. */
+ * episodes.  An episode that ends inside the first stage is bit-identical to the one-pass rollout;
+ * one that is handed on resumes from its exact state in another instantiation of the kernel, so
+ * rounding-level differences (summation order of the cooperative RBF sums, FMA contraction; in the
+ * fp32 build atan2 against its incremental form) appear from there on: 99 % of the fitness values
+ * within 1e-9 relative in the fp64 build, 1e-4 in the fp32 build
+ * (tests/test_gpu_parity.py::test_rollout_stage_chain_every_lane_choice).
+ * steps = 0: off.  steps2 <= steps: 2 x steps. */
 int pd_set_rollout_handoff(PdEnv *env, int steps);
 int pd_set_rollout_stages(PdEnv *env, int steps, int steps2);
 /* Survivor counts at or below which a record-fed stage uses 8 / 32 lanes per episode

@@ -823,6 +823,53 @@ def test_rollout_straggler_handoff(envs_mod):
     assert np.max(np.abs(f0[late][same] - f1[late][same]) / np.maximum(np.abs(f0[late][same]), 1.0)) < 1e-6
 
 
+@pytest.mark.parametrize("precision,wind", [("fp64", True), ("fp32", True), ("fp32", False)])
+def test_rollout_stage_chain_every_lane_choice(envs_mod, precision, wind):
+    """Doubling stage chain (pd_set_rollout_stages) with the lane choice of the record-fed stages
+    forced to 1, 8 and 32 lanes per episode (pd_set_rollout_lanes), windy and not: every variant
+    resumes every episode from its exact state.  Same Philox counters whichever lane draws the gust
+    noise, so with wind the episodes are the same episodes; what differs is the summation order of
+    the cooperative RBF sums, the FMA contraction of the other kernel instantiation and, in the
+    fp32 build, atan2 against its incremental form, which a few chaotic episodes turn into a
+    different length."""
+    from psso_sac_for_powered_descent_b200 import _native as N
+    n = 8192                          # more than 3/4 of the lanes / 8: the first stage is one lane per episode
+    rng = np.random.default_rng(11)
+    pos = torch.as_tensor(rng.uniform(-1.5, 1.5, (n, 249)).astype(np.float32)).cuda()
+    env = envs_mod.BatchedRocketEnv(1, "pso", P, precision=precision, enable_wind=wind, stochastic_wind=wind, seed=5)
+    out = {}
+    for name, stages, lanes in (("one pass", (0, 0), (0, 0)), ("default", (128, 256), (0, 0)),
+                                ("1 lane", (64, 128), (1, 1)), ("8 lanes", (64, 128), (1 << 20, 1)),
+                                ("32 lanes", (64, 128), (1 << 20, 1 << 20))):
+        N.check(env.lib.pd_set_rollout_stages(env._h, *stages))
+        N.check(env.lib.pd_set_rollout_lanes(env._h, *lanes))
+        fit, st, tid = env.rollout_pso(pos, max_steps=1200)
+        env.check_status()
+        out[name] = (fit.cpu().numpy(), st.cpu().numpy(), tid.cpu().numpy())
+    f0, s0, t0 = out["one pass"]
+    assert (s0 > 256).sum() > 40 and np.isfinite(f0).all()
+    for name in ("default", "1 lane", "8 lanes", "32 lanes"):
+        f, s, t = out[name]
+        first = 128 if name == "default" else 64
+        early = s0 < first            # finished inside the first stage: the same instructions
+        assert np.array_equal(f[early], f0[early]) and np.array_equal(s[early], s0[early])
+        same = s == s0
+        assert same.mean() > 0.97, (name, same.mean())
+        assert np.array_equal(t[same], t0[same])
+        rel = np.abs(f[same] - f0[same]) / np.maximum(np.abs(f0[same]), 1.0)
+        # rounding-level differences grow along an episode (parity.py conditioning baseline): bound the
+        # bulk tightly and the worst episode loosely
+        assert np.quantile(rel, 0.99) < (1e-9 if precision == "fp64" else 1e-4), (name, np.quantile(rel, 0.99))
+        assert rel.max() < (1e-5 if precision == "fp64" else 5e-2), (name, rel.max())
+    # record-fed 1-lane stages: the same arithmetic in another instantiation of the kernel, whose
+    # FMA contraction differs in places (first difference 4e-16 in theta_dot, one step after the
+    # resume) - rounding-level, then amplified like any perturbation
+    f, s, t = out["1 lane"]
+    assert (s == s0).mean() > 0.999
+    with pytest.raises(RuntimeError):
+        N.check(env.lib.pd_set_rollout_lanes(env._h, 8, 16))
+
+
 # --------------------------------------------------------------------------- round-2 robustness
 def test_captured_graph_survives_other_handles(envs_mod):
     """A handle's constants travel with every launch (a __grid_constant__ kernel parameter): a CUDA
