@@ -155,7 +155,9 @@ typedef struct {
                                  rl_wrapped_env_pytorch.augment_action (log-compression for
                                  landing_burn, reference-speed scaling for P-control) in the kernel;
                                  1: actions are already what rocket_environment_pre_wrap.step expects */
-    int32_t _pad;
+    int32_t exact_aero;       /* PD_FP32 only.  0: C_L / C_D from the bicubic patches of the thin-plate sums
+                                 (1e-8 absolute, csrc/pd_patch.h; queries on a rejected patch or a walk cell
+                                 take the exact sum); 1: the exact 50-term sums everywhere, as PD_FP64 */
 } PdConfig;
 
 typedef struct PdEnv PdEnv;
@@ -238,6 +240,11 @@ int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_para
                    int max_steps, double *fitness, int32_t *steps, int32_t *trunc_id,
                    double *terminal_state, double *traj, float *actions_out, double *rewards,
                    void *stream);
+
+/* PD_FP32 handles without exact_aero: counts[0..3] = bicubic patches built / rejected by the 1e-8
+ * validation for C_D, then for C_L (all zero otherwise); *max_err (may be NULL) = largest validation
+ * error among the patches in use. */
+int pd_aero_patch_stats(PdEnv *env, int64_t *counts, double *max_err);
 
 /* Straggler hand-off of pd_rollout_pso.  Episode lengths are ragged (a random
  * landing_burn_pure_throttle swarm has a median of 130 steps, 2 % above 512 and a few episodes at

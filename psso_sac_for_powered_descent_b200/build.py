@@ -23,7 +23,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + \
     os.environ.get("PD_EXTRA_NVCC_FLAGS", "").split()
-UNITS = ["pd_fp64_roll.cu", "pd_fp32_roll.cu", "pd_fp64.cu", "pd_fp32.cu", "pd_api.cu", "pd_actor.cu", "pd_pso.cu", "pd_peak.cu"]
+UNITS = ["pd_fp64_roll.cu", "pd_fp32_roll.cu", "pd_fp64.cu", "pd_fp32.cu", "pd_api.cu", "pd_actor.cu", "pd_pso.cu", "pd_peak.cu", "pd_patch.cu"]
 
 
 def _sources():

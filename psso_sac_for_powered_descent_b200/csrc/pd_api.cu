@@ -14,6 +14,9 @@
 #include "pd_actor.h"
 #include "pd_pso.h"
 #include "pd_peak.h"
+#include "pd_patch.h"
+#include <map>
+#include <mutex>
 
 using namespace pd;
 
@@ -58,6 +61,8 @@ struct PdEnv {
     int handoff2_steps = 256;
     int lanes8_below = 0, lanes32_below = 0;   // pd_set_rollout_lanes (0 = default)
     bool handoff_default = true;     // thresholds never set by the caller: per-phase defaults apply
+    long long patch_stats[4] = {0, 0, 0, 0};   // aero patches: built / rejected for C_D, for C_L
+    double patch_max_err = 0.0;
     // shared-actor collection
     void *w2_img = nullptr;          // bf16 smem image of W2
     const float *w2_src = nullptr;   // which W2 the image was built from
@@ -138,6 +143,66 @@ static int upload_rbf(PdEnv *e, const PdRbfTable &t, RbfDev &d, double *levels_o
         o.imp_hint = ih;
         if (dev_copy(e, s.n_impure ? s.imp_id : &zero32, (size_t)(s.n_impure ? s.n_impure : 1), &o.imp_id)) return 1;
     }
+    return 0;
+}
+
+// ---- bicubic patches of the fp32 build (pd_patch.h): one set per (device, table contents), built
+// on first use and kept for the life of the process (C_L 4 096 x 512 x (1 x 2) sub-cells: 0.6 GB)
+struct PatchKey {
+    int device;
+    uint64_t sig;
+    bool operator<(const PatchKey &o) const { return device != o.device ? device < o.device : sig < o.sig; }
+};
+static std::mutex g_patch_mu;
+static std::map<PatchKey, PatchGridOut> g_patches;
+
+static uint64_t mix_words(uint64_t h, const void *data, size_t bytes) {
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, b + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ULL;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; ++i) h = (h ^ b[i]) * 0x100000001B3ULL;
+    return h;
+}
+
+#define PD_PATCH_TOL 1e-8     // absolute, on coefficients of order 1: a sixth of an fp32 ulp at 0.5
+
+static int attach_patches(PdEnv *e, const PdRbfTable &t, RbfDev &d, int g, int sub_x, int sub_y, int which_table) {
+    const PdRbfGrid &s = t.grids[g];
+    RbfGrid &o = d.grid[g];
+    uint64_t sig = 0xCBF29CE484222325ULL;
+    sig = mix_words(sig, t.rows, (size_t)t.n_sets * PD_RBF_ROW_BYTES);
+    sig = mix_words(sig, t.points, (size_t)t.n_points * 16);
+    sig = mix_words(sig, s.cells, (size_t)s.nm * s.na * 4);
+    if (s.n_impure) sig = mix_words(sig, s.imp_hint, (size_t)s.n_impure * 8);
+    const double hdr[6] = {s.m0, s.dm, s.a0, s.da, (double)(s.nm * 65536 + s.na), (double)(sub_x * 256 + sub_y)};
+    sig = mix_words(sig, hdr, sizeof(hdr));
+    std::lock_guard<std::mutex> lock(g_patch_mu);
+    const PatchKey key{e->cfg.device, sig};
+    auto it = g_patches.find(key);
+    if (it == g_patches.end()) {
+        PatchGridIn in;
+        in.rows = d.rows; in.points = d.points; in.cells = o.cells; in.imp_hint = o.imp_hint; in.imp_id = o.imp_id;
+        in.cells_host = s.cells; in.imp_hint_host = s.imp_hint;
+        in.m0 = s.m0; in.dm = s.dm; in.a0 = s.a0; in.da = s.da; in.nm = s.nm; in.na = s.na;
+        in.sub_x = sub_x; in.sub_y = sub_y;
+        PatchGridOut out;
+        if (build_patch_grid(in, PD_PATCH_TOL, &out, 0)) {
+            free_patch_grid(&out);
+            return fail(std::string("pd_create: building the aero patches failed: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+        it = g_patches.emplace(key, out).first;
+    }
+    e->patch_stats[2 * which_table] += it->second.n_patches;
+    e->patch_stats[2 * which_table + 1] += it->second.n_failed;
+    e->patch_max_err = std::max(e->patch_max_err, it->second.max_err_kept);
+    o.pbase = it->second.pbase;
+    o.patch = it->second.patch;
+    o.sub_x = sub_x; o.sub_y = sub_y;
     return 0;
 }
 
@@ -334,6 +399,14 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     int rc = upload_rbf(e, p->cd, e->tb.cd, e->sd.cd_levels, 192) || upload_rbf(e, p->cl, e->tb.cl, e->sd.cl_levels, 144);
     rc = rc || upload_segments(e, p->gf_ca_mach, p->gf_ca_val, p->n_gf_ca, &e->tb.ca_x, &e->tb.ca_y, &e->tb.ca_s);
     rc = rc || upload_segments(e, p->gf_cn_mach, p->gf_cn_val, p->n_gf_cn, &e->tb.cn_x, &e->tb.cn_y, &e->tb.cn_s);
+    if (!rc && cfg->precision == PD_FP32 && !cfg->exact_aero) {
+        // fp32 production build: bicubic patches of the thin-plate sums (pd_patch.h)
+        rc = attach_patches(e, p->cd, e->tb.cd, 0, 4, 8, 0);
+        e->tb.cd.grid[1] = e->tb.cd.grid[0];
+        rc = rc || attach_patches(e, p->cl, e->tb.cl, 0, 1, 2, 1);
+        if (p->cl.n_grids > 1) rc = rc || attach_patches(e, p->cl, e->tb.cl, 1, 2, 1, 1);
+        else e->tb.cl.grid[1] = e->tb.cl.grid[0];
+    }
     if (rc) { pd_destroy(e); return 1; }
     {   // fast_log table: u_j = double(1/c_j), c_j = 1 + (j + 0.5)/256; second word -log(u_j)
         std::vector<double> tab(2 * PD_LOG_N);
@@ -460,6 +533,13 @@ int pd_set_rollout_lanes(PdEnv *e, int lanes8_below, int lanes32_below) {
         return fail("pd_set_rollout_lanes: need 0 <= lanes32_below <= lanes8_below (0 = default)");
     e->lanes8_below = lanes8_below;
     e->lanes32_below = lanes32_below;
+    return 0;
+}
+
+int pd_aero_patch_stats(PdEnv *e, int64_t *counts, double *max_err) {
+    if (!e || !counts) return fail("pd_aero_patch_stats: null argument");
+    for (int k = 0; k < 4; ++k) counts[k] = e->patch_stats[k];
+    if (max_err) *max_err = e->patch_max_err;
     return 0;
 }
 

@@ -90,6 +90,10 @@ struct RbfGrid {
     const int *cells;
     const unsigned long long *imp_hint;
     const int *imp_id;
+    // fp32 build: bicubic patches per sub-cell (pd_patch.h); pbase == nullptr: none
+    const int *pbase;        // [nm*na]: (first patch << 1) | two_sets, -1 = no patch (walk cell)
+    const float *patch;      // [n][16] C[q][p] of u^p v^q (constant = [0] + [15]), [0] = NaN: rejected
+    int sub_x, sub_y;
 };
 
 struct RbfDev {
@@ -720,6 +724,104 @@ __device__ __forceinline__ void rbf_eval2_coop(const double *__restrict__ rowsL,
     vD = rbf_poly(rd, d, M, aD);
 }
 
+// ---- fp32 production build: bicubic patches of the thin-plate sums (pd_patch.h)
+// A lookup runs in three steps so that the loads of BOTH tables of a sub-step are in flight together
+// (the kernel is bound by the latency of these dependent loads, not by their bytes):
+//   patch_locate : cell index, local coordinates, load of the cell's patch base
+//   patch_fetch  : address of the sub-cell's patch (side of the bisector for a cell cut by one
+//                  Voronoi edge), its 8 x 16-byte loads; a cell without patches reads patch 0
+//   patch_value  : false if there is no usable patch (a cell that needs the walk, or a fit the builder
+//                  rejected: first coefficient NaN) - the caller evaluates the exact sum
+struct PatchRef {
+    float u, v;
+    int cell, sub, pb;
+};
+struct PatchCoef {
+    float4 c[4];
+};
+__device__ __forceinline__ PatchRef patch_locate(const RbfGrid &G, double M, double a) {
+    PatchRef r;
+    const double x = (M - G.m0) * G.inv_dm, y = (a - G.a0) * G.inv_da;
+    int im = (int)x, ia = (int)y;
+    im = max(0, min(im, G.nm - 1));
+    ia = max(0, min(ia, G.na - 1));
+    r.cell = ia * G.nm + im;
+    r.pb = __ldg(G.pbase + r.cell);
+    const double fx = (x - (double)im) * (double)G.sub_x, fy = (y - (double)ia) * (double)G.sub_y;
+    int sx = (int)fx, sy = (int)fy;
+    sx = max(0, min(sx, G.sub_x - 1));
+    sy = max(0, min(sy, G.sub_y - 1));
+    r.u = (float)(2.0 * (fx - (double)sx) - 1.0);
+    r.v = (float)(2.0 * (fy - (double)sy) - 1.0);
+    r.sub = sy * G.sub_x + sx;
+    return r;
+}
+__device__ __forceinline__ void patch_fetch(const RbfGrid &G, const double2 *__restrict__ pts, const PatchRef &r,
+                                            double M, double a, PatchCoef &k) {
+    const int pb = r.pb < 0 ? 0 : r.pb;
+    const int two = pb & 1;
+    int w = 0;
+    if (two) {      // cut by one order-50 Voronoi edge: the side of the bisector of p and q (rbf_resolve)
+        const unsigned long long hint = __ldg(G.imp_hint + (-__ldg(G.cells + r.cell) - 1));
+        const double2 P = pts[(int)((hint >> 8) & 255) * PD_REP], Q = pts[(int)(hint & 255) * PD_REP];
+        const double px = M - P.x, py = a - P.y, qx = M - Q.x, qy = a - Q.y;
+        w = fma(px, px, py * py) <= fma(qx, qx, qy * qy) ? 0 : 1;
+    }
+    const float4 *c = reinterpret_cast<const float4 *>(G.patch) +
+                      ((size_t)(pb >> 1) + (size_t)r.sub * (size_t)(1 + two) + (size_t)w) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k.c[i] = __ldg(c + i);
+}
+// everything but the constant term is the variation of the coefficient over the sub-cell (2e-3 of its
+// value): fp32 Horner, then the constant (a float pair) is added in double
+__device__ __forceinline__ bool patch_value(const PatchRef &r, const PatchCoef &k, double &val) {
+    const float u = r.u, v = r.v;
+    const float r0 = fmaf(fmaf(fmaf(k.c[0].w, u, k.c[0].z), u, k.c[0].y), u, 0.0f);
+    const float r1 = fmaf(fmaf(fmaf(k.c[1].w, u, k.c[1].z), u, k.c[1].y), u, k.c[1].x);
+    const float r2 = fmaf(fmaf(fmaf(k.c[2].w, u, k.c[2].z), u, k.c[2].y), u, k.c[2].x);
+    const float r3 = fmaf(fmaf(k.c[3].z, u, k.c[3].y), u, k.c[3].x);
+    const float var = fmaf(fmaf(fmaf(r3, v, r2), v, r1), v, r0);
+    val = (double)k.c[0].x + ((double)k.c[3].w + (double)var);
+    return r.pb >= 0 && k.c[0].x == k.c[0].x;
+}
+
+// exact sum of one table, one lane on its own (partial warps only)
+template <int DEG>
+__device__ __noinline__ double rbf_eval1(const double *__restrict__ rows, int sid, const double2 *__restrict__ pts,
+                                         double a, double M, const double2 *__restrict__ logtab) {
+    const RbfRow r = rbf_row(rows, sid);
+    const unsigned char *ib = reinterpret_cast<const unsigned char *>(r.ib);
+    double acc = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < 50; ++k)
+        acc = tps_acc<DEG>(acc, __ldg(r.base + k), M, a, pts[(int)__ldg(ib + k) * PD_REP], logtab);
+    return rbf_poly(r, acc, M, a);
+}
+
+// exact sums for the lanes in `need`, by the whole warp: the query of each such lane is broadcast,
+// every lane takes terms lane and lane + 32, a butterfly adds them up - ~100 instructions per
+// query instead of the 3 500 of a serial sum that the other 31 lanes would wait for
+template <int DEG>
+__device__ __forceinline__ double rbf_eval1_warp(unsigned need, const double *__restrict__ rows, int sid,
+                                                 const double2 *__restrict__ pts, double a, double M,
+                                                 const double2 *__restrict__ logtab, double mine) {
+    const int lane = threadIdx.x & 31;
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const double Ms = __shfl_sync(0xffffffffu, M, src), as = __shfl_sync(0xffffffffu, a, src);
+        const RbfRow r = rbf_row(rows, __shfl_sync(0xffffffffu, sid, src));
+        const unsigned char *ib = reinterpret_cast<const unsigned char *>(r.ib);
+        double acc = tps_acc<DEG>(0.0, __ldg(r.base + lane), Ms, as, pts[(int)__ldg(ib + lane) * PD_REP], logtab);
+        if (lane < 18)
+            acc = tps_acc<DEG>(acc, __ldg(r.base + lane + 32), Ms, as, pts[(int)__ldg(ib + lane + 32) * PD_REP], logtab);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == src) mine = rbf_poly(r, acc, Ms, as);
+    }
+    return mine;
+}
+
 // C_L and C_D of one sub-step.
 //  C_D: CD_func passes degrees into a clamp written for radians
 //       (rockets_physics.py:712, aerodynamic_coefficients.py:108-114)
@@ -750,8 +852,42 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
         aL = __shfl_sync(m, aL, me);
         aD = __shfl_sync(m, aD, me);
     }
-    // both grid-cell loads in flight before either is consumed
     const RbfGrid &GL = neg_line ? tb.cl.grid[1] : tb.cl.grid[0];
+    if constexpr (sizeof(R) == 4 && COOP == 1) {
+        if (tb.cd.grid[0].pbase) {
+            const unsigned lanes = __activemask();
+            const int copy = threadIdx.x & (PD_REP - 1);
+            double vL = 0.0, vD = 0.0;
+            const PatchRef rD = patch_locate(tb.cd.grid[0], M, aD), rL = patch_locate(GL, M, aL);
+            PatchCoef kD, kL;
+            patch_fetch(tb.cd.grid[0], sh->cd_pts + copy, rD, M, aD, kD);
+            patch_fetch(GL, sh->cl_pts + copy, rL, M, aL, kL);
+            const bool okD = patch_value(rD, kD, vD);
+            const bool okL = patch_value(rL, kL, vL);
+            const unsigned needD = __ballot_sync(lanes, !okD), needL = __ballot_sync(lanes, !okL);
+            if (needD | needL) {
+                constexpr int DEG = 4 - (PD_LOG_BITS >= 9 ? 1 : 0);
+                int sidD = 0, sidL = 0;
+                if (!okD) sidD = rbf_resolve<5>(tb.cd, tb.cd.grid[0], sd.cd_levels, sh->cd_pts + copy, M, aD,
+                                                __ldg(rbf_cell_ptr(tb.cd.grid[0], M, aD)), status);
+                if (!okL) sidL = rbf_resolve<5>(tb.cl, GL, sd.cl_levels, sh->cl_pts + copy, M, aL,
+                                                __ldg(rbf_cell_ptr(GL, M, aL)), status);
+                if (lanes == 0xffffffffu) {
+                    __syncwarp();
+                    vD = rbf_eval1_warp<DEG>(needD, tb.cd.rows, sidD, sh->cd_pts + copy, aD, M, sh->logtab + copy, vD);
+                    vL = rbf_eval1_warp<DEG>(needL, tb.cl.rows, sidL, sh->cl_pts + copy, aL, M, sh->logtab + copy, vL);
+                } else {
+                    if (!okD) vD = rbf_eval1<DEG>(tb.cd.rows, sidD, sh->cd_pts + copy, aD, M, sh->logtab + copy);
+                    if (!okL) vL = rbf_eval1<DEG>(tb.cl.rows, sidL, sh->cl_pts + copy, aL, M, sh->logtab + copy);
+                }
+            }
+            C_L = zero ? R(0) : (R)(flip ? -vL : vL);
+            C_D = (R)vD;
+            if (status) { C_L = R(NAN); C_D = R(NAN); }
+            return;
+        }
+    }
+    // both grid-cell loads in flight before either is consumed
     const int cellD = __ldg(rbf_cell_ptr(tb.cd.grid[0], M, aD));
     const int cellL = __ldg(rbf_cell_ptr(GL, M, aL));
     const int copy = threadIdx.x & (PD_REP - 1);          // this lane's replica of the tables

@@ -59,7 +59,8 @@ class BatchedRocketEnv:
     def __init__(self, n_envs, type="pso", flight_phase="landing_burn_pure_throttle",
                  enable_wind=False, stochastic_wind=False, horiontal_wind_percentile=50,
                  trajectory_length=1, discount_factor=0.99, precision="fp32", auto_reset=False,
-                 device=None, seed=0, params: RocketParams | None = None, raw_actions=False):
+                 device=None, seed=0, params: RocketParams | None = None, raw_actions=False,
+                 exact_aero=None):
         """raw_actions (type 'rl'): False = `step` takes the policy's action and applies
         rl_wrapped_env_pytorch.augment_action inside the kernel (landing_burn log-compression,
         P-control reference-speed scaling); True = actions are what
@@ -104,6 +105,11 @@ class BatchedRocketEnv:
         cfg.rl_reward_scale = (1 - g) / (1 - g ** L) if (g is not None and L) else 1.0
         cfg.discount_factor = g if g is not None else 0.99
         cfg.raw_actions = int(bool(raw_actions))
+        # fp32 build: C_L / C_D from the bicubic patches of the thin-plate sums (csrc/pd_patch.h);
+        # exact_aero=True (or PD_EXACT_AERO=1) keeps the 50-term sums, as the fp64 build always does
+        if exact_aero is None:
+            exact_aero = os.environ.get("PD_EXACT_AERO", "0") == "1"
+        cfg.exact_aero = int(bool(exact_aero))
         self._cparams, self._keep = N.make_params(self.params, horiontal_wind_percentile)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -327,6 +333,14 @@ class BatchedRocketEnv:
             return dict(fitness=fit, steps=steps, trunc_id=tid, terminal=term, traj=traj,
                         actions=acts, rewards=rews)
         return (fit, steps, tid, term) if terminal else (fit, steps, tid)
+
+    def aero_patch_stats(self):
+        """fp32 build: how many bicubic aero patches were built / rejected (csrc/pd_patch.h)."""
+        counts = (C.c_int64 * 4)()
+        err = C.c_double(0.0)
+        N.check(self.lib.pd_aero_patch_stats(self._h, counts, C.byref(err)))
+        return {"cd_patches": counts[0], "cd_rejected": counts[1], "cl_patches": counts[2],
+                "cl_rejected": counts[3], "max_abs_error_in_use": err.value}
 
     def rollout_tape(self, actions: torch.Tensor, record=False):
         """actions [T, n_episodes, A] (float64 or float32): an env.reset() + env.step loop per
