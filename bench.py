@@ -520,8 +520,16 @@ def run_cuda(args):
         "config": {"workload": f"config2: {B} envs/GPU x {K} steps, landing_burn_pure_throttle, pso rtd, "
                                "random U(-1,1) float32 actions, ISA, no wind, auto-reset",
                    "envs_per_gpu": B, "precision_build": args.precision,
+                   "aero": ("exact 50-term thin-plate sums (--exact-aero)" if os.environ.get("PD_EXACT_AERO") == "1"
+                            or args.precision == "fp64" else
+                            "C_L / C_D from bicubic patches of the thin-plate sums, each validated to 1e-8 against "
+                            "the exact sum when the handle is created (csrc/pd_patch.h); rejected patches and walk "
+                            "cells take the exact sum"),
+                   "aero_patches": env.aero_patch_stats(),
                    "l2": "state (~19 MB/step at 65 536 envs) stays L2-resident between launches as in the "
-                         "real rollout; the kernel is FP-pipe bound.  roofline / fp_roofline are quoted on the "
+                         "real rollout; with the patches the kernel is bound by the latency of its dependent loads "
+                         "and scalar chain (one warp per SM: 22 us per step), with --exact-aero by FP64 issue.  "
+                         "roofline / fp_roofline are quoted on the "
                          "SAME time base as `value` (average launch duration inside the timed region); their "
                          "`cold_l2` sub-objects repeat them on single launches separated by a 256 MB L2 flush",
                    "launch": "K step launches captured in one CUDA graph"},
@@ -571,6 +579,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--exact-aero", action="store_true",
+                    help="fp32 build with the exact thin-plate sums instead of the bicubic patches")
     ap.add_argument("--cpu-steps-per-core", type=int, default=3000)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-envs", type=int, default=65536)
@@ -583,6 +593,8 @@ def main():
     ap.add_argument("--sac-envs", type=int, default=131072)
     ap.add_argument("--sac-steps", type=int, default=40)
     args = ap.parse_args()
+    if args.exact_aero:
+        os.environ["PD_EXACT_AERO"] = "1"
     if args.impl == "reference":
         run_reference(args)
     else:

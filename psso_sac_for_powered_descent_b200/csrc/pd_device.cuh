@@ -91,7 +91,8 @@ struct RbfGrid {
     const unsigned long long *imp_hint;
     const int *imp_id;
     // fp32 build: bicubic patches per sub-cell (pd_patch.h); pbase == nullptr: none
-    const int *pbase;        // [nm*na]: (first patch << 1) | two_sets, -1 = no patch (walk cell)
+    const int2 *pbase;       // [nm*na]: x = (first patch << 1) | two_sets, -1 = no patch (walk cell);
+                             //          y = point slots p << 8 | q of the bisector (two_sets cells)
     const float *patch;      // [n][16] C[q][p] of u^p v^q (constant = [0] + [15]), [0] = NaN: rejected
     int sub_x, sub_y;
 };
@@ -727,50 +728,49 @@ __device__ __forceinline__ void rbf_eval2_coop(const double *__restrict__ rowsL,
 // ---- fp32 production build: bicubic patches of the thin-plate sums (pd_patch.h)
 // A lookup runs in three steps so that the loads of BOTH tables of a sub-step are in flight together
 // (the kernel is bound by the latency of these dependent loads, not by their bytes):
-//   patch_locate : cell index, local coordinates, load of the cell's patch base
-//   patch_fetch  : address of the sub-cell's patch (side of the bisector for a cell cut by one
-//                  Voronoi edge), its 8 x 16-byte loads; a cell without patches reads patch 0
+//   patch_locate : cell index, local coordinates, one 8-byte load of the cell's patch base and
+//                  bisector slots, address of the sub-cell's patch (side of the bisector for a cell
+//                  cut by one Voronoi edge); a cell without patches points at patch 0
+//   patch_fetch  : the 4 x 16-byte loads of the patch
 //   patch_value  : false if there is no usable patch (a cell that needs the walk, or a fit the builder
 //                  rejected: first coefficient NaN) - the caller evaluates the exact sum
 struct PatchRef {
     float u, v;
-    int cell, sub, pb;
+    const float4 *c;      // the sub-cell's patch (patch 0 for a cell without patches)
+    bool have;
 };
 struct PatchCoef {
     float4 c[4];
 };
-__device__ __forceinline__ PatchRef patch_locate(const RbfGrid &G, double M, double a) {
+__device__ __forceinline__ PatchRef patch_locate(const RbfGrid &G, const double2 *__restrict__ pts, double M, double a) {
     PatchRef r;
     const double x = (M - G.m0) * G.inv_dm, y = (a - G.a0) * G.inv_da;
     int im = (int)x, ia = (int)y;
     im = max(0, min(im, G.nm - 1));
     ia = max(0, min(ia, G.na - 1));
-    r.cell = ia * G.nm + im;
-    r.pb = __ldg(G.pbase + r.cell);
+    const int2 e = __ldg(G.pbase + ia * G.nm + im);
     const double fx = (x - (double)im) * (double)G.sub_x, fy = (y - (double)ia) * (double)G.sub_y;
     int sx = (int)fx, sy = (int)fy;
     sx = max(0, min(sx, G.sub_x - 1));
     sy = max(0, min(sy, G.sub_y - 1));
     r.u = (float)(2.0 * (fx - (double)sx) - 1.0);
     r.v = (float)(2.0 * (fy - (double)sy) - 1.0);
-    r.sub = sy * G.sub_x + sx;
-    return r;
-}
-__device__ __forceinline__ void patch_fetch(const RbfGrid &G, const double2 *__restrict__ pts, const PatchRef &r,
-                                            double M, double a, PatchCoef &k) {
-    const int pb = r.pb < 0 ? 0 : r.pb;
+    r.have = e.x >= 0;
+    const int pb = r.have ? e.x : 0;
     const int two = pb & 1;
     int w = 0;
     if (two) {      // cut by one order-50 Voronoi edge: the side of the bisector of p and q (rbf_resolve)
-        const unsigned long long hint = __ldg(G.imp_hint + (-__ldg(G.cells + r.cell) - 1));
-        const double2 P = pts[(int)((hint >> 8) & 255) * PD_REP], Q = pts[(int)(hint & 255) * PD_REP];
+        const double2 P = pts[((e.y >> 8) & 255) * PD_REP], Q = pts[(e.y & 255) * PD_REP];
         const double px = M - P.x, py = a - P.y, qx = M - Q.x, qy = a - Q.y;
         w = fma(px, px, py * py) <= fma(qx, qx, qy * qy) ? 0 : 1;
     }
-    const float4 *c = reinterpret_cast<const float4 *>(G.patch) +
-                      ((size_t)(pb >> 1) + (size_t)r.sub * (size_t)(1 + two) + (size_t)w) * 4;
+    r.c = reinterpret_cast<const float4 *>(G.patch) +
+          ((size_t)(pb >> 1) + (size_t)(sy * G.sub_x + sx) * (size_t)(1 + two) + (size_t)w) * 4;
+    return r;
+}
+__device__ __forceinline__ void patch_fetch(const PatchRef &r, PatchCoef &k) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) k.c[i] = __ldg(c + i);
+    for (int i = 0; i < 4; ++i) k.c[i] = __ldg(r.c + i);
 }
 // everything but the constant term is the variation of the coefficient over the sub-cell (2e-3 of its
 // value): fp32 Horner, then the constant (a float pair) is added in double
@@ -782,7 +782,7 @@ __device__ __forceinline__ bool patch_value(const PatchRef &r, const PatchCoef &
     const float r3 = fmaf(fmaf(k.c[3].z, u, k.c[3].y), u, k.c[3].x);
     const float var = fmaf(fmaf(fmaf(r3, v, r2), v, r1), v, r0);
     val = (double)k.c[0].x + ((double)k.c[3].w + (double)var);
-    return r.pb >= 0 && k.c[0].x == k.c[0].x;
+    return r.have && k.c[0].x == k.c[0].x;
 }
 
 // exact sum of one table, one lane on its own (partial warps only)
@@ -858,10 +858,11 @@ __device__ __forceinline__ void aero_coefficients(R mach, R alpha_eff, R &C_L, R
             const unsigned lanes = __activemask();
             const int copy = threadIdx.x & (PD_REP - 1);
             double vL = 0.0, vD = 0.0;
-            const PatchRef rD = patch_locate(tb.cd.grid[0], M, aD), rL = patch_locate(GL, M, aL);
+            const PatchRef rD = patch_locate(tb.cd.grid[0], sh->cd_pts + copy, M, aD);
+            const PatchRef rL = patch_locate(GL, sh->cl_pts + copy, M, aL);
             PatchCoef kD, kL;
-            patch_fetch(tb.cd.grid[0], sh->cd_pts + copy, rD, M, aD, kD);
-            patch_fetch(GL, sh->cl_pts + copy, rL, M, aL, kL);
+            patch_fetch(rD, kD);
+            patch_fetch(rL, kL);
             const bool okD = patch_value(rD, kD, vD);
             const bool okL = patch_value(rL, kL, vL);
             const unsigned needD = __ballot_sync(lanes, !okD), needL = __ballot_sync(lanes, !okL);
@@ -1434,9 +1435,9 @@ __device__ __forceinline__ void substep(State &s, const Action<phase_adim(PHASE)
     s.theta += s.theta_dot * dt;
     double gam;
     bool turned = false;
-    if constexpr (sizeof(R) == 4 && COOP > 1) {
-        // Straggler stages of the fp32 build: atan2 is 12 % of the dependent instruction chain
-        // that bounds a lone episode.  The velocity turns by a few mrad per 25 ms sub-step, so
+    if constexpr (sizeof(R) == 4) {
+        // fp32 build: atan2 is 11-12 % of the dependent instruction chain that bounds a lone episode
+        // and, with the aero patches, the step kernel.  The velocity turns by a few mrad per 25 ms sub-step, so
         // gamma advances by atan(cross / dot) of the old and new velocity, |t| < 2^-5: a
         // float-seeded Newton reciprocal and five series terms, 1e-16 rad from atan2 per
         // sub-step against the 1e-7 relative rounding of the fp32 forces.

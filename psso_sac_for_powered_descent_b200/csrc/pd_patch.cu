@@ -32,13 +32,13 @@ __device__ double tps_exact(const double *__restrict__ rows, const double2 *__re
     return acc + r[50] + r[51] * xh + r[52] * yh;
 }
 
-__global__ void fit_kernel(PatchGridIn g, FitConst fc, const int *__restrict__ pbase, float *__restrict__ patch,
+__global__ void fit_kernel(PatchGridIn g, FitConst fc, const int2 *__restrict__ pbase, float *__restrict__ patch,
                            double tol, unsigned long long *n_failed, unsigned long long *max_err_bits) {
     const long long nsub = (long long)g.sub_x * g.sub_y;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)g.nm * g.na * nsub) return;
     const int cell = (int)(t / nsub), sub = (int)(t % nsub);
-    const int pb = pbase[cell];
+    const int pb = pbase[cell].x;
     if (pb < 0) return;
     const int two = pb & 1;
     const int c = g.cells[cell];
@@ -110,21 +110,22 @@ __global__ void fit_kernel(PatchGridIn g, FitConst fc, const int *__restrict__ p
 int build_patch_grid(const PatchGridIn &in, double tol, PatchGridOut *out, cudaStream_t st) {
     const size_t ncell = (size_t)in.nm * in.na;
     const long long nsub = (long long)in.sub_x * in.sub_y;
-    std::vector<int> pbase(ncell);
+    std::vector<int2> pbase(ncell);
     long long n = 0;
     for (size_t c = 0; c < ncell; ++c) {
         const int v = in.cells_host[c];
         int sets = 1;
         if (v < 0) sets = (in.imp_hint_host[-v - 1] >> 63) ? 2 : 0;
-        if (sets == 0) { pbase[c] = -1; continue; }
+        if (sets == 0) { pbase[c] = make_int2(-1, 0); continue; }
         if (n + nsub * sets >= (1LL << 30)) return 1;       // index packed into 31 bits with the flag
-        pbase[c] = (int)((n << 1) | (sets - 1));
+        pbase[c] = make_int2((int)((n << 1) | (sets - 1)),
+                             sets == 2 ? (int)(in.imp_hint_host[-v - 1] & 0xFFFF) : 0);   // slots p << 8 | q
         n += nsub * sets;
     }
     out->n_patches = n;
-    if (cudaMalloc(&out->pbase, ncell * sizeof(int)) != cudaSuccess) return 1;
+    if (cudaMalloc(&out->pbase, ncell * sizeof(int2)) != cudaSuccess) return 1;
     if (cudaMalloc(&out->patch, (size_t)(n > 0 ? n : 1) * 16 * sizeof(float)) != cudaSuccess) return 1;
-    if (cudaMemcpyAsync(out->pbase, pbase.data(), ncell * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
+    if (cudaMemcpyAsync(out->pbase, pbase.data(), ncell * sizeof(int2), cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
     unsigned long long *stats = nullptr;
     if (cudaMalloc(&stats, 2 * sizeof(unsigned long long)) != cudaSuccess) return 1;
     cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), st);

@@ -26,7 +26,7 @@ struct PatchGridIn {
     int sub_x, sub_y;
 };
 struct PatchGridOut {
-    int *pbase = nullptr;                  // device [nm*na]: (first patch << 1) | two_sets, or -1
+    int2 *pbase = nullptr;                 // device [nm*na]: x = (first patch << 1) | two_sets or -1, y = bisector slots p << 8 | q
     float *patch = nullptr;                // device [n_patches][16] (64 B): C[q][p] of u^p v^q, constant hi / lo in [0] / [15]
     long long n_patches = 0;
     long long n_failed = 0;                // patches over the tolerance

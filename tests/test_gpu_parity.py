@@ -870,6 +870,51 @@ def test_rollout_stage_chain_every_lane_choice(envs_mod, precision, wind):
         N.check(env.lib.pd_set_rollout_lanes(env._h, 8, 16))
 
 
+@pytest.mark.parametrize("phase,rtd", [(P, "pso"), (G, "rl")])
+def test_aero_patches_against_exact_sums(envs_mod, phase, rtd):
+    """fp32 build: C_L / C_D come from bicubic patches of the 50-term thin-plate sums
+    (csrc/pd_patch.h) unless exact_aero is set.  The builder keeps a patch only if it reproduces the
+    exact sum to 1e-8 at 25 check points; here 65 536 spread-out states take one step through both
+    variants: the new states agree far below the fp32 build's own rounding and every flag is equal
+    except where a thresholded quantity sits within fp32 resolution of its threshold."""
+    B = 65536
+    adim = 1 if phase == P else 4
+    patched = envs_mod.BatchedRocketEnv(B, rtd, phase, precision="fp32", auto_reset=True)
+    exact = envs_mod.BatchedRocketEnv(B, rtd, phase, precision="fp32", auto_reset=True, exact_aero=True)
+    st = patched.aero_patch_stats()
+    assert st["cd_patches"] > 100000 and st["cl_patches"] > 1000000
+    assert st["cd_rejected"] < 0.005 * st["cd_patches"] and st["cl_rejected"] < 0.005 * st["cl_patches"]
+    assert 0.0 < st["max_abs_error_in_use"] <= 1e-8
+    assert exact.aero_patch_stats()["cl_patches"] == 0
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for _ in range(24 if phase == G else 150):          # spread the batch over the flight envelope
+        exact.step(torch.rand(B, adim, device="cuda", generator=gen) * 2 - 1)
+    worst, bulk, flag_diff = 0.0, 0.0, 0
+    for _ in range(8):
+        state = exact.get_state(full=True)
+        patched.set_state(*state)
+        act = torch.rand(B, adim, device="cuda", generator=gen) * 2 - 1
+        oe = exact.step(act)
+        op = patched.step(act)
+        same = (oe[2] == op[2]) & (oe[3] == op[3])
+        flag_diff += int((~same).sum())
+        live = same & ~(oe[2].bool() | oe[3].bool())     # ended episodes were reset in place
+        a, b = patched.get_state()[live], exact.get_state()[live]
+        # theta_dot is the integral of a small difference of large moments: absolute scale 1 rad/s
+        scale = b.abs().clamp_min(torch.tensor([1e3, 1e3, 10., 10., 1., 1., 1., 1., 1e3, 1e3, 1.], device="cuda",
+                                               dtype=torch.float64))
+        per_env = ((a - b).abs() / scale).max(dim=1).values
+        worst = max(worst, float(per_env.max()))
+        bulk = max(bulk, float(torch.quantile(per_env, 0.999)))
+        assert float(torch.quantile((op[1][live].double() - oe[1][live].double()).abs(), 0.999)) < 1e-6
+    patched.check_status(); exact.check_status()
+    # landing_burn's pitch channel amplifies a one-ulp change of a float force by orders of magnitude
+    # inside one 0.4 s step on the few envs that tumble (theta_dot 0.35 -> -1.1 rad/s in the worst one)
+    assert bulk < (1e-7 if phase == P else 1e-6), bulk
+    assert worst < (1e-7 if phase == P else 1e-3), worst
+    assert flag_diff <= 4, flag_diff
+
+
 # --------------------------------------------------------------------------- round-2 robustness
 def test_captured_graph_survives_other_handles(envs_mod):
     """A handle's constants travel with every launch (a __grid_constant__ kernel parameter): a CUDA
