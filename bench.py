@@ -210,6 +210,7 @@ def run_cuda(args):
     lib = _native.load_library()
     env = envs.BatchedRocketEnv(B, "pso", P, precision=args.precision, auto_reset=True, device=local,
                                 seed=1234 + rank)
+    aero_patches = env.aero_patch_stats()
     gen = torch.Generator(device=dev)
     gen.manual_seed(rank)
     tape = torch.rand(K + W, B, 1, device=dev, generator=gen, dtype=torch.float32) * 2 - 1
@@ -385,12 +386,16 @@ def run_cuda(args):
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             per_gen = []        # the step counters are reduced after the timed region (each generation
             barrier()           # leaves a fresh tensor), so no torch kernel is first loaded inside it
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_gen + 1)]
             g0.record()
-            for _ in range(n_gen):
+            marks[0].record()
+            for k in range(n_gen):
                 sw.step()
                 per_gen.append(sw.last_steps)
+                marks[k + 1].record()
             g1.record()
             barrier()
+            each = [marks[k].elapsed_time(marks[k + 1]) for k in range(n_gen)]
             gsteps = sum(float(t.sum()) for t in per_gen)
             glong = max(int(t.max()) for t in per_gen)
             gms, = allmax(g0.elapsed_time(g1) / n_gen)
@@ -401,6 +406,8 @@ def run_cuda(args):
                    "episodes_per_s": sw.N_total * seeds / (gms * 1e-3), "env_steps_per_s": tot / (gms * 1e-3),
                    "mean_episode_steps": tot / (sw.N_total * seeds),
                    "episodes_hitting_step_cap_total": int(capped), "generations_timed": n_gen,
+                   "ms_each_generation_rank0": [round(x, 3) for x in each],
+                   "ms_median_generation_rank0": sorted(each)[n_gen // 2],
                    "longest_episode_steps": int(longest),
                    "sequential_floor_ms": longest * (LONE_EPISODE_US_PER_STEP_WINDY if wind else LONE_EPISODE_US_PER_STEP)[phase] * 1e-3,
                    "global_best_fitness": sw.global_best_fitness,
@@ -525,7 +532,7 @@ def run_cuda(args):
                             "C_L / C_D from bicubic patches of the thin-plate sums, each validated to 1e-8 against "
                             "the exact sum when the handle is created (csrc/pd_patch.h); rejected patches and walk "
                             "cells take the exact sum"),
-                   "aero_patches": env.aero_patch_stats(),
+                   "aero_patches": aero_patches,
                    "l2": "state (~19 MB/step at 65 536 envs) stays L2-resident between launches as in the "
                          "real rollout; with the patches the kernel is bound by the latency of its dependent loads "
                          "and scalar chain (one warp per SM: 22 us per step), with --exact-aero by FP64 issue.  "
