@@ -245,6 +245,10 @@ int pd_rollout_pso(PdEnv *env, const float *weights, int n_particles, int n_para
  * validation for C_D, then for C_L (all zero otherwise); *max_err (may be NULL) = largest validation
  * error among the patches in use. */
 int pd_aero_patch_stats(PdEnv *env, int64_t *counts, double *max_err);
+/* The patch sets are shared by all handles of a process (one per GPU and table, 0.34 GB) and stay
+ * cached after the last handle is destroyed, so that the next pd_create does not rebuild them
+ * (0.2 s).  This frees the sets no live handle uses; returns the bytes of patches released. */
+int64_t pd_release_aero_patches(void);
 
 /* Straggler hand-off of pd_rollout_pso.  Episode lengths are ragged (a random
  * landing_burn_pure_throttle swarm has a median of 130 steps, 2 % above 512 and a few episodes at

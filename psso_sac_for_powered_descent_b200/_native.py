@@ -92,7 +92,7 @@ EXPORTS = ["pd_last_error", "pd_version", "pd_create", "pd_destroy", "pd_reset",
            "pd_get_state", "pd_set_state", "pd_set_wind_tape", "pd_rollout_pso", "pd_rollout_policy",
            "pd_collect_shared_actor", "pd_actor_forward", "pd_pso_update", "pd_pso_seed_mean", "pd_pso_select", "pd_pso_gather", "pd_pso_apply",
            "pd_set_rollout_stream", "pd_measure_fma_peak", "pd_check_status", "pd_launch_count",
-           "pd_set_info_mode", "pd_set_rollout_handoff", "pd_set_rollout_stages", "pd_set_rollout_lanes", "pd_aero_patch_stats"]
+           "pd_set_info_mode", "pd_set_rollout_handoff", "pd_set_rollout_stages", "pd_set_rollout_lanes", "pd_aero_patch_stats", "pd_release_aero_patches"]
 
 _lib = None
 
@@ -129,6 +129,8 @@ def load_library():
     lib.pd_set_rollout_stages.argtypes = [vp, i32, i32]
     lib.pd_set_rollout_lanes.argtypes = [vp, i32, i32]
     lib.pd_aero_patch_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    lib.pd_release_aero_patches.argtypes = []
+    lib.pd_release_aero_patches.restype = C.c_int64
     lib.pd_measure_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pd_pso_seed_mean.argtypes = [vp, i32, i32, vp, vp]
     lib.pd_pso_select.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]

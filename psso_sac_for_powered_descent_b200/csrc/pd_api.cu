@@ -62,6 +62,7 @@ struct PdEnv {
     int lanes8_below = 0, lanes32_below = 0;   // pd_set_rollout_lanes (0 = default)
     bool handoff_default = true;     // thresholds never set by the caller: per-phase defaults apply
     long long patch_stats[4] = {0, 0, 0, 0};   // aero patches: built / rejected for C_D, for C_L
+    std::vector<std::pair<int, uint64_t>> patch_keys_raw;   // (device, signature) of the shared patch sets in use
     double patch_max_err = 0.0;
     // shared-actor collection
     void *w2_img = nullptr;          // bf16 smem image of W2
@@ -153,8 +154,12 @@ struct PatchKey {
     uint64_t sig;
     bool operator<(const PatchKey &o) const { return device != o.device ? device < o.device : sig < o.sig; }
 };
+struct PatchEntry {
+    PatchGridOut out;
+    int refs;            // live handles using it; pd_release_aero_patches frees the entries at 0
+};
 static std::mutex g_patch_mu;
-static std::map<PatchKey, PatchGridOut> g_patches;
+static std::map<PatchKey, PatchEntry> g_patches;
 
 static uint64_t mix_words(uint64_t h, const void *data, size_t bytes) {
     const unsigned char *b = static_cast<const unsigned char *>(data);
@@ -195,20 +200,38 @@ static int attach_patches(PdEnv *e, const PdRbfTable &t, RbfDev &d, int g, int s
             free_patch_grid(&out);
             return fail(std::string("pd_create: building the aero patches failed: ") + cudaGetErrorString(cudaGetLastError()));
         }
-        it = g_patches.emplace(key, out).first;
+        it = g_patches.emplace(key, PatchEntry{out, 0}).first;
     }
-    e->patch_stats[2 * which_table] += it->second.n_patches;
-    e->patch_stats[2 * which_table + 1] += it->second.n_failed;
-    e->patch_max_err = std::max(e->patch_max_err, it->second.max_err_kept);
-    o.pbase = it->second.pbase;
-    o.patch = it->second.patch;
+    it->second.refs++;
+    e->patch_keys_raw.push_back({key.device, key.sig});
+    e->patch_stats[2 * which_table] += it->second.out.n_patches;
+    e->patch_stats[2 * which_table + 1] += it->second.out.n_failed;
+    e->patch_max_err = std::max(e->patch_max_err, it->second.out.max_err_kept);
+    o.pbase = it->second.out.pbase;
+    o.patch = it->second.out.patch;
     o.sub_x = sub_x; o.sub_y = sub_y;
     return 0;
 }
 
 static int upload_segments(PdEnv *e, const double *x, const double *y, int n, const double **dx,
-                           const double **dy, const double **ds) {
-    if (n < 2) return fail("grid fin table too short");
+                           const double **dy, const double **ds, const unsigned char **dlut, double *x0,
+                           double *inv_w) {
+    if (n < 2 || n > 255) return fail("grid fin table: need 2..255 points");
+    if (!(x[n - 1] > x[0])) return fail("grid fin table: abscissae must ascend");
+    {   // seg_index_lut: lut[b] = #{x_i < x0 + b w}
+        const double range = x[n - 1] - x[0];
+        const double w = range / 256.0;
+        *x0 = x[0];
+        *inv_w = 256.0 / range;
+        unsigned char lut[256];
+        for (int b = 0; b < 256; ++b) {
+            const double start = x[0] + b * w;
+            int c = 0;
+            while (c < n && x[c] < start) ++c;
+            lut[b] = (unsigned char)c;
+        }
+        if (dev_copy(e, lut, (size_t)256, dlut)) return 1;
+    }
     std::vector<double> s(n);
     for (int i = 0; i + 1 < n; ++i) s[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
     s[n - 1] = s[n - 2];
@@ -397,8 +420,10 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
     fill_scalars(*cfg, *p, e->sd);
     memset(&e->tb, 0, sizeof(e->tb));
     int rc = upload_rbf(e, p->cd, e->tb.cd, e->sd.cd_levels, 192) || upload_rbf(e, p->cl, e->tb.cl, e->sd.cl_levels, 144);
-    rc = rc || upload_segments(e, p->gf_ca_mach, p->gf_ca_val, p->n_gf_ca, &e->tb.ca_x, &e->tb.ca_y, &e->tb.ca_s);
-    rc = rc || upload_segments(e, p->gf_cn_mach, p->gf_cn_val, p->n_gf_cn, &e->tb.cn_x, &e->tb.cn_y, &e->tb.cn_s);
+    rc = rc || upload_segments(e, p->gf_ca_mach, p->gf_ca_val, p->n_gf_ca, &e->tb.ca_x, &e->tb.ca_y, &e->tb.ca_s,
+                               &e->tb.ca_lut, &e->tb.ca_x0, &e->tb.ca_inv_w);
+    rc = rc || upload_segments(e, p->gf_cn_mach, p->gf_cn_val, p->n_gf_cn, &e->tb.cn_x, &e->tb.cn_y, &e->tb.cn_s,
+                               &e->tb.cn_lut, &e->tb.cn_x0, &e->tb.cn_inv_w);
     if (!rc && cfg->precision == PD_FP32 && !cfg->exact_aero) {
         // fp32 production build: bicubic patches of the thin-plate sums (pd_patch.h)
         rc = attach_patches(e, p->cd, e->tb.cd, 0, 4, 8, 0);
@@ -486,6 +511,13 @@ int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
 int pd_destroy(PdEnv *e) {
     if (!e) return 0;
     DeviceGuard guard(e->cfg.device);
+    {
+        std::lock_guard<std::mutex> lock(g_patch_mu);
+        for (const auto &k : e->patch_keys_raw) {
+            auto it = g_patches.find(PatchKey{k.first, k.second});
+            if (it != g_patches.end() && it->second.refs > 0) it->second.refs--;
+        }
+    }
     for (void *a : e->allocs) cudaFree(a);
     if (e->wT) cudaFree(e->wT);
     for (int k = 0; k < 2; ++k) {
@@ -534,6 +566,22 @@ int pd_set_rollout_lanes(PdEnv *e, int lanes8_below, int lanes32_below) {
     e->lanes8_below = lanes8_below;
     e->lanes32_below = lanes32_below;
     return 0;
+}
+
+int64_t pd_release_aero_patches(void) {
+    std::lock_guard<std::mutex> lock(g_patch_mu);
+    int64_t freed = 0;
+    for (auto it = g_patches.begin(); it != g_patches.end();) {
+        if (it->second.refs == 0) {
+            DeviceGuard guard(it->first.device);
+            freed += (int64_t)it->second.out.n_patches * 64;
+            free_patch_grid(&it->second.out);
+            it = g_patches.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    return freed;
 }
 
 int pd_aero_patch_stats(PdEnv *e, int64_t *counts, double *max_err) {

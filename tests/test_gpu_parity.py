@@ -915,6 +915,27 @@ def test_aero_patches_against_exact_sums(envs_mod, phase, rtd):
     assert flag_diff <= 4, flag_diff
 
 
+def test_aero_patch_cache_is_shared_and_releasable(envs_mod):
+    """One patch set per GPU and table serves every fp32 handle of the process; it stays cached after the
+    last handle is gone (the next pd_create does not rebuild it) until pd_release_aero_patches."""
+    import gc
+    from psso_sac_for_powered_descent_b200 import _native as N
+    lib = N.load_library()
+    a = envs_mod.BatchedRocketEnv(64, "pso", P, precision="fp32")
+    b = envs_mod.BatchedRocketEnv(64, "rl", G, precision="fp32")
+    st = a.aero_patch_stats()
+    assert st == b.aero_patch_stats()
+    assert lib.pd_release_aero_patches() == 0          # sets in use are never freed
+    a.step(torch.zeros(64, 1, device="cuda")); a.check_status()
+    a.close(); b.close()
+    gc.collect()
+    freed = lib.pd_release_aero_patches()
+    assert freed in (0, 64 * (st["cd_patches"] + st["cl_patches"]))     # 0: another live handle still holds them
+    c = envs_mod.BatchedRocketEnv(64, "pso", P, precision="fp32")       # rebuilt (or still cached)
+    assert c.aero_patch_stats() == st
+    c.step(torch.zeros(64, 1, device="cuda")); c.check_status()
+
+
 # --------------------------------------------------------------------------- round-2 robustness
 def test_captured_graph_survives_other_handles(envs_mod):
     """A handle's constants travel with every launch (a __grid_constant__ kernel parameter): a CUDA
