@@ -384,7 +384,7 @@ static void fill_scalars(const PdConfig &cfg, const PdParams &p, Scalars<double>
 extern "C" {
 
 const char *pd_last_error(void) { return g_err.c_str(); }
-int pd_version(void) { return 200; }
+int pd_version(void) { return 210; }
 uint64_t pd_launch_count(void) { return g_launches.load(); }
 
 int pd_create(const PdConfig *cfg, const PdParams *p, PdEnv **out) {
