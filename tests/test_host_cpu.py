@@ -144,6 +144,60 @@ def test_rbf_tables_cover_random_queries_and_match_scipy(tables, oracle_tables):
     assert worst < 5e-10, worst
 
 
+def test_bicubic_patch_of_a_grid_cell_follows_scipy(tables, oracle_tables):
+    """The fp32 build's aero patches (csrc/pd_patch.cu), restated in numpy: the interpolating bicubic
+    through the exact thin-plate sum at the 4 x 4 Chebyshev nodes of a sub-cell, stored as floats
+    with a float-pair constant and evaluated in float32, is within 2e-8 of what scipy's
+    RBFInterpolator(neighbors=50) - the reference's call - returns anywhere in the sub-cell, for
+    every patch that passes the builder's own 25-point check (1e-8)."""
+    cd, cl = tables
+    nodes = np.cos(np.pi * (np.arange(4) + 0.5) / 4)
+    vinv = np.linalg.inv(np.vander(nodes, 4, increasing=True))
+    chk = np.array([-1.0, -0.7, 0.0, 0.7, 1.0])
+    rng = np.random.default_rng(8)
+
+    def stored_eval(S, u, v):
+        u, v = np.float32(u), np.float32(v)
+        f = np.float32
+        r0 = f(f(f(S[3] * u + S[2]) * u + S[1]) * u)
+        r1 = f(f(f(S[7] * u + S[6]) * u + S[5]) * u + S[4])
+        r2 = f(f(f(S[11] * u + S[10]) * u + S[9]) * u + S[8])
+        r3 = f(f(S[14] * u + S[13]) * u + S[12])
+        var = f(f(f(r3 * v + r2) * v + r1) * v + r0)
+        return float(S[0]) + (float(S[15]) + float(var))
+
+    kept = tried = 0
+    worst = 0.0
+    for tbl, ref, sub in ((cl, oracle_tables.cl_rbf, (1, 2)), (cd, oracle_tables.cd_rbf, (4, 8))):
+        g = tbl.grids[0]
+        pure = np.nonzero(g.cells >= 0)[0]
+        cols = pure % g.nm
+        pure = pure[cols * g.dm < 3.5]                     # the Mach range the flights visit
+        for cell in rng.choice(pure, 60, replace=False):
+            ia, im = divmod(int(cell), g.nm)
+            sx, sy = rng.integers(sub[0]), rng.integers(sub[1])
+            hx, hy = 0.5 * g.dm / sub[0], 0.5 * g.da / sub[1]
+            mc, ac = g.m0 + g.dm * im + hx * (2 * sx + 1), g.a0 + g.da * ia + hy * (2 * sy + 1)
+            F = np.array([[tbl.evaluate(mc + hx * u, ac + hy * v) for v in nodes] for u in nodes])
+            Cpq = vinv @ F @ vinv.T                         # coefficient of u^p v^q
+            S = np.zeros(16, np.float32)
+            for q in range(4):
+                for pw in range(4):
+                    S[q * 4 + pw] = Cpq[pw, q]
+            S[15] = np.float32(Cpq[0, 0] - float(S[0]))
+            err = max(abs(stored_eval(S, u, v) - tbl.evaluate(mc + hx * u, ac + hy * v)) for u in chk for v in chk)
+            tried += 1
+            if err > 1e-8:
+                continue
+            kept += 1
+            for _ in range(6):
+                u, v = rng.uniform(-1, 1, 2)
+                m, a = mc + hx * float(np.float32(u)), ac + hy * float(np.float32(v))
+                worst = max(worst, abs(stored_eval(S, u, v) - float(ref(m, a))))
+    assert kept >= 0.9 * tried, (kept, tried)
+    assert worst < 2e-8, worst
+
+
 def test_rbf_conditioning_noise_floor(tables, oracle_tables):
     """Why theta_dot cannot be held to 1e-12 relative: kappa = sum|c_i phi_i| / |f|."""
     cd, cl = tables
