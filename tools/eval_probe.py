@@ -1,5 +1,6 @@
+"""Wall time of pso_wrapped_env.evaluate (host list in, fitness out) per swarm size and phase (one GPU)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from psso_sac_for_powered_descent_b200 import envs
 for phase, P in (("landing_burn", 372), ("landing_burn_pure_throttle", 249)):

@@ -1,5 +1,7 @@
+"""Wall time of every generation of the device-resident optimiser over 65 generations (one GPU): shows the
+one-off cost of the first migration / sharing steps and their steady-state cost."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from psso_sac_for_powered_descent_b200 import envs, pso as pso_mod
 G = "landing_burn"

@@ -1,3 +1,4 @@
+"""SAC collection smoke / timing run: shared tensor-core actor + fused env step, a few steps, prints rewards."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn as nn
