@@ -12,4 +12,4 @@ for path in paths:
     print(f"| {d['n_gpus']} | {d['value']:.3e} | {d['ms_per_step'] * 1e3:.1f} | {d['e2e']['value']:.3e} | {p['config3_P']['ms']:.2f} | "
           f"{p['config3_G']['ms']:.2f} | {p['swarm_65536_P']['ms']:.1f} | {p['config5_G']['ms_per_generation']:.2f} | "
           f"{p['config5_P']['ms_per_generation']:.1f} | {p['device_swarm_65536_P_nowind']['ms_per_generation']:.1f} | "
-          f"{d['sac_collect']['env_steps_per_s']:.3e} |")
+          f"{(d.get('sac_collect') or {}).get('env_steps_per_s', float('nan')):.3e} |")
