@@ -257,7 +257,7 @@ int64_t pd_release_aero_patches(void);
  *     reset -> steps -> steps2 -> 2 steps2 -> 4 steps2 -> ... -> end:
  * an episode still running at a boundary is appended, with its complete state, to continuation
  * records, and the next stage serves the records with 1, 8 or 32 lanes per episode depending on how
- * many there are (per-step latency of a lone episode 50 / 11 / 7.6 us, instructions per
+ * many there are (per-step latency of a lone episode 31 / 10 / 7.1 us, instructions per
  * episode-step 625 / 2 000 / 3 000).  Defaults: 128 / 256 for landing_burn_pure_throttle; one
  * hand-off after 16 steps for landing_burn while a call has at most 1.5 x the GPU's lane count of
  * episodes.  An episode that ends inside the first stage is bit-identical to the one-pass rollout;
