@@ -635,6 +635,11 @@ class pso_wrapped_env:
         `self.capped` = number of episodes of this call that hit max_steps (trunc_id -1)."""
         if isinstance(positions, torch.Tensor) and positions.is_cuda:
             wt = positions.reshape(-1, self.actor.number_of_network_parameters)
+        elif not isinstance(positions, np.ndarray) and len(positions) * self.actor.number_of_network_parameters < (1 << 21):
+            # a list of per-particle arrays (what ParticleSubswarmOptimisation passes): one conversion
+            # straight to float32 - the same rounding as float64 -> float32, half the time
+            wt = torch.as_tensor(np.asarray(positions, dtype=np.float32).reshape(
+                -1, self.actor.number_of_network_parameters)).to(self._b.device)
         else:
             w = np.ascontiguousarray(np.asarray(positions, dtype=np.float64).reshape(
                 -1, self.actor.number_of_network_parameters))
